@@ -1,0 +1,297 @@
+"""Generate tests/golden/*.npz by RUNNING THE REFERENCE (dev container only).
+
+    python tests/golden/make_golden.py            # needs /root/reference and `make -C oracle ref`
+
+What runs:
+  * the reference's compiled CPU ops (oracle/_ref/libabr_ref_cpu.so, built in place from
+    csrc/cpu/ROIAlign_cpu.cpp and csrc/cpu/nms_cpu.cpp) for ROIAlign forward and NMS;
+  * the reference's own Python, imported from /root/reference through stub modules for the
+    packages this image lacks (apex, maskrcnn_benchmark._C, tools.extract_memory, ...):
+    distillation.calculate_attentive_roi_feature_distillation (+ torch autograd),
+    modeling.poolers.Pooler / LevelMapper, structures.boxlist_ops.boxlist_nms, and
+    PascalVOCDataset_ABR._start_mixup / _start_boxes_mosaic / transform_current_data_with_ABR.
+The fixtures are small (KBs) and committed; this script is never imported by tests.
+"""
+import importlib.util
+import io
+import os
+import random
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+REFERENCE = os.environ.get("ABR_REFERENCE", "/root/reference")
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+
+import oracle  # noqa: E402
+
+
+# --------------------------------------------------------------------------- stubs
+class _AnyAttr(types.ModuleType):
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+
+        def _missing(*a, **k):
+            raise RuntimeError("stubbed native op %s called" % name)
+
+        return _missing
+
+
+def install_reference_stubs():
+    sys.path.insert(0, REFERENCE)
+    apex = types.ModuleType("apex")
+    amp = types.ModuleType("apex.amp")
+    amp.float_function = lambda f: f
+    apex.amp = amp
+    sys.modules["apex"], sys.modules["apex.amp"] = apex, amp
+
+    C = _AnyAttr("maskrcnn_benchmark._C")
+
+    def roi_align_forward(inp, rois, scale, ph, pw, ratio):
+        out = oracle.roi_align_forward(inp.numpy(), rois.numpy(), scale, ph, pw, ratio, use_ref=True)
+        return torch.from_numpy(out)
+
+    def nms(dets, scores, thr):
+        return torch.from_numpy(oracle.nms(dets.numpy(), scores.numpy(), thr, "cpu", use_ref=True))
+
+    C.roi_align_forward = roi_align_forward
+    C.nms = nms
+    sys.modules["maskrcnn_benchmark._C"] = C
+    import maskrcnn_benchmark
+
+    maskrcnn_benchmark._C = C
+
+
+def load_voc_abr():
+    """voc_abr.py imports maskrcnn_benchmark.data (which needs `imp`, gone in 3.12) and
+    tools.extract_memory; load it by path with those two stubbed."""
+    data = types.ModuleType("maskrcnn_benchmark.data")
+    tr = types.ModuleType("maskrcnn_benchmark.data.transforms")
+    tr.Compose = object
+    data.transforms = tr
+    sys.modules["maskrcnn_benchmark.data"] = data
+    sys.modules["maskrcnn_benchmark.data.transforms"] = tr
+    tools = types.ModuleType("tools")
+    em = types.ModuleType("tools.extract_memory")
+    em.Mem = object
+    tools.extract_memory = em
+    sys.modules["tools"], sys.modules["tools.extract_memory"] = tools, em
+    path = os.path.join(REFERENCE, "maskrcnn_benchmark/data/datasets/voc_abr.py")
+    spec = importlib.util.spec_from_file_location("ref_voc_abr", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+from inputs import make_boxes, make_rois  # noqa: E402  (tests/inputs.py, shared with the tests)
+
+
+def gen_roi_align(out):
+    rng = np.random.default_rng(11)
+    B, C, H, W = 2, 5, 19, 31
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    rois = make_rois(rng, 40, B, W * 16, H * 16)
+    d = {"input": x, "rois": rois}
+    for P, ratio in [(7, 0), (7, 2), (14, 0), (3, 1)]:
+        d["out_p%d_r%d" % (P, ratio)] = oracle.roi_align_forward(x, rois, 1 / 16, P, P, ratio, use_ref=True)
+    np.savez_compressed(os.path.join(out, "roi_align_fwd.npz"), **d)
+
+
+def gen_nms(out):
+    rng = np.random.default_rng(12)
+    d = {}
+    for n in (1, 63, 64, 65, 300, 1500):
+        b, s = make_boxes(rng, n)
+        d["boxes_%d" % n], d["scores_%d" % n] = b, s
+        for thr in (0.5, 0.7):
+            d["keep_%d_t%d" % (n, int(thr * 10))] = oracle.nms(b, s, thr, "cpu", use_ref=True)
+    np.savez_compressed(os.path.join(out, "nms_cpu.npz"), **d)
+
+
+def gen_ard(out):
+    from maskrcnn_benchmark.distillation.distillation import calculate_attentive_roi_feature_distillation as ref_ard
+
+    rng = np.random.default_rng(13)
+    d = {}
+    for tag, (N, C, P, scale) in {"a": (3, 16, 7, 1.0), "b": (2, 24, 14, 0.5), "c": (2, 10, 7, 3.0)}.items():
+        fo = (scale * rng.standard_normal((N, C, P, P))).astype(np.float32)
+        fn = (fo + 0.1 * scale * rng.standard_normal((N, C, P, P))).astype(np.float32)
+        for gamma in (1.0, 0.25):
+            t_o = torch.from_numpy(fo)
+            t_n = torch.from_numpy(fn).requires_grad_(True)
+            loss = ref_ard(t_o, t_n, gamma)  # call-site order: (teacher, student), train_incremental.py:115
+            loss.backward()
+            t_n64 = torch.from_numpy(fn).double().requires_grad_(True)
+            loss64 = ref_ard(t_o.double(), t_n64, gamma)
+            loss64.backward()
+            k = "%s_g%d" % (tag, int(gamma * 100))
+            d["fo_" + tag], d["fn_" + tag] = fo, fn
+            d["loss32_" + k], d["grad32_" + k] = np.float32(loss.item()), t_n.grad.numpy()
+            d["loss64_" + k], d["grad64_" + k] = np.float64(loss64.item()), t_n64.grad.numpy()
+    np.savez_compressed(os.path.join(out, "ard.npz"), **d)
+
+
+def gen_pooler(out):
+    from maskrcnn_benchmark.modeling.poolers import Pooler
+    from maskrcnn_benchmark.structures.bounding_box import BoxList
+
+    rng = np.random.default_rng(14)
+    B, C = 2, 2
+    im_w, im_h = 800, 640
+    scales = (0.25, 0.125, 0.0625, 0.03125)
+    feats = [rng.standard_normal((B, C, int(im_h * s), int(im_w * s))).astype(np.float32) for s in scales]
+    boxes = []
+    for b in range(B):
+        n = 20 + 5 * b
+        x1, y1 = rng.uniform(0, im_w - 8, n), rng.uniform(0, im_h - 8, n)
+        side = np.exp(rng.uniform(np.log(6), np.log(900), n))
+        x2, y2 = np.minimum(x1 + side, im_w - 1), np.minimum(y1 + side * rng.uniform(0.5, 2, n), im_h - 1)
+        bx = np.stack([x1, y1, x2, y2], 1).astype(np.float32)
+        big = np.array([[0, 0, im_w - 1, im_h - 1], [100, 50, 700, 600], [40, 30, 420, 390], [300, 200, 560, 470]],
+                       np.float32)
+        boxes.append(np.concatenate([bx, big[b::2]], 0))
+    d = {"boxes_%d" % b: bx for b, bx in enumerate(boxes)}
+    d.update({"feat_%d" % i: f for i, f in enumerate(feats)})
+    d["scales"] = np.array(scales, np.float64)
+    d["image_size"] = np.array([im_w, im_h])
+    lists = [BoxList(torch.from_numpy(bx), (im_w, im_h), mode="xyxy") for bx in boxes]
+    for ratio in (2, 0):
+        multi = Pooler((7, 7), scales, ratio)
+        d["multi_r%d" % ratio] = multi([torch.from_numpy(f) for f in feats], lists).numpy()
+        single = Pooler((7, 7), (scales[2],), ratio)
+        d["single_r%d" % ratio] = single([torch.from_numpy(feats[2])], lists).numpy()
+    d["levels"] = multi.map_levels(lists).numpy()
+    np.savez_compressed(os.path.join(out, "pooler.npz"), **d)
+
+
+def gen_boxlist_nms(out):
+    from maskrcnn_benchmark.structures.bounding_box import BoxList
+    from maskrcnn_benchmark.structures.boxlist_ops import boxlist_nms
+
+    rng = np.random.default_rng(15)
+    b, s = make_boxes(rng, 400)
+    labels = rng.integers(1, 21, 400)
+    d = {"boxes": b, "scores": s, "labels": labels}
+    for mode in ("xyxy", "xywh"):
+        bl = BoxList(torch.from_numpy(b), (1000, 600), "xyxy").convert(mode)
+        bl.add_field("scores", torch.from_numpy(s))
+        bl.add_field("labels", torch.from_numpy(labels))
+        for thr, maxp in ((0.7, 50), (0.5, -1), (0.0, -1)):
+            r = boxlist_nms(bl, thr, max_proposals=maxp, score_field="scores")
+            k = "%s_t%d_m%d" % (mode, int(thr * 10), maxp)
+            d["bbox_" + k], d["scores_" + k], d["labels_" + k] = (
+                r.bbox.numpy(), r.get_field("scores").numpy(), r.get_field("labels").numpy())
+    np.savez_compressed(os.path.join(out, "boxlist_nms.npz"), **d)
+
+
+# --------------------------------------------------------------------------- paste
+def _pattern(rng, h, w):
+    """Compressible but non-trivial RGB content: per-channel ramps modulo 256 plus a few flat blocks."""
+    yy, xx = np.mgrid[0:h, 0:w]
+    a, b, c0 = rng.integers(1, 7, 3), rng.integers(1, 7, 3), rng.integers(0, 256, 3)
+    arr = ((xx[..., None] * a + yy[..., None] * b + c0) % 256).astype(np.uint8)
+    for _ in range(4):
+        y, x = int(rng.integers(0, h)), int(rng.integers(0, w))
+        arr[y:y + h // 4, x:x + w // 4] = rng.integers(0, 256, 3)
+    return arr
+
+
+def make_prototypes(rng, n, lo=15, hi=130):
+    """Synthetic Box-Rehearsal memory: ``{cls}_{idx:05d}.png`` -> RGB uint8 array."""
+    protos = []
+    for i in range(n):
+        w, h = int(rng.integers(lo, hi)), int(rng.integers(lo, hi))
+        protos.append(("%d_%05d.png" % (int(rng.integers(1, 16)), i), _pattern(rng, h, w)))
+    return protos
+
+
+def make_scene(rng, W=250, H=188, n_gt=2, big_single=False):
+    img = _pattern(rng, H, W)
+    if big_single:
+        gts = np.array([[10.0, 8.0, W - 12.0, H - 9.0, 17.0]])
+    else:
+        x1, y1 = rng.uniform(0, W * 0.6, n_gt), rng.uniform(0, H * 0.6, n_gt)
+        gts = np.stack([x1, y1, x1 + rng.uniform(15, W * 0.35, n_gt), y1 + rng.uniform(15, H * 0.35, n_gt),
+                        rng.integers(16, 21, n_gt)], 1).astype(np.float64)
+        gts[:, 2] = np.minimum(gts[:, 2], W - 1)
+        gts[:, 3] = np.minimum(gts[:, 3], H - 1)
+    return img, gts
+
+
+def gen_paste(out):
+    from PIL import Image
+
+    voc_abr = load_voc_abr()
+    from maskrcnn_benchmark.structures.bounding_box import BoxList
+    import tempfile
+
+    rng = np.random.default_rng(16)
+    protos = make_prototypes(rng, 24)
+    tmp = tempfile.mkdtemp(prefix="abr_protos_")
+    for name, arr in protos:
+        Image.fromarray(arr).save(os.path.join(tmp, name))
+
+    def new_dataset(batch_size=4):
+        ds = voc_abr.PascalVOCDataset_ABR.__new__(voc_abr.PascalVOCDataset_ABR)
+        ds.PrototypeBoxSelection = types.SimpleNamespace(current_mem_path=tmp, first_mem_path=tmp)
+        ds.BoxRehearsal_path = [n for n, _ in protos]
+        ds.boxes_index = list(range(len(protos)))
+        ds.batch_size = batch_size
+        ds.bg_size = 0
+        return ds
+
+    d = {"proto_names": np.array([n for n, _ in protos])}
+    for i, (_, arr) in enumerate(protos):
+        d["proto_%02d" % i] = arr
+    cases = []
+    # a stream of calls on ONE dataset object so that boxes_index shrinks / refills like in training
+    ds = new_dataset()
+    for case in range(14):
+        seed = 100 + case
+        W, H = (250, 188) if case % 3 else (167, 250)
+        img, gts = make_scene(rng, W, H, n_gt=1 + case % 3, big_single=(case == 5))
+        if case in (8, 9):  # crowded image: forces the retry / bottom-right branches
+            gts = np.array([[5.0, 5.0, W * 0.7, H * 0.55, 16.0], [W * 0.3, H * 0.3, W - 5.0, H - 5.0, 18.0],
+                            [0.0, H * 0.5, W * 0.6, H - 1.0, 17.0]])
+        target = BoxList(torch.tensor(gts[:, :4]), (W, H), mode="xyxy")
+        target.add_field("labels", torch.tensor(gts[:, 4]).long())
+        random.seed(seed)
+        torch.manual_seed(seed)
+        if case < 6 or case in (8, 9):
+            kind = "mixup"
+            o_img, o_t = ds._start_mixup(Image.fromarray(img), target)
+        elif case < 8 or case in (10, 11):
+            kind = "mosaic"
+            o_img, o_t = ds._start_boxes_mosaic(Image.fromarray(img), [], num_boxes=4)
+        else:
+            kind = "auto"
+            o_img, o_t = ds.transform_current_data_with_ABR(Image.fromarray(img), target)
+        k = "case%02d" % case
+        d[k + "_img"], d[k + "_gts"] = img, gts
+        d[k + "_out_img"] = np.array(o_img)
+        d[k + "_out_bbox"] = o_t.bbox.numpy()
+        d[k + "_out_labels"] = o_t.get_field("labels").numpy()
+        d[k + "_out_size"] = np.array(o_t.size)
+        d[k + "_index_after"] = np.array(ds.boxes_index)
+        cases.append("%s:%s:%d" % (k, kind, seed))
+    d["cases"] = np.array(cases)
+    np.savez_compressed(os.path.join(out, "paste.npz"), **d)
+
+
+def main():
+    assert os.path.isdir(REFERENCE), "the reference tree is needed to (re)generate golden vectors"
+    assert oracle.ref_available(), "run `make -C oracle ref` first"
+    install_reference_stubs()
+    for fn in (gen_roi_align, gen_nms, gen_ard, gen_pooler, gen_boxlist_nms, gen_paste):
+        fn(HERE)
+        print("wrote", fn.__name__)
+
+
+if __name__ == "__main__":
+    main()
