@@ -1,0 +1,111 @@
+"""ctypes binding of ``libabr_b200.so`` (the C ABI declared in ``include/abr_b200.h``).
+
+There is no CPU fallback and no alternative backend: if the shared library is missing the import of
+any op fails with instructions to build it, and every op raises on non-CUDA tensors.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libabr_b200.so")
+
+ABR_F32, ABR_BF16 = 0, 1
+ABR_NCHW, ABR_NHWC = 0, 1
+ABR_MAX_LEVELS = 8
+
+_vp, _int, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+
+
+class PasteImage(ctypes.Structure):
+    """``abr_paste_image_t``"""
+    _fields_ = [("offset", ctypes.c_int64), ("height", ctypes.c_int32), ("width", ctypes.c_int32),
+                ("first_op", ctypes.c_int32), ("n_ops", ctypes.c_int32)]
+
+
+class PasteOp(ctypes.Structure):
+    """``abr_paste_op_t``"""
+    _fields_ = [("kind", ctypes.c_int32), ("y0", ctypes.c_int32), ("x0", ctypes.c_int32), ("y1", ctypes.c_int32),
+                ("x1", ctypes.c_int32), ("src_width", ctypes.c_int32), ("sy0", ctypes.c_int32), ("sx0", ctypes.c_int32),
+                ("src_offset", ctypes.c_int64), ("lam", ctypes.c_double), ("fill", ctypes.c_int32),
+                ("pad_", ctypes.c_int32)]
+
+
+PASTE_FILL, PASTE_COPY, PASTE_BLEND = 0, 1, 2
+
+# name -> (restype, argtypes); mirrors include/abr_b200.h one to one (tests/test_abi.py checks the header)
+SIGNATURES = {
+    "abr_version": (_int, []),
+    "abr_last_error": (ctypes.c_char_p, []),
+    "abr_launch_count": (ctypes.c_uint64, []),
+    "abr_roi_align_forward": (_int, [_vp, _vp, _vp] + [_int] * 7 + [_f, _int, _int, _int, _vp]),
+    "abr_roi_align_backward": (_int, [_vp, _vp, _vp] + [_int] * 7 + [_f, _int, _int, _int, _int, _vp]),
+    "abr_roi_align_multilevel_forward": (_int, [_vp, _vp, _vp, _vp, _int, _vp, _vp, _vp] + [_int] * 8 + [_vp]),
+    "abr_roi_align_multilevel_backward": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _int] + [_int] * 9 + [_vp]),
+    "abr_fpn_map_levels": (_int, [_vp, _vp, _int, _f, _f, _f, _f, _f, _vp]),
+    "abr_roi_pool_forward": (_int, [_vp, _vp, _vp, _vp] + [_int] * 7 + [_f, _int, _int, _vp]),
+    "abr_roi_pool_backward": (_int, [_vp, _vp, _vp, _vp] + [_int] * 7 + [_int, _int, _int, _vp]),
+    "abr_nms_workspace_bytes": (_sz, [_vp, _int]),
+    "abr_nms_batched": (_int, [_vp, _vp, _vp, _int, _f, _int, _int, _vp, _int, _vp, _vp, _sz, _vp]),
+    "abr_ard_workspace_bytes": (_sz, [_int, _int, _int]),
+    "abr_ard_forward_backward": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _f, _f, _int, _int, _vp, _sz, _vp]),
+    "abr_scale_if_needed": (_int, [_vp, _sz, _vp, _f, _int, _vp]),
+    "abr_paste_batch": (_int, [_vp, _vp, _int, _vp, _int, _vp, _int, _vp]),
+}
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "abr_iod_b200: %s is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C abr_iod_b200/csrc`); there is no CPU or PyTorch fallback." % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    """The reference surfaces native failures as RuntimeError (AT_ASSERTM / THCudaCheck); so do we."""
+    if rc != 0:
+        raise RuntimeError("abr_b200 error %d: %s" % (rc, lib().abr_last_error().decode()))
+
+
+def stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor: abr_iod_b200 has no CPU path (got device %s)" % (what, t.device))
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return ABR_F32
+    if t.dtype == torch.bfloat16:
+        return ABR_BF16
+    raise RuntimeError("unsupported dtype %s (float32 and bfloat16 are native; float16 is upcast by the wrappers)" % t.dtype)
+
+
+def as_compute_dtype(t: torch.Tensor) -> torch.Tensor:
+    """``amp.float_function`` of the reference (layers/roi_align.py:58, nms.py:8) runs these ops in fp32;
+    bfloat16 additionally has a native path here, everything else is upcast."""
+    return t if t.dtype in (torch.float32, torch.bfloat16) else t.float()
+
+
+def is_channels_last(t: torch.Tensor) -> bool:
+    return t.dim() == 4 and not t.is_contiguous() and t.is_contiguous(memory_format=torch.channels_last)
+
+
+def launch_count() -> int:
+    return int(lib().abr_launch_count())

@@ -1,0 +1,308 @@
+// ard.cu -- Attentive RoI Distillation loss, forward + backward in ONE kernel (sm_100a).
+//
+// Semantics: distillation/distillation.py:86-130 of the reference with the call-site argument order of
+// tools/train_incremental.py:115 (f_old = teacher / old model, no grad; f_new = student):
+//     m_x[n,p] = mean_c f_x^2          A_x = HW * softmax_p(m_x)
+//     L = mean_{n,c,p} A_old (f_old - f_new)^2  +  gamma * mean_{n,p} |A_new - A_old|
+//     dL/df_new = 2 A_old (f_new - f_old)/(N C HW) + (2 f_new / C) HW s_p (g_p - sum_q g_q s_q),
+//         s = softmax(m_new),  g = gamma sign(A_new - A_old)/(N HW)
+// The reference runs ~16 full-tensor PyTorch kernels forward plus autograd's backward and keeps ~10 [N,C,H,W]
+// temporaries.  Here one CTA owns one RoI: pass 1 streams f_old / f_new once (coalesced, vectorised) and reduces
+// sum_c f_old^2, sum_c f_new^2 and sum_c (f_new - f_old)^2 per position; one warp then does both softmaxes and
+// every per-position coefficient in shared memory; pass 2 re-reads the RoI (it was just read by this SM, 0.4-1.6 MB,
+// so it is served from L2) and writes the gradient.  HBM traffic = read 2 tensors + write 1.  The per-RoI loss
+// partials are reduced in fixed order by the last CTA to finish (deterministic, no float atomics).
+#include "common.cuh"
+
+namespace abr {
+
+struct ArdParams {
+  int N, C, HW;
+  float gamma, grad_scale;
+  float* partials;        // [N][2]: sum_p A_old[p] * dd[p],  sum_p |A_new - A_old|
+  unsigned int* counter;  // zeroed before launch
+  float* loss3;
+};
+
+// Shared memory (floats): m_old[HW] m_new[HW] dd[HW] a_old[HW] kk[HW]
+__device__ __forceinline__ void ard_position_phase(const ArdParams& p, float* m_old, float* m_new, const float* dd,
+                                                   float* a_old, float* kk, int n) {
+  // executed by warp 0 only; m_* hold sum_c f^2 on entry
+  const int lane = threadIdx.x & 31;
+  const int HW = p.HW;
+  const float invC = 1.f / (float)p.C;
+  float mxo = -INFINITY, mxn = -INFINITY;
+  for (int i = lane; i < HW; i += 32) {
+    const float a = m_old[i] * invC, b = m_new[i] * invC;
+    m_old[i] = a; m_new[i] = b;
+    mxo = fmaxf(mxo, a); mxn = fmaxf(mxn, b);
+  }
+  mxo = warp_max(mxo); mxn = warp_max(mxn);
+  float so = 0.f, sn = 0.f;
+  for (int i = lane; i < HW; i += 32) {
+    const float eo = expf(m_old[i] - mxo), en = expf(m_new[i] - mxn);
+    m_old[i] = eo; m_new[i] = en;
+    so += eo; sn += en;
+  }
+  so = warp_sum(so); sn = warp_sum(sn);
+  const float fHW = (float)HW;
+  const float gmag = p.gamma / ((float)p.N * fHW);
+  float pad = 0.f, gs = 0.f, afd = 0.f;
+  for (int i = lane; i < HW; i += 32) {
+    const float ao = fHW * (m_old[i] / so);
+    const float s = m_new[i] / sn;
+    const float d = fHW * s - ao;
+    pad += fabsf(d);
+    const float g = d > 0.f ? gmag : (d < 0.f ? -gmag : 0.f);
+    gs = fmaf(g, s, gs);
+    afd = fmaf(ao, dd[i], afd);
+    a_old[i] = ao;
+    m_new[i] = s;  // keep the softmax
+    kk[i] = g;
+  }
+  pad = warp_sum(pad); gs = warp_sum(gs); afd = warp_sum(afd);
+  const float inv_all = 1.f / ((float)p.N * (float)p.C * fHW);
+  const float ka = 2.f * inv_all * p.grad_scale;
+  const float kb = 2.f * invC * fHW * p.grad_scale;
+  for (int i = lane; i < HW; i += 32) {
+    kk[i] = kb * m_new[i] * (kk[i] - gs);
+    a_old[i] *= ka;  // pass 2 needs only ka * A_old
+  }
+  if (lane == 0) {
+    p.partials[2 * n] = afd;
+    p.partials[2 * n + 1] = pad;
+  }
+}
+
+// Last CTA: fixed-order reduction of the per-RoI partials (double accumulation).
+__device__ __forceinline__ void ard_finish(const ArdParams& p) {
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(p.counter, 1u) == (unsigned)(p.N - 1));
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (threadIdx.x < 32) {
+    double afd = 0.0, pad = 0.0;
+    const volatile float* part = p.partials;
+    for (int i = threadIdx.x; i < p.N; i += 32) { afd += (double)part[2 * i]; pad += (double)part[2 * i + 1]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      afd += __shfl_xor_sync(0xffffffffu, afd, o);
+      pad += __shfl_xor_sync(0xffffffffu, pad, o);
+    }
+    if (threadIdx.x == 0) {
+      const double l_afd = afd / ((double)p.N * p.C * p.HW);
+      const double l_pad = pad / ((double)p.N * p.HW);
+      p.loss3[0] = (float)(l_afd + (double)p.gamma * l_pad);
+      p.loss3[1] = (float)l_afd;
+      p.loss3[2] = (float)l_pad;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ NHWC: [N][HW][C]
+// A warp owns whole position rows (C contiguous elements); lanes read 16-byte vectors.
+template <typename T, int V, bool GRAD>
+__global__ void __launch_bounds__(256) ard_nhwc_kernel(ArdParams p, const T* __restrict__ f_old,
+                                                      const T* __restrict__ f_new, T* __restrict__ grad) {
+  extern __shared__ float sm[];
+  const int HW = p.HW, C = p.C, n = blockIdx.x;
+  float* m_old = sm;
+  float* m_new = m_old + HW;
+  float* dd = m_new + HW;
+  float* a_old = dd + HW;
+  float* kk = a_old + HW;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const size_t base = (size_t)n * HW * C;
+  const T* __restrict__ fo = f_old + base;
+  const T* __restrict__ fn = f_new + base;
+
+  for (int pos = warp; pos < HW; pos += nwarp) {
+    const T* ro = fo + (size_t)pos * C;
+    const T* rn = fn + (size_t)pos * C;
+    float so = 0.f, sn = 0.f, sd = 0.f;
+#pragma unroll 4
+    for (int c = lane * V; c < C; c += 32 * V) {
+      float a[V], b[V];
+      VecIO<T, V>::load(ro + c, a);
+      VecIO<T, V>::load(rn + c, b);
+#pragma unroll
+      for (int k = 0; k < V; k++) {
+        so = fmaf(a[k], a[k], so);
+        sn = fmaf(b[k], b[k], sn);
+        const float d = b[k] - a[k];
+        sd = fmaf(d, d, sd);
+      }
+    }
+    so = warp_sum(so); sn = warp_sum(sn); sd = warp_sum(sd);
+    if (lane == 0) { m_old[pos] = so; m_new[pos] = sn; dd[pos] = sd; }
+  }
+  __syncthreads();
+  if (warp == 0) ard_position_phase(p, m_old, m_new, dd, a_old, kk, n);
+  if (GRAD) {
+    __syncthreads();
+    T* g = grad + base;
+    for (int pos = warp; pos < HW; pos += nwarp) {
+      const T* ro = fo + (size_t)pos * C;
+      const T* rn = fn + (size_t)pos * C;
+      T* rg = g + (size_t)pos * C;
+      const float ka = a_old[pos], kb = kk[pos];
+#pragma unroll 4
+      for (int c = lane * V; c < C; c += 32 * V) {
+        float a[V], b[V], o[V];
+        VecIO<T, V>::load(ro + c, a);
+        VecIO<T, V>::load(rn + c, b);
+#pragma unroll
+        for (int k = 0; k < V; k++) o[k] = fmaf(ka, b[k] - a[k], kb * b[k]);
+        VecIO<T, V>::store(rg + c, o);
+      }
+    }
+  }
+  ard_finish(p);
+}
+
+// ------------------------------------------------------------------------------------------ NCHW: [N][C][HW]
+// blockDim.x = G*HW: thread t owns position t % HW and channels t / HW, t / HW + G, ... so that the threads of a
+// CTA always touch blockDim.x consecutive elements (coalesced) and accumulate their position in a register.
+template <typename T, bool GRAD>
+__global__ void __launch_bounds__(1024) ard_nchw_kernel(ArdParams p, const T* __restrict__ f_old,
+                                                       const T* __restrict__ f_new, T* __restrict__ grad, int G) {
+  extern __shared__ float sm[];
+  const int HW = p.HW, C = p.C, n = blockIdx.x;
+  float* m_old = sm;
+  float* m_new = m_old + HW;
+  float* dd = m_new + HW;
+  float* a_old = dd + HW;
+  float* kk = a_old + HW;
+  float* red = kk + HW;  // [3][G*HW]
+  const int T_ = G * HW;  // blockDim.x is T_ rounded up to whole warps; the surplus threads only hit the barriers
+  const int tid = threadIdx.x;
+  const bool active = tid < T_;
+  const int grp = active ? tid / HW : C, pos = active ? tid - grp * HW : 0;  // grp == C: loops are empty
+  const size_t base = (size_t)n * HW * C;
+  const T* __restrict__ fo = f_old + base;
+  const T* __restrict__ fn = f_new + base;
+
+  float so = 0.f, sn = 0.f, sd = 0.f;
+#pragma unroll 4
+  for (int c = grp; c < C; c += G) {
+    float a[1], b[1];
+    VecIO<T, 1>::load(fo + (size_t)c * HW + pos, a);
+    VecIO<T, 1>::load(fn + (size_t)c * HW + pos, b);
+    so = fmaf(a[0], a[0], so);
+    sn = fmaf(b[0], b[0], sn);
+    const float d = b[0] - a[0];
+    sd = fmaf(d, d, sd);
+  }
+  if (active) { red[tid] = so; red[T_ + tid] = sn; red[2 * T_ + tid] = sd; }
+  __syncthreads();
+  if (tid < HW) {
+    float x = 0.f, y = 0.f, z = 0.f;
+    for (int g = 0; g < G; g++) { x += red[g * HW + tid]; y += red[T_ + g * HW + tid]; z += red[2 * T_ + g * HW + tid]; }
+    m_old[tid] = x; m_new[tid] = y; dd[tid] = z;
+  }
+  __syncthreads();
+  if (tid < 32) ard_position_phase(p, m_old, m_new, dd, a_old, kk, n);
+  if (GRAD) {
+    __syncthreads();
+    T* g = grad + base;
+    const float ka = a_old[pos], kb = kk[pos];
+#pragma unroll 4
+    for (int c = grp; c < C; c += G) {
+      float a[1], b[1], o[1];
+      VecIO<T, 1>::load(fo + (size_t)c * HW + pos, a);
+      VecIO<T, 1>::load(fn + (size_t)c * HW + pos, b);
+      o[0] = fmaf(ka, b[0] - a[0], kb * b[0]);
+      VecIO<T, 1>::store(g + (size_t)c * HW + pos, o);
+    }
+  }
+  ard_finish(p);
+}
+
+template <typename T>
+__global__ void scale_if_needed_kernel(T* data, size_t n, const float* __restrict__ scale, float expected) {
+  const float s = *scale;
+  if (s == expected) return;
+  const float f = s / expected;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float v[1];
+    v[0] = (float)data[i] * f;
+    VecIO<T, 1>::store(data + i, v);
+  }
+}
+
+template <typename T, int V>
+static int launch_nhwc(const ArdParams& p, const void* fo, const void* fn, void* g, cudaStream_t st) {
+  const size_t smem = (size_t)5 * p.HW * sizeof(float);
+  if (g) ard_nhwc_kernel<T, V, true><<<p.N, 256, smem, st>>>(p, static_cast<const T*>(fo), static_cast<const T*>(fn), static_cast<T*>(g));
+  else ard_nhwc_kernel<T, V, false><<<p.N, 256, smem, st>>>(p, static_cast<const T*>(fo), static_cast<const T*>(fn), nullptr);
+  ABR_CHECK_LAUNCH("ard_forward_backward");
+  return ABR_OK;
+}
+
+template <typename T>
+static int launch_nchw(const ArdParams& p, const void* fo, const void* fn, void* g, cudaStream_t st) {
+  int G = 512 / p.HW;
+  if (G < 1) G = 1;
+  if (G > p.C) G = p.C;
+  const int threads = ceil_div(G * p.HW, 32) * 32;
+  const size_t smem = (size_t)(5 * p.HW + 3 * G * p.HW) * sizeof(float);
+  if (g) ard_nchw_kernel<T, true><<<p.N, threads, smem, st>>>(p, static_cast<const T*>(fo), static_cast<const T*>(fn), static_cast<T*>(g), G);
+  else ard_nchw_kernel<T, false><<<p.N, threads, smem, st>>>(p, static_cast<const T*>(fo), static_cast<const T*>(fn), nullptr, G);
+  ABR_CHECK_LAUNCH("ard_forward_backward");
+  return ABR_OK;
+}
+
+}  // namespace abr
+
+using namespace abr;
+
+extern "C" {
+
+size_t abr_ard_workspace_bytes(int N, int C, int HW) {
+  (void)C; (void)HW;
+  if (N < 0) return 0;
+  return 256 + (size_t)N * 2 * sizeof(float);
+}
+
+int abr_ard_forward_backward(const void* f_old, const void* f_new, void* grad_new, float* loss3, int N, int C, int HW,
+                             float gamma, float grad_scale, int dtype, int layout, void* workspace,
+                             size_t workspace_bytes, abr_stream_t stream) {
+  ABR_REQUIRE(N > 0 && C > 0 && HW > 0, ABR_ERR_BAD_ARG, "ard: bad sizes N=%d C=%d HW=%d (the reference's mean over an empty tensor is NaN)", N, C, HW);
+  ABR_REQUIRE(f_old && f_new && loss3, ABR_ERR_BAD_ARG, "ard: null pointer");
+  ABR_REQUIRE(dtype == ABR_F32 || dtype == ABR_BF16, ABR_ERR_UNSUPPORTED, "ard: dtype %d not supported", dtype);
+  ABR_REQUIRE(layout == ABR_NCHW || layout == ABR_NHWC, ABR_ERR_UNSUPPORTED, "ard: layout %d not supported", layout);
+  ABR_REQUIRE(HW <= 1024, ABR_ERR_UNSUPPORTED, "ard: %d positions per RoI (max 1024)", HW);
+  ABR_REQUIRE(workspace && workspace_bytes >= abr_ard_workspace_bytes(N, C, HW), ABR_ERR_WORKSPACE,
+              "ard: workspace %zu B < %zu B", workspace_bytes, abr_ard_workspace_bytes(N, C, HW));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ArdParams p;
+  p.N = N; p.C = C; p.HW = HW; p.gamma = gamma; p.grad_scale = grad_scale;
+  p.counter = static_cast<unsigned int*>(workspace);
+  p.partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
+  p.loss3 = loss3;
+  ABR_CUDA_OK(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), st));
+  if (layout == ABR_NHWC) {
+    if (dtype == ABR_F32) return (C % 4 == 0) ? launch_nhwc<float, 4>(p, f_old, f_new, grad_new, st) : launch_nhwc<float, 1>(p, f_old, f_new, grad_new, st);
+    return (C % 8 == 0) ? launch_nhwc<__nv_bfloat16, 8>(p, f_old, f_new, grad_new, st) : launch_nhwc<__nv_bfloat16, 1>(p, f_old, f_new, grad_new, st);
+  }
+  if (dtype == ABR_F32) return launch_nchw<float>(p, f_old, f_new, grad_new, st);
+  return launch_nchw<__nv_bfloat16>(p, f_old, f_new, grad_new, st);
+}
+
+int abr_scale_if_needed(void* data, size_t n, const float* scale_dev, float expected, int dtype, abr_stream_t stream) {
+  ABR_REQUIRE(dtype == ABR_F32 || dtype == ABR_BF16, ABR_ERR_UNSUPPORTED, "scale: dtype %d not supported", dtype);
+  ABR_REQUIRE(expected != 0.f, ABR_ERR_BAD_ARG, "scale: expected scale must be non-zero");
+  if (n == 0) return ABR_OK;
+  ABR_REQUIRE(data && scale_dev, ABR_ERR_BAD_ARG, "scale: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = (int)std::min<size_t>(ceil_div<size_t>(n, 256), (size_t)num_sms() * 16);
+  if (dtype == ABR_F32) scale_if_needed_kernel<float><<<blocks, 256, 0, st>>>(static_cast<float*>(data), n, scale_dev, expected);
+  else scale_if_needed_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<__nv_bfloat16*>(data), n, scale_dev, expected);
+  ABR_CHECK_LAUNCH("scale_if_needed");
+  return ABR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,351 @@
+"""Box-Rehearsal replay (ABR mixup / mosaic) with the pixels pasted on the GPU by ONE kernel per batch.
+
+Mirrors ``PascalVOCDataset_ABR`` of the reference (data/datasets/voc_abr.py): ``_sample_per_bbox_from_boxrehearsal``
+(:512-553), ``_start_mixup`` (:555-698), ``_start_boxes_mosaic`` (:700-816), ``transform_current_data_with_ABR``
+(:821-858) and ``compute_overlap`` (:932-954) keep their names, argument meaning, random draw ORDER (Python ``random``
+and ``torch.distributions.Beta``) and integer coordinate arithmetic, so seeded runs give the same boxes and the same
+pixels as the reference.  What changes is where the pixels move: the host only PLANS rectangles
+(:class:`PastePlan`); ``abr_paste_batch`` of libabr_b200 executes the plans of a whole batch in one launch, reading
+prototypes from a device-resident pool (the Box-Rehearsal memory is uploaded once per rank).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import random
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+from PIL import Image
+
+from .. import _lib
+from ..structures.bounding_box import BoxList
+
+
+@dataclass
+class PasteOpPlan:
+    kind: int                      # _lib.PASTE_FILL / PASTE_COPY / PASTE_BLEND
+    dst: tuple                     # (y0, x0, y1, x1)
+    proto: int = -1                # index into the resident pool, or -1 when `pixels` carries a resized crop
+    pixels: np.ndarray = None      # HWC uint8 (only when the prototype had to be resized on the host)
+    src_hw: tuple = (0, 0)         # prototype height, width
+    src_origin: tuple = (0, 0)     # (sy0, sx0)
+    lam: float = 0.0
+    fill: int = 0
+
+
+@dataclass
+class PastePlan:
+    kind: str                      # "none" | "mixup" | "mosaic"
+    height: int
+    width: int
+    base: np.ndarray = None        # HWC uint8 the ops start from (None for mosaic: the canvas is filled)
+    ops: list = field(default_factory=list)
+    gts: np.ndarray = None         # [G,5] x1,y1,x2,y2,label (float64 for mixup/none, int64 for mosaic)
+
+
+class BoxRehearsalPaster:
+    """Holds the Box-Rehearsal memory (prototype crops) and replays it into images.
+
+    Arguments:
+        prototypes: list of ``(file_name, image)`` with ``file_name = "{class}_{index}.ext"`` as written by
+            tools/extract_memory.py:220-236 and ``image`` a PIL image or HWC uint8 array -- the list is used in
+            the given order (the reference shuffles it once, voc_abr.py:397).
+        batch_size: ``cfg.SOLVER.IMS_PER_BATCH``; ``boxes_index`` is refilled when fewer entries remain.
+        device: CUDA device of the pool and of the pasted batch.
+    """
+
+    def __init__(self, prototypes, batch_size, bg_size=0, device="cuda"):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("BoxRehearsalPaster needs a CUDA device: abr_iod_b200 has no CPU path")
+        self.BoxRehearsal_path = [n for n, _ in prototypes]
+        self._pil = [im if isinstance(im, Image.Image) else Image.fromarray(np.asarray(im)) for _, im in prototypes]
+        self._pil = [im.convert("RGB") for im in self._pil]
+        self.boxes_index = list(range(len(self.BoxRehearsal_path)))
+        self.batch_size = batch_size
+        self.bg_size = bg_size
+        # device-resident pool of the prototypes at their native size
+        arrays = [np.ascontiguousarray(np.asarray(im)) for im in self._pil]
+        self._pool_offsets = np.zeros(len(arrays) + 1, np.int64)
+        for i, a in enumerate(arrays):
+            self._pool_offsets[i + 1] = self._pool_offsets[i] + a.size
+        self._pool_bytes = int(self._pool_offsets[-1])
+        host = np.concatenate([a.reshape(-1) for a in arrays]) if arrays else np.zeros(0, np.uint8)
+        self._arena = torch.empty((max(self._pool_bytes, 1) + (8 << 20),), dtype=torch.uint8, device=self.device)
+        if self._pool_bytes:
+            self._arena[: self._pool_bytes].copy_(torch.from_numpy(host))
+
+    # ------------------------------------------------------------------ planning (host; reference draw order)
+    def _sample_per_bbox_from_boxrehearsal(self, i, im_shape):
+        """voc_abr.py:512-553.  Returns (prototype id, scaled width, scaled height, class, resized pixels or None)."""
+        pid = self.boxes_index[i]
+        name = self.BoxRehearsal_path[pid]
+        cls_name, _ = os.path.splitext(name)[0].split("_")
+        box_im = self._pil[pid]
+        box_o_w, box_o_h = box_im.size
+        im_mean_size = np.mean(im_shape)
+        box_mean_size = np.mean(np.array([int(box_o_w), int(box_o_h)]))
+        if float(im_mean_size * 0.2) <= float(box_mean_size) <= float(im_mean_size * 0.7):
+            box_scale = 1.0
+        else:
+            box_scale = random.uniform(float(im_mean_size * 0.4), float(im_mean_size * 0.6)) / float(box_mean_size)
+        w, h = int(box_scale * box_o_w), int(box_scale * box_o_h)
+        pixels = None
+        if (w, h) != (box_o_w, box_o_h):
+            pixels = np.ascontiguousarray(np.asarray(box_im.resize((w, h))))  # PIL default filter, as the reference
+        return pid, w, h, int(cls_name), pixels
+
+    @staticmethod
+    def compute_overlap(a, b):
+        """voc_abr.py:932-954"""
+        area = (b[2] - b[0] + 1) * (b[3] - b[1] + 1)
+        iw = np.maximum(np.minimum(a[2], b[2]) - np.maximum(a[0], b[0]) + 1, 0)
+        ih = np.maximum(np.minimum(a[3], b[3]) - np.maximum(a[1], b[1]) + 1, 0)
+        aa = (a[2] - a[0] + 1) * (a[3] - a[1] + 1)
+        inter = iw * ih
+        flag = bool(inter / aa > 0.3 or inter / area > 0.3)
+        return inter / area, flag
+
+    def _refill(self):
+        if len(self.boxes_index) < self.batch_size:
+            self.boxes_index = list(range(len(self.BoxRehearsal_path)))
+
+    def plan_mixup(self, image, gts, alpha=2.0, beta=5.0) -> PastePlan:
+        """Coordinates of voc_abr.py:555-698 for one image (HWC uint8 array, gts [G,5])."""
+        image = np.ascontiguousarray(np.asarray(image))
+        H, W = image.shape[0], image.shape[1]
+        gts = np.array(gts, dtype=np.float64).reshape(-1, 5)
+        plan = PastePlan("mixup", H, W, base=image)
+        mix = True
+        if gts.shape[0] == 1:
+            gw, gh = gts[0][2] - gts[0][0], gts[0][3] - gts[0][1]
+            if (W - gw) < (W * 0.25) and (H - gh) < (H * 0.25):
+                mix = False
+        if mix:
+            lam = torch.distributions.beta.Beta(alpha, beta).sample().item()
+            self._refill()
+            count = 0
+            for i in range(3):
+                pid, bw, bh, cls, pixels = self._sample_per_bbox_from_boxrehearsal(i, image.shape)
+                pos_x = random.randint(0, int(W * 0.6))
+                pos_y = random.randint(0, int(H * 0.4))
+                new_gt = [pos_x, pos_y, bw + pos_x, bh + pos_y]
+                if gts.shape[0] == 0:
+                    raise RuntimeError("mixup needs at least one ground-truth box (the reference loops forever)")
+                tries, restart = 0, True
+                while restart:
+                    for g in gts:
+                        _, overlap = self.compute_overlap(g, new_gt)
+                        if tries >= 20:
+                            restart = False
+                        elif tries < 10 and overlap:
+                            pos_x = random.randint(0, int(W * 0.6))
+                            pos_y = random.randint(0, int(H * 0.4))
+                            new_gt = [pos_x, pos_y, bw + pos_x, bh + pos_y]
+                            tries += 1
+                            restart = True
+                            break
+                        elif 10 <= tries < 20 and overlap:
+                            pos_x = random.randint(int(W * 0.4), W)
+                            pos_y = random.randint(int(H * 0.6), H)
+                            new_gt = [pos_x - bw, pos_y - bh, pos_x, pos_y]
+                            tries += 1
+                            restart = True
+                            break
+                        else:
+                            restart = False
+                if tries < 20:
+                    a = b = c = d = 0
+                    if new_gt[3] >= H:
+                        a, new_gt[3] = new_gt[3] - H, H
+                    if new_gt[2] >= W:
+                        b, new_gt[2] = new_gt[2] - W, W
+                    if new_gt[0] < 0:
+                        c, new_gt[0] = -new_gt[0], 0
+                    if new_gt[1] < 0:
+                        d, new_gt[1] = -new_gt[1], 0
+                    if a == 0 and b == 0:
+                        sy0, sx0, sy1, sx1 = d, c, bh, bw
+                    elif a == 0:
+                        sy0, sx0, sy1, sx1 = 0, 0, bh, bw - b
+                    elif b == 0:
+                        sy0, sx0, sy1, sx1 = 0, 0, bh - a, bw
+                    else:
+                        sy0, sx0, sy1, sx1 = 0, 0, bh - a, bw - b
+                    x0, y0, x1, y1 = new_gt
+                    if (y1 - y0, x1 - x0) != (sy1 - sy0, sx1 - sx0):
+                        raise ValueError("could not broadcast input array from shape (%d,%d,3) into shape (%d,%d,3)"
+                                         % (sy1 - sy0, sx1 - sx0, y1 - y0, x1 - x0))
+                    plan.ops.append(PasteOpPlan(_lib.PASTE_BLEND, (y0, x0, y1, x1), proto=pid if pixels is None else -1,
+                                                pixels=pixels, src_hw=(bh, bw), src_origin=(sy0, sx0), lam=lam))
+                    row = np.array([[x0, y0, x1, y1, cls]], dtype=np.float64)
+                    gts = row if gts.shape[0] == 0 else np.insert(gts, 0, values=row, axis=0)
+                    if pid in self.boxes_index:
+                        self.boxes_index.remove(pid)
+                count += 1
+                if count >= 2:
+                    break
+        plan.gts = gts
+        return plan
+
+    def plan_mosaic(self, image_size, num_boxes=4) -> PastePlan:
+        """Coordinates of voc_abr.py:700-816 (``targets=[]`` as at :841).  ``image_size`` is PIL's (W, H)."""
+        s = int(np.mean(image_size))
+        yc = int(random.uniform(s * 0.4, s * 0.6))
+        xc = int(random.uniform(s * 0.4, s * 0.6))
+        self._refill()
+        picks = [self._sample_per_bbox_from_boxrehearsal(i, image_size) for i in range(num_boxes)]
+        plan = PastePlan("mosaic", s, s)
+        gt4 = []
+        for i, (pid, w, h, cls, pixels) in enumerate(picks):
+            if i % 4 == 0:    # top right
+                xc_, yc_ = xc + self.bg_size, yc - self.bg_size
+                plan.ops.append(PasteOpPlan(_lib.PASTE_FILL, (0, 0, s, s), fill=114))  # new canvas (voc_abr.py:744)
+                x1a, y1a, x2a, y2a = xc_, max(yc_ - h, 0), min(xc_ + w, s), yc_
+                x1b, y1b, x2b, y2b = 0, h - (y2a - y1a), min(w, x2a - x1a), h
+            elif i % 4 == 1:  # bottom left
+                xc_, yc_ = xc - self.bg_size, yc + self.bg_size
+                x1a, y1a, x2a, y2a = max(xc_ - w, 0), yc_, xc_, min(s, yc_ + h)
+                x1b, y1b, x2b, y2b = w - (x2a - x1a), 0, max(xc_, w), min(y2a - y1a, h)
+            elif i % 4 == 2:  # bottom right
+                xc_, yc_ = xc + self.bg_size, yc + self.bg_size
+                x1a, y1a, x2a, y2a = xc_, yc_, min(xc_ + w, s), min(s, yc_ + h)
+                x1b, y1b, x2b, y2b = 0, 0, min(w, x2a - x1a), min(y2a - y1a, h)
+            else:             # top left
+                xc_, yc_ = xc - self.bg_size, yc - self.bg_size
+                x1a, y1a, x2a, y2a = max(xc_ - w, 0), max(yc_ - h, 0), xc_, yc_
+                x1b, y1b, x2b, y2b = w - (x2a - x1a), h - (y2a - y1a), w, h
+            x2b, y2b = min(x2b, w), min(y2b, h)  # numpy clamps a slice stop
+            if (y2a - y1a, x2a - x1a) != (y2b - y1b, x2b - x1b) or x1b < 0 or y1b < 0:
+                raise ValueError("could not broadcast input array from shape (%d,%d,3) into shape (%d,%d,3)"
+                                 % (y2b - y1b, x2b - x1b, y2a - y1a, x2a - x1a))
+            plan.ops.append(PasteOpPlan(_lib.PASTE_COPY, (y1a, x1a, y2a, x2a), proto=pid if pixels is None else -1,
+                                        pixels=pixels, src_hw=(h, w), src_origin=(y1b, x1b)))
+            padw, padh = x1a - x1b, y1a - y1b
+            gt4.append(np.array([[0 + padw, 0 + padh, w + padw, h + padh, cls]]))
+            if pid in self.boxes_index:
+                self.boxes_index.remove(pid)
+        gt4 = np.concatenate(gt4, 0)
+        for col in (0, 2, 1, 3):
+            np.clip(gt4[:, col], 0, s, out=gt4[:, col])
+        keep = [r for r in range(gt4.shape[0])
+                if not ((gt4[r][2] - gt4[r][0]) <= 2.0 or (gt4[r][3] - gt4[r][1]) <= 2.0)]
+        plan.gts = gt4[keep]
+        return plan
+
+    def plan_transform(self, image, gts) -> PastePlan:
+        """Policy of voc_abr.py:821-858: 25 % mixup, 25 % mosaic, 50 % untouched.  ``image``: PIL image."""
+        kind = "none"
+        if random.randint(0, 1) == 0:
+            kind = "mixup" if random.randint(0, 1) == 0 else "mosaic"
+        if kind == "mosaic":
+            return self.plan_mosaic(image.size)
+        if kind == "mixup":
+            return self.plan_mixup(image, gts)
+        arr = np.ascontiguousarray(np.asarray(image))
+        return PastePlan("none", arr.shape[0], arr.shape[1], base=arr,
+                         gts=np.array(gts, dtype=np.float64).reshape(-1, 5))
+
+    # ------------------------------------------------------------------ execution (device)
+    def execute(self, plans):
+        """Run the plans of a batch in ONE ``abr_paste_batch`` launch.
+
+        Returns a list of uint8 CUDA tensors [H_i, W_i, 3] (views into an arena that the next call reuses)."""
+        n = len(plans)
+        # staging layout after the resident pool: [image 0][image 1]...[extra crops...]
+        img_off, cursor = [], 0
+        for p in plans:
+            img_off.append(cursor)
+            cursor += p.height * p.width * 3
+        extras = []
+        for p in plans:
+            for op in p.ops:
+                if op.pixels is not None:
+                    extras.append((cursor, op))
+                    cursor += op.pixels.size
+        need = self._pool_bytes + cursor
+        if need > self._arena.numel():
+            arena = torch.empty((need + (need >> 2),), dtype=torch.uint8, device=self.device)
+            arena[: self._pool_bytes].copy_(self._arena[: self._pool_bytes])
+            self._arena = arena
+        staging = torch.empty((max(cursor, 1),), dtype=torch.uint8, pin_memory=True)
+        snp = staging.numpy()
+        for p, off in zip(plans, img_off):
+            if p.base is not None:
+                snp[off: off + p.base.size] = p.base.reshape(-1)
+        extra_off = {}
+        for off, op in extras:
+            snp[off: off + op.pixels.size] = op.pixels.reshape(-1)
+            extra_off[id(op)] = off
+        n_ops = sum(len(p.ops) for p in plans)
+        images = (_lib.PasteImage * max(n, 1))()
+        ops = (_lib.PasteOp * max(n_ops, 1))()
+        k = 0
+        max_pix = 0
+        for i, (p, off) in enumerate(zip(plans, img_off)):
+            images[i] = _lib.PasteImage(off, p.height, p.width, k, len(p.ops))
+            max_pix = max(max_pix, p.height * p.width)
+            for op in p.ops:
+                if op.kind == _lib.PASTE_FILL:
+                    src_off = 0
+                elif op.pixels is not None:
+                    src_off = self._pool_bytes + extra_off[id(op)]
+                else:
+                    src_off = int(self._pool_offsets[op.proto])
+                y0, x0, y1, x1 = op.dst
+                ops[k] = _lib.PasteOp(op.kind, y0, x0, y1, x1, op.src_hw[1], op.src_origin[0], op.src_origin[1],
+                                      src_off, float(op.lam), int(op.fill), 0)
+                k += 1
+        canvas = self._arena[self._pool_bytes: self._pool_bytes + max(cursor, 1)]
+        with torch.cuda.device(self.device):
+            canvas[: max(cursor, 1)].copy_(staging[: max(cursor, 1)], non_blocking=True)
+            if n_ops:
+                desc = torch.frombuffer(bytearray(bytes(images)) + bytearray(bytes(ops)), dtype=torch.uint8)
+                desc_dev = desc.to(self.device)
+                img_bytes = ctypes.sizeof(_lib.PasteImage) * max(n, 1)
+                _lib.check(_lib.lib().abr_paste_batch(
+                    canvas.data_ptr(), desc_dev.data_ptr(), n, desc_dev.data_ptr() + img_bytes, n_ops,
+                    self._arena.data_ptr(), max_pix, _lib.stream_ptr(self.device)))
+        self._keepalive = (staging,)
+        return [canvas[off: off + p.height * p.width * 3].view(p.height, p.width, 3) for p, off in zip(plans, img_off)]
+
+    def paste_batch(self, images, targets):
+        """ABR replay of a batch: ``images`` list of PIL images, ``targets`` list of [G,5] arrays.
+        Returns (list of uint8 CUDA tensors [H,W,3], list of [G',5] arrays, list of kinds)."""
+        plans = [self.plan_transform(im, g) for im, g in zip(images, targets)]
+        return self.execute(plans), [p.gts for p in plans], [p.kind for p in plans]
+
+    # ------------------------------------------------------------------ the reference's per-image entry points
+    @staticmethod
+    def _targets_to_array(targets):
+        if isinstance(targets, np.ndarray):
+            return targets
+        bbox = targets.bbox.tolist()
+        labels = targets.get_field("labels").tolist()
+        return np.array([b + [l] for b, l in zip(bbox, labels)], dtype=np.float64).reshape(-1, 5)
+
+    def _finish(self, plan):
+        (out,) = self.execute([plan])
+        img = Image.fromarray(out.cpu().numpy())
+        target = BoxList(torch.as_tensor(plan.gts[:, :4]), (plan.width, plan.height))
+        target.add_field("labels", torch.tensor(plan.gts[:, 4]))
+        return img, target
+
+    def _start_mixup(self, image, targets, alpha=2.0, beta=5.0):
+        """voc_abr.py:555-698: (PIL image, BoxList|ndarray) -> (PIL image, BoxList with float64 ``labels``)."""
+        return self._finish(self.plan_mixup(np.array(image), self._targets_to_array(targets), alpha, beta))
+
+    def _start_boxes_mosaic(self, s_imgs=[], targets=[], num_boxes=4):
+        """voc_abr.py:700-816: only ``s_imgs.size`` is used; returns (PIL image, BoxList with int64 ``labels``)."""
+        if len(targets):
+            raise NotImplementedError("the reference only ever calls _start_boxes_mosaic with targets=[] (voc_abr.py:841)")
+        return self._finish(self.plan_mosaic(s_imgs.size, num_boxes))
+
+    def transform_current_data_with_ABR(self, img=None, target=None):
+        """voc_abr.py:821-858"""
+        plan = self.plan_transform(img, self._targets_to_array(target))
+        if plan.kind == "none":
+            return img, target
+        return self._finish(plan)

@@ -1,0 +1,99 @@
+"""``ROIAlign`` / ``roi_align`` with the reference's signatures (maskrcnn_benchmark/layers/roi_align.py:12-70),
+backed by ``abr_roi_align_forward/backward`` of libabr_b200 (sm_100a).
+
+Layout: a channels-last input (``x.contiguous(memory_format=torch.channels_last)``) takes the vectorised NHWC
+kernels and yields a channels-last output; anything else is treated as the reference's contiguous NCHW.
+"""
+import torch
+from torch import nn
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+from torch.nn.modules.utils import _pair
+
+from .. import _lib
+
+
+def _prep_rois(rois, device):
+    if rois.dim() != 2 or rois.size(1) != 5:
+        raise RuntimeError("rois must be [R,5] (batch_index, x1, y1, x2, y2), got %s" % (tuple(rois.shape),))
+    _lib.require_cuda(rois, "rois")
+    return rois.detach().to(dtype=torch.float32).contiguous()
+
+
+def roi_align_forward(input, rois, spatial_scale, pooled_h, pooled_w, sampling_ratio):
+    """``_C.roi_align_forward`` (csrc/ROIAlign.h:11-25)."""
+    _lib.require_cuda(input, "input")
+    rois = _prep_rois(rois, input.device)
+    nhwc = _lib.is_channels_last(input)
+    x = input if nhwc else input.contiguous()
+    B, C, H, W = x.shape
+    R = rois.size(0)
+    out = torch.empty((R, C, pooled_h, pooled_w), dtype=x.dtype, device=x.device,
+                      memory_format=torch.channels_last if nhwc else torch.contiguous_format)
+    if out.numel() == 0:
+        return out
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().abr_roi_align_forward(
+            x.data_ptr(), rois.data_ptr(), out.data_ptr(), B, C, H, W, R, pooled_h, pooled_w,
+            float(spatial_scale), int(sampling_ratio), _lib.dtype_code(x),
+            _lib.ABR_NHWC if nhwc else _lib.ABR_NCHW, _lib.stream_ptr(x.device)))
+    return out
+
+
+def roi_align_backward(grad, rois, spatial_scale, pooled_h, pooled_w, batch_size, channels, height, width,
+                       sampling_ratio, channels_last=None):
+    """``_C.roi_align_backward`` (csrc/ROIAlign.h:27-46).  ``channels_last=None`` follows ``grad``'s layout."""
+    _lib.require_cuda(grad, "grad")
+    rois = _prep_rois(rois, grad.device)
+    nhwc = _lib.is_channels_last(grad) if channels_last is None else bool(channels_last)
+    g = grad.contiguous(memory_format=torch.channels_last) if nhwc else grad.contiguous()
+    gin = torch.empty((batch_size, channels, height, width), dtype=g.dtype, device=g.device,
+                      memory_format=torch.channels_last if nhwc else torch.contiguous_format)
+    if gin.numel() == 0:
+        return gin
+    with torch.cuda.device(g.device):
+        _lib.check(_lib.lib().abr_roi_align_backward(
+            g.data_ptr(), rois.data_ptr(), gin.data_ptr(), batch_size, channels, height, width, rois.size(0),
+            pooled_h, pooled_w, float(spatial_scale), int(sampling_ratio), _lib.dtype_code(g),
+            _lib.ABR_NHWC if nhwc else _lib.ABR_NCHW, 1, _lib.stream_ptr(g.device)))
+    return gin
+
+
+class _ROIAlign(Function):
+    @staticmethod
+    def forward(ctx, input, roi, output_size, spatial_scale, sampling_ratio):
+        ctx.save_for_backward(roi)
+        ctx.output_size = _pair(output_size)
+        ctx.spatial_scale = spatial_scale
+        ctx.sampling_ratio = sampling_ratio
+        ctx.input_shape = input.size()
+        ctx.channels_last = _lib.is_channels_last(input)
+        return roi_align_forward(input, roi, spatial_scale, ctx.output_size[0], ctx.output_size[1], sampling_ratio)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        (rois,) = ctx.saved_tensors
+        bs, ch, h, w = ctx.input_shape
+        grad_input = roi_align_backward(grad_output, rois, ctx.spatial_scale, ctx.output_size[0], ctx.output_size[1],
+                                        bs, ch, h, w, ctx.sampling_ratio, channels_last=ctx.channels_last)
+        return grad_input, None, None, None, None
+
+
+def roi_align(input, rois, output_size, spatial_scale, sampling_ratio):
+    return _ROIAlign.apply(_lib.as_compute_dtype(input), rois, output_size, spatial_scale, sampling_ratio)
+
+
+class ROIAlign(nn.Module):
+    def __init__(self, output_size, spatial_scale, sampling_ratio):
+        super(ROIAlign, self).__init__()
+        self.output_size = output_size
+        self.spatial_scale = spatial_scale
+        self.sampling_ratio = sampling_ratio
+
+    def forward(self, input, rois):
+        return roi_align(input, rois, self.output_size, self.spatial_scale, self.sampling_ratio)
+
+    def __repr__(self):
+        return "%s(output_size=%s, spatial_scale=%s, sampling_ratio=%s)" % (
+            self.__class__.__name__, self.output_size, self.spatial_scale, self.sampling_ratio)

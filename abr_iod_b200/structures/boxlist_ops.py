@@ -1,0 +1,37 @@
+"""``boxlist_nms`` with the reference's signature (structures/boxlist_ops.py:9-31) and its batched form."""
+import torch
+
+from ..layers.nms import nms as _box_nms
+from ..layers.nms import nms_batched as _box_nms_batched
+
+
+def boxlist_nms(boxlist, nms_thresh, max_proposals=-1, score_field="scores"):
+    """Non-maximum suppression on a BoxList; scores come from ``score_field``.  If ``max_proposals > 0`` only the
+    first ``max_proposals`` kept boxes (in ascending index order, like the reference) survive."""
+    if nms_thresh <= 0:
+        return boxlist
+    mode = boxlist.mode
+    boxlist = boxlist.convert("xyxy")
+    keep = _box_nms(boxlist.bbox, boxlist.get_field(score_field), nms_thresh)
+    if max_proposals > 0:
+        keep = keep[:max_proposals]
+    boxlist = boxlist[keep.to(boxlist.bbox.device)]
+    return boxlist.convert(mode)
+
+
+def boxlist_nms_batched(boxlists, nms_thresh, max_proposals=-1, score_field="scores"):
+    """``[boxlist_nms(b, ...) for b in boxlists]`` with ONE device pass and one host sync for the whole batch
+    (replaces the per-image loop of modeling/rpn/inference.py:111-117)."""
+    if nms_thresh <= 0 or len(boxlists) == 0:
+        return list(boxlists)
+    modes = [b.mode for b in boxlists]
+    xyxy = [b.convert("xyxy") for b in boxlists]
+    nonempty = [i for i, b in enumerate(xyxy) if len(b) > 0]
+    out = list(xyxy)
+    if nonempty:
+        keep, n_keep = _box_nms_batched([xyxy[i].bbox for i in nonempty],
+                                        [xyxy[i].get_field(score_field) for i in nonempty], nms_thresh, max_proposals)
+        counts = n_keep.tolist()  # the only synchronisation of the batch
+        for j, i in enumerate(nonempty):
+            out[i] = xyxy[i][keep[j, : counts[j]]]
+    return [b.convert(m) for b, m in zip(out, modes)]

@@ -1,0 +1,175 @@
+/*
+ * abr_b200.h -- C ABI of libabr_b200.so: the RoI hot path of ABR_IOD on B200 (sm_100a).
+ *
+ * This is the drop-in boundary.  It replaces the pybind11 module `maskrcnn_benchmark._C`
+ * of the reference (maskrcnn_benchmark/csrc/vision.cpp:9-24) for the ops on the hot path and
+ * adds native entry points for the two ops the reference runs as Python (ARD loss, ABR paste).
+ * INTEGRATION.md shows the reference-side binding for every function.
+ *
+ * Conventions (all functions):
+ *   - plain C types only; every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - the caller owns every buffer, including workspaces; nothing is allocated, freed or
+ *     synchronised here; work is enqueued on `stream` (a cudaStream_t) and the call returns;
+ *   - return value: ABR_OK or an ABR_ERR_* code; abr_last_error() gives the thread-local text;
+ *   - `dtype`  : element type of feature maps / pooled tensors / gradients (rois are always fp32);
+ *   - `layout` : ABR_NCHW = the reference's contiguous [B,C,H,W] -> [R,C,PH,PW];
+ *                ABR_NHWC = channels-last storage of the same logical tensors,
+ *                [B,H,W,C] -> [R,PH,PW,C] (torch.channels_last), the vectorised fast path.
+ *   - rois are [R,5] fp32 rows (batch_index, x1, y1, x2, y2) in image pixels, exactly the
+ *     reference's format (modeling/poolers.py:73-78).
+ */
+#ifndef ABR_B200_H_
+#define ABR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABR_B200_VERSION 100 /* major*100 + minor */
+
+#if defined(__GNUC__)
+#define ABR_API __attribute__((visibility("default")))
+#else
+#define ABR_API
+#endif
+
+typedef void* abr_stream_t; /* cudaStream_t */
+
+enum abr_status {
+  ABR_OK = 0,
+  ABR_ERR_BAD_ARG = 1,     /* null pointer, negative size, rois not [R,5], ... */
+  ABR_ERR_UNSUPPORTED = 2, /* dtype / layout / size combination not implemented */
+  ABR_ERR_CUDA = 3,        /* launch or runtime error; text has cudaGetErrorString */
+  ABR_ERR_WORKSPACE = 4    /* workspace pointer null or smaller than *_workspace_bytes() */
+};
+
+enum abr_dtype { ABR_F32 = 0, ABR_BF16 = 1 };
+enum abr_layout { ABR_NCHW = 0, ABR_NHWC = 1 };
+
+ABR_API int abr_version(void);
+ABR_API const char* abr_last_error(void);
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+ABR_API uint64_t abr_launch_count(void);
+
+/* ---------------------------------------------------------------- ROIAlign
+ * Replaces _C.roi_align_forward / _C.roi_align_backward
+ *   (csrc/ROIAlign.h:11-46, csrc/cuda/ROIAlign_cuda.cu:257-346, csrc/cpu/ROIAlign_cpu.cpp:221-257).
+ * sampling_ratio <= 0 selects the adaptive grid ceil(roi_size / pooled_size) (ROIAlign_cuda.cu:100-101).
+ * R == 0 is a no-op (ROIAlign_cuda.cu:278-281). */
+ABR_API int abr_roi_align_forward(const void* input, const float* rois, void* output,
+                          int B, int C, int H, int W, int R, int PH, int PW,
+                          float spatial_scale, int sampling_ratio,
+                          int dtype, int layout, abr_stream_t stream);
+
+/* grad_input [B,C,H,W] is zero-filled first when zero_init != 0 (the reference always does,
+ * ROIAlign_cuda.cu:316); pass 0 to accumulate into an existing gradient. */
+ABR_API int abr_roi_align_backward(const void* grad_output, const float* rois, void* grad_input,
+                           int B, int C, int H, int W, int R, int PH, int PW,
+                           float spatial_scale, int sampling_ratio,
+                           int dtype, int layout, int zero_init, abr_stream_t stream);
+
+/* Multi-level (FPN) pooling in ONE launch: replaces the per-level nonzero / gather / launch / scatter
+ * loop of Pooler.forward (modeling/poolers.py:93-105).  `levels[r]` in [0,L) selects the feature map
+ * of RoI r (LevelMapper, modeling/poolers.py:31-42).  inputs_host / hs_host / ws_host / scales_host
+ * are HOST arrays of length L (L <= ABR_MAX_LEVELS); every level has the same B and C.
+ * Output rows stay in RoI order. */
+#define ABR_MAX_LEVELS 8
+ABR_API int abr_roi_align_multilevel_forward(const void* const* inputs_host, const int* hs_host, const int* ws_host,
+                                     const float* scales_host, int L,
+                                     const float* rois, const int32_t* levels, void* output,
+                                     int B, int C, int R, int PH, int PW, int sampling_ratio,
+                                     int dtype, int layout, abr_stream_t stream);
+ABR_API int abr_roi_align_multilevel_backward(const void* grad_output, const float* rois, const int32_t* levels,
+                                      void* const* grad_inputs_host, const int* hs_host, const int* ws_host,
+                                      const float* scales_host, int L,
+                                      int B, int C, int R, int PH, int PW, int sampling_ratio,
+                                      int dtype, int layout, int zero_init, abr_stream_t stream);
+
+/* FPN level of each RoI: floor(k0 + log2(sqrt(area)/s0 + eps)) clamped to [k_min,k_max], minus k_min,
+ * area with the +1 convention (modeling/poolers.py:31-42, structures/bounding_box.py:227-231). */
+ABR_API int abr_fpn_map_levels(const float* rois, int32_t* levels, int R, float k_min, float k_max,
+                       float canonical_scale, float canonical_level, float eps, abr_stream_t stream);
+
+/* ---------------------------------------------------------------- ROIPool
+ * Replaces _C.roi_pool_forward / _C.roi_pool_backward
+ *   (csrc/ROIPool.h:9-48, csrc/cuda/ROIPool_cuda.cu:16-202).
+ * argmax is int32 with the flat index h*W+w inside the (image, channel) plane or -1 for an empty
+ * bin (ROIPool_cuda.cu:57-75,125); it has the layout of `output`. */
+ABR_API int abr_roi_pool_forward(const void* input, const float* rois, void* output, int32_t* argmax,
+                         int B, int C, int H, int W, int R, int PH, int PW, float spatial_scale,
+                         int dtype, int layout, abr_stream_t stream);
+ABR_API int abr_roi_pool_backward(const void* grad_output, const int32_t* argmax, const float* rois, void* grad_input,
+                          int B, int C, int H, int W, int R, int PH, int PW,
+                          int dtype, int layout, int zero_init, abr_stream_t stream);
+
+/* ---------------------------------------------------------------- NMS (batched, no host sync)
+ * Replaces _C.nms (csrc/nms.h:10-28, csrc/cuda/nms.cu:70-131) and the per-image Python loop that
+ * calls it (modeling/rpn/inference.py:111-117, structures/boxlist_ops.py:9-31).
+ *   boxes  [total,4] fp32 xyxy, scores [total] fp32: the images' boxes back to back;
+ *   offsets_host [n_images+1]: HOST prefix offsets, image i owns [offsets[i], offsets[i+1]);
+ *   keep   [n_images, keep_stride] int64: per image the surviving indices RELATIVE TO THE IMAGE,
+ *          ascending (nms.cu:127-130), truncated to max_keep when max_keep > 0
+ *          (boxlist_ops.py:28-29); unused tail is filled with -1;  keep_stride >= min(n_i, max_keep);
+ *   n_keep [n_images] int32: number of valid entries per image.
+ * Greedy order is by score descending, ties by ascending index (torch.sort(stable=True)); the
+ * reference's tie order is whatever its torch.sort(stable=False) yields.  Suppression test is
+ * IoU > thresh with the +1 pixel convention, IEEE fp32 without contraction (nms.cu:13-21,60);
+ * `ge` != 0 selects the CPU flavour IoU >= thresh (csrc/cpu/nms_cpu.cpp:60). */
+ABR_API size_t abr_nms_workspace_bytes(const int* offsets_host, int n_images);
+ABR_API int abr_nms_batched(const float* boxes, const float* scores, const int* offsets_host, int n_images,
+                    float thresh, int ge, int max_keep, int64_t* keep, int keep_stride, int32_t* n_keep,
+                    void* workspace, size_t workspace_bytes, abr_stream_t stream);
+
+/* ---------------------------------------------------------------- Attentive RoI Distillation
+ * Native form of calculate_attentive_roi_feature_distillation (distillation/distillation.py:86-130)
+ * and of its autograd backward, in one kernel.  f_old = old model / teacher pooled features (argument 0
+ * at the call site, tools/train_incremental.py:115; no gradient), f_new = student features.
+ *   loss3 [3] fp32: { L_afd + gamma*L_pad, L_afd, L_pad }  (written, not accumulated)
+ *   grad_new: dL/df_new * grad_scale, same dtype/layout as f_new; may be NULL (loss only).
+ * Logical shape [N,C,H,W] with HW = H*W positions; layout ABR_NCHW ([N,C,HW]) or ABR_NHWC ([N,HW,C]). */
+ABR_API size_t abr_ard_workspace_bytes(int N, int C, int HW);
+ABR_API int abr_ard_forward_backward(const void* f_old, const void* f_new, void* grad_new, float* loss3,
+                             int N, int C, int HW, float gamma, float grad_scale,
+                             int dtype, int layout, void* workspace, size_t workspace_bytes,
+                             abr_stream_t stream);
+/* data[i] *= (*scale_dev / expected) unless *scale_dev == expected (then no memory is touched):
+ * lets the autograd backward apply an upstream gradient that differs from the grad_scale baked in. */
+ABR_API int abr_scale_if_needed(void* data, size_t n, const float* scale_dev, float expected, int dtype,
+                        abr_stream_t stream);
+
+/* ---------------------------------------------------------------- ABR paste (mixup / mosaic)
+ * Pixel part of PascalVOCDataset_ABR._start_mixup / _start_boxes_mosaic
+ * (data/datasets/voc_abr.py:659-678 and :744-763) for a whole batch in one launch.  All images are
+ * HWC uint8 (3 channels) inside one `canvas` buffer; prototypes are HWC uint8 inside one `pool`.
+ * Ops of one image are applied in order per pixel (a later mixup box sees the earlier blend). */
+enum abr_paste_kind {
+  ABR_PASTE_FILL = 0,  /* dst rect <- value (mosaic canvas, 114; voc_abr.py:744) */
+  ABR_PASTE_COPY = 1,  /* dst rect <- src rect (mosaic quadrant; voc_abr.py:763) */
+  ABR_PASTE_BLEND = 2  /* dst rect <- trunc(lambda*dst + (1-lambda)*src) in fp64 (voc_abr.py:659-678) */
+};
+typedef struct abr_paste_image {
+  int64_t offset; /* byte offset of pixel (0,0) inside canvas */
+  int32_t height, width;
+  int32_t first_op, n_ops; /* this image's slice of the ops array */
+} abr_paste_image_t;
+typedef struct abr_paste_op {
+  int32_t kind;
+  int32_t y0, x0, y1, x1; /* destination rectangle [y0,y1) x [x0,x1) */
+  int32_t src_width;      /* row pitch of the prototype in pixels */
+  int32_t sy0, sx0;       /* top-left of the source window inside the prototype */
+  int64_t src_offset;     /* byte offset of the prototype inside pool */
+  double lambda;          /* BLEND weight of the destination */
+  int32_t fill;           /* FILL value 0..255 */
+  int32_t pad_;
+} abr_paste_op_t;
+ABR_API int abr_paste_batch(uint8_t* canvas, const abr_paste_image_t* images, int n_images,
+                    const abr_paste_op_t* ops, int n_ops, const uint8_t* pool, int max_pixels_per_image,
+                    abr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABR_B200_H_ */

@@ -1,0 +1,179 @@
+"""GPU parity of ROIAlign / ROIPool / Pooler through the reference-shaped Python API (-> C ABI -> sm_100a kernels)
+against the CPU oracle and the golden vectors produced by the reference itself.
+
+Tolerance (north_star: "within 1e-5 relative error in fp32"): |a-b| <= 1e-5 * max|ref| + 1e-5 * |ref|.
+bf16 (stated tolerance): inputs are rounded to bf16 first, then |a-b| <= 2e-2 * max|ref|."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from inputs import make_rois
+
+pytestmark = pytest.mark.gpu
+
+
+def close(a, ref, rel=1e-5):
+    a, ref = np.asarray(a, np.float64), np.asarray(ref, np.float64)
+    scale = np.abs(ref).max() if ref.size else 1.0
+    err = np.abs(a - ref)
+    ok = err <= rel * scale + rel * np.abs(ref)
+    assert ok.all(), "max err %g (scale %g) at %s" % (err.max(), scale, np.unravel_index(err.argmax(), err.shape))
+
+
+def dev(x, channels_last=False):
+    t = torch.as_tensor(x).cuda()
+    return t.contiguous(memory_format=torch.channels_last) if channels_last else t
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_roi_align_forward_golden(golden, channels_last):
+    from abr_iod_b200.layers import ROIAlign
+
+    g = golden("roi_align_fwd.npz")
+    x, rois = dev(g["input"], channels_last), dev(g["rois"])
+    for P, ratio in [(7, 0), (7, 2), (14, 0), (3, 1)]:
+        out = ROIAlign((P, P), 1 / 16, ratio)(x, rois)
+        assert out.shape == (len(g["rois"]), x.shape[1], P, P) and out.dtype == torch.float32
+        assert out.is_contiguous(memory_format=torch.channels_last if channels_last else torch.contiguous_format)
+        close(out.cpu().numpy(), g["out_p%d_r%d" % (P, ratio)])
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+@pytest.mark.parametrize("C", [3, 8, 64, 260])
+@pytest.mark.parametrize("P,ratio", [(7, 0), (7, 2), (14, 0), (2, 3)])
+def test_roi_align_forward_backward_vs_oracle(channels_last, C, P, ratio):
+    from abr_iod_b200.layers import roi_align
+
+    rng = np.random.default_rng(C * 100 + P * 10 + ratio)
+    B, H, W = 3, 25, 38
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    rois = make_rois(rng, 50, B, W * 16, H * 16)
+    xt = dev(x, channels_last).requires_grad_(True)
+    out = roi_align(xt, dev(rois), (P, P), 1 / 16, ratio)
+    close(out.detach().cpu().numpy(), oracle.roi_align_forward(x, rois, 1 / 16, P, P, ratio))
+    gout = rng.standard_normal(out.shape).astype(np.float32)
+    out.backward(dev(gout, channels_last))
+    assert xt.grad.shape == xt.shape
+    close(xt.grad.cpu().numpy(), oracle.roi_align_backward(gout, rois, 1 / 16, P, P, B, C, H, W, ratio))
+
+
+def test_roi_align_empty_and_errors():
+    from abr_iod_b200.layers import ROIAlign
+
+    x = torch.randn(1, 4, 8, 8, device="cuda", requires_grad=True)
+    out = ROIAlign((7, 7), 0.25, 2)(x, torch.zeros((0, 5), device="cuda"))
+    assert out.shape == (0, 4, 7, 7)
+    out.sum().backward()
+    assert x.grad is not None and not x.grad.any()
+    with pytest.raises(RuntimeError):
+        ROIAlign((7, 7), 0.25, 2)(x, torch.zeros((3, 4), device="cuda"))
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_roi_align_bf16_and_fp16(channels_last):
+    from abr_iod_b200.layers import roi_align
+
+    rng = np.random.default_rng(3)
+    B, C, H, W, P = 2, 64, 20, 30, 7
+    x = torch.from_numpy(rng.standard_normal((B, C, H, W)).astype(np.float32)).bfloat16()
+    rois = make_rois(rng, 40, B, W * 16, H * 16)
+    ref = oracle.roi_align_forward(x.float().numpy(), rois, 1 / 16, P, P, 0)
+    xt = dev(x, channels_last).requires_grad_(True)
+    out = roi_align(xt, dev(rois), (P, P), 1 / 16, 0)
+    assert out.dtype == torch.bfloat16  # native bf16 path
+    assert np.abs(out.float().cpu().numpy() - ref).max() <= 2e-2 * np.abs(ref).max()
+    gout = torch.from_numpy(rng.standard_normal(out.shape).astype(np.float32)).bfloat16()
+    out.backward(dev(gout, channels_last))
+    gref = oracle.roi_align_backward(gout.float().numpy(), rois, 1 / 16, P, P, B, C, H, W, 0)
+    assert np.abs(xt.grad.float().cpu().numpy() - gref).max() <= 4e-2 * np.abs(gref).max()
+    # fp16 is upcast like amp.float_function does (layers/roi_align.py:58): fp32 out
+    out16 = roi_align(dev(x.half().float().half(), channels_last), dev(rois), (P, P), 1 / 16, 0)
+    assert out16.dtype == torch.float32
+    close(out16.cpu().numpy(), oracle.roi_align_forward(x.half().float().numpy(), rois, 1 / 16, P, P, 0))
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_roi_align_full_size_adjoint_property(channels_last):
+    """Config-1 shapes (B=2, C=1024, 38x63, 1024 RoIs, P=7): <fwd(x), g> == <x, bwd(g)> (the op is linear and the
+    backward is its transpose), plus a slice checked against the oracle."""
+    from abr_iod_b200.layers import roi_align
+
+    rng = np.random.default_rng(8)
+    B, C, H, W, P, R = 2, 1024, 38, 63, 7, 1024
+    x = torch.randn(B, C, H, W, device="cuda")
+    rois = make_rois(rng, R, B, 1000, 600)
+    xt = (x.contiguous(memory_format=torch.channels_last) if channels_last else x).requires_grad_(True)
+    out = roi_align(xt, dev(rois), (P, P), 1 / 16, 0)
+    g = torch.randn_like(out)
+    out.backward(g)
+    lhs = (out.detach().double() * g.double()).sum().item()
+    rhs = (x.double() * xt.grad.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), abs(rhs), 1.0) + 1e-3
+    sl = slice(100, 116)
+    ref = oracle.roi_align_forward(x[:, sl].cpu().numpy(), rois, 1 / 16, P, P, 0)
+    close(out.detach()[:, sl].cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_roi_pool_vs_oracle(channels_last):
+    from abr_iod_b200.layers import ROIPool
+    from abr_iod_b200.layers.roi_pool import roi_pool_forward
+
+    rng = np.random.default_rng(4)
+    B, C, H, W = 2, 10, 22, 33
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    rois = make_rois(rng, 60, B, W * 16, H * 16)
+    for P in (7, 3):
+        ref_out, ref_arg = oracle.roi_pool_forward(x, rois, 1 / 16, P, P)
+        out, arg = roi_pool_forward(dev(x, channels_last), dev(rois), 1 / 16, P, P)
+        assert arg.dtype == torch.int32
+        assert np.array_equal(out.cpu().numpy(), ref_out)  # max pooling is exact
+        assert np.array_equal(arg.cpu().numpy(), ref_arg)
+        xt = dev(x, channels_last).requires_grad_(True)
+        o = ROIPool((P, P), 1 / 16)(xt, dev(rois))
+        gout = rng.standard_normal(o.shape).astype(np.float32)
+        o.backward(dev(gout, channels_last))
+        close(xt.grad.cpu().numpy(), oracle.roi_pool_backward(gout, ref_arg, rois, B, C, H, W))
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_pooler_golden_single_and_multi_level(golden, channels_last):
+    from abr_iod_b200.modeling.poolers import Pooler
+    from abr_iod_b200.structures.bounding_box import BoxList
+
+    g = golden("pooler.npz")
+    feats = [dev(g["feat_%d" % i], channels_last) for i in range(4)]
+    size = tuple(int(v) for v in g["image_size"])
+    boxes = [BoxList(dev(g["boxes_%d" % b]), size, "xyxy") for b in range(2)]
+    scales = tuple(g["scales"].tolist())
+    for ratio in (2, 0):
+        multi = Pooler((7, 7), scales, ratio)
+        assert np.array_equal(multi.map_levels(boxes).cpu().numpy(), g["levels"].astype(np.int64))
+        close(multi(feats, boxes).cpu().numpy(), g["multi_r%d" % ratio])
+        single = Pooler((7, 7), (scales[2],), ratio)
+        close(single([feats[2]], boxes).cpu().numpy(), g["single_r%d" % ratio])
+
+
+def test_pooler_multilevel_backward_vs_per_level_oracle(golden):
+    from abr_iod_b200.modeling.poolers import Pooler
+    from abr_iod_b200.structures.bounding_box import BoxList
+    from oracle import pooler as opooler
+
+    g = golden("pooler.npz")
+    size = tuple(int(v) for v in g["image_size"])
+    boxes_np = [g["boxes_0"], g["boxes_1"]]
+    boxes = [BoxList(dev(b), size, "xyxy") for b in boxes_np]
+    scales = tuple(g["scales"].tolist())
+    feats = [dev(g["feat_%d" % i]).requires_grad_(True) for i in range(4)]
+    out = Pooler((7, 7), scales, 2)(feats, boxes)
+    rng = np.random.default_rng(2)
+    gout = rng.standard_normal(out.shape).astype(np.float32)
+    out.backward(dev(gout))
+    rois = opooler.to_roi_format(boxes_np)
+    levels = g["levels"].astype(np.int64)
+    for lvl in range(4):
+        idx = np.nonzero(levels == lvl)[0]
+        f = g["feat_%d" % lvl]
+        ref = oracle.roi_align_backward(gout[idx], rois[idx], scales[lvl], 7, 7, *f.shape, 2)
+        close(feats[lvl].grad.cpu().numpy(), ref)
