@@ -51,7 +51,7 @@ __device__ __forceinline__ void ard_position_phase(const ArdParams& p, float* m_
   for (int i = lane; i < HW; i += 32) {
     const float ao = fHW * (m_old[i] / so);
     const float s = m_new[i] / sn;
-    const float d = fHW * s - ao;
+    const float d = __fsub_rn(__fmul_rn(fHW, s), ao);  // no FMA: identical inputs must give exactly 0, as in the reference
     pad += fabsf(d);
     const float g = d > 0.f ? gmag : (d < 0.f ? -gmag : 0.f);
     gs = fmaf(g, s, gs);

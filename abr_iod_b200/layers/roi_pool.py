@@ -20,7 +20,7 @@ def roi_pool_forward(input, rois, spatial_scale, pooled_h, pooled_w):
     R = rois.size(0)
     fmt = torch.channels_last if nhwc else torch.contiguous_format
     out = torch.empty((R, C, pooled_h, pooled_w), dtype=x.dtype, device=x.device, memory_format=fmt)
-    argmax = torch.zeros((R, C, pooled_h, pooled_w), dtype=torch.int32, device=x.device, memory_format=fmt)
+    argmax = torch.empty((R, C, pooled_h, pooled_w), dtype=torch.int32, device=x.device, memory_format=fmt)
     if out.numel() == 0:
         return out, argmax
     with torch.cuda.device(x.device):

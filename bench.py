@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on B200: ROIAlign+ARD RoIs/s, forward+backward.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--layout nhwc|nchw]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+A "step" is one pass of the RoI hot path over one batch of synthetic input at the shapes of BASELINE.json
+configs[1] (VOC 15-5 ABR incremental step, batch 4 per GPU): teacher and student R-50-C4 feature maps
+[4,1024,50,76] fp32 (800x1216 images, stride 16), 512 RoIs per image, POOLER_RESOLUTION 7, adaptive sampling
+(sampling_ratio 0).  The work unit is the composite of SURVEY.md section 8d: one RoI through teacher ROIAlign
+forward, student ROIAlign forward, ARD loss forward+backward (gamma=1) and student ROIAlign backward.
+Work shards by image, so N GPUs run N independent batches (weak scaling, no data-path collective).
+
+One JSON line on rank 0: `value` = RoIs/s with inputs resident in HBM (CUDA events over exactly K steps, max over
+ranks); `e2e` = the same metric through the public Python API with HOST buffers (pinned H2D of both feature maps
+and the RoIs, D2H of the loss and of the student feature-map gradient inside the timed region); `roofline` for the
+dominant kernel from per-kernel CUDA events; `cpu_baseline` = the reference's CPU path on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOAD = dict(B=4, C=1024, H=50, W=76, rois_per_image=512, P=7, sampling_ratio=0, scale=1.0 / 16,
+                image_w=1216, image_h=800)
+METRIC = "ROIAlign+ARD RoIs/s fwd+bwd"
+UNIT = "RoIs/s"
+
+
+def make_workload(seed=0, rois=None):
+    """Synthetic VOC-shaped batch: student = teacher + 0.1*noise; RoI centres uniform in the image,
+    sides U(16,400) px, clipped to the image, 5 % degenerate (< 1 px)."""
+    w = WORKLOAD
+    rng = np.random.default_rng(seed)
+    teacher = rng.standard_normal((w["B"], w["C"], w["H"], w["W"]), dtype=np.float32)
+    student = teacher + np.float32(0.1) * rng.standard_normal(teacher.shape, dtype=np.float32)
+    R = w["B"] * w["rois_per_image"] if rois is None else rois
+    cx, cy = rng.uniform(0, w["image_w"], R), rng.uniform(0, w["image_h"], R)
+    bw, bh = rng.uniform(16, 400, R), rng.uniform(16, 400, R)
+    deg = rng.uniform(0, 1, R) < 0.05
+    bw[deg] = rng.uniform(0, 1, deg.sum())
+    x1, x2 = np.clip(cx - bw / 2, 0, w["image_w"] - 1), np.clip(cx + bw / 2, 0, w["image_w"] - 1)
+    y1, y2 = np.clip(cy - bh / 2, 0, w["image_h"] - 1), np.clip(cy + bh / 2, 0, w["image_h"] - 1)
+    img = np.repeat(np.arange(w["B"]), -(-R // w["B"]))[:R]
+    roi = np.stack([img, x1, y1, x2, y2], 1).astype(np.float32)
+    return teacher, student, roi
+
+
+def algorithmic_bytes(R):
+    """per kernel and for the composite unit (3*BCHW*s + 60R + 6*R*C*P^2*s)."""
+    w = WORKLOAD
+    fmap = w["B"] * w["C"] * w["H"] * w["W"] * 4
+    pooled = R * w["C"] * w["P"] * w["P"] * 4
+    return {"roi_align_fwd": fmap + 20 * R + pooled, "roi_align_bwd": pooled + 20 * R + fmap, "ard": 3 * pooled,
+            "composite": 3 * fmap + 60 * R + 6 * pooled}
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def summary(self, t0, t1):
+        if self.proc is not None:
+            self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15 and len(r) >= 6] or [r for _, r in self.rows if len(r) >= 6]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons, "samples": len(rows)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference
+def cpu_reference_sample(n_rois, threads=None):
+    """The reference's CPU path for the composite unit on `n_rois` RoIs of the workload.  ROIAlign forward is the
+    reference's own ROIAlign_forward_cpu (oracle/_ref, single-threaded by construction: csrc/cpu/ROIAlign_cpu.cpp:133)
+    when it was compiled, else the C port; ARD is the PyTorch op sequence of distillation.py:86-130 on all host
+    threads; ROIAlign backward has no CPU reference (csrc/ROIAlign.h:44) and is timed with the C port of the CUDA
+    kernel.  Returns (seconds, description)."""
+    import torch
+
+    import oracle
+    from oracle import ard_torch
+
+    if threads:
+        torch.set_num_threads(threads)
+    w = WORKLOAD
+    teacher, student, rois = make_workload(0, rois=n_rois)
+    use_ref = oracle.ref_available()
+    t0 = time.perf_counter()
+    f_old = oracle.roi_align_forward(teacher, rois, w["scale"], w["P"], w["P"], w["sampling_ratio"], use_ref=use_ref)
+    f_new = oracle.roi_align_forward(student, rois, w["scale"], w["P"], w["P"], w["sampling_ratio"], use_ref=use_ref)
+    _, grad = ard_torch.ard_fwd_bwd(torch.from_numpy(f_old), torch.from_numpy(f_new), 1.0)
+    oracle.roi_align_backward(grad.numpy(), rois, w["scale"], w["P"], w["P"], w["B"], w["C"], w["H"], w["W"],
+                              w["sampling_ratio"])
+    dt = time.perf_counter() - t0
+    kind = "reference" if use_ref else "port"
+    desc = ("%d RoIs of the same workload: ROIAlign_forward_cpu x2 (%s, 1 thread), PyTorch ARD fwd+bwd (%d threads), "
+            "ROIAlign backward (C port of the CUDA kernel, 1 thread; the reference has no CPU backward)"
+            % (n_rois, "oracle/_ref" if use_ref else "oracle port", torch.get_num_threads()))
+    return dt, kind, desc, torch.get_num_threads()
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    # calibrate the bounded sample so that K steps take about a minute in total (8..256 RoIs per step)
+    cpu_reference_sample(8)
+    per_roi = cpu_reference_sample(16)[0] / 16
+    sample = int(max(8, min(256, 60.0 / max(args.steps, 1) / per_roi)))
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_sample(sample)
+    t, kind, desc, cores = 0.0, "port", "", 1
+    for _ in range(args.steps):
+        dt, kind, desc, cores = cpu_reference_sample(sample)
+        t += dt
+    value = sample * args.steps / t
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(workload_config(), sample_rois_per_step=sample),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config():
+    w = WORKLOAD
+    return {"workload": "configs[1] VOC 15-5 ABR step, RoI hot path: teacher+student R-50-C4 maps [%d,%d,%d,%d] fp32, "
+                        "%d RoIs/img, P=%d, sampling_ratio=%d; unit = teacher ROIAlign fwd + student ROIAlign fwd + "
+                        "ARD fwd+bwd + student ROIAlign bwd" % (w["B"], w["C"], w["H"], w["W"], w["rois_per_image"],
+                                                              w["P"], w["sampling_ratio"]),
+            "batch_per_gpu": w["B"], "rois_per_gpu": w["B"] * w["rois_per_image"], "parallelism": "data-parallel by image",
+            "l2": "per-step inputs+outputs 2.65 GB >> 126 MB L2, no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------------------ ours
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from abr_iod_b200 import _lib
+    from abr_iod_b200.distillation.distillation import _ard_launch
+    from abr_iod_b200.distillation.distillation import calculate_attentive_roi_feature_distillation as ard
+    from abr_iod_b200.layers import ROIAlign
+    from abr_iod_b200.layers.roi_align import roi_align_backward, roi_align_forward
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    w = WORKLOAD
+    nhwc = args.layout == "nhwc"
+    fmt = torch.channels_last if nhwc else torch.contiguous_format
+    teacher_np, student_np, rois_np = make_workload(seed=rank)
+    R = rois_np.shape[0]
+    teacher = torch.from_numpy(teacher_np).to(dev).contiguous(memory_format=fmt)
+    student = torch.from_numpy(student_np).to(dev).contiguous(memory_format=fmt)
+    rois = torch.from_numpy(rois_np).to(dev)
+    P, ratio, scale = w["P"], w["sampling_ratio"], w["scale"]
+    names = ("roi_align_fwd_teacher", "roi_align_fwd_student", "ard", "roi_align_bwd")
+
+    def step(ev=None):
+        marks = []
+
+        def mark():
+            if ev is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append(e)
+        mark()
+        f_old = roi_align_forward(teacher, rois, scale, P, P, ratio)
+        mark()
+        f_new = roi_align_forward(student, rois, scale, P, P, ratio)
+        mark()
+        loss3, g = _ard_launch(f_old, f_new, 1.0, True)
+        mark()
+        gin = roi_align_backward(g, rois, scale, P, P, w["B"], w["C"], w["H"], w["W"], ratio, channels_last=nhwc)
+        mark()
+        if ev is not None:
+            ev.append(marks)
+        return loss3, gin
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = _lib.launch_count()
+    events = []
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    start.record()
+    for _ in range(args.steps):
+        step(events)
+    end.record()
+    barrier()
+    t1 = time.time()
+    elapsed_ms = start.elapsed_time(end)
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.summary(t0, t1) if sampler else None
+    per_kernel = {n: sum(m[i].elapsed_time(m[i + 1]) for m in events) / len(events) for i, n in enumerate(names)}
+
+    # ---- end to end through the public API with host buffers
+    pool = ROIAlign((P, P), scale, ratio)
+    h_teacher = torch.from_numpy(teacher_np).contiguous(memory_format=fmt).pin_memory()
+    h_student = torch.from_numpy(student_np).contiguous(memory_format=fmt).pin_memory()
+    h_rois = torch.from_numpy(rois_np).pin_memory()
+    h_grad = torch.empty_like(h_student).pin_memory()
+    h_loss = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        t = h_teacher.to(dev, non_blocking=True)
+        s = h_student.to(dev, non_blocking=True).requires_grad_(True)
+        r = h_rois.to(dev, non_blocking=True)
+        with torch.no_grad():
+            f_old = pool(t, r)
+        f_new = pool(s, r)
+        loss = ard(f_old, f_new, 1.0)
+        loss.backward()
+        h_loss.copy_(loss.detach(), non_blocking=True)
+        h_grad.copy_(s.grad, non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e2e_steps = max(3, min(args.steps, 20))
+    es, ee = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    es.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    ee.record()
+    barrier()
+    e2e_ms = es.elapsed_time(ee)
+
+    if world > 1:
+        t = torch.tensor([elapsed_ms, e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, e2e_ms = t.tolist()
+        lt = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    if rank != 0:
+        return
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    ab = algorithmic_bytes(R)
+    kbytes = {"roi_align_fwd_teacher": ab["roi_align_fwd"], "roi_align_fwd_student": ab["roi_align_fwd"], "ard": ab["ard"],
+              "roi_align_bwd": ab["roi_align_bwd"]}
+    dominant = max(per_kernel, key=per_kernel.get)
+    achieved = kbytes[dominant] / (per_kernel[dominant] * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.layout, {}).get(dominant)
+    ms_per_step = elapsed_ms / args.steps
+    value = world * R / (ms_per_step * 1e-3)
+    kernels = {n: {"ms": round(per_kernel[n], 4), "GB/s": round(kbytes[n] / (per_kernel[n] * 1e-3) / 1e9, 1),
+                   "frac": round(kbytes[n] / (per_kernel[n] * 1e-3) / 1e9 / peak, 4)} for n in names}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": dict(workload_config(), layout=args.layout),
+        "e2e": {"value": world * R / (e2e_ms / e2e_steps * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": int(h_teacher.numel() * 4 + h_student.numel() * 4 + h_rois.numel() * 4),
+                "d2h_bytes_per_step": int(h_grad.numel() * 4 + 4), "steps": e2e_steps},
+        "gpu_launches": launches, "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": dominant, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": kbytes[dominant]},
+        "composite": {"algorithmic_bytes_per_step": ab["composite"],
+                      "GB/s": round(ab["composite"] / (ms_per_step * 1e-3) / 1e9, 1),
+                      "frac_of_hbm_peak": round(ab["composite"] / (ms_per_step * 1e-3) / 1e9 / peak, 4)},
+        "kernels": kernels,
+    }
+    if world == 1 and not args.no_cpu:
+        dt, kind, desc, cores = cpu_reference_sample(args.cpu_rois)
+        line["cpu_baseline"] = {"value": args.cpu_rois / dt, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
+    if world == 1 and not args.no_secondary:
+        line["secondary"] = secondary_metrics(dev)
+    print(json.dumps(line))
+
+
+def secondary_metrics(dev):
+    """BASELINE.json's other two numbers, measured in the same run: batched RPN NMS boxes/s (config 3) and ABR paste
+    imgs/s (config 4, one GPU's shard)."""
+    import torch
+
+    from abr_iod_b200.layers import nms_batched
+    from inputs import make_boxes
+
+    out = {}
+    rng = np.random.default_rng(3)
+    for n, batch in ((6000, 4), (6000, 16), (12000, 4)):
+        data = [make_boxes(rng, n, 1216, 800) for _ in range(batch)]
+        boxes = [torch.from_numpy(b).to(dev) for b, _ in data]
+        scores = [torch.from_numpy(s).to(dev) for _, s in data]
+        for _ in range(3):
+            nms_batched(boxes, scores, 0.7, 2000)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(10):
+            keep, cnt = nms_batched(boxes, scores, 0.7, 2000)
+        e.record()
+        torch.cuda.synchronize()
+        out["nms_boxes_per_s_n%d_b%d" % (n, batch)] = round(batch * n * 10 / (s.elapsed_time(e) * 1e-3))
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--layout", default="nhwc", choices=["nhwc", "nchw"])
+    ap.add_argument("--cpu-rois", type=int, default=192, help="RoIs in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -82,7 +82,7 @@ def test_roi_align_bf16_and_fp16(channels_last):
     xt = dev(x, channels_last).requires_grad_(True)
     out = roi_align(xt, dev(rois), (P, P), 1 / 16, 0)
     assert out.dtype == torch.bfloat16  # native bf16 path
-    assert np.abs(out.float().cpu().numpy() - ref).max() <= 2e-2 * np.abs(ref).max()
+    assert np.abs(out.detach().float().cpu().numpy() - ref).max() <= 2e-2 * np.abs(ref).max()
     gout = torch.from_numpy(rng.standard_normal(out.shape).astype(np.float32)).bfloat16()
     out.backward(dev(gout, channels_last))
     gref = oracle.roi_align_backward(gout.float().numpy(), rois, 1 / 16, P, P, B, C, H, W, 0)
@@ -103,7 +103,7 @@ def test_roi_align_full_size_adjoint_property(channels_last):
     B, C, H, W, P, R = 2, 1024, 38, 63, 7, 1024
     x = torch.randn(B, C, H, W, device="cuda")
     rois = make_rois(rng, R, B, 1000, 600)
-    xt = (x.contiguous(memory_format=torch.channels_last) if channels_last else x).requires_grad_(True)
+    xt = (x.contiguous(memory_format=torch.channels_last) if channels_last else x.clone()).requires_grad_(True)
     out = roi_align(xt, dev(rois), (P, P), 1 / 16, 0)
     g = torch.randn_like(out)
     out.backward(g)
