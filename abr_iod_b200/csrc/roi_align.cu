@@ -102,7 +102,7 @@ __host__ __device__ inline size_t tables_floats(int PH, int PW, int Hs, int Ws) 
 // shared memory: [Wy PH*Hs][Wx PW*Ws][ylo PH][yhi PH][xlo PW][xhi PW][aux 2*Hs + 2*Ws (+4)]
 static size_t tables_bytes(int PH, int PW, int Hs, int Ws, bool backward) {
   size_t b = tables_floats(PH, PW, Hs, Ws) * 4 + (size_t)(2 * PH + 2 * PW) * 4;
-  if (backward) b += (size_t)(2 * Hs + 2 * Ws + 4) * 4;
+  if (backward) b += (size_t)(2 * Hs + 2 * Ws + 8) * 4 + (size_t)Hs * 16 + 16;
   return b;
 }
 __device__ __forceinline__ Tables carve(float* smem, int PH, int PW, int Hs, int Ws) {
@@ -117,12 +117,74 @@ __device__ __forceinline__ Tables carve(float* smem, int PH, int PW, int Hs, int
   return t;
 }
 
+// ------------------------------------------------------------------------------------------ backward helpers
+// After the two axis tables exist: overall footprint [Y0,Y1]x[X0,X1] and, for every map row / column inside it,
+// the (contiguous) range of bins whose support contains it.  aux = [plo Hs][phi Hs][qlo Ws][qhi Ws][Y0,Y1,X0,X1,span]
+// where span = max over rows of (number of bins containing the row) - 1.
+__device__ __forceinline__ void build_inverse_ranges(const Tables& t, int PH, int PW, int H, int W, int Hs, int Ws) {
+  int* plo = t.aux;
+  int* phi = plo + Hs;
+  int* qlo = phi + Hs;
+  int* qhi = qlo + Ws;
+  int* fp = qhi + Ws;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int y = tid; y < H; y += nt) {
+    int lo = PH, hi = -1;
+    for (int p = 0; p < PH; p++)
+      if (t.ylo[p] <= y && y <= t.yhi[p]) { lo = min(lo, p); hi = p; }
+    plo[y] = lo; phi[y] = hi;
+  }
+  for (int x = tid; x < W; x += nt) {
+    int lo = PW, hi = -1;
+    for (int p = 0; p < PW; p++)
+      if (t.xlo[p] <= x && x <= t.xhi[p]) { lo = min(lo, p); hi = p; }
+    qlo[x] = lo; qhi[x] = hi;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int a = H, b = -1, c = W, d = -1, span = 0;
+    for (int p = 0; p < PH; p++)
+      if (t.ylo[p] <= t.yhi[p]) { a = min(a, t.ylo[p]); b = max(b, t.yhi[p]); }
+    for (int p = 0; p < PW; p++)
+      if (t.xlo[p] <= t.xhi[p]) { c = min(c, t.xlo[p]); d = max(d, t.xhi[p]); }
+    for (int y = a; y <= b; y++) span = max(span, phi[y] - plo[y]);
+    fp[0] = a; fp[1] = b; fp[2] = c; fp[3] = d; fp[4] = span;
+  }
+  __syncthreads();
+}
+
+constexpr int kThinBins = 8;  // pooled heights up to this use the statically indexed thin-bin path
+
+// Per-row record for the row-sweep kernels (valid when every row feeds at most two bins): the first bin `a` holding
+// the row, its weight Wy[a][y] and the weight Wy[a+1][y] of the next bin (0 when the row is not shared).
+__device__ __forceinline__ void build_row_info(const Tables& t, float4* rinfo, int PH, int H, int Hs) {
+  const int* plo = t.aux;
+  const int* phi = plo + Hs;
+  for (int y = threadIdx.x; y < H; y += blockDim.x) {
+    const int p0 = plo[y], p1 = phi[y];
+    float4 v = make_float4(__int_as_float(-1), 0.f, 0.f, 0.f);
+    if (p0 <= p1) {
+      v.x = __int_as_float(p0);
+      v.y = t.Wy[(size_t)p0 * Hs + y];
+      v.z = (p1 > p0) ? t.Wy[(size_t)(p0 + 1) * Hs + y] : 0.f;
+    }
+    rinfo[y] = v;
+  }
+  __syncthreads();
+}
+
 // ------------------------------------------------------------------------------------------ forward, NHWC
+// A WARP owns (RoI, output column pw, slice of 32*V channels): its lanes read the same map pixel at consecutive
+// channels (one coalesced 512 B request), all weights are warp-uniform shared-memory broadcasts, and it sweeps the
+// RoI's footprint rows ONCE: for every row y it forms  t = sum_x Wx[pw][x] * v[y][x]  and adds  Wy[ph][y] * t  to the
+// (at most two) vertically adjacent bins that row belongs to, held in two rolling register accumulators.  Every
+// distinct pixel of the column's footprint is therefore loaded once per RoI, not once per bin or per sample tap.
+// RoIs whose rows feed more than two bins (bins thinner than one map pixel) take the plain per-bin loop.
 template <typename T, int V>
-__global__ void __launch_bounds__(256) roi_align_fwd_nhwc_kernel(LevelTable lv, const float* __restrict__ rois,
+__global__ void __launch_bounds__(896) roi_align_fwd_nhwc_kernel(LevelTable lv, const float* __restrict__ rois,
                                                                 const int32_t* __restrict__ levels,
                                                                 T* __restrict__ out, int C, int PH, int PW, int ratio,
-                                                                int Hs, int Ws) {
+                                                                int Hs, int Ws, int slices_per_cta) {
   extern __shared__ float smem[];
   const int r = blockIdx.x;
   const RoiGeom g = roi_geometry(rois, levels, lv, r, PH, PW, ratio);
@@ -130,41 +192,162 @@ __global__ void __launch_bounds__(256) roi_align_fwd_nhwc_kernel(LevelTable lv, 
   Tables t = carve(smem, PH, PW, Hs, Ws);
   build_axis_table(t.Wy, t.ylo, t.yhi, PH, H, Hs, g.start_h, g.bin_h, g.grid_h);
   build_axis_table(t.Wx, t.xlo, t.xhi, PW, W, Ws, g.start_w, g.bin_w, g.grid_w);
+  build_inverse_ranges(t, PH, PW, H, W, Hs, Ws);
+  const int* fp = t.aux + 2 * Hs + 2 * Ws;
+  float4* rinfo = reinterpret_cast<float4*>((reinterpret_cast<uintptr_t>(t.aux + 2 * Hs + 2 * Ws + 8) + 15) & ~uintptr_t(15));
+  build_row_info(t, rinfo, PH, H, Hs);
+  const int Y0 = fp[0], Y1 = fp[1];
+  const bool rolling = fp[4] <= 1;
 
-  const int cv = blockIdx.y * blockDim.x + threadIdx.x;
-  if (cv * V >= C) return;
-  const T* __restrict__ img = static_cast<const T*>(lv.ptr[g.level]) + (size_t)g.batch * H * W * C + (size_t)cv * V;
-  T* o = out + (size_t)r * PH * PW * C + (size_t)cv * V;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const size_t pix = (size_t)C;                // elements between horizontally adjacent pixels
+  const size_t rowstride = (size_t)W * C;      // ... and between vertically adjacent ones
+  const size_t binstride = (size_t)PW * C;     // output elements between vertically adjacent bins
+  const T* __restrict__ img0 = static_cast<const T*>(lv.ptr[g.level]) + (size_t)g.batch * H * W * C;
+  T* out0 = out + (size_t)r * PH * PW * C;
+  const float inv_count = 1.f / g.count;
 
-  for (int ph = 0; ph < PH; ph++) {
-    const int y0 = t.ylo[ph], y1 = t.yhi[ph];
-    const float* wy = t.Wy + (size_t)ph * Hs;
-    for (int pw = 0; pw < PW; pw++) {
-      const int x0 = t.xlo[pw], x1 = t.xhi[pw];
-      const float* wx = t.Wx + (size_t)pw * Ws;
-      float acc[V];
+  for (int task = warp; task < PW * slices_per_cta; task += nwarp) {
+    const int pw = task % PW;
+    const int c = ((blockIdx.y * slices_per_cta + task / PW) * 32 + lane) * V;
+    if (c >= C) continue;
+    const int x0 = t.xlo[pw], x1 = t.xhi[pw];
+    const float* wx = t.Wx + (size_t)pw * Ws;
+    const T* __restrict__ img = img0 + c;
+    T* o = out0 + (size_t)pw * C + c;
+    if (x0 > x1) {  // the whole column lies outside the map: every sample contributes 0
+      float z[V];
 #pragma unroll
-      for (int k = 0; k < V; k++) acc[k] = 0.f;
-      for (int y = y0; y <= y1; y++) {
-        const float a = wy[y];
-        const T* row = img + (size_t)y * W * C;
-        float racc[V];
+      for (int k = 0; k < V; k++) z[k] = 0.f;
+      for (int ph = 0; ph < PH; ph++) VecIO<T, V>::store(o + (size_t)ph * binstride, z);
+      continue;
+    }
+    // the first four column weights live in registers (columns are rarely wider); loads beyond the column are
+    // clamped onto its last pixel and carry weight 0, which keeps the row loop free of predicates
+    const int nx = x1 - x0 + 1;
+    const float w0 = wx[x0];
+    const float w1 = nx > 1 ? wx[x0 + 1] : 0.f;
+    const float w2 = nx > 2 ? wx[x0 + 2] : 0.f;
+    const float w3 = nx > 3 ? wx[x0 + 3] : 0.f;
+    const size_t o1 = (size_t)min(1, nx - 1) * pix, o2 = (size_t)min(2, nx - 1) * pix, o3 = (size_t)min(3, nx - 1) * pix;
+    const T* row = img + (size_t)Y0 * rowstride + (size_t)x0 * pix;
+    if (rolling) {
+      float accA[V], accB[V];
 #pragma unroll
-        for (int k = 0; k < V; k++) racc[k] = 0.f;
-#pragma unroll 4
-        for (int x = x0; x <= x1; x++) {
-          float v[V];
-          VecIO<T, V>::load(row + (size_t)x * C, v);
-          const float b = wx[x];
+      for (int k = 0; k < V; k++) accA[k] = accB[k] = 0.f;
+      int a = 0;
+      for (int y = Y0; y <= Y1; y++, row += rowstride) {
+        const float4 info = rinfo[y];
+        const int ra = __float_as_int(info.x);
+        if (ra < 0) continue;
+        float v0[V], v1[V], v2[V], v3[V];
+        VecIO<T, V>::load(row, v0);
+        VecIO<T, V>::load(row + o1, v1);
+        VecIO<T, V>::load(row + o2, v2);
+        VecIO<T, V>::load(row + o3, v3);
+        if (a != ra) {  // bins a .. ra-1 are complete: emit them and roll the two-bin window
+          do {
 #pragma unroll
-          for (int k = 0; k < V; k++) racc[k] = fmaf(b, v[k], racc[k]);
+            for (int k = 0; k < V; k++) accA[k] *= inv_count;
+            VecIO<T, V>::store(o + (size_t)a * binstride, accA);
+#pragma unroll
+            for (int k = 0; k < V; k++) { accA[k] = accB[k]; accB[k] = 0.f; }
+          } while (++a < ra);
+        }
+        float tr[V];
+#pragma unroll
+        for (int k = 0; k < V; k++) tr[k] = fmaf(w3, v3[k], fmaf(w2, v2[k], fmaf(w1, v1[k], w0 * v0[k])));
+        if (nx > 4) {
+          const T* q = row + 4 * pix;
+          for (int x = x0 + 4; x <= x1; x++, q += pix) {
+            float v[V];
+            VecIO<T, V>::load(q, v);
+            const float b = wx[x];
+#pragma unroll
+            for (int k = 0; k < V; k++) tr[k] = fmaf(b, v[k], tr[k]);
+          }
         }
 #pragma unroll
-        for (int k = 0; k < V; k++) acc[k] = fmaf(a, racc[k], acc[k]);
+        for (int k = 0; k < V; k++) {
+          accA[k] = fmaf(info.y, tr[k], accA[k]);
+          accB[k] = fmaf(info.z, tr[k], accB[k]);
+        }
+      }
+      for (; a < PH; a++) {
+#pragma unroll
+        for (int k = 0; k < V; k++) accA[k] *= inv_count;
+        VecIO<T, V>::store(o + (size_t)a * binstride, accA);
+#pragma unroll
+        for (int k = 0; k < V; k++) { accA[k] = accB[k]; accB[k] = 0.f; }
+      }
+    } else if (PH <= kThinBins) {
+      // thin bins (a row feeds three or more bins; the RoI is only a few rows tall): one accumulator per bin,
+      // statically indexed, every row added to every bin with its table weight (0 outside the bin's support)
+      float acc[kThinBins][V];
+#pragma unroll
+      for (int p = 0; p < kThinBins; p++)
+#pragma unroll
+        for (int k = 0; k < V; k++) acc[p][k] = 0.f;
+      for (int y = Y0; y <= Y1; y++, row += rowstride) {
+        float v0[V], v1[V], v2[V], v3[V];
+        VecIO<T, V>::load(row, v0);
+        VecIO<T, V>::load(row + o1, v1);
+        VecIO<T, V>::load(row + o2, v2);
+        VecIO<T, V>::load(row + o3, v3);
+        float tr[V];
+#pragma unroll
+        for (int k = 0; k < V; k++) tr[k] = fmaf(w3, v3[k], fmaf(w2, v2[k], fmaf(w1, v1[k], w0 * v0[k])));
+        if (nx > 4) {
+          const T* q = row + 4 * pix;
+          for (int x = x0 + 4; x <= x1; x++, q += pix) {
+            float v[V];
+            VecIO<T, V>::load(q, v);
+            const float b = wx[x];
+#pragma unroll
+            for (int k = 0; k < V; k++) tr[k] = fmaf(b, v[k], tr[k]);
+          }
+        }
+#pragma unroll
+        for (int p = 0; p < kThinBins; p++) {
+          const float wa = p < PH ? t.Wy[(size_t)p * Hs + y] : 0.f;
+#pragma unroll
+          for (int k = 0; k < V; k++) acc[p][k] = fmaf(wa, tr[k], acc[p][k]);
+        }
       }
 #pragma unroll
-      for (int k = 0; k < V; k++) acc[k] = acc[k] / g.count;
-      VecIO<T, V>::store(o + ((size_t)ph * PW + pw) * C, acc);
+      for (int p = 0; p < kThinBins; p++) {
+        if (p < PH) {
+#pragma unroll
+          for (int k = 0; k < V; k++) acc[p][k] *= inv_count;
+          VecIO<T, V>::store(o + (size_t)p * binstride, acc[p]);
+        }
+      }
+    } else {
+      for (int ph = 0; ph < PH; ph++) {
+        const float* wy = t.Wy + (size_t)ph * Hs;
+        float acc[V];
+#pragma unroll
+        for (int k = 0; k < V; k++) acc[k] = 0.f;
+        for (int y = t.ylo[ph]; y <= t.yhi[ph]; y++) {
+          float tr[V];
+#pragma unroll
+          for (int k = 0; k < V; k++) tr[k] = 0.f;
+          const T* q = img + ((size_t)y * W + x0) * pix;
+          for (int x = x0; x <= x1; x++, q += pix) {
+            float v[V];
+            VecIO<T, V>::load(q, v);
+            const float b = wx[x];
+#pragma unroll
+            for (int k = 0; k < V; k++) tr[k] = fmaf(b, v[k], tr[k]);
+          }
+          const float wa = wy[y];
+#pragma unroll
+          for (int k = 0; k < V; k++) acc[k] = fmaf(wa, tr[k], acc[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < V; k++) acc[k] *= inv_count;
+        VecIO<T, V>::store(o + (size_t)ph * binstride, acc);
+      }
     }
   }
 }
@@ -211,45 +394,16 @@ __global__ void __launch_bounds__(256) roi_align_fwd_nchw_kernel(LevelTable lv, 
   }
 }
 
-// ------------------------------------------------------------------------------------------ backward helpers
-// After the two axis tables exist: overall footprint [Y0,Y1]x[X0,X1] and, for every map row / column inside it,
-// the (contiguous) range of bins whose support contains it.  aux = [plo Hs][phi Hs][qlo Ws][qhi Ws][Y0,Y1,X0,X1].
-__device__ __forceinline__ void build_inverse_ranges(const Tables& t, int PH, int PW, int H, int W, int Hs, int Ws) {
-  int* plo = t.aux;
-  int* phi = plo + Hs;
-  int* qlo = phi + Hs;
-  int* qhi = qlo + Ws;
-  int* fp = qhi + Ws;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  for (int y = tid; y < H; y += nt) {
-    int lo = PH, hi = -1;
-    for (int p = 0; p < PH; p++)
-      if (t.ylo[p] <= y && y <= t.yhi[p]) { lo = min(lo, p); hi = p; }
-    plo[y] = lo; phi[y] = hi;
-  }
-  for (int x = tid; x < W; x += nt) {
-    int lo = PW, hi = -1;
-    for (int p = 0; p < PW; p++)
-      if (t.xlo[p] <= x && x <= t.xhi[p]) { lo = min(lo, p); hi = p; }
-    qlo[x] = lo; qhi[x] = hi;
-  }
-  if (tid == 0) {
-    int a = H, b = -1, c = W, d = -1;
-    for (int p = 0; p < PH; p++)
-      if (t.ylo[p] <= t.yhi[p]) { a = min(a, t.ylo[p]); b = max(b, t.yhi[p]); }
-    for (int p = 0; p < PW; p++)
-      if (t.xlo[p] <= t.xhi[p]) { c = min(c, t.xlo[p]); d = max(d, t.xhi[p]); }
-    fp[0] = a; fp[1] = b; fp[2] = c; fp[3] = d;
-  }
-  __syncthreads();
-}
-
 // ------------------------------------------------------------------------------------------ backward, NHWC
+// Same ownership as the forward: a warp = (RoI, column pw, 32*V channels).  For every footprint row y it folds the
+// (usually two) bins of its column that contain the row into  s = sum_p Wy[p][y] * g[p][pw]  and issues one vector
+// reduction  gin[y][x] += Wx[pw][x] * s / count  per footprint pixel of the column: a warp-wide, contiguous 512 B
+// red.global.add.v4.f32 instead of the reference's 4*g*g scalar atomicAdds per output element.
 template <typename T, int V>
-__global__ void __launch_bounds__(256) roi_align_bwd_nhwc_kernel(LevelTable lv, const float* __restrict__ rois,
+__global__ void __launch_bounds__(896) roi_align_bwd_nhwc_kernel(LevelTable lv, const float* __restrict__ rois,
                                                                 const int32_t* __restrict__ levels,
                                                                 const T* __restrict__ gout, int C, int PH, int PW,
-                                                                int ratio, int Hs, int Ws) {
+                                                                int ratio, int Hs, int Ws, int slices_per_cta) {
   extern __shared__ float smem[];
   const int r = blockIdx.x;
   const RoiGeom g = roi_geometry(rois, levels, lv, r, PH, PW, ratio);
@@ -260,39 +414,74 @@ __global__ void __launch_bounds__(256) roi_align_bwd_nhwc_kernel(LevelTable lv, 
   build_inverse_ranges(t, PH, PW, H, W, Hs, Ws);
   const int* plo = t.aux;
   const int* phi = plo + Hs;
-  const int* qlo = phi + Hs;
-  const int* qhi = qlo + Ws;
-  const int* fp = qhi + Ws;
+  const int* fp = phi + Hs + 2 * Ws;
+  const int Y0 = fp[0], Y1 = fp[1];
 
-  const int cv = blockIdx.y * blockDim.x + threadIdx.x;
-  if (cv * V >= C) return;
-  T* gin = static_cast<T*>(lv.ptr[g.level]) + (size_t)g.batch * H * W * C + (size_t)cv * V;
-  const T* __restrict__ go = gout + (size_t)r * PH * PW * C + (size_t)cv * V;
-  const float inv = 1.f / g.count;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const size_t pix = (size_t)C;
+  T* gin0 = static_cast<T*>(lv.ptr[g.level]) + (size_t)g.batch * H * W * C;
+  const T* __restrict__ go0 = gout + (size_t)r * PH * PW * C;
+  const float inv_count = 1.f / g.count;
 
-  for (int y = fp[0]; y <= fp[1]; y++) {
-    const int p0 = plo[y], p1 = phi[y];
-    for (int x = fp[2]; x <= fp[3]; x++) {
-      const int q0 = qlo[x], q1 = qhi[x];
-      float acc[V];
+  for (int task = warp; task < PW * slices_per_cta; task += nwarp) {
+    const int pw = task % PW;
+    const int c = ((blockIdx.y * slices_per_cta + task / PW) * 32 + lane) * V;
+    if (c >= C) continue;
+    const int x0 = t.xlo[pw], x1 = t.xhi[pw];
+    if (x0 > x1) continue;
+    const float* wx = t.Wx + (size_t)pw * Ws;
+    const T* __restrict__ go = go0 + (size_t)pw * C + c;
+    T* gin = gin0 + c;
+    int a = -2;  // no bin cached yet (a + 1 must not match any real bin)
+    float gA[V], gB[V];  // grad of bins a and a+1 of this column (rolling)
 #pragma unroll
-      for (int k = 0; k < V; k++) acc[k] = 0.f;
-      float wsum = 0.f;
-      for (int p = p0; p <= p1; p++) {
-        const float a = t.Wy[(size_t)p * Hs + y];
-        for (int q = q0; q <= q1; q++) {
-          const float w = a * t.Wx[(size_t)q * Ws + x];
+    for (int k = 0; k < V; k++) gA[k] = gB[k] = 0.f;
+    for (int y = Y0; y <= Y1; y++) {
+      const int p0 = plo[y], p1 = phi[y];
+      if (p0 > p1) continue;
+      float sacc[V];
+      if (p1 - p0 <= 1) {
+        if (a != p0) {
+          if (a + 1 == p0) {
+#pragma unroll
+            for (int k = 0; k < V; k++) gA[k] = gB[k];
+          } else {
+            VecIO<T, V>::load(go + (size_t)p0 * PW * C, gA);
+          }
+          a = p0;
+          if (a + 1 < PH) {
+            VecIO<T, V>::load(go + (size_t)(a + 1) * PW * C, gB);
+          } else {
+#pragma unroll
+            for (int k = 0; k < V; k++) gB[k] = 0.f;
+          }
+        }
+        const float wa = t.Wy[(size_t)a * Hs + y];
+        const float wb = p1 > a ? t.Wy[(size_t)(a + 1) * Hs + y] : 0.f;
+#pragma unroll
+        for (int k = 0; k < V; k++) sacc[k] = fmaf(wb, gB[k], wa * gA[k]);
+      } else {  // thin bins: several bins share the row
+#pragma unroll
+        for (int k = 0; k < V; k++) sacc[k] = 0.f;
+        for (int p = p0; p <= p1; p++) {
           float v[V];
-          VecIO<T, V>::load(go + ((size_t)p * PW + q) * C, v);
+          VecIO<T, V>::load(go + (size_t)p * PW * C, v);
+          const float w = t.Wy[(size_t)p * Hs + y];
 #pragma unroll
-          for (int k = 0; k < V; k++) acc[k] = fmaf(w, v[k], acc[k]);
-          wsum += w;
+          for (int k = 0; k < V; k++) sacc[k] = fmaf(w, v[k], sacc[k]);
         }
       }
-      if (wsum != 0.f) {  // warp-uniform: the weights do not depend on the channel
 #pragma unroll
-        for (int k = 0; k < V; k++) acc[k] *= inv;
-        VecIO<T, V>::red_add(gin + ((size_t)y * W + x) * C, acc);
+      for (int k = 0; k < V; k++) sacc[k] *= inv_count;
+      T* row = gin + ((size_t)y * W + x0) * pix;
+      for (int x = x0; x <= x1; x++, row += pix) {
+        const float b = wx[x];
+        if (b != 0.f) {
+          float v[V];
+#pragma unroll
+          for (int k = 0; k < V; k++) v[k] = b * sacc[k];
+          VecIO<T, V>::red_add(row, v);
+        }
       }
     }
   }
@@ -404,17 +593,29 @@ static inline int nchw_channel_chunk(int R, int C) {
   return chunk < C ? chunk : C;
 }
 
+// NHWC kernels: one warp per (pw, slice of 32*V channels); a CTA carries `spc` slices, i.e. PW*spc warps (<= 28).
+static inline void nhwc_launch_shape(int C, int V, int PW, int& spc, int& threads, int& gy) {
+  const int nslices = ceil_div(C, 32 * V);
+  spc = 28 / PW;
+  if (spc < 1) spc = 1;
+  if (spc > nslices) spc = nslices;
+  int warps = PW * spc;
+  if (warps > 28) warps = 28;  // wide poolers: warps loop over their tasks
+  threads = warps * 32;
+  gy = ceil_div(nslices, spc);
+}
+
 template <typename T, int V>
 static int launch_fwd(const LevelTable& lv, const float* rois, const int32_t* levels, void* out, int C, int R, int PH,
                       int PW, int ratio, int Hs, int Ws, int layout, cudaStream_t st) {
-  const size_t smem = tables_bytes(PH, PW, Hs, Ws, false);
+  const size_t smem = tables_bytes(PH, PW, Hs, Ws, true);
   if (layout == ABR_NHWC) {
-    const int nvec = ceil_div(C, V);
-    const int threads = min(256, ceil_div(nvec, 32) * 32);
-    dim3 grid(R, ceil_div(nvec, threads));
+    int spc, threads, gy;
+    nhwc_launch_shape(C, V, PW, spc, threads, gy);
+    dim3 grid(R, gy);
     int rc = set_smem(roi_align_fwd_nhwc_kernel<T, V>, smem, "roi_align_forward");
     if (rc) return rc;
-    roi_align_fwd_nhwc_kernel<T, V><<<grid, threads, smem, st>>>(lv, rois, levels, static_cast<T*>(out), C, PH, PW, ratio, Hs, Ws);
+    roi_align_fwd_nhwc_kernel<T, V><<<grid, threads, smem, st>>>(lv, rois, levels, static_cast<T*>(out), C, PH, PW, ratio, Hs, Ws, spc);
   } else {
     const int chunk = nchw_channel_chunk(R, C);
     dim3 grid(R, ceil_div(C, chunk));
@@ -431,12 +632,12 @@ static int launch_bwd(const LevelTable& lv, const float* rois, const int32_t* le
                       int PH, int PW, int ratio, int Hs, int Ws, int layout, cudaStream_t st) {
   const size_t smem = tables_bytes(PH, PW, Hs, Ws, true);
   if (layout == ABR_NHWC) {
-    const int nvec = ceil_div(C, V);
-    const int threads = min(256, ceil_div(nvec, 32) * 32);
-    dim3 grid(R, ceil_div(nvec, threads));
+    int spc, threads, gy;
+    nhwc_launch_shape(C, V, PW, spc, threads, gy);
+    dim3 grid(R, gy);
     int rc = set_smem(roi_align_bwd_nhwc_kernel<T, V>, smem, "roi_align_backward");
     if (rc) return rc;
-    roi_align_bwd_nhwc_kernel<T, V><<<grid, threads, smem, st>>>(lv, rois, levels, static_cast<const T*>(gout), C, PH, PW, ratio, Hs, Ws);
+    roi_align_bwd_nhwc_kernel<T, V><<<grid, threads, smem, st>>>(lv, rois, levels, static_cast<const T*>(gout), C, PH, PW, ratio, Hs, Ws, spc);
   } else {
     const int chunk = nchw_channel_chunk(R, C);
     dim3 grid(R, ceil_div(C, chunk));
