@@ -41,10 +41,11 @@ SIGNATURES = {
     "abr_version": (_int, []),
     "abr_last_error": (ctypes.c_char_p, []),
     "abr_launch_count": (ctypes.c_uint64, []),
-    "abr_roi_align_forward": (_int, [_vp, _vp, _vp] + [_int] * 7 + [_f, _int, _int, _int, _vp]),
-    "abr_roi_align_backward": (_int, [_vp, _vp, _vp] + [_int] * 7 + [_f, _int, _int, _int, _int, _vp]),
-    "abr_roi_align_multilevel_forward": (_int, [_vp, _vp, _vp, _vp, _int, _vp, _vp, _vp] + [_int] * 8 + [_vp]),
-    "abr_roi_align_multilevel_backward": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _int] + [_int] * 9 + [_vp]),
+    "abr_roi_align_workspace_bytes": (_sz, [_int, _int, _int, _int]),
+    "abr_roi_align_forward": (_int, [_vp, _vp, _vp] + [_int] * 7 + [_f, _int, _int, _int, _vp, _sz, _vp]),
+    "abr_roi_align_backward": (_int, [_vp, _vp, _vp] + [_int] * 7 + [_f, _int, _int, _int, _int, _vp, _sz, _vp]),
+    "abr_roi_align_multilevel_forward": (_int, [_vp, _vp, _vp, _vp, _int, _vp, _vp, _vp] + [_int] * 8 + [_vp, _sz, _vp]),
+    "abr_roi_align_multilevel_backward": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _int] + [_int] * 9 + [_vp, _sz, _vp]),
     "abr_fpn_map_levels": (_int, [_vp, _vp, _int, _f, _f, _f, _f, _f, _vp]),
     "abr_roi_pool_forward": (_int, [_vp, _vp, _vp, _vp] + [_int] * 7 + [_f, _int, _int, _vp]),
     "abr_roi_pool_backward": (_int, [_vp, _vp, _vp, _vp] + [_int] * 7 + [_int, _int, _int, _vp]),
@@ -105,6 +106,14 @@ def as_compute_dtype(t: torch.Tensor) -> torch.Tensor:
 
 def is_channels_last(t: torch.Tensor) -> bool:
     return t.dim() == 4 and not t.is_contiguous() and t.is_contiguous(memory_format=torch.channels_last)
+
+
+def roi_align_workspace(R, PH, PW, max_h, device, channels_last=True):
+    """Scratch for the per-RoI plans of the fast NHWC ROIAlign kernels (caller-owned, per call).  Returns (tensor|None, bytes)."""
+    if not channels_last or R == 0:
+        return None, 0
+    n = int(lib().abr_roi_align_workspace_bytes(R, PH, PW, max_h))
+    return torch.empty((n,), dtype=torch.uint8, device=device), n
 
 
 def launch_count() -> int:

@@ -2,20 +2,21 @@
 //
 // Semantics: maskrcnn_benchmark/csrc/cuda/ROIAlign_cuda.cu:64-254 of the reference (== csrc/cpu/ROIAlign_cpu.cpp).
 // Design (not a port): the reference gives every output scalar its own thread, which re-derives the RoI
-// geometry and issues 4*g*g scattered 4-byte gathers.  Here a CTA owns one RoI and
-//   1. builds, once, the two SEPARABLE interpolation tables of that RoI in shared memory:
+// geometry and issues 4*g*g scattered 4-byte gathers.  Here
+//   1. the two SEPARABLE interpolation tables of every RoI are built once (plan_kernel, or in shared memory by the
+//      self-contained kernels):
 //        Wy[ph][y] = sum over the bin's sample rows of the bilinear row weight landing on map row y
 //        Wx[pw][x] = same along x
 //      (the reference's weight w1..w4 of a sample is hy*hx, hy*lx, ly*hx, ly*lx and its "outside the
 //      map => 0" rule is the AND of a y-test and an x-test, so  out = Wy * V * Wx^T / count  exactly);
-//   2. NHWC path: every thread owns V consecutive channels (16-byte vectors: 4 x fp32 or 8 x bf16), so each
-//      map pixel is one coalesced 512 B warp load shared by all its channels, every distinct pixel of a bin's
-//      footprint is read once per bin instead of once per sample tap, and weights are warp-uniform broadcasts;
+//   2. NHWC path: a warp owns (RoI, bin column, 32*V channels) with V consecutive channels per lane (16-byte
+//      vectors: 4 x fp32 or 8 x bf16), so each map pixel is one coalesced 512 B warp load, every distinct pixel of
+//      the column's footprint is read once per RoI instead of once per sample tap, and all weights are warp-uniform;
 //      NCHW path (the reference's contiguous layout): threads walk the flat (c,ph,pw) output so stores are
-//      fully coalesced, with the same tables.
-//   3. backward is a GATHER over the RoI's footprint: each map pixel collects its (typically 2x2) contributing
-//      bins and is updated by ONE vector reduction per RoI (red.global.add.v4.f32 / v4.bf16x2, a contiguous
-//      512 B request per warp) instead of 4*g*g scalar atomicAdds per output element.
+//      fully coalesced, with the same tables in shared memory.
+//   3. backward mirrors the forward sweep: one vector reduction per footprint pixel of a column
+//      (red.global.add.v4.f32 / v4.bf16x2, a contiguous 512 B request per warp) instead of 4*g*g scalar atomicAdds
+//      per output element.
 // Sample coordinates are evaluated with explicitly rounded fp32 intrinsics in the reference's operation order
 // so that the in/out-of-map decisions (ROIAlign_cuda.cu:22-25) are identical to the reference's.
 #include "common.cuh"
@@ -102,7 +103,7 @@ __host__ __device__ inline size_t tables_floats(int PH, int PW, int Hs, int Ws) 
 // shared memory: [Wy PH*Hs][Wx PW*Ws][ylo PH][yhi PH][xlo PW][xhi PW][aux 2*Hs + 2*Ws (+4)]
 static size_t tables_bytes(int PH, int PW, int Hs, int Ws, bool backward) {
   size_t b = tables_floats(PH, PW, Hs, Ws) * 4 + (size_t)(2 * PH + 2 * PW) * 4;
-  if (backward) b += (size_t)(2 * Hs + 2 * Ws + 8) * 4 + (size_t)Hs * 16 + 16;
+  if (backward) b += (size_t)(2 * Hs + 2 * Ws + 8) * 4;
   return b;
 }
 __device__ __forceinline__ Tables carve(float* smem, int PH, int PW, int Hs, int Ws) {
@@ -153,39 +154,33 @@ __device__ __forceinline__ void build_inverse_ranges(const Tables& t, int PH, in
   __syncthreads();
 }
 
-constexpr int kThinBins = 8;  // pooled heights up to this use the statically indexed thin-bin path
+// ------------------------------------------------------------------------------------------ RoI plans
+// A "plan" is the compact form of one RoI's two interpolation tables, written once per call by plan_kernel (a small
+// CTA per RoI) into caller-provided workspace and then read, warp-uniformly and straight out of L1/L2, by the sweep
+// kernels, which therefore need no shared memory, no barriers and no per-CTA setup:
+//   hdr  [8 words]          mode, batch index, level, Y0, Y1, 1/count, H, W
+//   col  [PW][4 + kPlanNx]  x0, nx, -, -, then the nx column weights Wx[pw][x0 ..] zero-padded to kPlanNx
+//   row  [Y1-Y0+1][8]       ROLLING: first bin a holding the row (-1: none), Wy[a][y], Wy[a+1][y] (0 if not shared)
+//                           THIN:    Wy[0..7][y]
+// ROLLING = every map row feeds at most two vertically adjacent bins (bins at least ~1 map pixel tall);
+// THIN    = thinner bins and PH <= 8;  GENERIC = anything else (columns wider than kPlanNx pixels, thin bins with
+// PH > 8): those RoIs are left to the table-in-shared-memory kernels below;  EMPTY = no sample inside the map.
+constexpr int kPlanNx = 16;
+constexpr int kPlanHdr = 8;
+constexpr int kPlanCol = 4 + kPlanNx;
+constexpr int kPlanRow = 8;
+constexpr int kThinBins = 8;
+enum PlanMode { PLAN_EMPTY = 0, PLAN_ROLLING = 1, PLAN_THIN = 2, PLAN_GENERIC = 3 };
 
-// Per-row record for the row-sweep kernels (valid when every row feeds at most two bins): the first bin `a` holding
-// the row, its weight Wy[a][y] and the weight Wy[a+1][y] of the next bin (0 when the row is not shared).
-__device__ __forceinline__ void build_row_info(const Tables& t, float4* rinfo, int PH, int H, int Hs) {
-  const int* plo = t.aux;
-  const int* phi = plo + Hs;
-  for (int y = threadIdx.x; y < H; y += blockDim.x) {
-    const int p0 = plo[y], p1 = phi[y];
-    float4 v = make_float4(__int_as_float(-1), 0.f, 0.f, 0.f);
-    if (p0 <= p1) {
-      v.x = __int_as_float(p0);
-      v.y = t.Wy[(size_t)p0 * Hs + y];
-      v.z = (p1 > p0) ? t.Wy[(size_t)(p0 + 1) * Hs + y] : 0.f;
-    }
-    rinfo[y] = v;
-  }
-  __syncthreads();
+__host__ __device__ inline size_t plan_stride_words(int PW, int Hs) {
+  return (size_t)kPlanHdr + (size_t)PW * kPlanCol + (size_t)Hs * kPlanRow;
 }
 
-// ------------------------------------------------------------------------------------------ forward, NHWC
-// A WARP owns (RoI, output column pw, slice of 32*V channels): its lanes read the same map pixel at consecutive
-// channels (one coalesced 512 B request), all weights are warp-uniform shared-memory broadcasts, and it sweeps the
-// RoI's footprint rows ONCE: for every row y it forms  t = sum_x Wx[pw][x] * v[y][x]  and adds  Wy[ph][y] * t  to the
-// (at most two) vertically adjacent bins that row belongs to, held in two rolling register accumulators.  Every
-// distinct pixel of the column's footprint is therefore loaded once per RoI, not once per bin or per sample tap.
-// RoIs whose rows feed more than two bins (bins thinner than one map pixel) take the plain per-bin loop.
-template <typename T, int V>
-__global__ void __launch_bounds__(896) roi_align_fwd_nhwc_kernel(LevelTable lv, const float* __restrict__ rois,
-                                                                const int32_t* __restrict__ levels,
-                                                                T* __restrict__ out, int C, int PH, int PW, int ratio,
-                                                                int Hs, int Ws, int slices_per_cta) {
+__global__ void __launch_bounds__(128) plan_kernel(LevelTable lv, const float* __restrict__ rois,
+                                                  const int32_t* __restrict__ levels, int* __restrict__ plans,
+                                                  size_t stride, int PH, int PW, int ratio, int Hs, int Ws) {
   extern __shared__ float smem[];
+  __shared__ int s_mode;
   const int r = blockIdx.x;
   const RoiGeom g = roi_geometry(rois, levels, lv, r, PH, PW, ratio);
   const int H = lv.H[g.level], W = lv.W[g.level];
@@ -193,161 +188,370 @@ __global__ void __launch_bounds__(896) roi_align_fwd_nhwc_kernel(LevelTable lv, 
   build_axis_table(t.Wy, t.ylo, t.yhi, PH, H, Hs, g.start_h, g.bin_h, g.grid_h);
   build_axis_table(t.Wx, t.xlo, t.xhi, PW, W, Ws, g.start_w, g.bin_w, g.grid_w);
   build_inverse_ranges(t, PH, PW, H, W, Hs, Ws);
-  const int* fp = t.aux + 2 * Hs + 2 * Ws;
-  float4* rinfo = reinterpret_cast<float4*>((reinterpret_cast<uintptr_t>(t.aux + 2 * Hs + 2 * Ws + 8) + 15) & ~uintptr_t(15));
-  build_row_info(t, rinfo, PH, H, Hs);
+  const int* plo = t.aux;
+  const int* phi = plo + Hs;
+  const int* fp = phi + Hs + 2 * Ws;
   const int Y0 = fp[0], Y1 = fp[1];
-  const bool rolling = fp[4] <= 1;
-
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  const size_t pix = (size_t)C;                // elements between horizontally adjacent pixels
-  const size_t rowstride = (size_t)W * C;      // ... and between vertically adjacent ones
-  const size_t binstride = (size_t)PW * C;     // output elements between vertically adjacent bins
-  const T* __restrict__ img0 = static_cast<const T*>(lv.ptr[g.level]) + (size_t)g.batch * H * W * C;
-  T* out0 = out + (size_t)r * PH * PW * C;
-  const float inv_count = 1.f / g.count;
-
-  for (int task = warp; task < PW * slices_per_cta; task += nwarp) {
-    const int pw = task % PW;
-    const int c = ((blockIdx.y * slices_per_cta + task / PW) * 32 + lane) * V;
-    if (c >= C) continue;
-    const int x0 = t.xlo[pw], x1 = t.xhi[pw];
-    const float* wx = t.Wx + (size_t)pw * Ws;
-    const T* __restrict__ img = img0 + c;
-    T* o = out0 + (size_t)pw * C + c;
-    if (x0 > x1) {  // the whole column lies outside the map: every sample contributes 0
-      float z[V];
-#pragma unroll
-      for (int k = 0; k < V; k++) z[k] = 0.f;
-      for (int ph = 0; ph < PH; ph++) VecIO<T, V>::store(o + (size_t)ph * binstride, z);
-      continue;
+  int* plan = plans + (size_t)r * stride;
+  if (threadIdx.x == 0) {
+    int mode;
+    if (Y0 > Y1 || fp[2] > fp[3]) {
+      mode = PLAN_EMPTY;
+    } else {
+      bool wide = false;
+      for (int p = 0; p < PW; p++) wide |= (t.xhi[p] - t.xlo[p] + 1 > kPlanNx);
+      mode = wide ? PLAN_GENERIC : (fp[4] <= 1 ? PLAN_ROLLING : (PH <= kThinBins ? PLAN_THIN : PLAN_GENERIC));
     }
-    // the first four column weights live in registers (columns are rarely wider); loads beyond the column are
-    // clamped onto its last pixel and carry weight 0, which keeps the row loop free of predicates
-    const int nx = x1 - x0 + 1;
-    const float w0 = wx[x0];
-    const float w1 = nx > 1 ? wx[x0 + 1] : 0.f;
-    const float w2 = nx > 2 ? wx[x0 + 2] : 0.f;
-    const float w3 = nx > 3 ? wx[x0 + 3] : 0.f;
-    const size_t o1 = (size_t)min(1, nx - 1) * pix, o2 = (size_t)min(2, nx - 1) * pix, o3 = (size_t)min(3, nx - 1) * pix;
-    const T* row = img + (size_t)Y0 * rowstride + (size_t)x0 * pix;
-    if (rolling) {
-      float accA[V], accB[V];
+    s_mode = mode;
+    plan[0] = mode; plan[1] = g.batch; plan[2] = g.level; plan[3] = Y0; plan[4] = Y1;
+    plan[5] = __float_as_int(1.f / g.count); plan[6] = H; plan[7] = W;
+  }
+  __syncthreads();
+  const int mode = s_mode;
+  if (mode == PLAN_EMPTY || mode == PLAN_GENERIC) return;
+  int* col = plan + kPlanHdr;
+  for (int i = threadIdx.x; i < PW * kPlanCol; i += blockDim.x) {
+    const int p = i / kPlanCol, k = i - p * kPlanCol;
+    const int x0 = t.xlo[p], x1 = t.xhi[p];
+    const bool has = x0 <= x1;
+    int v = 0;
+    if (k == 0) v = has ? x0 : 0;
+    else if (k == 1) v = has ? x1 - x0 + 1 : 0;
+    else if (k >= 4) v = (has && x0 + (k - 4) <= x1) ? __float_as_int(t.Wx[(size_t)p * Ws + x0 + (k - 4)]) : 0;
+    col[i] = v;
+  }
+  int* row = col + PW * kPlanCol;
+  const int nrows = Y1 - Y0 + 1;
+  for (int i = threadIdx.x; i < nrows * kPlanRow; i += blockDim.x) {
+    const int y = Y0 + i / kPlanRow, k = i % kPlanRow;
+    int v = 0;
+    if (mode == PLAN_ROLLING) {
+      const int p0 = plo[y], p1 = phi[y];
+      if (k == 0) v = p0 <= p1 ? p0 : -1;
+      else if (k == 1) v = p0 <= p1 ? __float_as_int(t.Wy[(size_t)p0 * Hs + y]) : 0;
+      else if (k == 2) v = p1 > p0 ? __float_as_int(t.Wy[(size_t)(p0 + 1) * Hs + y]) : 0;
+    } else {
+      v = k < PH ? __float_as_int(t.Wy[(size_t)k * Hs + y]) : 0;
+    }
+    row[i] = v;
+  }
+}
+
+struct SweepTask {
+  int mode, batch, level, Y0, nrows, H, W, x0, nx, pw, c;
+  float inv_count;
+  bool active;
+  const int* col;
+  const int4* rows;
+};
+
+// Decodes the warp's task = (RoI, bin column pw, slice of 32*V channels).  Returns false when there is nothing to do.
+template <int V>
+__device__ __forceinline__ bool sweep_task(SweepTask& k, const int* __restrict__ plans, size_t stride, int C, int PW,
+                                           int nslices, long long ntasks, int& r) {
+  const long long task = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (task >= ntasks) return false;
+  const int per_roi = PW * nslices;
+  r = (int)(task / per_roi);
+  const int tt = (int)(task - (long long)r * per_roi);
+  const int slice = tt / PW;
+  k.pw = tt - slice * PW;
+  const int* plan = plans + (size_t)r * stride;
+  const int4 h0 = __ldg(reinterpret_cast<const int4*>(plan));
+  const int4 h1 = __ldg(reinterpret_cast<const int4*>(plan) + 1);
+  k.mode = h0.x; k.batch = h0.y; k.level = h0.z; k.Y0 = h0.w;
+  k.nrows = h1.x - h0.w + 1; k.inv_count = __int_as_float(h1.y); k.H = h1.z; k.W = h1.w;
+  if (k.mode == PLAN_GENERIC) return false;
+  k.c = (slice * 32 + (threadIdx.x & 31)) * V;
+  k.active = k.c < C;
+  if (!k.active) k.c = 0;  // idle lanes of a ragged last slice shadow channel 0 and never store
+  k.col = plan + kPlanHdr + k.pw * kPlanCol;
+  k.rows = reinterpret_cast<const int4*>(plan + kPlanHdr + PW * kPlanCol);
+  k.x0 = k.col[0];
+  k.nx = k.mode == PLAN_EMPTY ? 0 : k.col[1];
+  return true;
+}
+
+// t = sum over the column's pixels of Wx * v for one map row; q0..q3 point at the row's first four column pixels
+// (clamped onto the last one when the column is narrower; their weights are then 0).
+template <typename T, int V>
+__device__ __forceinline__ void row_dot(float (&tr)[V], const T* q0, const T* q1, const T* q2, const T* q3,
+                                        const float4 w, int nx, size_t pix, const int* __restrict__ col) {
+  float v0[V], v1[V], v2[V], v3[V];
+  VecIO<T, V>::load(q0, v0);
+  VecIO<T, V>::load(q1, v1);
+  VecIO<T, V>::load(q2, v2);
+  VecIO<T, V>::load(q3, v3);
 #pragma unroll
-      for (int k = 0; k < V; k++) accA[k] = accB[k] = 0.f;
-      int a = 0;
-      for (int y = Y0; y <= Y1; y++, row += rowstride) {
-        const float4 info = rinfo[y];
-        const int ra = __float_as_int(info.x);
-        if (ra < 0) continue;
-        float v0[V], v1[V], v2[V], v3[V];
-        VecIO<T, V>::load(row, v0);
-        VecIO<T, V>::load(row + o1, v1);
-        VecIO<T, V>::load(row + o2, v2);
-        VecIO<T, V>::load(row + o3, v3);
-        if (a != ra) {  // bins a .. ra-1 are complete: emit them and roll the two-bin window
-          do {
+  for (int k = 0; k < V; k++) tr[k] = fmaf(w.w, v3[k], fmaf(w.z, v2[k], fmaf(w.y, v1[k], w.x * v0[k])));
+  if (nx > 4) {  // warp-uniform, rare: columns of 5..kPlanNx pixels
+    const T* q = q0 + 4 * pix;
+    for (int j = 4; j < nx; j++, q += pix) {
+      float v[V];
+      VecIO<T, V>::load(q, v);
+      const float b = __int_as_float(__ldg(col + 4 + j));
 #pragma unroll
-            for (int k = 0; k < V; k++) accA[k] *= inv_count;
-            VecIO<T, V>::store(o + (size_t)a * binstride, accA);
+      for (int k = 0; k < V; k++) tr[k] = fmaf(b, v[k], tr[k]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ forward, NHWC, plan-driven
+// A WARP owns (RoI, output column pw, slice of 32*V channels): its lanes read the same map pixel at consecutive
+// channels (one coalesced 512 B request), all weights are warp-uniform, and it sweeps the column's footprint rows
+// ONCE: for every row y it forms  t = sum_x Wx[pw][x] * v[y][x]  and adds  Wy[ph][y] * t  to the (at most two)
+// vertically adjacent bins the row belongs to, held in two rolling register accumulators.  Every distinct pixel of
+// the column's footprint is loaded once per RoI, not once per bin or per sample tap.
+template <typename T, int V>
+__global__ void __launch_bounds__(256) roi_align_fwd_sweep_kernel(LevelTable lv, const int* __restrict__ plans,
+                                                                 size_t stride, T* __restrict__ out, int C, int PH,
+                                                                 int PW, int nslices, long long ntasks) {
+  SweepTask k;
+  int r;
+  if (!sweep_task<V>(k, plans, stride, C, PW, nslices, ntasks, r)) return;
+  const size_t pix = (size_t)C, binstride = (size_t)PW * C;
+  T* o = out + ((size_t)r * PH * PW + k.pw) * C + k.c;
+  if (k.nx == 0) {  // no sample of this column (or of the whole RoI) falls inside the map
+    float z[V];
 #pragma unroll
-            for (int k = 0; k < V; k++) { accA[k] = accB[k]; accB[k] = 0.f; }
-          } while (++a < ra);
-        }
-        float tr[V];
+    for (int i = 0; i < V; i++) z[i] = 0.f;
+    if (k.active)
+      for (int ph = 0; ph < PH; ph++) VecIO<T, V>::store(o + (size_t)ph * binstride, z);
+    return;
+  }
+  const size_t rowstride = (size_t)k.W * C;
+  const T* q0 = static_cast<const T*>(lv.ptr[k.level]) + ((size_t)k.batch * k.H + k.Y0) * rowstride + (size_t)k.x0 * pix + k.c;
+  const T* q1 = q0 + (size_t)min(1, k.nx - 1) * pix;
+  const T* q2 = q0 + (size_t)min(2, k.nx - 1) * pix;
+  const T* q3 = q0 + (size_t)min(3, k.nx - 1) * pix;
+  const float4 w = __ldg(reinterpret_cast<const float4*>(k.col + 4));
+  const int4* rr = k.rows;
+  const float inv_count = k.inv_count;
+  if (k.mode == PLAN_ROLLING) {
+    float accA[V], accB[V];
 #pragma unroll
-        for (int k = 0; k < V; k++) tr[k] = fmaf(w3, v3[k], fmaf(w2, v2[k], fmaf(w1, v1[k], w0 * v0[k])));
-        if (nx > 4) {
-          const T* q = row + 4 * pix;
-          for (int x = x0 + 4; x <= x1; x++, q += pix) {
-            float v[V];
-            VecIO<T, V>::load(q, v);
-            const float b = wx[x];
+    for (int i = 0; i < V; i++) accA[i] = accB[i] = 0.f;
+    int a = 0;
+    for (int n = k.nrows; n > 0; n--, rr += 2, q0 += rowstride, q1 += rowstride, q2 += rowstride, q3 += rowstride) {
+      const int4 info = __ldg(rr);
+      if (info.x < 0) continue;
+      float tr[V];
+      row_dot<T, V>(tr, q0, q1, q2, q3, w, k.nx, pix, k.col);
+      if (a != info.x) {  // bins a .. info.x-1 are complete: emit them and roll the two-bin window
+        do {
 #pragma unroll
-            for (int k = 0; k < V; k++) tr[k] = fmaf(b, v[k], tr[k]);
-          }
-        }
+          for (int i = 0; i < V; i++) accA[i] *= inv_count;
+          if (k.active) VecIO<T, V>::store(o + (size_t)a * binstride, accA);
 #pragma unroll
-        for (int k = 0; k < V; k++) {
-          accA[k] = fmaf(info.y, tr[k], accA[k]);
-          accB[k] = fmaf(info.z, tr[k], accB[k]);
-        }
+          for (int i = 0; i < V; i++) { accA[i] = accB[i]; accB[i] = 0.f; }
+        } while (++a < info.x);
       }
-      for (; a < PH; a++) {
+      const float wa = __int_as_float(info.y), wb = __int_as_float(info.z);
 #pragma unroll
-        for (int k = 0; k < V; k++) accA[k] *= inv_count;
-        VecIO<T, V>::store(o + (size_t)a * binstride, accA);
-#pragma unroll
-        for (int k = 0; k < V; k++) { accA[k] = accB[k]; accB[k] = 0.f; }
+      for (int i = 0; i < V; i++) {
+        accA[i] = fmaf(wa, tr[i], accA[i]);
+        accB[i] = fmaf(wb, tr[i], accB[i]);
       }
-    } else if (PH <= kThinBins) {
-      // thin bins (a row feeds three or more bins; the RoI is only a few rows tall): one accumulator per bin,
-      // statically indexed, every row added to every bin with its table weight (0 outside the bin's support)
-      float acc[kThinBins][V];
+    }
+    for (; a < PH; a++) {
+#pragma unroll
+      for (int i = 0; i < V; i++) accA[i] *= inv_count;
+      if (k.active) VecIO<T, V>::store(o + (size_t)a * binstride, accA);
+#pragma unroll
+      for (int i = 0; i < V; i++) { accA[i] = accB[i]; accB[i] = 0.f; }
+    }
+  } else {  // PLAN_THIN: one statically indexed accumulator per bin; rows carry all PH weights
+    float acc[kThinBins][V];
+#pragma unroll
+    for (int p = 0; p < kThinBins; p++)
+#pragma unroll
+      for (int i = 0; i < V; i++) acc[p][i] = 0.f;
+    for (int n = k.nrows; n > 0; n--, rr += 2, q0 += rowstride, q1 += rowstride, q2 += rowstride, q3 += rowstride) {
+      const int4 wlo = __ldg(rr), whi = __ldg(rr + 1);
+      float tr[V];
+      row_dot<T, V>(tr, q0, q1, q2, q3, w, k.nx, pix, k.col);
+      const float wy[kThinBins] = {__int_as_float(wlo.x), __int_as_float(wlo.y), __int_as_float(wlo.z), __int_as_float(wlo.w),
+                                   __int_as_float(whi.x), __int_as_float(whi.y), __int_as_float(whi.z), __int_as_float(whi.w)};
 #pragma unroll
       for (int p = 0; p < kThinBins; p++)
 #pragma unroll
-        for (int k = 0; k < V; k++) acc[p][k] = 0.f;
-      for (int y = Y0; y <= Y1; y++, row += rowstride) {
-        float v0[V], v1[V], v2[V], v3[V];
-        VecIO<T, V>::load(row, v0);
-        VecIO<T, V>::load(row + o1, v1);
-        VecIO<T, V>::load(row + o2, v2);
-        VecIO<T, V>::load(row + o3, v3);
-        float tr[V];
+        for (int i = 0; i < V; i++) acc[p][i] = fmaf(wy[p], tr[i], acc[p][i]);
+    }
 #pragma unroll
-        for (int k = 0; k < V; k++) tr[k] = fmaf(w3, v3[k], fmaf(w2, v2[k], fmaf(w1, v1[k], w0 * v0[k])));
-        if (nx > 4) {
-          const T* q = row + 4 * pix;
-          for (int x = x0 + 4; x <= x1; x++, q += pix) {
-            float v[V];
-            VecIO<T, V>::load(q, v);
-            const float b = wx[x];
+    for (int p = 0; p < kThinBins; p++) {
+      if (p < PH && k.active) {
 #pragma unroll
-            for (int k = 0; k < V; k++) tr[k] = fmaf(b, v[k], tr[k]);
-          }
+        for (int i = 0; i < V; i++) acc[p][i] *= inv_count;
+        VecIO<T, V>::store(o + (size_t)p * binstride, acc[p]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ backward, NHWC, plan-driven
+// Same ownership.  For every footprint row the warp folds the bins of its column that hold the row into
+// s = sum_p Wy[p][y] * g[p][pw] / count  (g kept in registers) and issues ONE vector reduction
+// gin[y][x] += Wx[pw][x] * s  per footprint pixel of the column: a warp-wide contiguous 512 B
+// red.global.add.v4.f32 (v4.bf16x2 for bf16) instead of the reference's 4*g*g scalar atomicAdds per output element.
+// gin[y][x0 + j] += w_j * s for the column's pixels of one row (zero weights skipped: the address may be a clamp).
+template <typename T, int V>
+__device__ __forceinline__ void row_scatter(T* q0, const float (&s)[V], const float4 w, int nx, size_t pix,
+                                            const int* __restrict__ col) {
+  float v[V];
+  if (w.x != 0.f) {
+#pragma unroll
+    for (int i = 0; i < V; i++) v[i] = w.x * s[i];
+    VecIO<T, V>::red_add(q0, v);
+  }
+  if (nx > 1 && w.y != 0.f) {
+#pragma unroll
+    for (int i = 0; i < V; i++) v[i] = w.y * s[i];
+    VecIO<T, V>::red_add(q0 + pix, v);
+  }
+  if (nx > 2 && w.z != 0.f) {
+#pragma unroll
+    for (int i = 0; i < V; i++) v[i] = w.z * s[i];
+    VecIO<T, V>::red_add(q0 + 2 * pix, v);
+  }
+  if (nx > 3 && w.w != 0.f) {
+#pragma unroll
+    for (int i = 0; i < V; i++) v[i] = w.w * s[i];
+    VecIO<T, V>::red_add(q0 + 3 * pix, v);
+  }
+  if (nx > 4) {
+    T* q = q0 + 4 * pix;
+    for (int j = 4; j < nx; j++, q += pix) {
+      const float b = __int_as_float(__ldg(col + 4 + j));
+      if (b != 0.f) {
+#pragma unroll
+        for (int i = 0; i < V; i++) v[i] = b * s[i];
+        VecIO<T, V>::red_add(q, v);
+      }
+    }
+  }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256) roi_align_bwd_sweep_kernel(LevelTable lv, const int* __restrict__ plans,
+                                                                 size_t stride, const T* __restrict__ gout, int C, int PH,
+                                                                 int PW, int nslices, long long ntasks) {
+  SweepTask k;
+  int r;
+  if (!sweep_task<V>(k, plans, stride, C, PW, nslices, ntasks, r)) return;
+  if (k.nx == 0 || !k.active) return;
+  const size_t pix = (size_t)C, binstride = (size_t)PW * C;
+  const T* __restrict__ go = gout + ((size_t)r * PH * PW + k.pw) * C + k.c;
+  const size_t rowstride = (size_t)k.W * C;
+  T* q0 = static_cast<T*>(lv.ptr[k.level]) + ((size_t)k.batch * k.H + k.Y0) * rowstride + (size_t)k.x0 * pix + k.c;
+  const float4 w = __ldg(reinterpret_cast<const float4*>(k.col + 4));
+  const int4* rr = k.rows;
+  const float inv_count = k.inv_count;
+  if (k.mode == PLAN_ROLLING) {
+    float gA[V], gB[V];  // gradients of bins a and a+1 of this column (rolling window)
+    int a = -2;          // no bin cached yet
+    for (int n = k.nrows; n > 0; n--, rr += 2, q0 += rowstride) {
+      const int4 info = __ldg(rr);
+      if (info.x < 0) continue;
+      if (a != info.x) {
+        if (a + 1 == info.x) {
+#pragma unroll
+          for (int i = 0; i < V; i++) gA[i] = gB[i];
+        } else {
+          VecIO<T, V>::load(go + (size_t)info.x * binstride, gA);
         }
+        a = info.x;
+        if (a + 1 < PH) {
+          VecIO<T, V>::load(go + (size_t)(a + 1) * binstride, gB);
+        } else {
 #pragma unroll
-        for (int p = 0; p < kThinBins; p++) {
-          const float wa = p < PH ? t.Wy[(size_t)p * Hs + y] : 0.f;
-#pragma unroll
-          for (int k = 0; k < V; k++) acc[p][k] = fmaf(wa, tr[k], acc[p][k]);
+          for (int i = 0; i < V; i++) gB[i] = 0.f;
         }
       }
+      const float wa = __int_as_float(info.y) * inv_count, wb = __int_as_float(info.z) * inv_count;
+      float s[V];
 #pragma unroll
-      for (int p = 0; p < kThinBins; p++) {
-        if (p < PH) {
+      for (int i = 0; i < V; i++) s[i] = fmaf(wb, gB[i], wa * gA[i]);
+      row_scatter<T, V>(q0, s, w, k.nx, pix, k.col);
+    }
+  } else {  // PLAN_THIN
+    float g[kThinBins][V];
 #pragma unroll
-          for (int k = 0; k < V; k++) acc[p][k] *= inv_count;
-          VecIO<T, V>::store(o + (size_t)p * binstride, acc[p]);
-        }
+    for (int p = 0; p < kThinBins; p++) {
+      if (p < PH) {
+        VecIO<T, V>::load(go + (size_t)p * binstride, g[p]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < V; i++) g[p][i] = 0.f;
       }
-    } else {
-      for (int ph = 0; ph < PH; ph++) {
-        const float* wy = t.Wy + (size_t)ph * Hs;
-        float acc[V];
+    }
+    for (int n = k.nrows; n > 0; n--, rr += 2, q0 += rowstride) {
+      const int4 wlo = __ldg(rr), whi = __ldg(rr + 1);
+      const float wy[kThinBins] = {__int_as_float(wlo.x), __int_as_float(wlo.y), __int_as_float(wlo.z), __int_as_float(wlo.w),
+                                   __int_as_float(whi.x), __int_as_float(whi.y), __int_as_float(whi.z), __int_as_float(whi.w)};
+      float s[V];
 #pragma unroll
-        for (int k = 0; k < V; k++) acc[k] = 0.f;
-        for (int y = t.ylo[ph]; y <= t.yhi[ph]; y++) {
-          float tr[V];
+      for (int i = 0; i < V; i++) s[i] = 0.f;
 #pragma unroll
-          for (int k = 0; k < V; k++) tr[k] = 0.f;
-          const T* q = img + ((size_t)y * W + x0) * pix;
-          for (int x = x0; x <= x1; x++, q += pix) {
-            float v[V];
-            VecIO<T, V>::load(q, v);
-            const float b = wx[x];
+      for (int p = 0; p < kThinBins; p++)
 #pragma unroll
-            for (int k = 0; k < V; k++) tr[k] = fmaf(b, v[k], tr[k]);
-          }
-          const float wa = wy[y];
+        for (int i = 0; i < V; i++) s[i] = fmaf(wy[p], g[p][i], s[i]);
 #pragma unroll
-          for (int k = 0; k < V; k++) acc[k] = fmaf(wa, tr[k], acc[k]);
+      for (int i = 0; i < V; i++) s[i] *= inv_count;
+      row_scatter<T, V>(q0, s, w, k.nx, pix, k.col);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ forward, NHWC, self-contained
+// Table-in-shared-memory kernel: a CTA owns one RoI, every thread V consecutive channels, plain per-bin loops over the
+// separable tables.  Used when the caller passes no workspace, and for the RoIs a plan marks GENERIC.
+template <typename T, int V>
+__global__ void __launch_bounds__(256) roi_align_fwd_nhwc_kernel(LevelTable lv, const float* __restrict__ rois,
+                                                                const int32_t* __restrict__ levels,
+                                                                T* __restrict__ out, int C, int PH, int PW, int ratio,
+                                                                int Hs, int Ws, const int* __restrict__ plans,
+                                                                size_t plan_stride) {
+  extern __shared__ float smem[];
+  const int r = blockIdx.x;
+  if (plans && plans[(size_t)r * plan_stride] != PLAN_GENERIC) return;
+  const RoiGeom g = roi_geometry(rois, levels, lv, r, PH, PW, ratio);
+  const int H = lv.H[g.level], W = lv.W[g.level];
+  Tables t = carve(smem, PH, PW, Hs, Ws);
+  build_axis_table(t.Wy, t.ylo, t.yhi, PH, H, Hs, g.start_h, g.bin_h, g.grid_h);
+  build_axis_table(t.Wx, t.xlo, t.xhi, PW, W, Ws, g.start_w, g.bin_w, g.grid_w);
+
+  const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+  if (cv * V >= C) return;
+  const T* __restrict__ img = static_cast<const T*>(lv.ptr[g.level]) + (size_t)g.batch * H * W * C + (size_t)cv * V;
+  T* o = out + (size_t)r * PH * PW * C + (size_t)cv * V;
+  for (int ph = 0; ph < PH; ph++) {
+    const int y0 = t.ylo[ph], y1 = t.yhi[ph];
+    const float* wy = t.Wy + (size_t)ph * Hs;
+    for (int pw = 0; pw < PW; pw++) {
+      const int x0 = t.xlo[pw], x1 = t.xhi[pw];
+      const float* wx = t.Wx + (size_t)pw * Ws;
+      float acc[V];
+#pragma unroll
+      for (int k = 0; k < V; k++) acc[k] = 0.f;
+      for (int y = y0; y <= y1; y++) {
+        const float a = wy[y];
+        const T* row = img + (size_t)y * W * C;
+        float racc[V];
+#pragma unroll
+        for (int k = 0; k < V; k++) racc[k] = 0.f;
+        for (int x = x0; x <= x1; x++) {
+          float v[V];
+          VecIO<T, V>::load(row + (size_t)x * C, v);
+          const float b = wx[x];
+#pragma unroll
+          for (int k = 0; k < V; k++) racc[k] = fmaf(b, v[k], racc[k]);
         }
 #pragma unroll
-        for (int k = 0; k < V; k++) acc[k] *= inv_count;
-        VecIO<T, V>::store(o + (size_t)ph * binstride, acc);
+        for (int k = 0; k < V; k++) acc[k] = fmaf(a, racc[k], acc[k]);
       }
+#pragma unroll
+      for (int k = 0; k < V; k++) acc[k] = acc[k] / g.count;
+      VecIO<T, V>::store(o + ((size_t)ph * PW + pw) * C, acc);
     }
   }
 }
@@ -394,18 +598,18 @@ __global__ void __launch_bounds__(256) roi_align_fwd_nchw_kernel(LevelTable lv, 
   }
 }
 
-// ------------------------------------------------------------------------------------------ backward, NHWC
-// Same ownership as the forward: a warp = (RoI, column pw, 32*V channels).  For every footprint row y it folds the
-// (usually two) bins of its column that contain the row into  s = sum_p Wy[p][y] * g[p][pw]  and issues one vector
-// reduction  gin[y][x] += Wx[pw][x] * s / count  per footprint pixel of the column: a warp-wide, contiguous 512 B
-// red.global.add.v4.f32 instead of the reference's 4*g*g scalar atomicAdds per output element.
+// ------------------------------------------------------------------------------------------ backward, NHWC, self-contained
+// Gather over the RoI's footprint: each map pixel collects its contributing bins and is updated by one vector
+// reduction per RoI.  Used when the caller passes no workspace, and for the RoIs a plan marks GENERIC.
 template <typename T, int V>
-__global__ void __launch_bounds__(896) roi_align_bwd_nhwc_kernel(LevelTable lv, const float* __restrict__ rois,
+__global__ void __launch_bounds__(256) roi_align_bwd_nhwc_kernel(LevelTable lv, const float* __restrict__ rois,
                                                                 const int32_t* __restrict__ levels,
                                                                 const T* __restrict__ gout, int C, int PH, int PW,
-                                                                int ratio, int Hs, int Ws, int slices_per_cta) {
+                                                                int ratio, int Hs, int Ws, const int* __restrict__ plans,
+                                                                size_t plan_stride) {
   extern __shared__ float smem[];
   const int r = blockIdx.x;
+  if (plans && plans[(size_t)r * plan_stride] != PLAN_GENERIC) return;
   const RoiGeom g = roi_geometry(rois, levels, lv, r, PH, PW, ratio);
   const int H = lv.H[g.level], W = lv.W[g.level];
   Tables t = carve(smem, PH, PW, Hs, Ws);
@@ -414,74 +618,38 @@ __global__ void __launch_bounds__(896) roi_align_bwd_nhwc_kernel(LevelTable lv, 
   build_inverse_ranges(t, PH, PW, H, W, Hs, Ws);
   const int* plo = t.aux;
   const int* phi = plo + Hs;
-  const int* fp = phi + Hs + 2 * Ws;
-  const int Y0 = fp[0], Y1 = fp[1];
+  const int* qlo = phi + Hs;
+  const int* qhi = qlo + Ws;
+  const int* fp = qhi + Ws;
 
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  const size_t pix = (size_t)C;
-  T* gin0 = static_cast<T*>(lv.ptr[g.level]) + (size_t)g.batch * H * W * C;
-  const T* __restrict__ go0 = gout + (size_t)r * PH * PW * C;
-  const float inv_count = 1.f / g.count;
-
-  for (int task = warp; task < PW * slices_per_cta; task += nwarp) {
-    const int pw = task % PW;
-    const int c = ((blockIdx.y * slices_per_cta + task / PW) * 32 + lane) * V;
-    if (c >= C) continue;
-    const int x0 = t.xlo[pw], x1 = t.xhi[pw];
-    if (x0 > x1) continue;
-    const float* wx = t.Wx + (size_t)pw * Ws;
-    const T* __restrict__ go = go0 + (size_t)pw * C + c;
-    T* gin = gin0 + c;
-    int a = -2;  // no bin cached yet (a + 1 must not match any real bin)
-    float gA[V], gB[V];  // grad of bins a and a+1 of this column (rolling)
+  const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+  if (cv * V >= C) return;
+  T* gin = static_cast<T*>(lv.ptr[g.level]) + (size_t)g.batch * H * W * C + (size_t)cv * V;
+  const T* __restrict__ go = gout + (size_t)r * PH * PW * C + (size_t)cv * V;
+  const float inv = 1.f / g.count;
+  for (int y = fp[0]; y <= fp[1]; y++) {
+    const int p0 = plo[y], p1 = phi[y];
+    for (int x = fp[2]; x <= fp[3]; x++) {
+      const int q0 = qlo[x], q1 = qhi[x];
+      float acc[V];
 #pragma unroll
-    for (int k = 0; k < V; k++) gA[k] = gB[k] = 0.f;
-    for (int y = Y0; y <= Y1; y++) {
-      const int p0 = plo[y], p1 = phi[y];
-      if (p0 > p1) continue;
-      float sacc[V];
-      if (p1 - p0 <= 1) {
-        if (a != p0) {
-          if (a + 1 == p0) {
-#pragma unroll
-            for (int k = 0; k < V; k++) gA[k] = gB[k];
-          } else {
-            VecIO<T, V>::load(go + (size_t)p0 * PW * C, gA);
-          }
-          a = p0;
-          if (a + 1 < PH) {
-            VecIO<T, V>::load(go + (size_t)(a + 1) * PW * C, gB);
-          } else {
-#pragma unroll
-            for (int k = 0; k < V; k++) gB[k] = 0.f;
-          }
-        }
-        const float wa = t.Wy[(size_t)a * Hs + y];
-        const float wb = p1 > a ? t.Wy[(size_t)(a + 1) * Hs + y] : 0.f;
-#pragma unroll
-        for (int k = 0; k < V; k++) sacc[k] = fmaf(wb, gB[k], wa * gA[k]);
-      } else {  // thin bins: several bins share the row
-#pragma unroll
-        for (int k = 0; k < V; k++) sacc[k] = 0.f;
-        for (int p = p0; p <= p1; p++) {
+      for (int k = 0; k < V; k++) acc[k] = 0.f;
+      float wsum = 0.f;
+      for (int p = p0; p <= p1; p++) {
+        const float a = t.Wy[(size_t)p * Hs + y];
+        for (int q = q0; q <= q1; q++) {
+          const float w = a * t.Wx[(size_t)q * Ws + x];
           float v[V];
-          VecIO<T, V>::load(go + (size_t)p * PW * C, v);
-          const float w = t.Wy[(size_t)p * Hs + y];
+          VecIO<T, V>::load(go + ((size_t)p * PW + q) * C, v);
 #pragma unroll
-          for (int k = 0; k < V; k++) sacc[k] = fmaf(w, v[k], sacc[k]);
+          for (int k = 0; k < V; k++) acc[k] = fmaf(w, v[k], acc[k]);
+          wsum += w;
         }
       }
+      if (wsum != 0.f) {  // warp-uniform: the weights do not depend on the channel
 #pragma unroll
-      for (int k = 0; k < V; k++) sacc[k] *= inv_count;
-      T* row = gin + ((size_t)y * W + x0) * pix;
-      for (int x = x0; x <= x1; x++, row += pix) {
-        const float b = wx[x];
-        if (b != 0.f) {
-          float v[V];
-#pragma unroll
-          for (int k = 0; k < V; k++) v[k] = b * sacc[k];
-          VecIO<T, V>::red_add(row, v);
-        }
+        for (int k = 0; k < V; k++) acc[k] *= inv;
+        VecIO<T, V>::red_add(gin + ((size_t)y * W + x) * C, acc);
       }
     }
   }
@@ -575,6 +743,7 @@ static int fill_levels(LevelTable& lv, void* const* ptrs, const int* hs, const i
     Hs = hs[l] > Hs ? hs[l] : Hs;
     Ws = ws[l] > Ws ? ws[l] : Ws;
   }
+  for (int l = L; l < ABR_MAX_LEVELS; l++) { lv.ptr[l] = nullptr; lv.H[l] = lv.W[l] = 0; lv.scale[l] = 0.f; }
   return ABR_OK;
 }
 
@@ -593,85 +762,115 @@ static inline int nchw_channel_chunk(int R, int C) {
   return chunk < C ? chunk : C;
 }
 
-// NHWC kernels: one warp per (pw, slice of 32*V channels); a CTA carries `spc` slices, i.e. PW*spc warps (<= 28).
-static inline void nhwc_launch_shape(int C, int V, int PW, int& spc, int& threads, int& gy) {
-  const int nslices = ceil_div(C, 32 * V);
-  spc = 28 / PW;
-  if (spc < 1) spc = 1;
-  if (spc > nslices) spc = nslices;
-  int warps = PW * spc;
-  if (warps > 28) warps = 28;  // wide poolers: warps loop over their tasks
-  threads = warps * 32;
-  gy = ceil_div(nslices, spc);
+struct Call {
+  LevelTable lv;
+  const float* rois;
+  const int32_t* levels;
+  int C, R, PH, PW, ratio, Hs, Ws, layout;
+  int* plans;  // null: no workspace, self-contained kernels only
+  cudaStream_t st;
+};
+
+static size_t workspace_need(int R, int PW, int Hs) { return (size_t)R * plan_stride_words(PW, Hs) * sizeof(int); }
+
+static int run_plan(const Call& c) {
+  const size_t smem = tables_bytes(c.PH, c.PW, c.Hs, c.Ws, true);
+  int rc = set_smem(plan_kernel, smem, "roi_align plan");
+  if (rc) return rc;
+  plan_kernel<<<c.R, 128, smem, c.st>>>(c.lv, c.rois, c.levels, c.plans, plan_stride_words(c.PW, c.Hs), c.PH, c.PW, c.ratio, c.Hs, c.Ws);
+  ABR_CHECK_LAUNCH("roi_align_plan");
+  return ABR_OK;
 }
 
 template <typename T, int V>
-static int launch_fwd(const LevelTable& lv, const float* rois, const int32_t* levels, void* out, int C, int R, int PH,
-                      int PW, int ratio, int Hs, int Ws, int layout, cudaStream_t st) {
-  const size_t smem = tables_bytes(PH, PW, Hs, Ws, true);
-  if (layout == ABR_NHWC) {
-    int spc, threads, gy;
-    nhwc_launch_shape(C, V, PW, spc, threads, gy);
-    dim3 grid(R, gy);
+static int launch_fwd(const Call& c, void* out) {
+  const size_t smem = tables_bytes(c.PH, c.PW, c.Hs, c.Ws, false);
+  if (c.layout == ABR_NHWC) {
+    const size_t stride = plan_stride_words(c.PW, c.Hs);
+    if (c.plans) {
+      int rc = run_plan(c);
+      if (rc) return rc;
+      const int nslices = ceil_div(c.C, 32 * V);
+      const long long ntasks = (long long)c.R * c.PW * nslices;
+      const long long blocks = ceil_div<long long>(ntasks, 8);
+      ABR_REQUIRE(blocks <= 0x7fffffffLL, ABR_ERR_UNSUPPORTED, "roi_align_forward: too many tasks");
+      roi_align_fwd_sweep_kernel<T, V><<<(unsigned)blocks, 256, 0, c.st>>>(c.lv, c.plans, stride, static_cast<T*>(out), c.C, c.PH, c.PW, nslices, ntasks);
+      ABR_CHECK_LAUNCH("roi_align_forward_sweep");
+    }
+    const int nvec = ceil_div(c.C, V);
+    const int threads = min(256, ceil_div(nvec, 32) * 32);
+    dim3 grid(c.R, ceil_div(nvec, threads));
     int rc = set_smem(roi_align_fwd_nhwc_kernel<T, V>, smem, "roi_align_forward");
     if (rc) return rc;
-    roi_align_fwd_nhwc_kernel<T, V><<<grid, threads, smem, st>>>(lv, rois, levels, static_cast<T*>(out), C, PH, PW, ratio, Hs, Ws, spc);
+    roi_align_fwd_nhwc_kernel<T, V><<<grid, threads, smem, c.st>>>(c.lv, c.rois, c.levels, static_cast<T*>(out), c.C, c.PH, c.PW, c.ratio, c.Hs, c.Ws, c.plans, stride);
   } else {
-    const int chunk = nchw_channel_chunk(R, C);
-    dim3 grid(R, ceil_div(C, chunk));
+    const int chunk = nchw_channel_chunk(c.R, c.C);
+    dim3 grid(c.R, ceil_div(c.C, chunk));
     int rc = set_smem(roi_align_fwd_nchw_kernel<T>, smem, "roi_align_forward");
     if (rc) return rc;
-    roi_align_fwd_nchw_kernel<T><<<grid, 256, smem, st>>>(lv, rois, levels, static_cast<T*>(out), C, PH, PW, ratio, Hs, Ws, chunk);
+    roi_align_fwd_nchw_kernel<T><<<grid, 256, smem, c.st>>>(c.lv, c.rois, c.levels, static_cast<T*>(out), c.C, c.PH, c.PW, c.ratio, c.Hs, c.Ws, chunk);
   }
   ABR_CHECK_LAUNCH("roi_align_forward");
   return ABR_OK;
 }
 
 template <typename T, int V>
-static int launch_bwd(const LevelTable& lv, const float* rois, const int32_t* levels, const void* gout, int C, int R,
-                      int PH, int PW, int ratio, int Hs, int Ws, int layout, cudaStream_t st) {
-  const size_t smem = tables_bytes(PH, PW, Hs, Ws, true);
-  if (layout == ABR_NHWC) {
-    int spc, threads, gy;
-    nhwc_launch_shape(C, V, PW, spc, threads, gy);
-    dim3 grid(R, gy);
+static int launch_bwd(const Call& c, const void* gout) {
+  const size_t smem = tables_bytes(c.PH, c.PW, c.Hs, c.Ws, true);
+  if (c.layout == ABR_NHWC) {
+    const size_t stride = plan_stride_words(c.PW, c.Hs);
+    if (c.plans) {
+      int rc = run_plan(c);
+      if (rc) return rc;
+      const int nslices = ceil_div(c.C, 32 * V);
+      const long long ntasks = (long long)c.R * c.PW * nslices;
+      const long long blocks = ceil_div<long long>(ntasks, 8);
+      ABR_REQUIRE(blocks <= 0x7fffffffLL, ABR_ERR_UNSUPPORTED, "roi_align_backward: too many tasks");
+      roi_align_bwd_sweep_kernel<T, V><<<(unsigned)blocks, 256, 0, c.st>>>(c.lv, c.plans, stride, static_cast<const T*>(gout), c.C, c.PH, c.PW, nslices, ntasks);
+      ABR_CHECK_LAUNCH("roi_align_backward_sweep");
+    }
+    const int nvec = ceil_div(c.C, V);
+    const int threads = min(256, ceil_div(nvec, 32) * 32);
+    dim3 grid(c.R, ceil_div(nvec, threads));
     int rc = set_smem(roi_align_bwd_nhwc_kernel<T, V>, smem, "roi_align_backward");
     if (rc) return rc;
-    roi_align_bwd_nhwc_kernel<T, V><<<grid, threads, smem, st>>>(lv, rois, levels, static_cast<const T*>(gout), C, PH, PW, ratio, Hs, Ws, spc);
+    roi_align_bwd_nhwc_kernel<T, V><<<grid, threads, smem, c.st>>>(c.lv, c.rois, c.levels, static_cast<const T*>(gout), c.C, c.PH, c.PW, c.ratio, c.Hs, c.Ws, c.plans, stride);
   } else {
-    const int chunk = nchw_channel_chunk(R, C);
-    dim3 grid(R, ceil_div(C, chunk));
+    const int chunk = nchw_channel_chunk(c.R, c.C);
+    dim3 grid(c.R, ceil_div(c.C, chunk));
     int rc = set_smem(roi_align_bwd_nchw_kernel<T>, smem, "roi_align_backward");
     if (rc) return rc;
-    roi_align_bwd_nchw_kernel<T><<<grid, 256, smem, st>>>(lv, rois, levels, static_cast<const T*>(gout), C, PH, PW, ratio, Hs, Ws, chunk);
+    roi_align_bwd_nchw_kernel<T><<<grid, 256, smem, c.st>>>(c.lv, c.rois, c.levels, static_cast<const T*>(gout), c.C, c.PH, c.PW, c.ratio, c.Hs, c.Ws, chunk);
   }
   ABR_CHECK_LAUNCH("roi_align_backward");
   return ABR_OK;
 }
 
-static int dispatch_fwd(const LevelTable& lv, const float* rois, const int32_t* levels, void* out, int C, int R, int PH,
-                        int PW, int ratio, int Hs, int Ws, int dtype, int layout, cudaStream_t st) {
+static int dispatch_fwd(const Call& c, void* out, int dtype) {
   if (dtype == ABR_F32) {
-    if (layout == ABR_NHWC && C % 4 == 0) return launch_fwd<float, 4>(lv, rois, levels, out, C, R, PH, PW, ratio, Hs, Ws, layout, st);
-    return launch_fwd<float, 1>(lv, rois, levels, out, C, R, PH, PW, ratio, Hs, Ws, layout, st);
+    if (c.layout == ABR_NHWC && c.C % 4 == 0) return launch_fwd<float, 4>(c, out);
+    return launch_fwd<float, 1>(c, out);
   }
-  if (layout == ABR_NHWC && C % 8 == 0)
-    return launch_fwd<__nv_bfloat16, 8>(lv, rois, levels, out, C, R, PH, PW, ratio, Hs, Ws, layout, st);
-  return launch_fwd<__nv_bfloat16, 1>(lv, rois, levels, out, C, R, PH, PW, ratio, Hs, Ws, layout, st);
+  if (c.layout == ABR_NHWC && c.C % 8 == 0) return launch_fwd<__nv_bfloat16, 8>(c, out);
+  return launch_fwd<__nv_bfloat16, 1>(c, out);
 }
 
-static int dispatch_bwd(const LevelTable& lv, const float* rois, const int32_t* levels, const void* gout, int C, int R,
-                        int PH, int PW, int ratio, int Hs, int Ws, int dtype, int layout, cudaStream_t st) {
+static int dispatch_bwd(const Call& c, const void* gout, int dtype) {
   if (dtype == ABR_F32) {
-    if (layout == ABR_NHWC && C % 4 == 0) return launch_bwd<float, 4>(lv, rois, levels, gout, C, R, PH, PW, ratio, Hs, Ws, layout, st);
-    return launch_bwd<float, 1>(lv, rois, levels, gout, C, R, PH, PW, ratio, Hs, Ws, layout, st);
+    if (c.layout == ABR_NHWC && c.C % 4 == 0) return launch_bwd<float, 4>(c, gout);
+    return launch_bwd<float, 1>(c, gout);
   }
-  if (layout == ABR_NHWC && C % 8 == 0)
-    return launch_bwd<__nv_bfloat16, 8>(lv, rois, levels, gout, C, R, PH, PW, ratio, Hs, Ws, layout, st);
-  return launch_bwd<__nv_bfloat16, 1>(lv, rois, levels, gout, C, R, PH, PW, ratio, Hs, Ws, layout, st);
+  if (c.layout == ABR_NHWC && c.C % 8 == 0) return launch_bwd<__nv_bfloat16, 8>(c, gout);
+  return launch_bwd<__nv_bfloat16, 1>(c, gout);
 }
 
 static size_t elem_size(int dtype) { return dtype == ABR_F32 ? 4 : 2; }
+
+// The plans are only used by the NHWC kernels; a workspace that is absent or too small selects the self-contained path.
+static int* usable_workspace(void* ws, size_t bytes, int R, int PW, int Hs, int layout) {
+  if (!ws || layout != ABR_NHWC || (reinterpret_cast<uintptr_t>(ws) & 15)) return nullptr;
+  return bytes >= workspace_need(R, PW, Hs) ? static_cast<int*>(ws) : nullptr;
+}
 
 }  // namespace abr
 
@@ -679,62 +878,73 @@ using namespace abr;
 
 extern "C" {
 
+size_t abr_roi_align_workspace_bytes(int R, int PH, int PW, int max_h) {
+  (void)PH;
+  if (R <= 0 || PW <= 0 || max_h <= 0) return 0;
+  return workspace_need(R, PW, max_h);
+}
+
 int abr_roi_align_multilevel_forward(const void* const* inputs_host, const int* hs_host, const int* ws_host,
                                      const float* scales_host, int L, const float* rois, const int32_t* levels,
                                      void* output, int B, int C, int R, int PH, int PW, int sampling_ratio, int dtype,
-                                     int layout, abr_stream_t stream) {
+                                     int layout, void* workspace, size_t workspace_bytes, abr_stream_t stream) {
   ABR_REQUIRE(inputs_host && hs_host && ws_host && scales_host, ABR_ERR_BAD_ARG, "roi_align: null level arrays");
   int rc = check_common(inputs_host, rois, output, B, C, R, PH, PW, dtype, layout);
   if (rc) return rc;
   if (R == 0) return ABR_OK;  // ROIAlign_cuda.cu:278-281
   ABR_REQUIRE(L == 1 || levels, ABR_ERR_BAD_ARG, "roi_align: %d levels but no per-RoI level array", L);
-  LevelTable lv;
-  int Hs, Ws;
-  rc = fill_levels(lv, const_cast<void* const*>(reinterpret_cast<const void* const*>(inputs_host)), hs_host, ws_host,
-                   scales_host, L, Hs, Ws);
+  Call c;
+  rc = fill_levels(c.lv, const_cast<void* const*>(reinterpret_cast<const void* const*>(inputs_host)), hs_host, ws_host,
+                   scales_host, L, c.Hs, c.Ws);
   if (rc) return rc;
-  return dispatch_fwd(lv, rois, L == 1 ? nullptr : levels, output, C, R, PH, PW, sampling_ratio, Hs, Ws, dtype, layout,
-                      static_cast<cudaStream_t>(stream));
+  c.rois = rois; c.levels = L == 1 ? nullptr : levels;
+  c.C = C; c.R = R; c.PH = PH; c.PW = PW; c.ratio = sampling_ratio; c.layout = layout;
+  c.plans = usable_workspace(workspace, workspace_bytes, R, PW, c.Hs, layout);
+  c.st = static_cast<cudaStream_t>(stream);
+  return dispatch_fwd(c, output, dtype);
 }
 
 int abr_roi_align_multilevel_backward(const void* grad_output, const float* rois, const int32_t* levels,
                                       void* const* grad_inputs_host, const int* hs_host, const int* ws_host,
                                       const float* scales_host, int L, int B, int C, int R, int PH, int PW,
-                                      int sampling_ratio, int dtype, int layout, int zero_init, abr_stream_t stream) {
+                                      int sampling_ratio, int dtype, int layout, int zero_init, void* workspace,
+                                      size_t workspace_bytes, abr_stream_t stream) {
   ABR_REQUIRE(grad_inputs_host && hs_host && ws_host && scales_host, ABR_ERR_BAD_ARG, "roi_align: null level arrays");
   int rc = check_common(grad_inputs_host, rois, grad_output, B, C, R, PH, PW, dtype, layout);
   if (rc) return rc;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  LevelTable lv;
-  int Hs, Ws;
-  rc = fill_levels(lv, grad_inputs_host, hs_host, ws_host, scales_host, L, Hs, Ws);
+  Call c;
+  c.st = static_cast<cudaStream_t>(stream);
+  rc = fill_levels(c.lv, grad_inputs_host, hs_host, ws_host, scales_host, L, c.Hs, c.Ws);
   if (rc) return rc;
   if (zero_init)
     for (int l = 0; l < L; l++)
-      ABR_CUDA_OK(cudaMemsetAsync(lv.ptr[l], 0, (size_t)B * C * lv.H[l] * lv.W[l] * elem_size(dtype), st));
+      ABR_CUDA_OK(cudaMemsetAsync(c.lv.ptr[l], 0, (size_t)B * C * c.lv.H[l] * c.lv.W[l] * elem_size(dtype), c.st));
   if (R == 0) return ABR_OK;  // ROIAlign_cuda.cu:323-326
   ABR_REQUIRE(L == 1 || levels, ABR_ERR_BAD_ARG, "roi_align: %d levels but no per-RoI level array", L);
-  return dispatch_bwd(lv, rois, L == 1 ? nullptr : levels, grad_output, C, R, PH, PW, sampling_ratio, Hs, Ws, dtype,
-                      layout, st);
+  c.rois = rois; c.levels = L == 1 ? nullptr : levels;
+  c.C = C; c.R = R; c.PH = PH; c.PW = PW; c.ratio = sampling_ratio; c.layout = layout;
+  c.plans = usable_workspace(workspace, workspace_bytes, R, PW, c.Hs, layout);
+  return dispatch_bwd(c, grad_output, dtype);
 }
 
 int abr_roi_align_forward(const void* input, const float* rois, void* output, int B, int C, int H, int W, int R, int PH,
-                          int PW, float spatial_scale, int sampling_ratio, int dtype, int layout, abr_stream_t stream) {
+                          int PW, float spatial_scale, int sampling_ratio, int dtype, int layout, void* workspace,
+                          size_t workspace_bytes, abr_stream_t stream) {
   if (R > 0) ABR_REQUIRE(input && H > 0 && W > 0, ABR_ERR_BAD_ARG, "roi_align_forward: null or empty input");
   if (R == 0) return check_common(&input, rois, output, B, C, R, PH, PW, dtype, layout);
   const void* ptrs[1] = {input};
   return abr_roi_align_multilevel_forward(ptrs, &H, &W, &spatial_scale, 1, rois, nullptr, output, B, C, R, PH, PW,
-                                          sampling_ratio, dtype, layout, stream);
+                                          sampling_ratio, dtype, layout, workspace, workspace_bytes, stream);
 }
 
 int abr_roi_align_backward(const void* grad_output, const float* rois, void* grad_input, int B, int C, int H, int W,
                            int R, int PH, int PW, float spatial_scale, int sampling_ratio, int dtype, int layout,
-                           int zero_init, abr_stream_t stream) {
+                           int zero_init, void* workspace, size_t workspace_bytes, abr_stream_t stream) {
   ABR_REQUIRE(grad_input || (size_t)B * C * H * W == 0, ABR_ERR_BAD_ARG, "roi_align_backward: null grad_input");
   if ((size_t)B * C * H * W == 0) return ABR_OK;
   void* ptrs[1] = {grad_input};
   return abr_roi_align_multilevel_backward(grad_output, rois, nullptr, ptrs, &H, &W, &spatial_scale, 1, B, C, R, PH, PW,
-                                           sampling_ratio, dtype, layout, zero_init, stream);
+                                           sampling_ratio, dtype, layout, zero_init, workspace, workspace_bytes, stream);
 }
 
 int abr_fpn_map_levels(const float* rois, int32_t* levels, int R, float k_min, float k_max, float canonical_scale,

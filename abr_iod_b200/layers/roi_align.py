@@ -33,10 +33,12 @@ def roi_align_forward(input, rois, spatial_scale, pooled_h, pooled_w, sampling_r
     if out.numel() == 0:
         return out
     with torch.cuda.device(x.device):
+        ws, ws_bytes = _lib.roi_align_workspace(R, pooled_h, pooled_w, H, x.device, nhwc)
         _lib.check(_lib.lib().abr_roi_align_forward(
             x.data_ptr(), rois.data_ptr(), out.data_ptr(), B, C, H, W, R, pooled_h, pooled_w,
             float(spatial_scale), int(sampling_ratio), _lib.dtype_code(x),
-            _lib.ABR_NHWC if nhwc else _lib.ABR_NCHW, _lib.stream_ptr(x.device)))
+            _lib.ABR_NHWC if nhwc else _lib.ABR_NCHW, ws.data_ptr() if ws is not None else None, ws_bytes,
+            _lib.stream_ptr(x.device)))
     return out
 
 
@@ -52,10 +54,12 @@ def roi_align_backward(grad, rois, spatial_scale, pooled_h, pooled_w, batch_size
     if gin.numel() == 0:
         return gin
     with torch.cuda.device(g.device):
+        ws, ws_bytes = _lib.roi_align_workspace(rois.size(0), pooled_h, pooled_w, height, g.device, nhwc)
         _lib.check(_lib.lib().abr_roi_align_backward(
             g.data_ptr(), rois.data_ptr(), gin.data_ptr(), batch_size, channels, height, width, rois.size(0),
             pooled_h, pooled_w, float(spatial_scale), int(sampling_ratio), _lib.dtype_code(g),
-            _lib.ABR_NHWC if nhwc else _lib.ABR_NCHW, 1, _lib.stream_ptr(g.device)))
+            _lib.ABR_NHWC if nhwc else _lib.ABR_NCHW, 1, ws.data_ptr() if ws is not None else None, ws_bytes,
+            _lib.stream_ptr(g.device)))
     return gin
 
 

@@ -77,10 +77,11 @@ class _MultiLevelROIAlign(Function):
         if out.numel():
             ptrs, hs, ws, sc = _level_arrays(feats, scales)
             with torch.cuda.device(out.device):
+                wk, wk_bytes = _lib.roi_align_workspace(R, PH, PW, max(f.shape[2] for f in feats), out.device, nhwc)
                 _lib.check(_lib.lib().abr_roi_align_multilevel_forward(
                     ptrs, hs, ws, sc, len(feats), rois.data_ptr(), levels.data_ptr(), out.data_ptr(), B, C, R, PH, PW,
                     int(sampling_ratio), _lib.dtype_code(out), _lib.ABR_NHWC if nhwc else _lib.ABR_NCHW,
-                    _lib.stream_ptr(out.device)))
+                    wk.data_ptr() if wk is not None else None, wk_bytes, _lib.stream_ptr(out.device)))
         return out
 
     @staticmethod
@@ -94,10 +95,11 @@ class _MultiLevelROIAlign(Function):
         B, C = shapes[0][:2]
         ptrs, hs, ws, sc = _level_arrays(grads, scales)
         with torch.cuda.device(g.device):
+            wk, wk_bytes = _lib.roi_align_workspace(rois.size(0), PH, PW, max(s[2] for s in shapes), g.device, nhwc)
             _lib.check(_lib.lib().abr_roi_align_multilevel_backward(
                 g.data_ptr(), rois.data_ptr(), levels.data_ptr(), ptrs, hs, ws, sc, len(grads), B, C, rois.size(0),
                 PH, PW, int(sampling_ratio), _lib.dtype_code(g), _lib.ABR_NHWC if nhwc else _lib.ABR_NCHW, 1,
-                _lib.stream_ptr(g.device)))
+                wk.data_ptr() if wk is not None else None, wk_bytes, _lib.stream_ptr(g.device)))
         return (None, None, None, None, None) + tuple(grads)
 
 

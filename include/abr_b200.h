@@ -58,18 +58,23 @@ ABR_API uint64_t abr_launch_count(void);
  * Replaces _C.roi_align_forward / _C.roi_align_backward
  *   (csrc/ROIAlign.h:11-46, csrc/cuda/ROIAlign_cuda.cu:257-346, csrc/cpu/ROIAlign_cpu.cpp:221-257).
  * sampling_ratio <= 0 selects the adaptive grid ceil(roi_size / pooled_size) (ROIAlign_cuda.cu:100-101).
- * R == 0 is a no-op (ROIAlign_cuda.cu:278-281). */
+ * R == 0 is a no-op (ROIAlign_cuda.cu:278-281).
+ * `workspace` (optional, 16-byte aligned, abr_roi_align_workspace_bytes(R, PH, PW, max H over levels) bytes) holds the
+ * per-RoI interpolation plans of the fast NHWC kernels; with NULL (or the NCHW layout) the self-contained kernels run.
+ * Its contents are scratch: nothing is carried from one call to the next. */
+ABR_API size_t abr_roi_align_workspace_bytes(int R, int PH, int PW, int max_h);
 ABR_API int abr_roi_align_forward(const void* input, const float* rois, void* output,
                           int B, int C, int H, int W, int R, int PH, int PW,
                           float spatial_scale, int sampling_ratio,
-                          int dtype, int layout, abr_stream_t stream);
+                          int dtype, int layout, void* workspace, size_t workspace_bytes, abr_stream_t stream);
 
 /* grad_input [B,C,H,W] is zero-filled first when zero_init != 0 (the reference always does,
  * ROIAlign_cuda.cu:316); pass 0 to accumulate into an existing gradient. */
 ABR_API int abr_roi_align_backward(const void* grad_output, const float* rois, void* grad_input,
                            int B, int C, int H, int W, int R, int PH, int PW,
                            float spatial_scale, int sampling_ratio,
-                           int dtype, int layout, int zero_init, abr_stream_t stream);
+                           int dtype, int layout, int zero_init, void* workspace, size_t workspace_bytes,
+                           abr_stream_t stream);
 
 /* Multi-level (FPN) pooling in ONE launch: replaces the per-level nonzero / gather / launch / scatter
  * loop of Pooler.forward (modeling/poolers.py:93-105).  `levels[r]` in [0,L) selects the feature map
@@ -81,12 +86,14 @@ ABR_API int abr_roi_align_multilevel_forward(const void* const* inputs_host, con
                                      const float* scales_host, int L,
                                      const float* rois, const int32_t* levels, void* output,
                                      int B, int C, int R, int PH, int PW, int sampling_ratio,
-                                     int dtype, int layout, abr_stream_t stream);
+                                     int dtype, int layout, void* workspace, size_t workspace_bytes,
+                                     abr_stream_t stream);
 ABR_API int abr_roi_align_multilevel_backward(const void* grad_output, const float* rois, const int32_t* levels,
                                       void* const* grad_inputs_host, const int* hs_host, const int* ws_host,
                                       const float* scales_host, int L,
                                       int B, int C, int R, int PH, int PW, int sampling_ratio,
-                                      int dtype, int layout, int zero_init, abr_stream_t stream);
+                                      int dtype, int layout, int zero_init, void* workspace, size_t workspace_bytes,
+                                      abr_stream_t stream);
 
 /* FPN level of each RoI: floor(k0 + log2(sqrt(area)/s0 + eps)) clamped to [k_min,k_max], minus k_min,
  * area with the +1 convention (modeling/poolers.py:31-42, structures/bounding_box.py:227-231). */

@@ -177,3 +177,37 @@ def test_pooler_multilevel_backward_vs_per_level_oracle(golden):
         f = g["feat_%d" % lvl]
         ref = oracle.roi_align_backward(gout[idx], rois[idx], scales[lvl], 7, 7, *f.shape, 2)
         close(feats[lvl].grad.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("use_workspace", [True, False])
+@pytest.mark.parametrize("P,ratio", [(7, 0), (14, 0), (7, 2), (14, 3)])
+def test_roi_align_nhwc_every_plan_mode(monkeypatch, use_workspace, P, ratio):
+    """Channels-last kernels on a large map: RoIs chosen to hit every plan mode of csrc/roi_align.cu -- EMPTY (outside
+    the map), ROLLING (thick bins), THIN (bins thinner than a pixel), GENERIC (columns wider than 16 pixels, thin bins
+    with P > 8) -- and the self-contained kernels that run when the caller passes no workspace."""
+    from abr_iod_b200 import _lib
+    from abr_iod_b200.layers import roi_align
+
+    if not use_workspace:
+        monkeypatch.setattr(_lib, "roi_align_workspace", lambda *a, **k: (None, 0))
+    rng = np.random.default_rng(P * 10 + ratio)
+    B, C, H, W = 2, 12, 120, 200
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    s = 16.0
+    rois = np.array([
+        [0, -900, -900, -500, -500],            # EMPTY
+        [1, 100, 100, 900, 700],                # ROLLING, moderately wide
+        [0, 0, 0, W * s - 1, H * s - 1],        # whole map: columns ~28 px wide -> GENERIC
+        [1, 320, 160, 360, 190],                # THIN: ~2.5 x 1.9 feature px
+        [0, 50.5, 60.25, 51.0, 60.5],           # degenerate, forced to 1x1
+        [1, 10, 10, 2000, 40],                  # very wide, very flat: GENERIC columns + thin rows
+        [0, 3000, 100, 3400, 1800],             # partly off the right/bottom edge
+        [1, -200, -200, 300, 250],              # partly off the top-left
+    ], np.float32)
+    rois = np.concatenate([rois, make_rois(rng, 24, B, int(W * s), int(H * s), adversarial=False)], 0)
+    xt = dev(x, True).requires_grad_(True)
+    out = roi_align(xt, dev(rois), (P, P), 1 / s, ratio)
+    close(out.detach().cpu().numpy(), oracle.roi_align_forward(x, rois, 1 / s, P, P, ratio))
+    gout = rng.standard_normal(out.shape).astype(np.float32)
+    out.backward(dev(gout, True))
+    close(xt.grad.cpu().numpy(), oracle.roi_align_backward(gout, rois, 1 / s, P, P, B, C, H, W, ratio))
