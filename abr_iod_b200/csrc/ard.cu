@@ -79,7 +79,7 @@ __device__ __forceinline__ void ard_finish(const ArdParams& p) {
   __shared__ bool last;
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) last = (atomicAdd(p.counter, 1u) == (unsigned)(p.N - 1));
+  if (threadIdx.x == 0) last = (atomicAdd(p.counter, 1u) == gridDim.x - 1);
   __syncthreads();
   if (!last) return;
   __threadfence();
@@ -105,16 +105,19 @@ __device__ __forceinline__ void ard_finish(const ArdParams& p) {
 // ------------------------------------------------------------------------------------------ NHWC: [N][HW][C]
 // A warp owns whole position rows (C contiguous elements); lanes read 16-byte vectors.
 template <typename T, int V, bool GRAD>
-__global__ void __launch_bounds__(256) ard_nhwc_kernel(ArdParams p, const T* __restrict__ f_old,
-                                                      const T* __restrict__ f_new, T* __restrict__ grad) {
+__global__ void __launch_bounds__(1024) ard_nhwc_kernel(ArdParams p, const T* __restrict__ f_old,
+                                                       const T* __restrict__ f_new, T* __restrict__ grad) {
   extern __shared__ float sm[];
-  const int HW = p.HW, C = p.C, n = blockIdx.x;
+  const int HW = p.HW, C = p.C;
   float* m_old = sm;
   float* m_new = m_old + HW;
   float* dd = m_new + HW;
   float* a_old = dd + HW;
   float* kk = a_old + HW;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  // persistent: one CTA per SM walks the RoIs, so the RoIs in flight (148 x 2*C*HW elements) stay L2-resident
+  // between pass 1 and pass 2
+  for (int n = blockIdx.x; n < p.N; n += gridDim.x) {
   const size_t base = (size_t)n * HW * C;
   const T* __restrict__ fo = f_old + base;
   const T* __restrict__ fn = f_new + base;
@@ -160,6 +163,8 @@ __global__ void __launch_bounds__(256) ard_nhwc_kernel(ArdParams p, const T* __r
       }
     }
   }
+  __syncthreads();  // the per-position tables are reused by the next RoI
+  }
   ard_finish(p);
 }
 
@@ -170,7 +175,7 @@ template <typename T, bool GRAD>
 __global__ void __launch_bounds__(1024) ard_nchw_kernel(ArdParams p, const T* __restrict__ f_old,
                                                        const T* __restrict__ f_new, T* __restrict__ grad, int G) {
   extern __shared__ float sm[];
-  const int HW = p.HW, C = p.C, n = blockIdx.x;
+  const int HW = p.HW, C = p.C;
   float* m_old = sm;
   float* m_new = m_old + HW;
   float* dd = m_new + HW;
@@ -181,6 +186,7 @@ __global__ void __launch_bounds__(1024) ard_nchw_kernel(ArdParams p, const T* __
   const int tid = threadIdx.x;
   const bool active = tid < T_;
   const int grp = active ? tid / HW : C, pos = active ? tid - grp * HW : 0;  // grp == C: loops are empty
+  for (int n = blockIdx.x; n < p.N; n += gridDim.x) {  // persistent, see ard_nhwc_kernel
   const size_t base = (size_t)n * HW * C;
   const T* __restrict__ fo = f_old + base;
   const T* __restrict__ fn = f_new + base;
@@ -218,6 +224,8 @@ __global__ void __launch_bounds__(1024) ard_nchw_kernel(ArdParams p, const T* __
       VecIO<T, 1>::store(g + (size_t)c * HW + pos, o);
     }
   }
+  __syncthreads();  // red[] and the per-position tables are reused by the next RoI
+  }
   ard_finish(p);
 }
 
@@ -236,21 +244,24 @@ __global__ void scale_if_needed_kernel(T* data, size_t n, const float* __restric
 template <typename T, int V>
 static int launch_nhwc(const ArdParams& p, const void* fo, const void* fn, void* g, cudaStream_t st) {
   const size_t smem = (size_t)5 * p.HW * sizeof(float);
-  if (g) ard_nhwc_kernel<T, V, true><<<p.N, 256, smem, st>>>(p, static_cast<const T*>(fo), static_cast<const T*>(fn), static_cast<T*>(g));
-  else ard_nhwc_kernel<T, V, false><<<p.N, 256, smem, st>>>(p, static_cast<const T*>(fo), static_cast<const T*>(fn), nullptr);
+  const int grid = p.N < num_sms() ? p.N : num_sms();  // 1024 threads: one CTA per SM
+  if (g) ard_nhwc_kernel<T, V, true><<<grid, 1024, smem, st>>>(p, static_cast<const T*>(fo), static_cast<const T*>(fn), static_cast<T*>(g));
+  else ard_nhwc_kernel<T, V, false><<<grid, 1024, smem, st>>>(p, static_cast<const T*>(fo), static_cast<const T*>(fn), nullptr);
   ABR_CHECK_LAUNCH("ard_forward_backward");
   return ABR_OK;
 }
 
 template <typename T>
 static int launch_nchw(const ArdParams& p, const void* fo, const void* fn, void* g, cudaStream_t st) {
-  int G = 512 / p.HW;
+  int G = 1024 / p.HW;
   if (G < 1) G = 1;
   if (G > p.C) G = p.C;
   const int threads = ceil_div(G * p.HW, 32) * 32;
   const size_t smem = (size_t)(5 * p.HW + 3 * G * p.HW) * sizeof(float);
-  if (g) ard_nchw_kernel<T, true><<<p.N, threads, smem, st>>>(p, static_cast<const T*>(fo), static_cast<const T*>(fn), static_cast<T*>(g), G);
-  else ard_nchw_kernel<T, false><<<p.N, threads, smem, st>>>(p, static_cast<const T*>(fo), static_cast<const T*>(fn), nullptr, G);
+  const int per_sm = 2048 / threads > 0 ? 2048 / threads : 1;  // resident CTAs per SM at this block size
+  const int grid = p.N < num_sms() * per_sm ? p.N : num_sms() * per_sm;
+  if (g) ard_nchw_kernel<T, true><<<grid, threads, smem, st>>>(p, static_cast<const T*>(fo), static_cast<const T*>(fn), static_cast<T*>(g), G);
+  else ard_nchw_kernel<T, false><<<grid, threads, smem, st>>>(p, static_cast<const T*>(fo), static_cast<const T*>(fn), nullptr, G);
   ABR_CHECK_LAUNCH("ard_forward_backward");
   return ABR_OK;
 }

@@ -332,8 +332,11 @@ __global__ void __launch_bounds__(256) roi_align_fwd_sweep_kernel(LevelTable lv,
 #pragma unroll
     for (int i = 0; i < V; i++) accA[i] = accB[i] = 0.f;
     int a = 0;
-    for (int n = k.nrows; n > 0; n--, rr += 2, q0 += rowstride, q1 += rowstride, q2 += rowstride, q3 += rowstride) {
-      const int4 info = __ldg(rr);
+    int4 info_next = __ldg(rr);
+    for (int n = k.nrows; n > 0; n--, q0 += rowstride, q1 += rowstride, q2 += rowstride, q3 += rowstride) {
+      const int4 info = info_next;
+      rr += 2;
+      if (n > 1) info_next = __ldg(rr);  // row records are fetched one row ahead
       if (info.x < 0) continue;
       float tr[V];
       row_dot<T, V>(tr, q0, q1, q2, q3, w, k.nx, pix, k.col);
