@@ -73,7 +73,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -337,13 +337,60 @@ def secondary_metrics(dev):
         e.record()
         torch.cuda.synchronize()
         out["nms_boxes_per_s_n%d_b%d" % (n, batch)] = round(batch * n * 10 / (s.elapsed_time(e) * 1e-3))
+    out.update(paste_metrics(dev))
     return out
+
+
+def paste_metrics(dev, n_proto=2000, batch=16, rounds=8):
+    """Config 4 on one GPU's shard: 2000 synthetic prototypes (sides U(71,300)), batches of 16 images 375x500 at the
+    reference's 25/25/50 mixup/mosaic/untouched policy.  imgs/s for the whole call (host planning in the reference's
+    draw order + pinned H2D + ONE paste launch) and for the kernel alone."""
+    import random
+
+    import torch
+    from PIL import Image
+
+    from abr_iod_b200.data.abr_paste import BoxRehearsalPaster
+
+    rng = np.random.default_rng(4)
+    protos = []
+    for i in range(n_proto):
+        h, w = int(rng.integers(71, 301)), int(rng.integers(71, 301))
+        protos.append(("%d_%05d.jpg" % (int(rng.integers(1, 16)), i),
+                       np.broadcast_to(rng.integers(0, 256, (1, 1, 3), dtype=np.uint8), (h, w, 3)).copy()))
+    paster = BoxRehearsalPaster(protos, batch_size=batch, device=dev)
+    images = [Image.fromarray(rng.integers(0, 256, (375, 500, 3), dtype=np.uint8)) for _ in range(batch)]
+    targets = []
+    for _ in range(batch):
+        x1, y1 = rng.uniform(0, 250, 3), rng.uniform(0, 180, 3)
+        targets.append(np.stack([x1, y1, x1 + rng.uniform(30, 200, 3), y1 + rng.uniform(30, 150, 3), rng.integers(16, 21, 3)], 1))
+    random.seed(0)
+    torch.manual_seed(0)
+    paster.paste_batch(images, targets)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    plans_all = []
+    for _ in range(rounds):
+        plans = [paster.plan_transform(im, g) for im, g in zip(images, targets)]
+        plans_all.append(plans)
+        paster.execute(plans)
+    torch.cuda.synchronize()
+    t_all = time.perf_counter() - t0
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # kernel + H2D only (plans precomputed)
+    s.record()
+    for plans in plans_all:
+        paster.execute(plans)
+    e.record()
+    torch.cuda.synchronize()
+    return {"paste_imgs_per_s_plan+h2d+kernel": round(batch * rounds / t_all),
+            "paste_imgs_per_s_h2d+kernel": round(batch * rounds / (s.elapsed_time(e) * 1e-3))}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layout", default="nhwc", choices=["nhwc", "nchw"])
