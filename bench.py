@@ -173,6 +173,7 @@ def run_ours(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    sampler = ClockSampler(local_rank) if rank == 0 else None  # started early: nvidia-smi needs a second to warm up
     w = WORKLOAD
     nhwc = args.layout == "nhwc"
     fmt = torch.channels_last if nhwc else torch.contiguous_format
@@ -213,7 +214,6 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = _lib.launch_count()
     events = []
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
