@@ -121,7 +121,7 @@ __device__ __forceinline__ Tables carve(float* smem, int PH, int PW, int Hs, int
 // ------------------------------------------------------------------------------------------ backward helpers
 // After the two axis tables exist: overall footprint [Y0,Y1]x[X0,X1] and, for every map row / column inside it,
 // the (contiguous) range of bins whose support contains it.  aux = [plo Hs][phi Hs][qlo Ws][qhi Ws][Y0,Y1,X0,X1,span]
-// where span = max over rows of (number of bins containing the row) - 1.
+// where span = max over rows of (number of bins containing the row) - 1 (xspan: the same over columns).
 __device__ __forceinline__ void build_inverse_ranges(const Tables& t, int PH, int PW, int H, int W, int Hs, int Ws) {
   int* plo = t.aux;
   int* phi = plo + Hs;
@@ -148,8 +148,10 @@ __device__ __forceinline__ void build_inverse_ranges(const Tables& t, int PH, in
       if (t.ylo[p] <= t.yhi[p]) { a = min(a, t.ylo[p]); b = max(b, t.yhi[p]); }
     for (int p = 0; p < PW; p++)
       if (t.xlo[p] <= t.xhi[p]) { c = min(c, t.xlo[p]); d = max(d, t.xhi[p]); }
+    int xspan = 0;
     for (int y = a; y <= b; y++) span = max(span, phi[y] - plo[y]);
-    fp[0] = a; fp[1] = b; fp[2] = c; fp[3] = d; fp[4] = span;
+    for (int x = c; x <= d; x++) xspan = max(xspan, qhi[x] - qlo[x]);
+    fp[0] = a; fp[1] = b; fp[2] = c; fp[3] = d; fp[4] = span; fp[5] = xspan;
   }
   __syncthreads();
 }
@@ -214,9 +216,15 @@ __global__ void __launch_bounds__(128) plan_kernel(LevelTable lv, const float* _
     const int p = i / kPlanCol, k = i - p * kPlanCol;
     const int x0 = t.xlo[p], x1 = t.xhi[p];
     const bool has = x0 <= x1;
+    // backward only: a map pixel shared by two adjacent columns is reduced ONCE, by the later column, which adds the
+    // earlier column's term; [2] = trailing pixels this column leaves to the next one, [3] = leading pixels for which it
+    // also carries the previous column.  Valid when no pixel lies in three columns and rows are ROLLING.
+    const bool pair = mode == PLAN_ROLLING && fp[5] <= 1;
     int v = 0;
     if (k == 0) v = has ? x0 : 0;
     else if (k == 1) v = has ? x1 - x0 + 1 : 0;
+    else if (k == 2) v = (pair && has && p + 1 < PW && t.xlo[p + 1] <= t.xhi[p + 1]) ? max(0, x1 - t.xlo[p + 1] + 1) : 0;
+    else if (k == 3) v = (pair && has && p > 0 && t.xlo[p - 1] <= t.xhi[p - 1]) ? max(0, t.xhi[p - 1] - x0 + 1) : 0;
     else if (k >= 4) v = (has && x0 + (k - 4) <= x1) ? __float_as_int(t.Wx[(size_t)p * Ws + x0 + (k - 4)]) : 0;
     col[i] = v;
   }
@@ -441,7 +449,8 @@ __global__ void __launch_bounds__(256) roi_align_bwd_sweep_kernel(LevelTable lv,
   SweepTask k;
   int r;
   if (!sweep_task<V>(k, plans, stride, C, PW, nslices, ntasks, r)) return;
-  if (k.nx == 0 || !k.active) return;
+  if (k.nx == 0) return;  // warp-uniform
+  const bool active = k.active;  // idle lanes of a ragged last slice shadow channel 0 and never reduce
   const size_t pix = (size_t)C, binstride = (size_t)PW * C;
   const T* __restrict__ go = gout + ((size_t)r * PH * PW + k.pw) * C + k.c;
   const size_t rowstride = (size_t)k.W * C;
@@ -450,31 +459,97 @@ __global__ void __launch_bounds__(256) roi_align_bwd_sweep_kernel(LevelTable lv,
   const int4* rr = k.rows;
   const float inv_count = k.inv_count;
   if (k.mode == PLAN_ROLLING) {
-    float gA[V], gB[V];  // gradients of bins a and a+1 of this column (rolling window)
-    int a = -2;          // no bin cached yet
-    for (int n = k.nrows; n > 0; n--, rr += 2, q0 += rowstride) {
-      const int4 info = __ldg(rr);
-      if (info.x < 0) continue;
-      if (a != info.x) {
-        if (a + 1 == info.x) {
+    // Pixels shared with the next column are left to it; for the leading pixels shared with the previous column this
+    // warp adds that column's term too, so every footprint pixel of the RoI receives exactly one reduction.
+    const int n_emit = k.nx - k.col[2], n_prev = k.col[3];
+    const int* pcol = k.col - kPlanCol;  // previous column's record (only read when n_prev > 0)
+    const int poff = n_prev > 0 ? k.x0 - pcol[0] : 0;
+    float4 wp = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n_prev > 0) {
+      wp.x = __int_as_float(pcol[4 + poff]);
+      if (n_prev > 1) wp.y = __int_as_float(pcol[4 + poff + 1]);
+      if (n_prev > 2) wp.z = __int_as_float(pcol[4 + poff + 2]);
+      if (n_prev > 3) wp.w = __int_as_float(pcol[4 + poff + 3]);
+    }
+    const T* __restrict__ gp = go - C;  // the previous column's bins
+    // the column's PH gradient vectors come from DRAM exactly once: start all of them now so that the rolling window
+    // below finds them in L1/L2 instead of paying one exposed DRAM latency per bin
+    for (int p = 0; p < PH; p++) {
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(go + (size_t)p * binstride));
+      if (n_prev > 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(gp + (size_t)p * binstride));
+    }
+    float gA[V], gB[V], pA[V], pB[V];  // gradients of bins a and a+1 of this column and of the previous one
 #pragma unroll
-          for (int i = 0; i < V; i++) gA[i] = gB[i];
-        } else {
-          VecIO<T, V>::load(go + (size_t)info.x * binstride, gA);
+    for (int i = 0; i < V; i++) pA[i] = pB[i] = 0.f;
+    int a = -2;  // no bin cached yet
+    const int lane = threadIdx.x & 31;
+    for (int base = 0; base < k.nrows; base += 32) {  // row records: one coalesced fetch per 32 rows, then shuffles
+      const int cnt = min(32, k.nrows - base);
+      const int4 mine = lane < cnt ? __ldg(rr + 2 * (base + lane)) : make_int4(-1, 0, 0, 0);
+      for (int j = 0; j < cnt; j++, q0 += rowstride) {
+        int4 info;
+        info.x = __shfl_sync(0xffffffffu, mine.x, j);
+        info.y = __shfl_sync(0xffffffffu, mine.y, j);
+        info.z = __shfl_sync(0xffffffffu, mine.z, j);
+        if (info.x < 0) continue;
+        if (a != info.x) {
+          if (a + 1 == info.x) {
+#pragma unroll
+            for (int i = 0; i < V; i++) { gA[i] = gB[i]; pA[i] = pB[i]; }
+          } else {
+            VecIO<T, V>::load(go + (size_t)info.x * binstride, gA);
+            if (n_prev > 0) VecIO<T, V>::load(gp + (size_t)info.x * binstride, pA);
+          }
+          a = info.x;
+          if (a + 1 < PH) {
+            VecIO<T, V>::load(go + (size_t)(a + 1) * binstride, gB);
+            if (n_prev > 0) VecIO<T, V>::load(gp + (size_t)(a + 1) * binstride, pB);
+          } else {
+#pragma unroll
+            for (int i = 0; i < V; i++) gB[i] = pB[i] = 0.f;
+          }
         }
-        a = info.x;
-        if (a + 1 < PH) {
-          VecIO<T, V>::load(go + (size_t)(a + 1) * binstride, gB);
-        } else {
+        const float wa = __int_as_float(info.y) * inv_count, wb = __int_as_float(info.z) * inv_count;
+        float s[V], sp[V];
 #pragma unroll
-          for (int i = 0; i < V; i++) gB[i] = 0.f;
+        for (int i = 0; i < V; i++) {
+          s[i] = fmaf(wb, gB[i], wa * gA[i]);
+          sp[i] = fmaf(wb, pB[i], wa * pA[i]);
+        }
+        float v[V];
+        if (n_emit > 0 && (w.x != 0.f || wp.x != 0.f)) {
+#pragma unroll
+          for (int i = 0; i < V; i++) v[i] = fmaf(wp.x, sp[i], w.x * s[i]);
+          if (active) VecIO<T, V>::red_add(q0, v);
+        }
+        if (n_emit > 1 && (w.y != 0.f || wp.y != 0.f)) {
+#pragma unroll
+          for (int i = 0; i < V; i++) v[i] = fmaf(wp.y, sp[i], w.y * s[i]);
+          if (active) VecIO<T, V>::red_add(q0 + pix, v);
+        }
+        if (n_emit > 2 && (w.z != 0.f || wp.z != 0.f)) {
+#pragma unroll
+          for (int i = 0; i < V; i++) v[i] = fmaf(wp.z, sp[i], w.z * s[i]);
+          if (active) VecIO<T, V>::red_add(q0 + 2 * pix, v);
+        }
+        if (n_emit > 3 && (w.w != 0.f || wp.w != 0.f)) {
+#pragma unroll
+          for (int i = 0; i < V; i++) v[i] = fmaf(wp.w, sp[i], w.w * s[i]);
+          if (active) VecIO<T, V>::red_add(q0 + 3 * pix, v);
+        }
+        if (n_emit > 4) {  // warp-uniform, rare: columns of 5..kPlanNx pixels
+          T* q = q0 + 4 * pix;
+          for (int jj = 4; jj < n_emit; jj++, q += pix) {
+            const float bw = __int_as_float(__ldg(k.col + 4 + jj));
+            const float bp = jj < n_prev ? __int_as_float(__ldg(pcol + 4 + poff + jj)) : 0.f;
+            if (bw != 0.f || bp != 0.f) {
+#pragma unroll
+              for (int i = 0; i < V; i++) v[i] = fmaf(bp, sp[i], bw * s[i]);
+              if (active) VecIO<T, V>::red_add(q, v);
+            }
+          }
         }
       }
-      const float wa = __int_as_float(info.y) * inv_count, wb = __int_as_float(info.z) * inv_count;
-      float s[V];
-#pragma unroll
-      for (int i = 0; i < V; i++) s[i] = fmaf(wb, gB[i], wa * gA[i]);
-      row_scatter<T, V>(q0, s, w, k.nx, pix, k.col);
     }
   } else {  // PLAN_THIN
     float g[kThinBins][V];
@@ -500,7 +575,7 @@ __global__ void __launch_bounds__(256) roi_align_bwd_sweep_kernel(LevelTable lv,
         for (int i = 0; i < V; i++) s[i] = fmaf(wy[p], g[p][i], s[i]);
 #pragma unroll
       for (int i = 0; i < V; i++) s[i] *= inv_count;
-      row_scatter<T, V>(q0, s, w, k.nx, pix, k.col);
+      if (active) row_scatter<T, V>(q0, s, w, k.nx, pix, k.col);
     }
   }
 }
