@@ -12,6 +12,8 @@
 // every per-position coefficient in shared memory; pass 2 re-reads the RoI (it was just read by this SM, 0.4-1.6 MB,
 // so it is served from L2) and writes the gradient.  HBM traffic = read 2 tensors + write 1.  The per-RoI loss
 // partials are reduced in fixed order by the last CTA to finish (deterministic, no float atomics).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace abr {
@@ -244,9 +246,11 @@ __global__ void scale_if_needed_kernel(T* data, size_t n, const float* __restric
 template <typename T, int V>
 static int launch_nhwc(const ArdParams& p, const void* fo, const void* fn, void* g, cudaStream_t st) {
   const size_t smem = (size_t)5 * p.HW * sizeof(float);
-  const int grid = p.N < num_sms() ? p.N : num_sms();  // 1024 threads: one CTA per SM
-  if (g) ard_nhwc_kernel<T, V, true><<<grid, 1024, smem, st>>>(p, static_cast<const T*>(fo), static_cast<const T*>(fn), static_cast<T*>(g));
-  else ard_nhwc_kernel<T, V, false><<<grid, 1024, smem, st>>>(p, static_cast<const T*>(fo), static_cast<const T*>(fn), nullptr);
+  static const int threads = getenv("ABR_ARD_THREADS") ? atoi(getenv("ABR_ARD_THREADS")) : 1024;
+  const int per_sm = 2048 / threads;
+  const int grid = p.N < num_sms() * per_sm ? p.N : num_sms() * per_sm;
+  if (g) ard_nhwc_kernel<T, V, true><<<grid, threads, smem, st>>>(p, static_cast<const T*>(fo), static_cast<const T*>(fn), static_cast<T*>(g));
+  else ard_nhwc_kernel<T, V, false><<<grid, threads, smem, st>>>(p, static_cast<const T*>(fo), static_cast<const T*>(fn), nullptr);
   ABR_CHECK_LAUNCH("ard_forward_backward");
   return ABR_OK;
 }
