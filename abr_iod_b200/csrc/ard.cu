@@ -28,7 +28,7 @@ struct ArdParams {
 
 // Shared memory (floats): m_old[HW] m_new[HW] dd[HW] a_old[HW] kk[HW]
 __device__ __forceinline__ void ard_position_phase(const ArdParams& p, float* m_old, float* m_new, const float* dd,
-                                                   float* a_old, float* kk, int n) {
+                                                   float* a_old, float* kk, int n, bool write_partials = true) {
   // executed by warp 0 only; m_* hold sum_c f^2 on entry
   const int lane = threadIdx.x & 31;
   const int HW = p.HW;
@@ -70,7 +70,7 @@ __device__ __forceinline__ void ard_position_phase(const ArdParams& p, float* m_
     kk[i] = kb * m_new[i] * (kk[i] - gs);
     a_old[i] *= ka;  // pass 2 needs only ka * A_old
   }
-  if (lane == 0) {
+  if (lane == 0 && write_partials) {
     p.partials[2 * n] = afd;
     p.partials[2 * n + 1] = pad;
   }
@@ -231,6 +231,174 @@ __global__ void __launch_bounds__(1024) ard_nchw_kernel(ArdParams p, const T* __
   ard_finish(p);
 }
 
+// ------------------------------------------------------------------------------------------ NHWC, shared-memory resident
+// One thread-block CLUSTER owns one RoI at a time and keeps BOTH tensors of it in shared memory, so HBM is touched
+// exactly once per element (read f_old, read f_new, write the gradient): CTA k of the cluster holds the position
+// rows [k*rows_per_cta, ...) -- for C=1024, P=7 that is 25 rows x 4 KB x 2 tensors = 200 KB in each of 2 CTAs.
+// The rows arrive by TMA bulk copies (cp.async.bulk, a few rows per mbarrier so that pass 1 starts while the rest is
+// still in flight); the per-position sums are exchanged through distributed shared memory (every CTA writes its rows'
+// sums into all peers' tables, one cluster barrier), every CTA then evaluates the softmaxes redundantly and runs pass 2
+// out of its own shared memory.
+constexpr int kArdChunks = 8;
+constexpr int kArdClusterThreads = 512;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_nctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA bulk copy global -> this CTA's shared memory, completion counted in bytes on `bar`
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// store one float into the same shared-memory variable of cluster CTA `rank`
+__device__ __forceinline__ void dsmem_store(float* local_addr, unsigned rank, float v) {
+  unsigned remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_addr)), "r"(rank));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+}
+
+template <bool GRAD>
+__global__ void __launch_bounds__(kArdClusterThreads, 1) ard_nhwc_cluster_kernel(ArdParams p, const float* __restrict__ f_old,
+                                                                              const float* __restrict__ f_new,
+                                                                              float* __restrict__ grad, int rows_per_cta) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int HW = p.HW, C = p.C;
+  float* t_old = reinterpret_cast<float*>(smem_raw);                 // [rows_per_cta][C]
+  float* t_new = t_old + (size_t)rows_per_cta * C;                   // [rows_per_cta][C]
+  float* ex = t_new + (size_t)rows_per_cta * C;                      // [2 parities][3][HW]: sum f_old^2, sum f_new^2, sum diff^2
+  float* a_old = ex + 6 * HW;
+  float* kk = a_old + HW;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(kk + HW);  // 2*rows*C + 8*HW floats: 8-byte aligned
+  const unsigned rank = cluster_ctarank(), csize = cluster_nctarank();
+  const int cluster_id = blockIdx.x / csize, nclusters = gridDim.x / csize;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = kArdClusterThreads / 32;
+  const int row0 = rank * rows_per_cta;
+  const int nrows = max(0, min(rows_per_cta, HW - row0));
+  const int chunk_rows = max(1, ceil_div(rows_per_cta, kArdChunks));
+  const int nchunks = ceil_div(nrows, chunk_rows);
+  if (tid == 0) {
+    for (int i = 0; i < kArdChunks; i++) mbar_init(&bars[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  cluster_sync_all();  // barriers visible; every peer's shared memory is live before the first remote store
+
+  int iter = 0;
+  for (int n = cluster_id; n < p.N; n += nclusters, iter++) {
+    const unsigned parity = iter & 1;
+    const size_t base = ((size_t)n * HW + row0) * C;
+    if (tid == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy reads of the previous RoI are done
+      for (int ch = 0; ch < nchunks; ch++) {
+        const int r0 = ch * chunk_rows, rn = min(chunk_rows, nrows - r0);
+        const unsigned bytes = (unsigned)rn * C * sizeof(float);
+        mbar_expect_tx(&bars[ch], 2 * bytes);
+        tma_load_1d(t_old + (size_t)r0 * C, f_old + base + (size_t)r0 * C, bytes, &bars[ch]);
+        tma_load_1d(t_new + (size_t)r0 * C, f_new + base + (size_t)r0 * C, bytes, &bars[ch]);
+      }
+    }
+    float* ex_old = ex + parity * 3 * HW;
+    float* ex_new = ex_old + HW;
+    float* ex_dd = ex_new + HW;
+    // pass 1 out of shared memory, chunk by chunk as the copies land
+    for (int row = warp; row < nrows; row += nwarp) {
+      mbar_wait(&bars[row / chunk_rows], parity);
+      const float4* ro = reinterpret_cast<const float4*>(t_old + (size_t)row * C);
+      const float4* rn = reinterpret_cast<const float4*>(t_new + (size_t)row * C);
+      float so = 0.f, sn = 0.f, sd = 0.f;
+#pragma unroll 4
+      for (int c = lane; c < C / 4; c += 32) {
+        const float4 a = ro[c], b = rn[c];
+        so = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, so))));
+        sn = fmaf(b.x, b.x, fmaf(b.y, b.y, fmaf(b.z, b.z, fmaf(b.w, b.w, sn))));
+        const float d0 = b.x - a.x, d1 = b.y - a.y, d2 = b.z - a.z, d3 = b.w - a.w;
+        sd = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, sd))));
+      }
+      so = warp_sum(so); sn = warp_sum(sn); sd = warp_sum(sd);
+      if (lane < (int)csize) {  // lane r publishes this row's sums in CTA r's table
+        dsmem_store(ex_old + row0 + row, lane, so);
+        dsmem_store(ex_new + row0 + row, lane, sn);
+        dsmem_store(ex_dd + row0 + row, lane, sd);
+      }
+    }
+    cluster_sync_all();  // all HW sums of this RoI are in every CTA's table
+    if (warp == 0) ard_position_phase(p, ex_old, ex_new, ex_dd, a_old, kk, n, rank == 0);
+    __syncthreads();
+    if (GRAD) {
+      float* g = grad + base;
+      for (int row = warp; row < nrows; row += nwarp) {
+        const float4* ro = reinterpret_cast<const float4*>(t_old + (size_t)row * C);
+        const float4* rn = reinterpret_cast<const float4*>(t_new + (size_t)row * C);
+        float4* rg = reinterpret_cast<float4*>(g + (size_t)row * C);
+        const float ka = a_old[row0 + row], kb = kk[row0 + row];
+#pragma unroll 4
+        for (int c = lane; c < C / 4; c += 32) {
+          const float4 a = ro[c], b = rn[c];
+          float4 o;
+          o.x = fmaf(ka, b.x - a.x, kb * b.x);
+          o.y = fmaf(ka, b.y - a.y, kb * b.y);
+          o.z = fmaf(ka, b.z - a.z, kb * b.z);
+          o.w = fmaf(ka, b.w - a.w, kb * b.w);
+          rg[c] = o;
+        }
+      }
+    }
+    __syncthreads();  // the tiles and a_old / kk are free for the next RoI
+  }
+  cluster_sync_all();  // no CTA exits while a peer may still store into its shared memory
+  ard_finish(p);
+}
+
+// cluster size and rows per CTA for the shared-memory resident kernel; 0 = does not fit (use the two-pass kernel)
+static int ard_cluster_size(int C, int HW, size_t& smem_bytes, int& rows_per_cta) {
+  for (int cs = 1; cs <= 8; cs *= 2) {
+    if (cs > HW) break;
+    rows_per_cta = ceil_div(HW, cs);
+    smem_bytes = (size_t)2 * rows_per_cta * C * sizeof(float) + (size_t)(8 * HW + 2) * sizeof(float) + kArdChunks * 8 + 128;
+    if (smem_bytes <= 227 * 1024) return cs;
+  }
+  return 0;
+}
+
+static int launch_nhwc_cluster(const ArdParams& p, const void* fo, const void* fn, void* g, cudaStream_t st, int cs,
+                               size_t smem, int rows_per_cta) {
+  auto kern = g ? ard_nhwc_cluster_kernel<true> : ard_nhwc_cluster_kernel<false>;
+  ABR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int clusters = num_sms() / cs;
+  if (clusters > p.N) clusters = p.N;
+  if (clusters < 1) clusters = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * cs);
+  cfg.blockDim = dim3(kArdClusterThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ABR_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p, static_cast<const float*>(fo), static_cast<const float*>(fn), static_cast<float*>(g), rows_per_cta));
+  ABR_CHECK_LAUNCH("ard_forward_backward (cluster)");
+  return ABR_OK;
+}
+
 template <typename T>
 __global__ void scale_if_needed_kernel(T* data, size_t n, const float* __restrict__ scale, float expected) {
   const float s = *scale;
@@ -300,7 +468,15 @@ int abr_ard_forward_backward(const void* f_old, const void* f_new, void* grad_ne
   p.loss3 = loss3;
   ABR_CUDA_OK(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), st));
   if (layout == ABR_NHWC) {
-    if (dtype == ABR_F32) return (C % 4 == 0) ? launch_nhwc<float, 4>(p, f_old, f_new, grad_new, st) : launch_nhwc<float, 1>(p, f_old, f_new, grad_new, st);
+    if (dtype == ABR_F32 && C % 4 == 0) {
+      static const bool use_cluster = getenv("ABR_ARD_CLUSTER") ? atoi(getenv("ABR_ARD_CLUSTER")) != 0 : true;
+      size_t smem = 0;
+      int rows = 0;
+      const int cs = use_cluster ? ard_cluster_size(C, HW, smem, rows) : 0;
+      if (cs > 0) return launch_nhwc_cluster(p, f_old, f_new, grad_new, st, cs, smem, rows);
+      return launch_nhwc<float, 4>(p, f_old, f_new, grad_new, st);
+    }
+    if (dtype == ABR_F32) return launch_nhwc<float, 1>(p, f_old, f_new, grad_new, st);
     return (C % 8 == 0) ? launch_nhwc<__nv_bfloat16, 8>(p, f_old, f_new, grad_new, st) : launch_nhwc<__nv_bfloat16, 1>(p, f_old, f_new, grad_new, st);
   }
   if (dtype == ABR_F32) return launch_nchw<float>(p, f_old, f_new, grad_new, st);
