@@ -19,6 +19,10 @@
 //      per output element.
 // Sample coordinates are evaluated with explicitly rounded fp32 intrinsics in the reference's operation order
 // so that the in/out-of-map decisions (ROIAlign_cuda.cu:22-25) are identical to the reference's.
+#include <cuda.h>
+
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace abr {
@@ -160,7 +164,7 @@ __device__ __forceinline__ void build_inverse_ranges(const Tables& t, int PH, in
 // A "plan" is the compact form of one RoI's two interpolation tables, written once per call by plan_kernel (a small
 // CTA per RoI) into caller-provided workspace and then read, warp-uniformly and straight out of L1/L2, by the sweep
 // kernels, which therefore need no shared memory, no barriers and no per-CTA setup:
-//   hdr  [8 words]          mode, batch index, level, Y0, Y1, 1/count, H, W
+//   hdr  [16 words]         mode, batch index, level, Y0, Y1, 1/count, H, W, X0, X1, (6 spare)
 //   col  [PW][4 + kPlanNx]  x0, nx, -, -, then the nx column weights Wx[pw][x0 ..] zero-padded to kPlanNx
 //   row  [Y1-Y0+1][8]       ROLLING: first bin a holding the row (-1: none), Wy[a][y], Wy[a+1][y] (0 if not shared)
 //                           THIN:    Wy[0..7][y]
@@ -168,7 +172,8 @@ __device__ __forceinline__ void build_inverse_ranges(const Tables& t, int PH, in
 // THIN    = thinner bins and PH <= 8;  GENERIC = anything else (columns wider than kPlanNx pixels, thin bins with
 // PH > 8): those RoIs are left to the table-in-shared-memory kernels below;  EMPTY = no sample inside the map.
 constexpr int kPlanNx = 16;
-constexpr int kPlanHdr = 8;
+constexpr int kTileMaxPx = 32;  // widest footprint row the TMA-staged kernel holds in one ring slot
+constexpr int kPlanHdr = 16;
 constexpr int kPlanCol = 4 + kPlanNx;
 constexpr int kPlanRow = 8;
 constexpr int kThinBins = 8;
@@ -200,13 +205,15 @@ __global__ void __launch_bounds__(128) plan_kernel(LevelTable lv, const float* _
     if (Y0 > Y1 || fp[2] > fp[3]) {
       mode = PLAN_EMPTY;
     } else {
-      bool wide = false;
+      bool wide = fp[3] - fp[2] + 1 > kTileMaxPx;  // footprint wider than the staged row tile
       for (int p = 0; p < PW; p++) wide |= (t.xhi[p] - t.xlo[p] + 1 > kPlanNx);
       mode = wide ? PLAN_GENERIC : (fp[4] <= 1 ? PLAN_ROLLING : (PH <= kThinBins ? PLAN_THIN : PLAN_GENERIC));
     }
     s_mode = mode;
     plan[0] = mode; plan[1] = g.batch; plan[2] = g.level; plan[3] = Y0; plan[4] = Y1;
     plan[5] = __float_as_int(1.f / g.count); plan[6] = H; plan[7] = W;
+    plan[8] = fp[2]; plan[9] = fp[3];
+    for (int i = 10; i < kPlanHdr; i++) plan[i] = 0;
   }
   __syncthreads();
   const int mode = s_mode;
@@ -580,6 +587,297 @@ __global__ void __launch_bounds__(256) roi_align_bwd_sweep_kernel(LevelTable lv,
   }
 }
 
+// ------------------------------------------------------------------------------------------ forward, NHWC, TMA-staged
+// Warp-specialised, persistent.  A CTA owns (RoI, slice of 32*V channels = 512 bytes per pixel) at a time:
+//   * warp 0 (producer) streams the RoI's footprint, one map row per ring slot, with TMA bulk copies (one 512-byte
+//     cp.async.bulk per footprint pixel, issued by 32 lanes in parallel, completion counted on the slot's mbarrier),
+//     and the RoI's plan (column records + per-row bin weights) into a double-buffered plan area;
+//   * warps 1..PW (consumers, one per bin column) wait for a row, take their column's pixels out of shared memory,
+//     form t = sum_x Wx*v and add Wy[p][y]*t to one register accumulator per bin, then hand the slot back.
+// Every distinct footprint pixel leaves L2 exactly once per (RoI, slice) -- the columns share the staged row -- the
+// loads are asynchronous and kRing rows deep, and no thread ever waits on a dependent global load.  PH <= 8.
+constexpr int kRing = 4;  // power of two: slot = it & (kRing - 1)
+constexpr int kMaxBins = 8;
+
+__device__ __forceinline__ unsigned s_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(unsigned long long* b, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mb_expect_tx(unsigned long long* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_arrive(unsigned long long* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mb_wait(unsigned long long* b, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tW_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra D_%=;\n\tbra W_%=;\n\tD_%=:\n\t}" ::"r"(s_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mb_wait_a(unsigned addr, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tW_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra D_%=;\n\tbra W_%=;\n\tD_%=:\n\t}" ::"r"(addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mb_arrive_a(unsigned addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(unsigned addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void tma_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s_u32(dst)),
+               "l"(src), "r"(bytes), "r"(s_u32(b))
+               : "memory");
+}
+
+// One TMA tensor op: a box of bh rows x bw pixels x 512 bytes of the [B*H rows][W pixels][C channels] view of a map
+// (bw * bh = kTileMaxPx, so every box is one 16 KB ring slot).
+__device__ __forceinline__ void tma_box_g2s(void* dst, const CUtensorMap* map, int c0, int x, int row, unsigned long long* b) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(s_u32(dst)),
+               "l"(map), "r"(c0), "r"(x), "r"(row), "r"(s_u32(b))
+               : "memory");
+}
+constexpr int kTmaLevels = 4;  // feature levels the tensor-map path carries (kernel parameter space)
+constexpr int kTmaBoxes = 5;   // boxes of 2x16, 4x8, 8x4, 16x2, 32x1 (pixels x rows)
+struct TmaMaps {
+  CUtensorMap m[kTmaLevels][kTmaBoxes];
+};
+
+template <typename T, int V>
+__device__ __forceinline__ void unpack16(const uint4 raw, float (&v)[V]);
+template <>
+__device__ __forceinline__ void unpack16<float, 4>(const uint4 raw, float (&v)[4]) {
+  v[0] = __uint_as_float(raw.x); v[1] = __uint_as_float(raw.y); v[2] = __uint_as_float(raw.z); v[3] = __uint_as_float(raw.w);
+}
+template <>
+__device__ __forceinline__ void unpack16<__nv_bfloat16, 8>(const uint4 raw, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256, 3) roi_align_fwd_tma_kernel(const __grid_constant__ TmaMaps maps,
+                                                               const int* __restrict__ plans, size_t stride,
+                                                               T* __restrict__ out, int C, int PH, int PW, int R,
+                                                               int nslices, int Hs) {
+  static_assert(V * sizeof(T) == 16, "one lane moves 16 bytes");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // [ring kRing][kTileMaxPx][32 lanes] uint4 | [plan 2][hdr+cols | wrow Hs*8] ints | barriers
+  uint4* ring = reinterpret_cast<uint4*>(smem_raw);
+  const int headw = kPlanHdr + PW * kPlanCol;   // words of header + column records
+  const int planw = headw + Hs * 8;             // ... + per-row weights
+  int* planbuf = reinterpret_cast<int*>(ring + (size_t)kRing * kTileMaxPx * 32);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(planbuf + 2 * (size_t)planw);
+  unsigned long long* full = bars;              // [kRing] producer -> consumers (tx bytes)
+  unsigned long long* empty = bars + kRing;     // [kRing] consumers -> producer (PW arrivals)
+  unsigned long long* pfull = bars + 2 * kRing; // [2]
+  unsigned long long* pempty = pfull + 2;       // [2]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kRing; i++) { mb_init(&full[i], 1); mb_init(&empty[i], PW * 32); }
+    for (int i = 0; i < 2; i++) { mb_init(&pfull[i], 1); mb_init(&pempty[i], PW * 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long ntasks = (long long)R * nslices;
+  unsigned it = 0;  // rows streamed so far by this CTA (ring position), identical in every warp
+  int ti = 0;       // tasks done so far (plan buffer position)
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer
+    for (long long task = blockIdx.x; task < ntasks; task += gridDim.x, ti++) {
+      const int r = (int)(task / nslices), slice = (int)(task - (long long)r * nslices);
+      const int* plan = plans + (size_t)r * stride;
+      const int4 h0 = __ldg(reinterpret_cast<const int4*>(plan));
+      const int4 h1 = __ldg(reinterpret_cast<const int4*>(plan) + 1);
+      const int4 h2 = __ldg(reinterpret_cast<const int4*>(plan) + 2);
+      const int mode = h0.x, batch = h0.y, level = h0.z, Y0 = h0.w, nrows = h1.x - h0.w + 1, H = h1.z, W = h1.w;
+      const int X0 = h2.x, wf = h2.y - h2.x + 1;
+      const int pb = ti & 1;
+      mb_wait(&pempty[pb], ((ti >> 1) & 1) ^ 1);
+      int* dst = planbuf + (size_t)pb * planw;
+      const bool live = mode == PLAN_ROLLING || mode == PLAN_THIN;
+      if (lane == 0) {
+        const unsigned rowbytes = live ? (unsigned)nrows * 32u : 0u;
+        mb_expect_tx(&pfull[pb], (unsigned)headw * 4u + rowbytes);
+        tma_g2s(dst, plan, (unsigned)headw * 4u, &pfull[pb]);
+        if (rowbytes) tma_g2s(dst + headw, plan + headw, rowbytes, &pfull[pb]);
+      }
+      if (!live) continue;
+      // one tensor op per ring slot: the narrowest box (2..32 pixels wide) that covers the footprint width, as many
+      // rows tall as fit in the slot; channels beyond C and pixels beyond the map's width are zero-filled by the TMA unit
+      int bi = 0;
+      while ((2 << bi) < wf) bi++;
+      const int bh = kTileMaxPx >> (bi + 1);
+      const CUtensorMap* map = &maps.m[level][bi];
+      const int c0 = slice * 32 * V;
+      int grow = batch * H + Y0;
+      for (int row = 0; row < nrows; row += bh, it++, grow += bh) {
+        const int slot = it % kRing;
+        mb_wait(&empty[slot], ((it / kRing) & 1) ^ 1);
+        if (lane == 0) {
+          mb_expect_tx(&full[slot], (unsigned)kTileMaxPx * 512u);
+          tma_box_g2s(ring + (size_t)slot * kTileMaxPx * 32, map, c0, X0, grow, &full[slot]);
+        }
+      }
+    }
+  } else if (warp <= PW) {
+    // ------------------------------------------------------------------ consumers: warp w owns bin column w-1
+    const int pw = warp - 1;
+    const unsigned ring_a = s_u32(ring) + lane * 16, full_a = s_u32(full), empty_a = s_u32(empty);
+    for (long long task = blockIdx.x; task < ntasks; task += gridDim.x, ti++) {
+      const int r = (int)(task / nslices), slice = (int)(task - (long long)r * nslices);
+      const int pb = ti & 1;
+      mb_wait(&pfull[pb], (ti >> 1) & 1);
+      const int* pl = planbuf + (size_t)pb * planw;
+      const int mode = pl[0], nrows = pl[4] - pl[3] + 1, X0 = pl[8];
+      const float inv_count = __int_as_float(pl[5]);
+      const int c = (slice * 32 + lane) * V;
+      const bool active = c < C;
+      T* o = out + ((size_t)r * PH * PW + pw) * C + c;
+      const size_t binstride = (size_t)PW * C;
+      if (mode == PLAN_GENERIC) {  // served by the self-contained kernel
+        mb_arrive(&pempty[pb]);
+        continue;
+      }
+      const int* col = pl + kPlanHdr + pw * kPlanCol;
+      const int nx = mode == PLAN_EMPTY ? 0 : col[1];
+      if (nx == 0) {  // no sample of this column (or of the whole RoI) falls inside the map: zeros, but keep the ring moving
+        if (mode != PLAN_EMPTY) {
+          const int wf = pl[9] - X0 + 1;
+          int bi = 0;
+          while ((2 << bi) < wf) bi++;
+          const int bh = kTileMaxPx >> (bi + 1);
+          for (int row0 = 0; row0 < nrows; row0 += bh, it++) {
+            const int slot = it % kRing;
+            mb_wait_a(full_a + slot * 8, (it / kRing) & 1);
+            mb_arrive_a(empty_a + slot * 8);
+          }
+        }
+        float z[V];
+#pragma unroll
+        for (int i = 0; i < V; i++) z[i] = 0.f;
+        if (active)
+          for (int p = 0; p < PH; p++) VecIO<T, V>::store(o + (size_t)p * binstride, z);
+        mb_arrive(&pempty[pb]);
+        continue;
+      }
+      const float w0 = __int_as_float(col[4]), w1 = __int_as_float(col[5]), w2 = __int_as_float(col[6]), w3 = __int_as_float(col[7]);
+      const int off = col[0] - X0;
+      const int wf = pl[9] - X0 + 1;
+      int bi = 0;
+      while ((2 << bi) < wf) bi++;
+      const int bw = 2 << bi, bh = kTileMaxPx >> (bi + 1);
+      // byte offsets of the column's first four pixels inside a staged row (clamped onto the last one, weight 0)
+      const unsigned p0 = (unsigned)off * 512u, p1 = p0 + (unsigned)min(1, nx - 1) * 512u, p2 = p0 + (unsigned)min(2, nx - 1) * 512u,
+                     p3 = p0 + (unsigned)min(3, nx - 1) * 512u;
+      const unsigned rowbytes = (unsigned)bw * 512u;
+      const unsigned rec_a = s_u32(pl + headw);
+      // t = sum_x Wx * v of the staged row at shared address `ra`
+      auto row_dot = [&](unsigned ra, float (&tr)[V]) {
+        float v0[V], v1[V], v2[V], v3[V];
+        unpack16<T, V>(lds128(ra + p0), v0);
+        unpack16<T, V>(lds128(ra + p1), v1);
+        unpack16<T, V>(lds128(ra + p2), v2);
+        unpack16<T, V>(lds128(ra + p3), v3);
+#pragma unroll
+        for (int i = 0; i < V; i++) tr[i] = fmaf(w3, v3[i], fmaf(w2, v2[i], fmaf(w1, v1[i], w0 * v0[i])));
+        for (int j = 4; j < nx; j++) {  // warp-uniform, rare: columns of 5..kPlanNx pixels
+          float x[V];
+          unpack16<T, V>(lds128(ra + p0 + j * 512u), x);
+          const float bw_ = __int_as_float(col[4 + j]);
+#pragma unroll
+          for (int i = 0; i < V; i++) tr[i] = fmaf(bw_, x[i], tr[i]);
+        }
+      };
+      if (mode == PLAN_ROLLING) {
+        float accA[V], accB[V];
+#pragma unroll
+        for (int i = 0; i < V; i++) accA[i] = accB[i] = 0.f;
+        int a = 0;
+        for (int row0 = 0; row0 < nrows; row0 += bh, it++) {
+          const int slot = it % kRing;
+          mb_wait_a(full_a + slot * 8, (it / kRing) & 1);
+          const int rows_here = min(bh, nrows - row0);
+          unsigned ra = ring_a + (unsigned)slot * (kTileMaxPx * 512u);
+          for (int rr = 0; rr < rows_here; rr++, ra += rowbytes) {
+            const uint4 info = lds128(rec_a + (unsigned)(row0 + rr) * 32u);
+            const int ia = (int)info.x;
+            if (ia < 0) continue;  // a map row between two bins' supports (sparse fixed-ratio sampling)
+            float tr[V];
+            row_dot(ra, tr);
+            if (a != ia) {  // bins a .. ia-1 are complete: emit them and roll the two-bin window
+              do {
+#pragma unroll
+                for (int i = 0; i < V; i++) accA[i] *= inv_count;
+                if (active) VecIO<T, V>::store(o + (size_t)a * binstride, accA);
+#pragma unroll
+                for (int i = 0; i < V; i++) { accA[i] = accB[i]; accB[i] = 0.f; }
+              } while (++a < ia);
+            }
+            const float wa = __uint_as_float(info.y), wb = __uint_as_float(info.z);
+#pragma unroll
+            for (int i = 0; i < V; i++) {
+              accA[i] = fmaf(wa, tr[i], accA[i]);
+              accB[i] = fmaf(wb, tr[i], accB[i]);
+            }
+          }
+          mb_arrive_a(empty_a + slot * 8);
+        }
+        for (; a < PH; a++) {
+#pragma unroll
+          for (int i = 0; i < V; i++) accA[i] *= inv_count;
+          if (active) VecIO<T, V>::store(o + (size_t)a * binstride, accA);
+#pragma unroll
+          for (int i = 0; i < V; i++) { accA[i] = accB[i]; accB[i] = 0.f; }
+        }
+      } else {  // PLAN_THIN: one accumulator per bin; a row record holds all PH weights
+        float acc[kMaxBins][V];
+#pragma unroll
+        for (int p = 0; p < kMaxBins; p++)
+#pragma unroll
+          for (int i = 0; i < V; i++) acc[p][i] = 0.f;
+        for (int row0 = 0; row0 < nrows; row0 += bh, it++) {
+          const int slot = it % kRing;
+          mb_wait_a(full_a + slot * 8, (it / kRing) & 1);
+          const int rows_here = min(bh, nrows - row0);
+          unsigned ra = ring_a + (unsigned)slot * (kTileMaxPx * 512u);
+          for (int rr = 0; rr < rows_here; rr++, ra += rowbytes) {
+            float tr[V];
+            row_dot(ra, tr);
+            const uint4 wl = lds128(rec_a + (unsigned)(row0 + rr) * 32u), wh = lds128(rec_a + (unsigned)(row0 + rr) * 32u + 16u);
+            const float wy[kMaxBins] = {__uint_as_float(wl.x), __uint_as_float(wl.y), __uint_as_float(wl.z), __uint_as_float(wl.w),
+                                        __uint_as_float(wh.x), __uint_as_float(wh.y), __uint_as_float(wh.z), __uint_as_float(wh.w)};
+#pragma unroll
+            for (int p = 0; p < kMaxBins; p++)
+#pragma unroll
+              for (int i = 0; i < V; i++) acc[p][i] = fmaf(wy[p], tr[i], acc[p][i]);
+          }
+          mb_arrive_a(empty_a + slot * 8);
+        }
+#pragma unroll
+        for (int p = 0; p < kMaxBins; p++) {
+          if (p < PH && active) {
+#pragma unroll
+            for (int i = 0; i < V; i++) acc[p][i] *= inv_count;
+            VecIO<T, V>::store(o + (size_t)p * binstride, acc[p]);
+          }
+        }
+      }
+      mb_arrive(&pempty[pb]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ forward, NHWC, self-contained
 // Table-in-shared-memory kernel: a CTA owns one RoI, every thread V consecutive channels, plain per-bin loops over the
 // separable tables.  Used when the caller passes no workspace, and for the RoIs a plan marks GENERIC.
@@ -840,7 +1138,22 @@ static inline int nchw_channel_chunk(int R, int C) {
   return chunk < C ? chunk : C;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
 struct Call {
+  int B, L;
   LevelTable lv;
   const float* rois;
   const int32_t* levels;
@@ -850,6 +1163,29 @@ struct Call {
 };
 
 static size_t workspace_need(int R, int PW, int Hs) { return (size_t)R * plan_stride_words(PW, Hs) * sizeof(int); }
+
+// Tensor maps of every level's [B*H rows][W pixels][C channels] view, one per box shape.  False when the driver entry point is
+// missing or a map cannot be encoded (the caller then uses the sweep kernel).
+template <typename T>
+static bool build_tma_maps(const Call& c, TmaMaps& maps) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc || c.L > kTmaLevels) return false;
+  for (int l = 0; l < kTmaLevels; l++) {
+    const int ll = l < c.L ? l : 0;
+    const cuuint64_t dims[3] = {(cuuint64_t)c.C, (cuuint64_t)c.lv.W[ll], (cuuint64_t)c.B * c.lv.H[ll]};
+    const cuuint64_t strides[2] = {(cuuint64_t)c.C * sizeof(T), (cuuint64_t)c.lv.W[ll] * c.C * sizeof(T)};
+    if (strides[0] % 16 != 0 || (reinterpret_cast<uintptr_t>(c.lv.ptr[ll]) & 15)) return false;
+    for (int b = 0; b < kTmaBoxes; b++) {
+      const cuuint32_t box[3] = {(cuuint32_t)(512 / sizeof(T)), (cuuint32_t)(2 << b), (cuuint32_t)(kTileMaxPx >> (b + 1))};
+      const cuuint32_t estr[3] = {1, 1, 1};
+      const CUresult rc = enc(&maps.m[l][b], sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                              c.lv.ptr[ll], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (rc != CUDA_SUCCESS) return false;
+    }
+  }
+  return true;
+}
 
 static int run_plan(const Call& c) {
   const size_t smem = tables_bytes(c.PH, c.PW, c.Hs, c.Ws, true);
@@ -869,11 +1205,31 @@ static int launch_fwd(const Call& c, void* out) {
       int rc = run_plan(c);
       if (rc) return rc;
       const int nslices = ceil_div(c.C, 32 * V);
-      const long long ntasks = (long long)c.R * c.PW * nslices;
-      const long long blocks = ceil_div<long long>(ntasks, 8);
-      ABR_REQUIRE(blocks <= 0x7fffffffLL, ABR_ERR_UNSUPPORTED, "roi_align_forward: too many tasks");
-      roi_align_fwd_sweep_kernel<T, V><<<(unsigned)blocks, 256, 0, c.st>>>(c.lv, c.plans, stride, static_cast<T*>(out), c.C, c.PH, c.PW, nslices, ntasks);
-      ABR_CHECK_LAUNCH("roi_align_forward_sweep");
+      bool staged = false;
+      if constexpr (V * sizeof(T) == 16) {
+        static const bool use_tma = getenv("ABR_FWD_TMA") ? atoi(getenv("ABR_FWD_TMA")) != 0 : true;
+        const size_t planw = (size_t)kPlanHdr + (size_t)c.PW * kPlanCol + (size_t)c.Hs * 8;
+        const size_t tma_smem = (size_t)kRing * kTileMaxPx * 32 * 16 + 2 * planw * 4 + (2 * kRing + 4) * 8;
+        TmaMaps maps;
+        if (use_tma && c.PH <= kMaxBins && c.PW <= 7 && tma_smem <= 200 * 1024 && build_tma_maps<T>(c, maps)) {
+          auto kern = roi_align_fwd_tma_kernel<T, V>;
+          ABR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem));
+          int per_sm = 0;
+          if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, tma_smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+          long long blocks = (long long)per_sm * num_sms();
+          if (blocks > (long long)c.R * nslices) blocks = (long long)c.R * nslices;
+          kern<<<(unsigned)blocks, 256, tma_smem, c.st>>>(maps, c.plans, stride, static_cast<T*>(out), c.C, c.PH, c.PW, c.R, nslices, c.Hs);
+          ABR_CHECK_LAUNCH("roi_align_forward_tma");
+          staged = true;
+        }
+      }
+      if (!staged) {
+        const long long ntasks = (long long)c.R * c.PW * nslices;
+        const long long blocks = ceil_div<long long>(ntasks, 8);
+        ABR_REQUIRE(blocks <= 0x7fffffffLL, ABR_ERR_UNSUPPORTED, "roi_align_forward: too many tasks");
+        roi_align_fwd_sweep_kernel<T, V><<<(unsigned)blocks, 256, 0, c.st>>>(c.lv, c.plans, stride, static_cast<T*>(out), c.C, c.PH, c.PW, nslices, ntasks);
+        ABR_CHECK_LAUNCH("roi_align_forward_sweep");
+      }
     }
     const int nvec = ceil_div(c.C, V);
     const int threads = min(256, ceil_div(nvec, 32) * 32);
@@ -976,6 +1332,7 @@ int abr_roi_align_multilevel_forward(const void* const* inputs_host, const int* 
                    scales_host, L, c.Hs, c.Ws);
   if (rc) return rc;
   c.rois = rois; c.levels = L == 1 ? nullptr : levels;
+  c.B = B; c.L = L;
   c.C = C; c.R = R; c.PH = PH; c.PW = PW; c.ratio = sampling_ratio; c.layout = layout;
   c.plans = usable_workspace(workspace, workspace_bytes, R, PW, c.Hs, layout);
   c.st = static_cast<cudaStream_t>(stream);
@@ -1000,6 +1357,7 @@ int abr_roi_align_multilevel_backward(const void* grad_output, const float* rois
   if (R == 0) return ABR_OK;  // ROIAlign_cuda.cu:323-326
   ABR_REQUIRE(L == 1 || levels, ABR_ERR_BAD_ARG, "roi_align: %d levels but no per-RoI level array", L);
   c.rois = rois; c.levels = L == 1 ? nullptr : levels;
+  c.B = B; c.L = L;
   c.C = C; c.R = R; c.PH = PH; c.PW = PW; c.ratio = sampling_ratio; c.layout = layout;
   c.plans = usable_workspace(workspace, workspace_bytes, R, PW, c.Hs, layout);
   return dispatch_bwd(c, grad_output, dtype);
