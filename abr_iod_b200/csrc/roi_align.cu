@@ -878,6 +878,167 @@ __global__ void __launch_bounds__(256, 3) roi_align_fwd_tma_kernel(const __grid_
   }
 }
 
+// ------------------------------------------------------------------------------------------ backward, NHWC, TMA-staged
+// Same warp specialisation as the forward.  Per (RoI, slice of 32*V channels) the producer warp brings, with ONE TMA
+// tensor op, the RoI's whole [PH*PW bins][32*V channels] gradient tile (25 KB for P=7) plus the plan into a
+// double-buffered stage; the consumer warps (one per bin column) then sweep the footprint rows reading bin gradients
+// out of shared memory -- no dependent global load anywhere -- and issue one vector reduction per distinct footprint
+// pixel (pixels shared by two columns are reduced once, by the later column, see plan_kernel).
+template <typename T, int V>
+__global__ void __launch_bounds__(256) roi_align_bwd_tma_kernel(const __grid_constant__ CUtensorMap gmap, LevelTable lv,
+                                                               const int* __restrict__ plans, size_t stride, int C, int PH,
+                                                               int PW, int R, int nslices, int Hs) {
+  static_assert(V * sizeof(T) == 16, "one lane moves 16 bytes");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int nbin = PH * PW;
+  const unsigned gbytes = (unsigned)nbin * 512u;             // one stage of bin gradients
+  const unsigned gstage = (gbytes + 127u) & ~127u;
+  const int headw = kPlanHdr + PW * kPlanCol;
+  const int planw = headw + Hs * kPlanRow;
+  uint4* gtile = reinterpret_cast<uint4*>(smem_raw);         // [2][nbin][32 lanes]
+  int* planbuf = reinterpret_cast<int*>(smem_raw + 2 * (size_t)gstage);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(planbuf + 2 * (size_t)planw);
+  unsigned long long* pfull = bars;        // [2] producer -> consumers (tx bytes)
+  unsigned long long* pempty = bars + 2;   // [2] consumers -> producer
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; i++) { mb_init(&pfull[i], 1); mb_init(&pempty[i], PW * 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long ntasks = (long long)R * nslices;
+  int ti = 0;
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer
+    for (long long task = blockIdx.x; task < ntasks; task += gridDim.x, ti++) {
+      const int r = (int)(task / nslices), slice = (int)(task - (long long)r * nslices);
+      const int* plan = plans + (size_t)r * stride;
+      const int4 h0 = __ldg(reinterpret_cast<const int4*>(plan));
+      const int4 h1 = __ldg(reinterpret_cast<const int4*>(plan) + 1);
+      const int mode = h0.x, nrows = h1.x - h0.w + 1;
+      const int pb = ti & 1;
+      mb_wait(&pempty[pb], ((ti >> 1) & 1) ^ 1);
+      const bool live = mode == PLAN_ROLLING || mode == PLAN_THIN;
+      if (lane == 0) {
+        const unsigned rowbytes = live ? (unsigned)nrows * (kPlanRow * 4u) : 0u;
+        mb_expect_tx(&pfull[pb], (unsigned)headw * 4u + rowbytes + (live ? gbytes : 0u));
+        int* dst = planbuf + (size_t)pb * planw;
+        tma_g2s(dst, plan, (unsigned)headw * 4u, &pfull[pb]);
+        if (live) {
+          tma_g2s(dst + headw, plan + headw, rowbytes, &pfull[pb]);
+          tma_box_g2s(smem_raw + (size_t)pb * gstage, &gmap, slice * 32 * V, 0, r, &pfull[pb]);
+        }
+      }
+    }
+  } else if (warp <= PW) {
+    // ------------------------------------------------------------------ consumers: warp w owns bin column w-1
+    const int pw = warp - 1;
+    for (long long task = blockIdx.x; task < ntasks; task += gridDim.x, ti++) {
+      const int r = (int)(task / nslices), slice = (int)(task - (long long)r * nslices);
+      (void)r;
+      const int pb = ti & 1;
+      mb_wait(&pfull[pb], (ti >> 1) & 1);
+      const int* pl = planbuf + (size_t)pb * planw;
+      const int mode = pl[0];
+      const int* col = pl + kPlanHdr + pw * kPlanCol;
+      const int nx = (mode == PLAN_ROLLING || mode == PLAN_THIN) ? col[1] : 0;
+      const int c = (slice * 32 + lane) * V;
+      if (nx == 0 || c >= C) {  // nothing to reduce (EMPTY / GENERIC RoI, column outside the map, idle lane of a ragged slice)
+        mb_arrive(&pempty[pb]);
+        continue;
+      }
+      const int batch = pl[1], level = pl[2], Y0 = pl[3], nrows = pl[4] - pl[3] + 1, H = pl[6], W = pl[7];
+      const float inv_count = __int_as_float(pl[5]);
+      const size_t pix = (size_t)C, rowstride = (size_t)W * C;
+      T* q0 = static_cast<T*>(lv.ptr[level]) + (((size_t)batch * H + Y0) * W + col[0]) * C + c;
+      const float w0 = __int_as_float(col[4]), w1 = __int_as_float(col[5]), w2 = __int_as_float(col[6]), w3 = __int_as_float(col[7]);
+      // pixels shared with the next column are left to it; for the leading pixels shared with the previous column this
+      // warp adds that column's term too: every footprint pixel of the RoI receives exactly one reduction
+      const int n_emit = nx - col[2], n_prev = col[3];
+      const int* pcol = col - kPlanCol;
+      const int poff = n_prev > 0 ? col[0] - pcol[0] : 0;
+      const float wp0 = n_prev > 0 ? __int_as_float(pcol[4 + poff]) : 0.f, wp1 = n_prev > 1 ? __int_as_float(pcol[5 + poff]) : 0.f,
+                  wp2 = n_prev > 2 ? __int_as_float(pcol[6 + poff]) : 0.f, wp3 = n_prev > 3 ? __int_as_float(pcol[7 + poff]) : 0.f;
+      const unsigned g_a = s_u32(smem_raw + (size_t)pb * gstage) + lane * 16 + (unsigned)pw * 512u;  // bin (0, pw)
+      const unsigned binrow = (unsigned)PW * 512u;                                                    // next bin row
+      const unsigned rec_a = s_u32(pl + headw);
+      for (int row = 0; row < nrows; row++, q0 += rowstride) {
+        float s[V], sp[V];
+        if (mode == PLAN_ROLLING) {
+          const uint4 info = lds128(rec_a + (unsigned)row * 32u);
+          const int a = (int)info.x;
+          if (a < 0) continue;
+          const float wa = __uint_as_float(info.y) * inv_count, wb = __uint_as_float(info.z) * inv_count;
+          float gA[V], gB[V];
+          unpack16<T, V>(lds128(g_a + (unsigned)a * binrow), gA);
+          if (a + 1 < PH) {
+            unpack16<T, V>(lds128(g_a + (unsigned)(a + 1) * binrow), gB);
+          } else {
+#pragma unroll
+            for (int i = 0; i < V; i++) gB[i] = 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < V; i++) s[i] = fmaf(wb, gB[i], wa * gA[i]);
+          if (n_prev > 0) {
+            unpack16<T, V>(lds128(g_a - 512u + (unsigned)a * binrow), gA);
+            if (a + 1 < PH) unpack16<T, V>(lds128(g_a - 512u + (unsigned)(a + 1) * binrow), gB);
+#pragma unroll
+            for (int i = 0; i < V; i++) sp[i] = fmaf(wb, gB[i], wa * gA[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < V; i++) sp[i] = 0.f;
+          }
+        } else {  // PLAN_THIN: the row record holds all PH weights (the pair scheme is off: n_prev == 0)
+#pragma unroll
+          for (int i = 0; i < V; i++) s[i] = sp[i] = 0.f;
+          for (int p = 0; p < PH; p++) {
+            const float wy = __int_as_float(pl[headw + row * kPlanRow + p]) * inv_count;
+            if (wy == 0.f) continue;
+            float g[V];
+            unpack16<T, V>(lds128(g_a + (unsigned)p * binrow), g);
+#pragma unroll
+            for (int i = 0; i < V; i++) s[i] = fmaf(wy, g[i], s[i]);
+          }
+        }
+        float v[V];
+        if (n_emit > 0 && (w0 != 0.f || wp0 != 0.f)) {
+#pragma unroll
+          for (int i = 0; i < V; i++) v[i] = fmaf(wp0, sp[i], w0 * s[i]);
+          VecIO<T, V>::red_add(q0, v);
+        }
+        if (n_emit > 1 && (w1 != 0.f || wp1 != 0.f)) {
+#pragma unroll
+          for (int i = 0; i < V; i++) v[i] = fmaf(wp1, sp[i], w1 * s[i]);
+          VecIO<T, V>::red_add(q0 + pix, v);
+        }
+        if (n_emit > 2 && (w2 != 0.f || wp2 != 0.f)) {
+#pragma unroll
+          for (int i = 0; i < V; i++) v[i] = fmaf(wp2, sp[i], w2 * s[i]);
+          VecIO<T, V>::red_add(q0 + 2 * pix, v);
+        }
+        if (n_emit > 3 && (w3 != 0.f || wp3 != 0.f)) {
+#pragma unroll
+          for (int i = 0; i < V; i++) v[i] = fmaf(wp3, sp[i], w3 * s[i]);
+          VecIO<T, V>::red_add(q0 + 3 * pix, v);
+        }
+        if (n_emit > 4) {  // warp-uniform, rare: columns of 5..kPlanNx pixels
+          T* q = q0 + 4 * pix;
+          for (int j = 4; j < n_emit; j++, q += pix) {
+            const float bw = __int_as_float(col[4 + j]);
+            const float bp = j < n_prev ? __int_as_float(pcol[4 + poff + j]) : 0.f;
+            if (bw != 0.f || bp != 0.f) {
+#pragma unroll
+              for (int i = 0; i < V; i++) v[i] = fmaf(bp, sp[i], bw * s[i]);
+              VecIO<T, V>::red_add(q, v);
+            }
+          }
+        }
+      }
+      mb_arrive(&pempty[pb]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ forward, NHWC, self-contained
 // Table-in-shared-memory kernel: a CTA owns one RoI, every thread V consecutive channels, plain per-bin loops over the
 // separable tables.  Used when the caller passes no workspace, and for the RoIs a plan marks GENERIC.
@@ -1257,11 +1418,45 @@ static int launch_bwd(const Call& c, const void* gout) {
       int rc = run_plan(c);
       if (rc) return rc;
       const int nslices = ceil_div(c.C, 32 * V);
-      const long long ntasks = (long long)c.R * c.PW * nslices;
-      const long long blocks = ceil_div<long long>(ntasks, 8);
-      ABR_REQUIRE(blocks <= 0x7fffffffLL, ABR_ERR_UNSUPPORTED, "roi_align_backward: too many tasks");
-      roi_align_bwd_sweep_kernel<T, V><<<(unsigned)blocks, 256, 0, c.st>>>(c.lv, c.plans, stride, static_cast<const T*>(gout), c.C, c.PH, c.PW, nslices, ntasks);
-      ABR_CHECK_LAUNCH("roi_align_backward_sweep");
+      bool staged = false;
+      if constexpr (V * sizeof(T) == 16) {
+        static const bool use_tma = getenv("ABR_BWD_TMA") ? atoi(getenv("ABR_BWD_TMA")) != 0 : true;
+        const int nbin = c.PH * c.PW;
+        const size_t gstage = ((size_t)nbin * 512 + 127) & ~(size_t)127;
+        const size_t planw = (size_t)kPlanHdr + (size_t)c.PW * kPlanCol + (size_t)c.Hs * kPlanRow;
+        const size_t tma_smem = 2 * gstage + 2 * planw * 4 + 4 * 8;
+        EncodeTiledFn enc = encode_tiled_fn();
+        CUtensorMap gmap;
+        bool ok = use_tma && enc && nbin <= 256 && c.PW <= 7 && tma_smem <= 200 * 1024 && (reinterpret_cast<uintptr_t>(gout) & 15) == 0 &&
+                  ((size_t)c.C * sizeof(T)) % 16 == 0;
+        if (ok) {
+          const cuuint64_t dims[3] = {(cuuint64_t)c.C, (cuuint64_t)nbin, (cuuint64_t)c.R};
+          const cuuint64_t strides[2] = {(cuuint64_t)c.C * sizeof(T), (cuuint64_t)nbin * c.C * sizeof(T)};
+          const cuuint32_t box[3] = {(cuuint32_t)(512 / sizeof(T)), (cuuint32_t)nbin, 1};
+          const cuuint32_t estr[3] = {1, 1, 1};
+          ok = enc(&gmap, sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(gout),
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        }
+        if (ok) {
+          auto kern = roi_align_bwd_tma_kernel<T, V>;
+          ABR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem));
+          int per_sm = 0;
+          if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, tma_smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+          long long blocks = (long long)per_sm * num_sms();
+          if (blocks > (long long)c.R * nslices) blocks = (long long)c.R * nslices;
+          kern<<<(unsigned)blocks, 256, tma_smem, c.st>>>(gmap, c.lv, c.plans, stride, c.C, c.PH, c.PW, c.R, nslices, c.Hs);
+          ABR_CHECK_LAUNCH("roi_align_backward_tma");
+          staged = true;
+        }
+      }
+      if (!staged) {
+        const long long ntasks = (long long)c.R * c.PW * nslices;
+        const long long blocks = ceil_div<long long>(ntasks, 8);
+        ABR_REQUIRE(blocks <= 0x7fffffffLL, ABR_ERR_UNSUPPORTED, "roi_align_backward: too many tasks");
+        roi_align_bwd_sweep_kernel<T, V><<<(unsigned)blocks, 256, 0, c.st>>>(c.lv, c.plans, stride, static_cast<const T*>(gout), c.C, c.PH, c.PW, nslices, ntasks);
+        ABR_CHECK_LAUNCH("roi_align_backward_sweep");
+      }
     }
     const int nvec = ceil_div(c.C, V);
     const int threads = min(256, ceil_div(nvec, 32) * 32);
