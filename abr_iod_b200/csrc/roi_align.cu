@@ -885,7 +885,7 @@ __global__ void __launch_bounds__(256, 3) roi_align_fwd_tma_kernel(const __grid_
 // out of shared memory -- no dependent global load anywhere -- and issue one vector reduction per distinct footprint
 // pixel (pixels shared by two columns are reduced once, by the later column, see plan_kernel).
 template <typename T, int V>
-__global__ void __launch_bounds__(256) roi_align_bwd_tma_kernel(const __grid_constant__ CUtensorMap gmap, LevelTable lv,
+__global__ void __launch_bounds__(256, 4) roi_align_bwd_tma_kernel(const __grid_constant__ CUtensorMap gmap, LevelTable lv,
                                                                const int* __restrict__ plans, size_t stride, int C, int PH,
                                                                int PW, int R, int nslices, int Hs) {
   static_assert(V * sizeof(T) == 16, "one lane moves 16 bytes");
