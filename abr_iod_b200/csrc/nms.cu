@@ -25,8 +25,10 @@ constexpr int kImagesPerLaunch = 32;
 
 struct NmsBatch {
   int n_images;
+  int first_image;                      // index of the launch group's first image in the whole call
   int box_off[kImagesPerLaunch];        // first box of the image inside boxes / scores
-  int n[kImagesPerLaunch];              // boxes in the image
+  int n[kImagesPerLaunch];              // boxes of the image this pass looks at (a prefix in the prefix pass)
+  int n_full[kImagesPerLaunch];         // boxes in the image
   long long mask_off[kImagesPerLaunch]; // first mask word of the image (u64 units)
 };
 
@@ -42,50 +44,60 @@ __device__ __forceinline__ unsigned long long sort_key(float s, int idx) {
   return ((unsigned long long)u << 32) | (unsigned int)(~(unsigned int)idx);
 }
 
-constexpr int kRankThreads = 256;
-constexpr int kRankPerThread = 4;
+// O(N) first step: assume the scores already are in stable descending order (true for the RPN, which feeds NMS the
+// output of a sorted top-k: modeling/rpn/inference.py:94-95) -- write the identity order and a copy of the boxes, and
+// raise unsorted[img] on the first adjacent pair that contradicts it.  rank_sort_kernel then only runs for unsorted
+// images.
+__global__ void presort_kernel(NmsBatch nb, const float* __restrict__ boxes, const float* __restrict__ scores,
+                               float4* __restrict__ sorted_boxes, int* __restrict__ order, int* __restrict__ unsorted) {
+  const int img = blockIdx.y;
+  const int n = nb.n_full[img], off = nb.box_off[img];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  order[off + i] = i;
+  sorted_boxes[off + i] = __ldg(reinterpret_cast<const float4*>(boxes) + off + i);
+  if (i + 1 < n && !(sort_key(scores[off + i], i) > sort_key(scores[off + i + 1], i + 1))) unsorted[nb.first_image + img] = 1;
+}
 
+constexpr int kRankThreads = 128;  // candidates per CTA: small, so that even one image fills the machine
+
+// Stable descending sort by all-pairs rank counting (only for images presort_kernel flagged as unsorted).
 __global__ void __launch_bounds__(kRankThreads) rank_sort_kernel(NmsBatch nb, const float* __restrict__ boxes,
                                                                 const float* __restrict__ scores,
                                                                 float4* __restrict__ sorted_boxes,
-                                                                int* __restrict__ order) {
+                                                                int* __restrict__ order, int* __restrict__ unsorted) {
   const int img = blockIdx.y;
-  const int n = nb.n[img], off = nb.box_off[img];
-  const int base = blockIdx.x * (kRankThreads * kRankPerThread);
-  if (base >= n) return;
-  __shared__ unsigned long long tile[kRankThreads * 2];
-  unsigned long long mine[kRankPerThread];
-  int rank[kRankPerThread];
-#pragma unroll
-  for (int k = 0; k < kRankPerThread; k++) {
-    const int i = base + k * kRankThreads + threadIdx.x;
-    mine[k] = i < n ? sort_key(scores[off + i], i) : 0ull;
-    rank[k] = 0;
-  }
-  for (int j0 = 0; j0 < n; j0 += kRankThreads * 2) {
+  const int n = nb.n_full[img], off = nb.box_off[img];
+  const int base = blockIdx.x * kRankThreads;
+  if (base >= n || unsorted[nb.first_image + img] == 0) return;  // presort_kernel found the image already sorted
+  __shared__ unsigned long long tile[512];
+  const int i = base + threadIdx.x;
+  const unsigned long long mine = i < n ? sort_key(scores[off + i], i) : 0ull;
+  int rank = 0;
+  for (int j0 = 0; j0 < n; j0 += 512) {
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < 512 / kRankThreads; k++) {
       const int j = j0 + k * kRankThreads + threadIdx.x;
-      // key 0 is smaller than every real key (a real key has a nonzero low word unless idx == 0xFFFFFFFF)
+      // key 0 is smaller than every real key (a real key's high word is at least 0x007fffff)
       tile[k * kRankThreads + threadIdx.x] = j < n ? sort_key(scores[off + j], j) : 0ull;
     }
     __syncthreads();
-    const int lim = min(kRankThreads * 2, n - j0);
-#pragma unroll 8
-    for (int j = 0; j < lim; j++) {
-      const unsigned long long kj = tile[j];
-#pragma unroll
-      for (int k = 0; k < kRankPerThread; k++) rank[k] += (kj > mine[k]) ? 1 : 0;
+    const int lim = min(512, n - j0);
+    int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+    int j = 0;
+    for (; j + 3 < lim; j += 4) {
+      r0 += tile[j] > mine;
+      r1 += tile[j + 1] > mine;
+      r2 += tile[j + 2] > mine;
+      r3 += tile[j + 3] > mine;
     }
+    for (; j < lim; j++) r0 += tile[j] > mine;
+    rank += r0 + r1 + r2 + r3;
   }
-#pragma unroll
-  for (int k = 0; k < kRankPerThread; k++) {
-    const int i = base + k * kRankThreads + threadIdx.x;
-    if (i < n) {
-      order[off + rank[k]] = i;
-      sorted_boxes[off + rank[k]] = __ldg(reinterpret_cast<const float4*>(boxes) + off + i);
-    }
+  if (i < n) {
+    order[off + rank] = i;
+    sorted_boxes[off + rank] = __ldg(reinterpret_cast<const float4*>(boxes) + off + i);
   }
 }
 
@@ -101,42 +113,69 @@ __device__ __forceinline__ float iou_plus_one(const float4 a, const float4 b) {
   return __fdiv_rn(inter, __fsub_rn(__fadd_rn(sa, sb), inter));
 }
 
-// One CTA of 64 threads per (column tile, row tile) with column >= row.  Thread t owns row box 64*row+t and emits the
-// 64-bit word of column boxes it suppresses (only boxes AFTER it in score order: csrc/cuda/nms.cu:53-65).
-__global__ void __launch_bounds__(kTile) iou_mask_kernel(NmsBatch nb, const float4* __restrict__ sorted_boxes,
-                                                        unsigned long long* __restrict__ mask, float thresh, int ge) {
-  const int img = blockIdx.z;
+// Upper-triangular tile pairs only, enumerated row-major: tile t of an image with cb tile rows is (row, col >= row).
+// A 256-thread CTA takes kMaskTilesPerCta consecutive pairs, one per 64-thread group; thread i of a group owns row box
+// 64*row+i and emits the 64-bit word of column boxes it suppresses (only boxes AFTER it in score order:
+// csrc/cuda/nms.cu:53-65).
+constexpr int kMaskTilesPerCta = 4;
+
+__global__ void __launch_bounds__(kTile * kMaskTilesPerCta) iou_mask_kernel(NmsBatch nb, const float4* __restrict__ sorted_boxes,
+                                                                          unsigned long long* __restrict__ mask,
+                                                                          float thresh, int ge, const int* __restrict__ done) {
+  const int img = blockIdx.y;
+  if (done && done[nb.first_image + img]) return;  // full pass: settled by the prefix pass; prefix pass: image not sorted
   const int n = nb.n[img];
   const int cb = ceil_div(n, kTile);
-  const int row = blockIdx.y, col = blockIdx.x;
-  if (row >= cb || col >= cb || col < row) return;
+  const long long ntiles = (long long)cb * (cb + 1) / 2;
+  const int grp = threadIdx.x / kTile, lane64 = threadIdx.x % kTile;
+  const long long t = (long long)blockIdx.x * kMaskTilesPerCta + grp;
+  __shared__ float4 cbox[kMaskTilesPerCta][kTile];
+  int row = 0, col = 0;
+  const bool live = t < ntiles;
+  if (live) {
+    // row r starts at tile index r*cb - r*(r-1)/2; invert with a float guess and fix up
+    const double fc = (double)cb + 0.5;
+    row = (int)(fc - sqrt(fc * fc - 2.0 * (double)t));
+    if (row < 0) row = 0;
+    if (row >= cb) row = cb - 1;
+    while (row > 0 && (long long)row * cb - (long long)row * (row - 1) / 2 > t) row--;
+    while ((long long)(row + 1) * cb - (long long)(row + 1) * row / 2 <= t) row++;
+    col = row + (int)(t - ((long long)row * cb - (long long)row * (row - 1) / 2));
+  }
   const float4* bx = sorted_boxes + nb.box_off[img];
-  __shared__ float4 cbox[kTile];
-  const int col_size = min(n - col * kTile, kTile), row_size = min(n - row * kTile, kTile);
-  if ((int)threadIdx.x < col_size) cbox[threadIdx.x] = bx[col * kTile + threadIdx.x];
+  const int col_size = live ? min(n - col * kTile, kTile) : 0, row_size = live ? min(n - row * kTile, kTile) : 0;
+  if (lane64 < col_size) cbox[grp][lane64] = bx[col * kTile + lane64];
   __syncthreads();
-  if ((int)threadIdx.x < row_size) {
-    const int cur = row * kTile + threadIdx.x;
+  if (lane64 < row_size) {
+    const int cur = row * kTile + lane64;
     const float4 a = bx[cur];
-    unsigned long long t = 0;
-    const int start = (row == col) ? threadIdx.x + 1 : 0;
+    unsigned long long w = 0;
+    const int start = (row == col) ? lane64 + 1 : 0;
     for (int i = start; i < col_size; i++) {
-      const float v = iou_plus_one(a, cbox[i]);
-      if (ge ? (v >= thresh) : (v > thresh)) t |= 1ull << i;
+      const float v = iou_plus_one(a, cbox[grp][i]);
+      if (ge ? (v >= thresh) : (v > thresh)) w |= 1ull << i;
     }
-    mask[nb.mask_off[img] + (long long)cur * cb + col] = t;
+    mask[nb.mask_off[img] + (long long)cur * cb + col] = w;
   }
 }
 
 constexpr int kSweepThreads = 512;
 
-// One CTA per image.  Dynamic shared memory: removed[cb], kept_sorted[cb], kept_orig[cb] (u64 each) + scan scratch.
+// One CTA per image.  Per 64-box tile: warp 0 resolves the greedy chain inside the tile from the diagonal mask words
+// (prefetched one tile ahead, suppression word and chain in registers), publishes the kept boxes, and then the WHOLE CTA
+// ORs the mask rows of the kept boxes into the shared-memory `removed` words -- (kept row, word) pairs are dealt out
+// to all threads, four independent 8-byte loads in flight per thread, merged with shared-memory atomicOr -- so a tile
+// step costs about one L2 latency instead of one per kept box.  Sorted inputs stop as soon as max_keep boxes are kept.
+// Dynamic shared memory: removed[cb], kept_sorted[cb], kept_orig[cb] (u64 each) + scan scratch.
 __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(NmsBatch nb, const unsigned long long* __restrict__ mask,
-                                                             const int* __restrict__ order, int max_keep,
+                                                             const int* __restrict__ order,
+                                                             const int* __restrict__ unsorted, int max_keep,
                                                              long long* __restrict__ keep, int keep_stride,
-                                                             int* __restrict__ n_keep, int image_base) {
+                                                             int* __restrict__ n_keep, int* __restrict__ done, int prefix_pass) {
   extern __shared__ unsigned long long sm[];
   const int img = blockIdx.x;
+  if (!prefix_pass && done && done[nb.first_image + img]) return;  // settled by the prefix pass
+  if (prefix_pass && unsorted[nb.first_image + img]) return;       // a prefix only answers for sorted images (done stays 0)
   const int n = nb.n[img];
   const int cb = ceil_div(n, kTile);
   unsigned long long* removed = sm;
@@ -144,49 +183,85 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(NmsBatch nb, const
   unsigned long long* kept_orig = kept_sorted + cb;
   int* scan = reinterpret_cast<int*>(kept_orig + cb);  // [kSweepThreads/32 + 1]
   __shared__ unsigned long long kept_now;
+  __shared__ int kept_rows[kTile];
+  __shared__ int kept_count, kept_total;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  long long* out = keep + (long long)(image_base + img) * keep_stride;
+  long long* out = keep + (long long)(nb.first_image + img) * keep_stride;
 
   for (int i = tid; i < cb; i += kSweepThreads) { removed[i] = 0; kept_orig[i] = 0; kept_sorted[i] = 0; }
+  if (tid == 0) kept_total = 0;
   __syncthreads();
   const unsigned long long* m = mask + nb.mask_off[img];
   const int* ord = order + nb.box_off[img];
+  const bool may_stop = max_keep > 0 && unsorted[nb.first_image + img] == 0;
 
+  // diagonal words of tile 0: lane l holds the words of boxes l and l+32
+  unsigned long long d0 = 0, d1 = 0;
+  if (warp == 0 && cb > 0) {
+    const int size = min(n, kTile);
+    d0 = lane < size ? m[(long long)lane * cb] : 0ull;
+    d1 = lane + 32 < size ? m[(long long)(lane + 32) * cb] : 0ull;
+  }
   for (int k = 0; k < cb; k++) {
     if (warp == 0) {
       const int first = k * kTile;
       const int size = min(n - first, kTile);
-      // diagonal tile: lane l holds the words of boxes first+l and first+l+32
-      const unsigned long long d0 = lane < size ? m[(long long)(first + lane) * cb + k] : 0ull;
-      const unsigned long long d1 = lane + 32 < size ? m[(long long)(first + lane + 32) * cb + k] : 0ull;
+      const unsigned long long c0 = d0, c1 = d1;
+      if (k + 1 < cb) {  // prefetch the next tile's diagonal words while this tile's chain runs
+        const int nfirst = first + kTile, nsize = min(n - nfirst, kTile);
+        d0 = lane < nsize ? m[(long long)(nfirst + lane) * cb + k + 1] : 0ull;
+        d1 = lane + 32 < nsize ? m[(long long)(nfirst + lane + 32) * cb + k + 1] : 0ull;
+      }
       const unsigned long long valid = size == kTile ? ~0ull : ((1ull << size) - 1ull);
       unsigned long long alive = ~removed[k] & valid;
       unsigned long long kept = 0;
+      int cnt = 0;
       while (alive) {  // greedy chain inside the tile (csrc/cuda/nms.cu:112-123)
         const int b = __ffsll((long long)alive) - 1;
         kept |= 1ull << b;
-        const unsigned long long lo = __shfl_sync(0xffffffffu, d0, b & 31);
-        const unsigned long long hi = __shfl_sync(0xffffffffu, d1, b & 31);
-        const unsigned long long d = (b < 32) ? lo : hi;
-        alive &= ~d;
+        if (lane == 0) kept_rows[cnt] = first + b;
+        cnt++;
+        const unsigned long long lo = __shfl_sync(0xffffffffu, c0, b & 31);
+        const unsigned long long hi = __shfl_sync(0xffffffffu, c1, b & 31);
+        alive &= ~((b < 32) ? lo : hi);
         alive &= ~(1ull << b);
       }
-      if (lane == 0) { kept_now = kept; kept_sorted[k] = kept; }
+      if (lane == 0) { kept_now = kept; kept_sorted[k] = kept; kept_count = cnt; kept_total += cnt; }
     }
     __syncthreads();
-    const unsigned long long kept = kept_now;
-    // OR the rows of the kept boxes into the later `removed` words; thread t owns word k+1+t, k+1+t+T, ...
-    for (int j = k + 1 + tid; j < cb; j += kSweepThreads) {
-      unsigned long long acc = 0;
-      unsigned long long bits = kept;
-      while (bits) {
-        const int b = __ffsll((long long)bits) - 1;
-        bits &= bits - 1;
-        acc |= m[(long long)(k * kTile + b) * cb + j];
+    if (may_stop && kept_total >= max_keep) break;  // every later box has a larger index than the max_keep-th kept one
+    const int cnt = kept_count;
+    const int nwords = cb - k - 1;
+    const int total = cnt * nwords;
+    // (kept row, later word) pairs over all threads; word index fastest so that a warp reads a contiguous run of a row
+    for (int t = tid; t < total; t += 4 * kSweepThreads) {
+      unsigned long long v[4];
+      int j[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int tt = t + u * kSweepThreads;
+        if (tt < total) {
+          const int ri = tt / nwords;
+          j[u] = k + 1 + (tt - ri * nwords);
+          v[u] = m[(long long)kept_rows[ri] * cb + j[u]];
+        } else {
+          j[u] = -1;
+          v[u] = 0;
+        }
       }
-      removed[j] |= acc;
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (j[u] >= 0 && v[u]) atomicOr(&removed[j[u]], v[u]);
     }
     __syncthreads();
+  }
+  __syncthreads();
+  if (prefix_pass) {
+    // Only a prefix of a SORTED image was examined: the answer is final iff it already holds max_keep boxes (later
+    // boxes could only add indices beyond the cut); otherwise the full pass redoes the image.
+    const bool final_answer = may_stop && kept_total >= max_keep;
+    if (tid == 0) done[nb.first_image + img] = final_answer ? 1 : 0;
+    if (!final_answer) return;
   }
 
   // kept (sorted positions) -> bitmap over original indices
@@ -216,14 +291,14 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(NmsBatch nb, const
     __syncthreads();
     if (warp == 0) {
       int v = lane < kSweepThreads / 32 ? scan[lane] : 0;
-      int s = v;
+      int s2 = v;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, s, o);
-        if (lane >= o) s += t;
+        const int t = __shfl_up_sync(0xffffffffu, s2, o);
+        if (lane >= o) s2 += t;
       }
-      if (lane < kSweepThreads / 32) scan[lane] = s - v;
-      if (lane == kSweepThreads / 32 - 1) scan[kSweepThreads / 32] = s;
+      if (lane < kSweepThreads / 32) scan[lane] = s2 - v;
+      if (lane == kSweepThreads / 32 - 1) scan[kSweepThreads / 32] = s2;
     }
     __syncthreads();
     int pos = running + scan[warp] + incl - cnt;
@@ -241,7 +316,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(NmsBatch nb, const
   if (max_keep > 0) total = min(total, max_keep);
   total = min(total, keep_stride);
   for (int i = total + tid; i < keep_stride; i += kSweepThreads) out[i] = -1;
-  if (tid == 0) n_keep[image_base + img] = total;
+  if (tid == 0) n_keep[nb.first_image + img] = total;
 }
 
 __global__ void nms_fill_empty_kernel(long long* keep, int keep_stride, int* n_keep, int image) {
@@ -250,7 +325,7 @@ __global__ void nms_fill_empty_kernel(long long* keep, int keep_stride, int* n_k
 }
 
 struct NmsLayout {
-  size_t sorted_boxes, order, mask, total;
+  size_t sorted_boxes, order, unsorted, done, mask, total;
 };
 static NmsLayout nms_layout(const int* offsets, int n_images) {
   NmsLayout l;
@@ -263,7 +338,9 @@ static NmsLayout nms_layout(const int* offsets, int n_images) {
   auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
   l.sorted_boxes = 0;
   l.order = align(total_boxes * sizeof(float4));
-  l.mask = l.order + align(total_boxes * sizeof(int));
+  l.unsorted = l.order + align(total_boxes * sizeof(int));
+  l.done = l.unsorted + align((size_t)n_images * sizeof(int));
+  l.mask = l.done + align((size_t)n_images * sizeof(int));
   l.total = l.mask + align(words * 8);
   return l;
 }
@@ -303,18 +380,23 @@ int abr_nms_batched(const float* boxes, const float* scores, const int* offsets_
   char* ws = static_cast<char*>(workspace);
   float4* sorted_boxes = reinterpret_cast<float4*>(ws + lay.sorted_boxes);
   int* order = reinterpret_cast<int*>(ws + lay.order);
+  int* unsorted = reinterpret_cast<int*>(ws + lay.unsorted);
+  int* done = reinterpret_cast<int*>(ws + lay.done);
+  // unsorted and done are adjacent regions: one memset clears both
+  if (total > 0) ABR_CUDA_OK(cudaMemsetAsync(unsorted, 0, lay.mask - lay.unsorted, st));
   unsigned long long* mask = reinterpret_cast<unsigned long long*>(ws + lay.mask);
 
   long long mask_cursor = 0;
   for (int base = 0; base < n_images; base += kImagesPerLaunch) {
     NmsBatch nb;
     nb.n_images = 0;
+    nb.first_image = base;
     int nmax = 0;
     const int lim = n_images - base < kImagesPerLaunch ? n_images - base : kImagesPerLaunch;
     for (int i = 0; i < lim; i++) {
       const int n = offsets_host[base + i + 1] - offsets_host[base + i];
       nb.box_off[i] = offsets_host[base + i];
-      nb.n[i] = n;
+      nb.n[i] = nb.n_full[i] = n;
       nb.mask_off[i] = mask_cursor;
       mask_cursor += (long long)n * ceil_div(n, kTile);
       nmax = n > nmax ? n : nmax;
@@ -329,14 +411,39 @@ int abr_nms_batched(const float* boxes, const float* scores, const int* offsets_
     }
     const int cbmax = ceil_div(nmax, kTile);
     ABR_REQUIRE(cbmax <= 65535, ABR_ERR_UNSUPPORTED, "nms: %d boxes in one image (max %d)", nmax, 65535 * kTile);
-    rank_sort_kernel<<<dim3(ceil_div(nmax, kRankThreads * kRankPerThread), lim), kRankThreads, 0, st>>>(nb, boxes, scores, sorted_boxes, order);
-    ABR_CHECK_LAUNCH("nms_rank_sort");
-    iou_mask_kernel<<<dim3(cbmax, cbmax, lim), kTile, 0, st>>>(nb, sorted_boxes, mask, thresh, ge);
-    ABR_CHECK_LAUNCH("nms_iou_mask");
     const size_t smem = (size_t)cbmax * 3 * 8 + (kSweepThreads / 32 + 1) * sizeof(int);
     ABR_REQUIRE(smem <= 200 * 1024, ABR_ERR_UNSUPPORTED, "nms: %d boxes in one image need %zu B of shared memory", nmax, smem);
     if (smem > 48 * 1024) ABR_CUDA_OK(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sweep_kernel<<<lim, kSweepThreads, smem, st>>>(nb, mask, order, max_keep, reinterpret_cast<long long*>(keep), keep_stride, n_keep, base);
+
+    presort_kernel<<<dim3(ceil_div(nmax, 256), lim), 256, 0, st>>>(nb, boxes, scores, sorted_boxes, order, unsorted);
+    ABR_CHECK_LAUNCH("nms_presort");
+    rank_sort_kernel<<<dim3(ceil_div(nmax, kRankThreads), lim), kRankThreads, 0, st>>>(nb, boxes, scores, sorted_boxes, order, unsorted);
+    ABR_CHECK_LAUNCH("nms_rank_sort");
+
+    // Prefix pass (only with a max_keep cut): sorted images rarely need more than the first ~2*max_keep boxes to collect
+    // max_keep survivors, and both the mask and the sweep are quadratic / linear in what they look at.  Images the prefix
+    // settles (sorted and max_keep reached) are skipped by the full pass; the others are redone in full.
+    const int prefix = max_keep > 0 ? ceil_div(2 * max_keep > 512 ? 2 * max_keep : 512, kTile) * kTile : 0;
+    const int* done_in = nullptr;
+    if (prefix > 0 && prefix < nmax) {
+      NmsBatch pb = nb;
+      int pmax = 0;
+      for (int i = 0; i < lim; i++) {
+        pb.n[i] = nb.n_full[i] < prefix ? nb.n_full[i] : prefix;
+        pmax = pb.n[i] > pmax ? pb.n[i] : pmax;
+      }
+      const int pcb = ceil_div(pmax, kTile);
+      const long long ptiles = (long long)pcb * (pcb + 1) / 2;
+      iou_mask_kernel<<<dim3((unsigned)ceil_div<long long>(ptiles, kMaskTilesPerCta), lim), kTile * kMaskTilesPerCta, 0, st>>>(pb, sorted_boxes, mask, thresh, ge, unsorted);
+      ABR_CHECK_LAUNCH("nms_iou_mask_prefix");
+      sweep_kernel<<<lim, kSweepThreads, smem, st>>>(pb, mask, order, unsorted, max_keep, reinterpret_cast<long long*>(keep), keep_stride, n_keep, done, 1);
+      ABR_CHECK_LAUNCH("nms_sweep_prefix");
+      done_in = done;
+    }
+    const long long tiles = (long long)cbmax * (cbmax + 1) / 2;
+    iou_mask_kernel<<<dim3((unsigned)ceil_div<long long>(tiles, kMaskTilesPerCta), lim), kTile * kMaskTilesPerCta, 0, st>>>(nb, sorted_boxes, mask, thresh, ge, done_in);
+    ABR_CHECK_LAUNCH("nms_iou_mask");
+    sweep_kernel<<<lim, kSweepThreads, smem, st>>>(nb, mask, order, unsorted, max_keep, reinterpret_cast<long long*>(keep), keep_stride, n_keep, done, 0);
     ABR_CHECK_LAUNCH("nms_sweep");
   }
   return ABR_OK;

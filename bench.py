@@ -323,20 +323,26 @@ def secondary_metrics(dev):
 
     out = {}
     rng = np.random.default_rng(3)
-    for n, batch in ((6000, 4), (6000, 16), (12000, 4)):
+    # RPN-shaped calls: per image N boxes, IoU 0.7, post-NMS cut; the RPN hands NMS the output of a
+    # sorted top-k (modeling/rpn/inference.py:94-95), so the scores arrive in descending order.  One unsorted line too.
+    for n, batch, keep_n, is_sorted in ((6000, 4, 1000, True), (6000, 16, 1000, True), (12000, 4, 2000, True), (12000, 16, 2000, True),
+                                        (6000, 4, 1000, False)):
         data = [make_boxes(rng, n, 1216, 800) for _ in range(batch)]
+        if is_sorted:
+            data = [(np.ascontiguousarray(b[np.argsort(-s, kind="stable")]), np.ascontiguousarray(np.sort(s)[::-1])) for b, s in data]
         boxes = [torch.from_numpy(b).to(dev) for b, _ in data]
         scores = [torch.from_numpy(s).to(dev) for _, s in data]
         for _ in range(3):
-            nms_batched(boxes, scores, 0.7, 2000)
+            nms_batched(boxes, scores, 0.7, keep_n)
         torch.cuda.synchronize()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         for _ in range(10):
-            keep, cnt = nms_batched(boxes, scores, 0.7, 2000)
+            keep, cnt = nms_batched(boxes, scores, 0.7, keep_n)
         e.record()
         torch.cuda.synchronize()
-        out["nms_boxes_per_s_n%d_b%d" % (n, batch)] = round(batch * n * 10 / (s.elapsed_time(e) * 1e-3))
+        out["nms_boxes_per_s_n%d_b%d_keep%d_%s" % (n, batch, keep_n, "sorted" if is_sorted else "unsorted")] = round(
+            batch * n * 10 / (s.elapsed_time(e) * 1e-3))
     out.update(paste_metrics(dev))
     return out
 

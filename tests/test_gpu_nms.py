@@ -108,3 +108,29 @@ def test_boxlist_nms_golden(golden):
                 np.testing.assert_allclose(r.bbox.cpu().numpy(), g["bbox_" + k], rtol=0, atol=1e-4)
                 assert np.array_equal(r.get_field("scores").cpu().numpy(), g["scores_" + k])
                 assert np.array_equal(r.get_field("labels").cpu().numpy(), g["labels_" + k])
+
+
+@pytest.mark.parametrize("n,max_proposals", [(6000, 1000), (12000, 2000), (3000, 2000), (700, 300)])
+def test_nms_sorted_input_prefix_pass(n, max_proposals):
+    """RPN-shaped call: scores already sorted (top-k output) and a post-NMS cut.  The kernel then settles the image
+    from a prefix of the boxes; the result must still equal the full greedy NMS cut to max_proposals -- also when the
+    prefix does not contain enough survivors (heavy duplication) and the full pass has to redo the image."""
+    from abr_iod_b200.layers import nms_batched
+
+    rng = np.random.default_rng(n + max_proposals)
+    imgs = []
+    for kind in ("plain", "duplicates", "unsorted"):
+        b, s = make_boxes(rng, n, 1216, 800)
+        if kind == "duplicates":  # ~everything suppressed: only a handful of distinct boxes, so the prefix is not enough
+            b = b[rng.integers(0, 40, n)] + rng.normal(0, 0.5, (n, 4)).astype(np.float32)
+        if kind != "unsorted":
+            o = np.argsort(-s, kind="stable")
+            b, s = np.ascontiguousarray(b[o]), np.ascontiguousarray(s[o])
+        imgs.append((b, s))
+    keep, cnt = nms_batched([torch.from_numpy(b).cuda() for b, _ in imgs], [torch.from_numpy(s).cuda() for _, s in imgs],
+                            0.7, max_proposals)
+    cnt = cnt.cpu().numpy()
+    for i, (b, s) in enumerate(imgs):
+        ref = opooler.boxlist_nms(b, s, 0.7, max_proposals)
+        assert cnt[i] == len(ref), (i, cnt[i], len(ref))
+        assert np.array_equal(keep[i, : cnt[i]].cpu().numpy(), ref)
