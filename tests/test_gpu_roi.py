@@ -211,3 +211,41 @@ def test_roi_align_nhwc_every_plan_mode(monkeypatch, use_workspace, P, ratio):
     gout = rng.standard_normal(out.shape).astype(np.float32)
     out.backward(dev(gout, True))
     close(xt.grad.cpu().numpy(), oracle.roi_align_backward(gout, rois, 1 / s, P, P, B, C, H, W, ratio))
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+@pytest.mark.parametrize("C,ratio", [(8, 2), (136, 0)])
+def test_pooler_multilevel_vector_paths_vs_oracle(channels_last, C, ratio):
+    """Four FPN levels with C % 4 == 0, so channels-last inputs take the 16-byte-lane kernels (one tensor map per level in
+    the TMA-staged forward, the level table in the backward); C=136 has a ragged last 128-channel slice."""
+    from abr_iod_b200.modeling.poolers import Pooler
+    from abr_iod_b200.structures.bounding_box import BoxList
+    from oracle import pooler as opooler
+
+    rng = np.random.default_rng(C + ratio)
+    B, im_w, im_h = 2, 640, 512
+    scales = (0.25, 0.125, 0.0625, 0.03125)
+    feats_np = [rng.standard_normal((B, C, int(im_h * s), int(im_w * s))).astype(np.float32) for s in scales]
+    boxes_np = []
+    for b in range(B):
+        n = 30
+        x1, y1 = rng.uniform(0, im_w - 8, n), rng.uniform(0, im_h - 8, n)
+        side = np.exp(rng.uniform(np.log(6), np.log(700), n))
+        bx = np.stack([x1, y1, np.minimum(x1 + side, im_w - 1), np.minimum(y1 + side * rng.uniform(0.5, 2, n), im_h - 1)], 1)
+        big = np.array([[0, 0, im_w - 1, im_h - 1], [60, 40, 600, 500], [20, 30, 420, 390]], np.float32)
+        boxes_np.append(np.concatenate([bx.astype(np.float32), big], 0))
+    feats = [dev(f, channels_last).requires_grad_(True) for f in feats_np]
+    boxes = [BoxList(dev(b), (im_w, im_h), "xyxy") for b in boxes_np]
+    out = Pooler((7, 7), scales, ratio)(feats, boxes)
+    ref = opooler.pooler(feats_np, boxes_np, 7, scales, ratio)
+    close(out.detach().cpu().numpy(), ref)
+    gout = rng.standard_normal(out.shape).astype(np.float32)
+    out.backward(dev(gout, channels_last))
+    rois = opooler.to_roi_format(boxes_np)
+    levels = opooler.map_levels(rois[:, 1:], 2.0, 5.0)
+    assert len(set(levels.tolist())) == 4
+    for lvl in range(4):
+        idx = np.nonzero(levels == lvl)[0]
+        f = feats_np[lvl]
+        gref = oracle.roi_align_backward(gout[idx], rois[idx], scales[lvl], 7, 7, *f.shape, ratio)
+        close(feats[lvl].grad.cpu().numpy(), gref)
