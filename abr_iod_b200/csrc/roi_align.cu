@@ -1320,6 +1320,7 @@ struct Call {
   const int32_t* levels;
   int C, R, PH, PW, ratio, Hs, Ws, layout;
   int* plans;  // null: no workspace, self-contained kernels only
+  bool plan_ready;  // the workspace already holds the plans of exactly these RoIs / levels / geometry
   cudaStream_t st;
 };
 
@@ -1349,6 +1350,7 @@ static bool build_tma_maps(const Call& c, TmaMaps& maps) {
 }
 
 static int run_plan(const Call& c) {
+  if (c.plan_ready) return ABR_OK;
   const size_t smem = tables_bytes(c.PH, c.PW, c.Hs, c.Ws, true);
   int rc = set_smem(plan_kernel, smem, "roi_align plan");
   if (rc) return rc;
@@ -1530,6 +1532,7 @@ int abr_roi_align_multilevel_forward(const void* const* inputs_host, const int* 
   c.B = B; c.L = L;
   c.C = C; c.R = R; c.PH = PH; c.PW = PW; c.ratio = sampling_ratio; c.layout = layout;
   c.plans = usable_workspace(workspace, workspace_bytes, R, PW, c.Hs, layout);
+  c.plan_ready = false;
   c.st = static_cast<cudaStream_t>(stream);
   return dispatch_fwd(c, output, dtype);
 }
@@ -1538,7 +1541,7 @@ int abr_roi_align_multilevel_backward(const void* grad_output, const float* rois
                                       void* const* grad_inputs_host, const int* hs_host, const int* ws_host,
                                       const float* scales_host, int L, int B, int C, int R, int PH, int PW,
                                       int sampling_ratio, int dtype, int layout, int zero_init, void* workspace,
-                                      size_t workspace_bytes, abr_stream_t stream) {
+                                      size_t workspace_bytes, int workspace_has_plan, abr_stream_t stream) {
   ABR_REQUIRE(grad_inputs_host && hs_host && ws_host && scales_host, ABR_ERR_BAD_ARG, "roi_align: null level arrays");
   int rc = check_common(grad_inputs_host, rois, grad_output, B, C, R, PH, PW, dtype, layout);
   if (rc) return rc;
@@ -1555,6 +1558,7 @@ int abr_roi_align_multilevel_backward(const void* grad_output, const float* rois
   c.B = B; c.L = L;
   c.C = C; c.R = R; c.PH = PH; c.PW = PW; c.ratio = sampling_ratio; c.layout = layout;
   c.plans = usable_workspace(workspace, workspace_bytes, R, PW, c.Hs, layout);
+  c.plan_ready = c.plans != nullptr && workspace_has_plan != 0;
   return dispatch_bwd(c, grad_output, dtype);
 }
 
@@ -1570,12 +1574,14 @@ int abr_roi_align_forward(const void* input, const float* rois, void* output, in
 
 int abr_roi_align_backward(const void* grad_output, const float* rois, void* grad_input, int B, int C, int H, int W,
                            int R, int PH, int PW, float spatial_scale, int sampling_ratio, int dtype, int layout,
-                           int zero_init, void* workspace, size_t workspace_bytes, abr_stream_t stream) {
+                           int zero_init, void* workspace, size_t workspace_bytes, int workspace_has_plan,
+                           abr_stream_t stream) {
   ABR_REQUIRE(grad_input || (size_t)B * C * H * W == 0, ABR_ERR_BAD_ARG, "roi_align_backward: null grad_input");
   if ((size_t)B * C * H * W == 0) return ABR_OK;
   void* ptrs[1] = {grad_input};
   return abr_roi_align_multilevel_backward(grad_output, rois, nullptr, ptrs, &H, &W, &spatial_scale, 1, B, C, R, PH, PW,
-                                           sampling_ratio, dtype, layout, zero_init, workspace, workspace_bytes, stream);
+                                           sampling_ratio, dtype, layout, zero_init, workspace, workspace_bytes, workspace_has_plan,
+                                           stream);
 }
 
 int abr_fpn_map_levels(const float* rois, int32_t* levels, int R, float k_min, float k_max, float canonical_scale,

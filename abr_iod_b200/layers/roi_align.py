@@ -20,8 +20,9 @@ def _prep_rois(rois, device):
     return rois.detach().to(dtype=torch.float32).contiguous()
 
 
-def roi_align_forward(input, rois, spatial_scale, pooled_h, pooled_w, sampling_ratio):
-    """``_C.roi_align_forward`` (csrc/ROIAlign.h:11-25)."""
+def roi_align_forward(input, rois, spatial_scale, pooled_h, pooled_w, sampling_ratio, return_plan=False):
+    """``_C.roi_align_forward`` (csrc/ROIAlign.h:11-25).  With ``return_plan`` also returns the workspace holding the
+    per-RoI plans, which ``roi_align_backward(..., plan=...)`` of the same RoIs can reuse."""
     _lib.require_cuda(input, "input")
     rois = _prep_rois(rois, input.device)
     nhwc = _lib.is_channels_last(input)
@@ -31,7 +32,7 @@ def roi_align_forward(input, rois, spatial_scale, pooled_h, pooled_w, sampling_r
     out = torch.empty((R, C, pooled_h, pooled_w), dtype=x.dtype, device=x.device,
                       memory_format=torch.channels_last if nhwc else torch.contiguous_format)
     if out.numel() == 0:
-        return out
+        return (out, None) if return_plan else out
     with torch.cuda.device(x.device):
         ws, ws_bytes = _lib.roi_align_workspace(R, pooled_h, pooled_w, H, x.device, nhwc)
         _lib.check(_lib.lib().abr_roi_align_forward(
@@ -39,12 +40,13 @@ def roi_align_forward(input, rois, spatial_scale, pooled_h, pooled_w, sampling_r
             float(spatial_scale), int(sampling_ratio), _lib.dtype_code(x),
             _lib.ABR_NHWC if nhwc else _lib.ABR_NCHW, ws.data_ptr() if ws is not None else None, ws_bytes,
             _lib.stream_ptr(x.device)))
-    return out
+    return (out, ws) if return_plan else out
 
 
 def roi_align_backward(grad, rois, spatial_scale, pooled_h, pooled_w, batch_size, channels, height, width,
-                       sampling_ratio, channels_last=None):
-    """``_C.roi_align_backward`` (csrc/ROIAlign.h:27-46).  ``channels_last=None`` follows ``grad``'s layout."""
+                       sampling_ratio, channels_last=None, plan=None):
+    """``_C.roi_align_backward`` (csrc/ROIAlign.h:27-46).  ``channels_last=None`` follows ``grad``'s layout; ``plan`` is
+    the workspace a forward over the same RoIs returned (skips re-planning)."""
     _lib.require_cuda(grad, "grad")
     rois = _prep_rois(rois, grad.device)
     nhwc = _lib.is_channels_last(grad) if channels_last is None else bool(channels_last)
@@ -54,11 +56,15 @@ def roi_align_backward(grad, rois, spatial_scale, pooled_h, pooled_w, batch_size
     if gin.numel() == 0:
         return gin
     with torch.cuda.device(g.device):
-        ws, ws_bytes = _lib.roi_align_workspace(rois.size(0), pooled_h, pooled_w, height, g.device, nhwc)
+        has_plan = int(plan is not None and nhwc)
+        if has_plan:
+            ws, ws_bytes = plan, plan.numel()
+        else:
+            ws, ws_bytes = _lib.roi_align_workspace(rois.size(0), pooled_h, pooled_w, height, g.device, nhwc)
         _lib.check(_lib.lib().abr_roi_align_backward(
             g.data_ptr(), rois.data_ptr(), gin.data_ptr(), batch_size, channels, height, width, rois.size(0),
             pooled_h, pooled_w, float(spatial_scale), int(sampling_ratio), _lib.dtype_code(g),
-            _lib.ABR_NHWC if nhwc else _lib.ABR_NCHW, 1, ws.data_ptr() if ws is not None else None, ws_bytes,
+            _lib.ABR_NHWC if nhwc else _lib.ABR_NCHW, 1, ws.data_ptr() if ws is not None else None, ws_bytes, has_plan,
             _lib.stream_ptr(g.device)))
     return gin
 
@@ -72,7 +78,9 @@ class _ROIAlign(Function):
         ctx.sampling_ratio = sampling_ratio
         ctx.input_shape = input.size()
         ctx.channels_last = _lib.is_channels_last(input)
-        return roi_align_forward(input, roi, spatial_scale, ctx.output_size[0], ctx.output_size[1], sampling_ratio)
+        out, ctx.plan = roi_align_forward(input, roi, spatial_scale, ctx.output_size[0], ctx.output_size[1], sampling_ratio,
+                                          return_plan=True)
+        return out
 
     @staticmethod
     @once_differentiable
@@ -80,7 +88,7 @@ class _ROIAlign(Function):
         (rois,) = ctx.saved_tensors
         bs, ch, h, w = ctx.input_shape
         grad_input = roi_align_backward(grad_output, rois, ctx.spatial_scale, ctx.output_size[0], ctx.output_size[1],
-                                        bs, ch, h, w, ctx.sampling_ratio, channels_last=ctx.channels_last)
+                                        bs, ch, h, w, ctx.sampling_ratio, channels_last=ctx.channels_last, plan=ctx.plan)
         return grad_input, None, None, None, None
 
 

@@ -74,6 +74,7 @@ class _MultiLevelROIAlign(Function):
         out = torch.empty((R, C, PH, PW), dtype=feats[0].dtype, device=feats[0].device, memory_format=fmt)
         ctx.save_for_backward(rois, levels)
         ctx.meta = (output_size, tuple(scales), sampling_ratio, [tuple(f.shape) for f in feats], nhwc)
+        ctx.plan = None
         if out.numel():
             ptrs, hs, ws, sc = _level_arrays(feats, scales)
             with torch.cuda.device(out.device):
@@ -82,6 +83,7 @@ class _MultiLevelROIAlign(Function):
                     ptrs, hs, ws, sc, len(feats), rois.data_ptr(), levels.data_ptr(), out.data_ptr(), B, C, R, PH, PW,
                     int(sampling_ratio), _lib.dtype_code(out), _lib.ABR_NHWC if nhwc else _lib.ABR_NCHW,
                     wk.data_ptr() if wk is not None else None, wk_bytes, _lib.stream_ptr(out.device)))
+                ctx.plan = wk
         return out
 
     @staticmethod
@@ -95,11 +97,15 @@ class _MultiLevelROIAlign(Function):
         B, C = shapes[0][:2]
         ptrs, hs, ws, sc = _level_arrays(grads, scales)
         with torch.cuda.device(g.device):
-            wk, wk_bytes = _lib.roi_align_workspace(rois.size(0), PH, PW, max(s[2] for s in shapes), g.device, nhwc)
+            has_plan = int(ctx.plan is not None)
+            if has_plan:
+                wk, wk_bytes = ctx.plan, ctx.plan.numel()
+            else:
+                wk, wk_bytes = _lib.roi_align_workspace(rois.size(0), PH, PW, max(s[2] for s in shapes), g.device, nhwc)
             _lib.check(_lib.lib().abr_roi_align_multilevel_backward(
                 g.data_ptr(), rois.data_ptr(), levels.data_ptr(), ptrs, hs, ws, sc, len(grads), B, C, rois.size(0),
                 PH, PW, int(sampling_ratio), _lib.dtype_code(g), _lib.ABR_NHWC if nhwc else _lib.ABR_NCHW, 1,
-                wk.data_ptr() if wk is not None else None, wk_bytes, _lib.stream_ptr(g.device)))
+                wk.data_ptr() if wk is not None else None, wk_bytes, has_plan, _lib.stream_ptr(g.device)))
         return (None, None, None, None, None) + tuple(grads)
 
 

@@ -61,7 +61,8 @@ ABR_API uint64_t abr_launch_count(void);
  * R == 0 is a no-op (ROIAlign_cuda.cu:278-281).
  * `workspace` (optional, 16-byte aligned, abr_roi_align_workspace_bytes(R, PH, PW, max H over levels) bytes) holds the
  * per-RoI interpolation plans of the fast NHWC kernels; with NULL (or the NCHW layout) the self-contained kernels run.
- * Its contents are scratch: nothing is carried from one call to the next. */
+ * The forward leaves the plans of its RoIs in the workspace; a backward for the SAME rois / levels / geometry may be
+ * handed that workspace with workspace_has_plan != 0 and then skips planning (0: contents are treated as scratch). */
 ABR_API size_t abr_roi_align_workspace_bytes(int R, int PH, int PW, int max_h);
 ABR_API int abr_roi_align_forward(const void* input, const float* rois, void* output,
                           int B, int C, int H, int W, int R, int PH, int PW,
@@ -74,7 +75,7 @@ ABR_API int abr_roi_align_backward(const void* grad_output, const float* rois, v
                            int B, int C, int H, int W, int R, int PH, int PW,
                            float spatial_scale, int sampling_ratio,
                            int dtype, int layout, int zero_init, void* workspace, size_t workspace_bytes,
-                           abr_stream_t stream);
+                           int workspace_has_plan, abr_stream_t stream);
 
 /* Multi-level (FPN) pooling in ONE launch: replaces the per-level nonzero / gather / launch / scatter
  * loop of Pooler.forward (modeling/poolers.py:93-105).  `levels[r]` in [0,L) selects the feature map
@@ -93,7 +94,7 @@ ABR_API int abr_roi_align_multilevel_backward(const void* grad_output, const flo
                                       const float* scales_host, int L,
                                       int B, int C, int R, int PH, int PW, int sampling_ratio,
                                       int dtype, int layout, int zero_init, void* workspace, size_t workspace_bytes,
-                                      abr_stream_t stream);
+                                      int workspace_has_plan, abr_stream_t stream);
 
 /* FPN level of each RoI: floor(k0 + log2(sqrt(area)/s0 + eps)) clamped to [k_min,k_max], minus k_min,
  * area with the +1 convention (modeling/poolers.py:31-42, structures/bounding_box.py:227-231). */
