@@ -42,6 +42,7 @@ SIGNATURES = {
     "abr_last_error": (ctypes.c_char_p, []),
     "abr_launch_count": (ctypes.c_uint64, []),
     "abr_roi_align_workspace_bytes": (_sz, [_int, _int, _int, _int]),
+    "abr_roi_align_workspace_bytes_nchw": (_sz, [_int, _int, _int, _int, _int, _int, ctypes.c_longlong, _int]),
     "abr_roi_align_forward": (_int, [_vp, _vp, _vp] + [_int] * 7 + [_f, _int, _int, _int, _vp, _sz, _vp]),
     "abr_roi_align_backward": (_int, [_vp, _vp, _vp] + [_int] * 7 + [_f, _int, _int, _int, _int, _vp, _sz, _int, _vp]),
     "abr_roi_align_multilevel_forward": (_int, [_vp, _vp, _vp, _vp, _int, _vp, _vp, _vp] + [_int] * 8 + [_vp, _sz, _vp]),
@@ -108,11 +109,22 @@ def is_channels_last(t: torch.Tensor) -> bool:
     return t.dim() == 4 and not t.is_contiguous() and t.is_contiguous(memory_format=torch.channels_last)
 
 
-def roi_align_workspace(R, PH, PW, max_h, device, channels_last=True):
-    """Scratch for the per-RoI plans of the fast NHWC ROIAlign kernels (caller-owned, per call).  Returns (tensor|None, bytes)."""
-    if not channels_last or R == 0:
+NCHW_STAGING = True  # run contiguous-NCHW ROIAlign calls through the channels-last kernels (costs scratch memory)
+
+
+def roi_align_workspace(R, PH, PW, max_h, device, channels_last=True, nchw_staging=None):
+    """Scratch for ROIAlign (caller-owned, per call): the per-RoI plans of the channels-last kernels and, for a
+    contiguous-NCHW call (``nchw_staging=(B, C, sum_hw, dtype_code)``), room for channels-last copies of the maps and
+    of the pooled tensor.  Returns (tensor|None, bytes)."""
+    if R == 0:
         return None, 0
-    n = int(lib().abr_roi_align_workspace_bytes(R, PH, PW, max_h))
+    if channels_last:
+        n = int(lib().abr_roi_align_workspace_bytes(R, PH, PW, max_h))
+    elif nchw_staging is not None and NCHW_STAGING:
+        B, C, sum_hw, code = nchw_staging
+        n = int(lib().abr_roi_align_workspace_bytes_nchw(R, PH, PW, max_h, B, C, sum_hw, code))
+    else:
+        return None, 0
     return torch.empty((n,), dtype=torch.uint8, device=device), n
 
 

@@ -1256,6 +1256,60 @@ __global__ void fpn_map_levels_kernel(const float* __restrict__ rois, int32_t* _
   levels[r] = (int32_t)((long long)lvl - (long long)k_min);
 }
 
+// ------------------------------------------------------------------------------------------ NCHW staging
+// src [batch][rows][cols] -> dst [batch][cols][rows] (32x32 tiles through padded shared memory, coalesced both ways).
+// With `add` the transposed values are accumulated into dst.  Used to run NCHW callers through the channels-last
+// kernels: [B][C][HW] <-> [B][HW][C] for the maps, [R][C][P*P] <-> [R][P*P][C] for the pooled tensors.
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ src, T* __restrict__ dst, int rows, int cols,
+                                                       long long batch, int add) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (long long b = blockIdx.z; b < batch; b += gridDim.z) {
+    const T* s = src + (size_t)b * rows * cols;
+    T* d = dst + (size_t)b * rows * cols;
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      const int r = r0 + ty + i, c = c0 + tx;
+      if (r < rows && c < cols) {
+        float v[1];
+        VecIO<T, 1>::load(s + (size_t)r * cols + c, v);
+        tile[ty + i][tx] = v[0];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      const int c = c0 + ty + i, r = r0 + tx;
+      if (r < rows && c < cols) {
+        float v[1] = {tile[tx][ty + i]};
+        T* p = d + (size_t)c * rows + r;
+        if (add) {
+          float o[1];
+          VecIO<T, 1>::load(p, o);
+          v[0] += o[0];
+        }
+        VecIO<T, 1>::store(p, v);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+static int launch_transpose(const void* src, void* dst, int rows, int cols, long long batch, int add, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0 || batch <= 0) return ABR_OK;
+  dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32), (unsigned)(batch < 65535 ? batch : 65535));
+  transpose_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(src), static_cast<T*>(dst), rows, cols, batch, add);
+  ABR_CHECK_LAUNCH("roi_align_transpose");
+  return ABR_OK;
+}
+static int transpose_any(const void* src, void* dst, int rows, int cols, long long batch, int add, int dtype, cudaStream_t st) {
+  return dtype == ABR_F32 ? launch_transpose<float>(src, dst, rows, cols, batch, add, st)
+                          : launch_transpose<__nv_bfloat16>(src, dst, rows, cols, batch, add, st);
+}
+
 // ------------------------------------------------------------------------------------------ host side
 static int check_common(const void* a, const float* rois, const void* b, int B, int C, int R, int PH, int PW,
                         int dtype, int layout) {
@@ -1497,6 +1551,13 @@ static int dispatch_bwd(const Call& c, const void* gout, int dtype) {
 
 static size_t elem_size(int dtype) { return dtype == ABR_F32 ? 4 : 2; }
 
+// NCHW callers can be run through the channels-last kernels when the workspace also has room for a channels-last copy
+// of every level's map and of the pooled tensor (after the plans, 256-byte aligned).
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+static size_t staging_need(int B, int C, long long sum_hw, int R, int PH, int PW, int dtype) {
+  return align256((size_t)B * C * sum_hw * (dtype == ABR_F32 ? 4 : 2)) + align256((size_t)R * C * PH * PW * (dtype == ABR_F32 ? 4 : 2));
+}
+
 // The plans are only used by the NHWC kernels; a workspace that is absent or too small selects the self-contained path.
 static int* usable_workspace(void* ws, size_t bytes, int R, int PW, int Hs, int layout) {
   if (!ws || layout != ABR_NHWC || (reinterpret_cast<uintptr_t>(ws) & 15)) return nullptr;
@@ -1515,6 +1576,11 @@ size_t abr_roi_align_workspace_bytes(int R, int PH, int PW, int max_h) {
   return workspace_need(R, PW, max_h);
 }
 
+size_t abr_roi_align_workspace_bytes_nchw(int R, int PH, int PW, int max_h, int B, int C, long long sum_hw, int dtype) {
+  if (R <= 0 || PW <= 0 || PH <= 0 || max_h <= 0 || B <= 0 || C <= 0 || sum_hw <= 0) return 0;
+  return align256(workspace_need(R, PW, max_h)) + staging_need(B, C, sum_hw, R, PH, PW, dtype);
+}
+
 int abr_roi_align_multilevel_forward(const void* const* inputs_host, const int* hs_host, const int* ws_host,
                                      const float* scales_host, int L, const float* rois, const int32_t* levels,
                                      void* output, int B, int C, int R, int PH, int PW, int sampling_ratio, int dtype,
@@ -1531,9 +1597,31 @@ int abr_roi_align_multilevel_forward(const void* const* inputs_host, const int* 
   c.rois = rois; c.levels = L == 1 ? nullptr : levels;
   c.B = B; c.L = L;
   c.C = C; c.R = R; c.PH = PH; c.PW = PW; c.ratio = sampling_ratio; c.layout = layout;
-  c.plans = usable_workspace(workspace, workspace_bytes, R, PW, c.Hs, layout);
   c.plan_ready = false;
   c.st = static_cast<cudaStream_t>(stream);
+  long long sum_hw = 0;
+  for (int l = 0; l < L; l++) sum_hw += (long long)hs_host[l] * ws_host[l];
+  const size_t plan_bytes = align256(workspace_need(R, PW, c.Hs));
+  if (layout == ABR_NCHW && workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 &&
+      workspace_bytes >= plan_bytes + staging_need(B, C, sum_hw, R, PH, PW, dtype)) {
+    // NCHW caller with staging room: channels-last copies of the maps, channels-last kernels, transposed result
+    const size_t es = elem_size(dtype);
+    char* stage = static_cast<char*>(workspace) + plan_bytes;
+    for (int l = 0; l < L; l++) {
+      const int hw = hs_host[l] * ws_host[l];
+      rc = transpose_any(inputs_host[l], stage, C, hw, B, 0, dtype, c.st);
+      if (rc) return rc;
+      c.lv.ptr[l] = stage;
+      stage += (size_t)B * C * hw * es;
+    }
+    void* pooled = static_cast<char*>(workspace) + plan_bytes + align256((size_t)B * C * sum_hw * es);
+    c.layout = ABR_NHWC;
+    c.plans = static_cast<int*>(workspace);
+    rc = dispatch_fwd(c, pooled, dtype);
+    if (rc) return rc;
+    return transpose_any(pooled, output, PH * PW, C, R, 0, dtype, c.st);
+  }
+  c.plans = usable_workspace(workspace, workspace_bytes, R, PW, c.Hs, layout);
   return dispatch_fwd(c, output, dtype);
 }
 
@@ -1557,6 +1645,41 @@ int abr_roi_align_multilevel_backward(const void* grad_output, const float* rois
   c.rois = rois; c.levels = L == 1 ? nullptr : levels;
   c.B = B; c.L = L;
   c.C = C; c.R = R; c.PH = PH; c.PW = PW; c.ratio = sampling_ratio; c.layout = layout;
+  long long sum_hw = 0;
+  for (int l = 0; l < L; l++) sum_hw += (long long)hs_host[l] * ws_host[l];
+  const size_t plan_bytes = align256(workspace_need(R, PW, c.Hs));
+  if (layout == ABR_NCHW && workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 &&
+      workspace_bytes >= plan_bytes + staging_need(B, C, sum_hw, R, PH, PW, dtype)) {
+    // NCHW caller with staging room: channels-last copy of the upstream gradient, channels-last kernels into zeroed
+    // channels-last maps, then transposed (added when zero_init == 0) into the caller's gradient maps
+    const size_t es = elem_size(dtype);
+    char* stage0 = static_cast<char*>(workspace) + plan_bytes;
+    void* pooled = stage0 + align256((size_t)B * C * sum_hw * es);
+    rc = transpose_any(grad_output, pooled, C, PH * PW, R, 0, dtype, c.st);
+    if (rc) return rc;
+    ABR_CUDA_OK(cudaMemsetAsync(stage0, 0, (size_t)B * C * sum_hw * es, c.st));
+    void* user[ABR_MAX_LEVELS];
+    char* stage = stage0;
+    for (int l = 0; l < L; l++) {
+      user[l] = c.lv.ptr[l];
+      c.lv.ptr[l] = stage;
+      stage += (size_t)B * C * hs_host[l] * ws_host[l] * es;
+    }
+    c.layout = ABR_NHWC;
+    c.plans = static_cast<int*>(workspace);
+    c.plan_ready = workspace_has_plan != 0;
+    rc = dispatch_bwd(c, pooled, dtype);
+    if (rc) return rc;
+    stage = stage0;
+    for (int l = 0; l < L; l++) {
+      const int hw = hs_host[l] * ws_host[l];
+      // the zero_init memset of the caller's maps above makes "add" and "store" equivalent; skip the read when zeroed
+      rc = transpose_any(stage, user[l], hw, C, B, zero_init ? 0 : 1, dtype, c.st);
+      if (rc) return rc;
+      stage += (size_t)B * C * hw * es;
+    }
+    return ABR_OK;
+  }
   c.plans = usable_workspace(workspace, workspace_bytes, R, PW, c.Hs, layout);
   c.plan_ready = c.plans != nullptr && workspace_has_plan != 0;
   return dispatch_bwd(c, grad_output, dtype);

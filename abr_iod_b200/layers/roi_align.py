@@ -34,7 +34,8 @@ def roi_align_forward(input, rois, spatial_scale, pooled_h, pooled_w, sampling_r
     if out.numel() == 0:
         return (out, None) if return_plan else out
     with torch.cuda.device(x.device):
-        ws, ws_bytes = _lib.roi_align_workspace(R, pooled_h, pooled_w, H, x.device, nhwc)
+        ws, ws_bytes = _lib.roi_align_workspace(R, pooled_h, pooled_w, H, x.device, nhwc,
+                                                nchw_staging=(B, C, H * W, _lib.dtype_code(x)))
         _lib.check(_lib.lib().abr_roi_align_forward(
             x.data_ptr(), rois.data_ptr(), out.data_ptr(), B, C, H, W, R, pooled_h, pooled_w,
             float(spatial_scale), int(sampling_ratio), _lib.dtype_code(x),
@@ -56,11 +57,12 @@ def roi_align_backward(grad, rois, spatial_scale, pooled_h, pooled_w, batch_size
     if gin.numel() == 0:
         return gin
     with torch.cuda.device(g.device):
-        has_plan = int(plan is not None and nhwc)
+        has_plan = int(plan is not None)
         if has_plan:
             ws, ws_bytes = plan, plan.numel()
         else:
-            ws, ws_bytes = _lib.roi_align_workspace(rois.size(0), pooled_h, pooled_w, height, g.device, nhwc)
+            ws, ws_bytes = _lib.roi_align_workspace(rois.size(0), pooled_h, pooled_w, height, g.device, nhwc,
+                                                    nchw_staging=(batch_size, channels, height * width, _lib.dtype_code(g)))
         _lib.check(_lib.lib().abr_roi_align_backward(
             g.data_ptr(), rois.data_ptr(), gin.data_ptr(), batch_size, channels, height, width, rois.size(0),
             pooled_h, pooled_w, float(spatial_scale), int(sampling_ratio), _lib.dtype_code(g),

@@ -78,7 +78,9 @@ class _MultiLevelROIAlign(Function):
         if out.numel():
             ptrs, hs, ws, sc = _level_arrays(feats, scales)
             with torch.cuda.device(out.device):
-                wk, wk_bytes = _lib.roi_align_workspace(R, PH, PW, max(f.shape[2] for f in feats), out.device, nhwc)
+                wk, wk_bytes = _lib.roi_align_workspace(
+                    R, PH, PW, max(f.shape[2] for f in feats), out.device, nhwc,
+                    nchw_staging=(B, C, sum(f.shape[2] * f.shape[3] for f in feats), _lib.dtype_code(out)))
                 _lib.check(_lib.lib().abr_roi_align_multilevel_forward(
                     ptrs, hs, ws, sc, len(feats), rois.data_ptr(), levels.data_ptr(), out.data_ptr(), B, C, R, PH, PW,
                     int(sampling_ratio), _lib.dtype_code(out), _lib.ABR_NHWC if nhwc else _lib.ABR_NCHW,
@@ -101,7 +103,9 @@ class _MultiLevelROIAlign(Function):
             if has_plan:
                 wk, wk_bytes = ctx.plan, ctx.plan.numel()
             else:
-                wk, wk_bytes = _lib.roi_align_workspace(rois.size(0), PH, PW, max(s[2] for s in shapes), g.device, nhwc)
+                wk, wk_bytes = _lib.roi_align_workspace(
+                    rois.size(0), PH, PW, max(s[2] for s in shapes), g.device, nhwc,
+                    nchw_staging=(B, C, sum(s[2] * s[3] for s in shapes), _lib.dtype_code(g)))
             _lib.check(_lib.lib().abr_roi_align_multilevel_backward(
                 g.data_ptr(), rois.data_ptr(), levels.data_ptr(), ptrs, hs, ws, sc, len(grads), B, C, rois.size(0),
                 PH, PW, int(sampling_ratio), _lib.dtype_code(g), _lib.ABR_NHWC if nhwc else _lib.ABR_NCHW, 1,

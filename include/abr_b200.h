@@ -64,6 +64,10 @@ ABR_API uint64_t abr_launch_count(void);
  * The forward leaves the plans of its RoIs in the workspace; a backward for the SAME rois / levels / geometry may be
  * handed that workspace with workspace_has_plan != 0 and then skips planning (0: contents are treated as scratch). */
 ABR_API size_t abr_roi_align_workspace_bytes(int R, int PH, int PW, int max_h);
+/* Workspace that additionally lets an ABR_NCHW call run through the channels-last kernels (256-byte aligned): plans + a
+ * channels-last copy of every level's map (sum_hw = sum over levels of H*W) + one of the pooled tensor.  With less, an
+ * NCHW call uses the direct NCHW kernels. */
+ABR_API size_t abr_roi_align_workspace_bytes_nchw(int R, int PH, int PW, int max_h, int B, int C, long long sum_hw, int dtype);
 ABR_API int abr_roi_align_forward(const void* input, const float* rois, void* output,
                           int B, int C, int H, int W, int R, int PH, int PW,
                           float spatial_scale, int sampling_ratio,

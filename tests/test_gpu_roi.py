@@ -213,15 +213,19 @@ def test_roi_align_nhwc_every_plan_mode(monkeypatch, use_workspace, P, ratio):
     close(xt.grad.cpu().numpy(), oracle.roi_align_backward(gout, rois, 1 / s, P, P, B, C, H, W, ratio))
 
 
-@pytest.mark.parametrize("channels_last", [False, True])
+@pytest.mark.parametrize("route", ["nchw_staged", "nchw_direct", "nhwc"])
 @pytest.mark.parametrize("C,ratio", [(8, 2), (136, 0)])
-def test_pooler_multilevel_vector_paths_vs_oracle(channels_last, C, ratio):
+def test_pooler_multilevel_vector_paths_vs_oracle(monkeypatch, route, C, ratio):
     """Four FPN levels with C % 4 == 0, so channels-last inputs take the 16-byte-lane kernels (one tensor map per level in
     the TMA-staged forward, the level table in the backward); C=136 has a ragged last 128-channel slice."""
     from abr_iod_b200.modeling.poolers import Pooler
     from abr_iod_b200.structures.bounding_box import BoxList
     from oracle import pooler as opooler
 
+    from abr_iod_b200 import _lib
+
+    channels_last = route == "nhwc"
+    monkeypatch.setattr(_lib, "NCHW_STAGING", route != "nchw_direct")
     rng = np.random.default_rng(C + ratio)
     B, im_w, im_h = 2, 640, 512
     scales = (0.25, 0.125, 0.0625, 0.03125)
@@ -249,3 +253,47 @@ def test_pooler_multilevel_vector_paths_vs_oracle(channels_last, C, ratio):
         f = feats_np[lvl]
         gref = oracle.roi_align_backward(gout[idx], rois[idx], scales[lvl], 7, 7, *f.shape, ratio)
         close(feats[lvl].grad.cpu().numpy(), gref)
+
+
+@pytest.mark.parametrize("C,P,ratio", [(8, 7, 0), (260, 7, 2), (30, 14, 0)])
+def test_roi_align_nchw_direct_kernels(monkeypatch, C, P, ratio):
+    """Contiguous-NCHW callers normally run through the channels-last kernels (staging copies in the workspace); without
+    the staging room the C ABI falls back to its direct NCHW kernels.  Both must match the oracle."""
+    from abr_iod_b200 import _lib
+    from abr_iod_b200.layers import roi_align
+
+    rng = np.random.default_rng(C + P)
+    B, H, W = 2, 25, 38
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    rois = make_rois(rng, 40, B, W * 16, H * 16)
+    gout = rng.standard_normal((40, C, P, P)).astype(np.float32)
+    ref = oracle.roi_align_forward(x, rois, 1 / 16, P, P, ratio)
+    gref = oracle.roi_align_backward(gout, rois, 1 / 16, P, P, B, C, H, W, ratio)
+    for staging in (False, True):
+        monkeypatch.setattr(_lib, "NCHW_STAGING", staging)
+        xt = dev(x).requires_grad_(True)
+        out = roi_align(xt, dev(rois), (P, P), 1 / 16, ratio)
+        assert out.is_contiguous()
+        close(out.detach().cpu().numpy(), ref)
+        out.backward(dev(gout))
+        close(xt.grad.cpu().numpy(), gref)
+
+
+def test_roi_align_nchw_staged_accumulates_when_not_zero_init():
+    """zero_init=0 through the C ABI adds into the caller's gradient map in both NCHW routes."""
+    from abr_iod_b200 import _lib
+
+    rng = np.random.default_rng(77)
+    B, C, H, W, P, R = 2, 16, 20, 31, 7, 30
+    rois = make_rois(rng, R, B, W * 16, H * 16)
+    gout = rng.standard_normal((R, C, P, P)).astype(np.float32)
+    base = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    gref = base + oracle.roi_align_backward(gout, rois, 1 / 16, P, P, B, C, H, W, 0)
+    g, r = dev(gout), dev(rois)
+    for staged in (True, False):
+        gin = dev(base.copy())
+        ws, n = (_lib.roi_align_workspace(R, P, P, H, g.device, False, nchw_staging=(B, C, H * W, 0)) if staged else (None, 0))
+        _lib.check(_lib.lib().abr_roi_align_backward(
+            g.data_ptr(), r.data_ptr(), gin.data_ptr(), B, C, H, W, R, P, P, 1 / 16, 0, 0, _lib.ABR_NCHW, 0,
+            ws.data_ptr() if ws is not None else None, n, 0, _lib.stream_ptr(g.device)))
+        close(gin.cpu().numpy(), gref)
