@@ -399,6 +399,158 @@ static int launch_nhwc_cluster(const ArdParams& p, const void* fo, const void* f
   return ABR_OK;
 }
 
+// ------------------------------------------------------------------------------------------ NCHW cluster kernel
+// [N][C][HW]: a RoI is the same contiguous C*HW*4 bytes as in NHWC, so the CTAs of a cluster take contiguous channel
+// ranges with 1-D bulk copies.  Thread (g, p) of the first G*HW threads owns position p and walks the channels
+// g, g+G, ... of the tile (consecutive threads -> consecutive shared-memory words and consecutive global words in the
+// gradient pass).  Per-position sums are partial per CTA: every CTA stores its three partial rows into every peer's
+// table and each CTA adds them up in rank order (deterministic).
+template <bool GRAD>
+__global__ void __launch_bounds__(kArdClusterThreads, 1) ard_nchw_cluster_kernel(ArdParams p, const float* __restrict__ f_old,
+                                                                              const float* __restrict__ f_new,
+                                                                              float* __restrict__ grad, int ch_per_cta, int G) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int HW = p.HW, C = p.C;
+  const unsigned rank = cluster_ctarank(), csize = cluster_nctarank();
+  float* t_old = reinterpret_cast<float*>(smem_raw);                 // [ch_per_cta][HW]
+  float* t_new = t_old + (size_t)ch_per_cta * HW;
+  float* ex = t_new + (size_t)ch_per_cta * HW;                       // [2 parities][3][csize][HW]
+  float* part = ex + (size_t)6 * csize * HW;                         // [3][G][HW]
+  float* tot = part + (size_t)3 * G * HW;                            // [3][HW]
+  float* a_old = tot + 3 * HW;
+  float* kk = a_old + HW;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(
+      (reinterpret_cast<uintptr_t>(kk + HW) + 7) & ~(uintptr_t)7);
+  const int cluster_id = blockIdx.x / csize, nclusters = gridDim.x / csize;
+  const int tid = threadIdx.x;
+  const int c0 = rank * ch_per_cta;
+  const int nch = max(0, min(ch_per_cta, C - c0));
+  const int chunk_ch = max(1, ceil_div(ch_per_cta, kArdChunks));
+  const int nchunks = ceil_div(nch, chunk_ch);
+  const bool active = tid < G * HW;
+  const int g = tid / HW, pos = tid - g * HW;
+  if (tid == 0) {
+    for (int i = 0; i < kArdChunks; i++) mbar_init(&bars[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  cluster_sync_all();
+
+  int iter = 0;
+  for (int n = cluster_id; n < p.N; n += nclusters, iter++) {
+    const unsigned parity = iter & 1;
+    const size_t base = ((size_t)n * C + c0) * HW;
+    if (tid == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      for (int ch = 0; ch < nchunks; ch++) {
+        const int r0 = ch * chunk_ch, rn = min(chunk_ch, nch - r0);
+        const unsigned bytes = (unsigned)rn * HW * sizeof(float);
+        mbar_expect_tx(&bars[ch], 2 * bytes);
+        tma_load_1d(t_old + (size_t)r0 * HW, f_old + base + (size_t)r0 * HW, bytes, &bars[ch]);
+        tma_load_1d(t_new + (size_t)r0 * HW, f_new + base + (size_t)r0 * HW, bytes, &bars[ch]);
+      }
+    }
+    float so = 0.f, sn = 0.f, sd = 0.f;
+    for (int ch = 0; ch < nchunks; ch++) {
+      mbar_wait(&bars[ch], parity);
+      if (active) {
+        const int cend = min((ch + 1) * chunk_ch, nch);
+        // this thread's channels of the chunk: c == g (mod G)
+        int c = ch * chunk_ch;
+        c += (g - c % G + G) % G;
+#pragma unroll 4
+        for (; c < cend; c += G) {
+          const float a = t_old[c * HW + pos], b = t_new[c * HW + pos];
+          so = fmaf(a, a, so);
+          sn = fmaf(b, b, sn);
+          const float d = b - a;
+          sd = fmaf(d, d, sd);
+        }
+      }
+    }
+    if (active) {
+      part[(0 * G + g) * HW + pos] = so;
+      part[(1 * G + g) * HW + pos] = sn;
+      part[(2 * G + g) * HW + pos] = sd;
+    }
+    __syncthreads();
+    float* ex_par = ex + (size_t)parity * 3 * csize * HW;
+    for (int t = tid; t < 3 * HW; t += kArdClusterThreads) {
+      const int q = t / HW, pp = t - q * HW;
+      float v = 0.f;
+      for (int gg = 0; gg < G; gg++) v += part[(q * G + gg) * HW + pp];
+      for (unsigned r = 0; r < csize; r++) dsmem_store(ex_par + ((size_t)q * csize + rank) * HW + pp, r, v);
+    }
+    cluster_sync_all();  // every CTA's partial rows are in every CTA's table
+    for (int t = tid; t < 3 * HW; t += kArdClusterThreads) {
+      const int q = t / HW, pp = t - q * HW;
+      float v = 0.f;
+      for (unsigned r = 0; r < csize; r++) v += ex_par[((size_t)q * csize + r) * HW + pp];
+      tot[t] = v;
+    }
+    __syncthreads();
+    if (tid < 32) ard_position_phase(p, tot, tot + HW, tot + 2 * HW, a_old, kk, n, rank == 0);
+    __syncthreads();
+    if (GRAD && active) {
+      float* gp = grad + base;
+      const float ka = a_old[pos], kb = kk[pos];
+#pragma unroll 4
+      for (int c = g; c < nch; c += G) {
+        const float a = t_old[c * HW + pos], b = t_new[c * HW + pos];
+        gp[c * HW + pos] = fmaf(ka, b - a, kb * b);
+      }
+    }
+    __syncthreads();  // tiles, part, tot, a_old / kk are free for the next RoI
+  }
+  cluster_sync_all();
+  ard_finish(p);
+}
+
+// cluster size, channels per CTA and thread groups for the NCHW shared-memory resident kernel; 0 = does not fit
+static int ard_nchw_cluster_size(int C, int HW, size_t& smem_bytes, int& ch_per_cta, int& G) {
+  if (HW > kArdClusterThreads || ((size_t)C * HW) % 4 != 0) return 0;
+  G = kArdClusterThreads / HW;
+  for (int cs = 1; cs <= 8; cs *= 2) {
+    if (cs > C) break;
+    ch_per_cta = ceil_div(C, cs);
+    if (((size_t)ch_per_cta * HW) % 4 != 0) continue;  // 16-byte bulk copies
+    // every chunk of channels must be a 16-byte multiple as well
+    const int chunk_ch = ceil_div(ch_per_cta, kArdChunks) > 0 ? ceil_div(ch_per_cta, kArdChunks) : 1;
+    if (((size_t)chunk_ch * HW) % 4 != 0) continue;
+    const int g = G < ch_per_cta ? G : ch_per_cta;
+    smem_bytes = ((size_t)2 * ch_per_cta * HW + (size_t)6 * cs * HW + (size_t)3 * g * HW + 5 * HW) * sizeof(float) + 8 +
+                 kArdChunks * 8 + 128;
+    if (smem_bytes <= 227 * 1024) {
+      G = g;
+      return cs;
+    }
+  }
+  return 0;
+}
+
+static int launch_nchw_cluster(const ArdParams& p, const void* fo, const void* fn, void* g, cudaStream_t st, int cs,
+                               size_t smem, int ch_per_cta, int G) {
+  auto kern = g ? ard_nchw_cluster_kernel<true> : ard_nchw_cluster_kernel<false>;
+  ABR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int clusters = num_sms() / cs;
+  if (clusters > p.N) clusters = p.N;
+  if (clusters < 1) clusters = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * cs);
+  cfg.blockDim = dim3(kArdClusterThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ABR_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p, static_cast<const float*>(fo), static_cast<const float*>(fn), static_cast<float*>(g), ch_per_cta, G));
+  ABR_CHECK_LAUNCH("ard_forward_backward (nchw cluster)");
+  return ABR_OK;
+}
+
 template <typename T>
 __global__ void scale_if_needed_kernel(T* data, size_t n, const float* __restrict__ scale, float expected) {
   const float s = *scale;
@@ -479,7 +631,15 @@ int abr_ard_forward_backward(const void* f_old, const void* f_new, void* grad_ne
     if (dtype == ABR_F32) return launch_nhwc<float, 1>(p, f_old, f_new, grad_new, st);
     return (C % 8 == 0) ? launch_nhwc<__nv_bfloat16, 8>(p, f_old, f_new, grad_new, st) : launch_nhwc<__nv_bfloat16, 1>(p, f_old, f_new, grad_new, st);
   }
-  if (dtype == ABR_F32) return launch_nchw<float>(p, f_old, f_new, grad_new, st);
+  if (dtype == ABR_F32) {
+    static const bool use_cluster = getenv("ABR_ARD_CLUSTER") ? atoi(getenv("ABR_ARD_CLUSTER")) != 0 : true;
+    size_t smem = 0;
+    int cpc = 0, G = 0;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(f_old) | reinterpret_cast<uintptr_t>(f_new)) & 15) == 0;
+    const int cs = use_cluster && aligned ? ard_nchw_cluster_size(C, HW, smem, cpc, G) : 0;
+    if (cs > 0) return launch_nchw_cluster(p, f_old, f_new, grad_new, st, cs, smem, cpc, G);
+    return launch_nchw<float>(p, f_old, f_new, grad_new, st);
+  }
   return launch_nchw<__nv_bfloat16>(p, f_old, f_new, grad_new, st);
 }
 

@@ -37,7 +37,8 @@ def test_ard_golden_vs_reference_python(golden, channels_last):
 
 
 @pytest.mark.parametrize("channels_last", [False, True])
-@pytest.mark.parametrize("N,C,P", [(5, 1024, 7), (3, 256, 14), (2, 37, 7), (1, 8, 1), (2, 16, 28), (4, 130, 5)])
+@pytest.mark.parametrize("N,C,P", [(5, 1024, 7), (3, 256, 14), (2, 37, 7), (1, 8, 1), (2, 16, 28), (4, 130, 5),
+                                   (3, 64, 7), (3, 2048, 7), (2, 900, 14)])
 def test_ard_vs_oracle_shapes(channels_last, N, C, P):
     rng = np.random.default_rng(N * 1000 + C + P)
     fo = rng.standard_normal((N, C, P, P)).astype(np.float32)
