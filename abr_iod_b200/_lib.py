@@ -52,6 +52,9 @@ SIGNATURES = {
     "abr_roi_pool_backward": (_int, [_vp, _vp, _vp, _vp] + [_int] * 7 + [_int, _int, _int, _vp]),
     "abr_nms_workspace_bytes": (_sz, [_vp, _int]),
     "abr_nms_batched": (_int, [_vp, _vp, _vp, _int, _f, _int, _int, _vp, _int, _vp, _vp, _sz, _vp]),
+    "abr_rpn_proposals_workspace_bytes": (_sz, [_int] * 6),
+    "abr_rpn_proposals": (_int, [_vp, _vp, _vp, ctypes.c_longlong, _vp] + [_int] * 7 + [_f, _int, _f, _vp, _f,
+                                 _vp, _vp, _vp, _vp, _int, _vp, _sz, _vp]),
     "abr_ard_workspace_bytes": (_sz, [_int, _int, _int]),
     "abr_ard_forward_backward": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _f, _f, _int, _int, _vp, _sz, _vp]),
     "abr_scale_if_needed": (_int, [_vp, _sz, _vp, _f, _int, _vp]),

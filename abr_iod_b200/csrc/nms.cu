@@ -30,7 +30,13 @@ struct NmsBatch {
   int n[kImagesPerLaunch];              // boxes of the image this pass looks at (a prefix in the prefix pass)
   int n_full[kImagesPerLaunch];         // boxes in the image
   long long mask_off[kImagesPerLaunch]; // first mask word of the image (u64 units)
+  const int* counts;                    // optional, device: boxes actually present per image (<= the host-side size)
 };
+
+// boxes of image `img` a kernel looks at: the host-side figure, cut to the device-side count when there is one
+__device__ __forceinline__ int live_boxes(const NmsBatch& nb, int img, int host_n) {
+  return nb.counts ? min(host_n, __ldg(nb.counts + nb.first_image + img)) : host_n;
+}
 
 // Ordered key: larger key = earlier in torch.sort(descending=True, stable=True).  NaN sorts first (torch treats NaN as
 // the largest value), -0.0 ties with +0.0, equal scores keep ascending index.
@@ -51,7 +57,7 @@ __device__ __forceinline__ unsigned long long sort_key(float s, int idx) {
 __global__ void presort_kernel(NmsBatch nb, const float* __restrict__ boxes, const float* __restrict__ scores,
                                float4* __restrict__ sorted_boxes, int* __restrict__ order, int* __restrict__ unsorted) {
   const int img = blockIdx.y;
-  const int n = nb.n_full[img], off = nb.box_off[img];
+  const int n = live_boxes(nb, img, nb.n_full[img]), off = nb.box_off[img];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   order[off + i] = i;
@@ -67,7 +73,7 @@ __global__ void __launch_bounds__(kRankThreads) rank_sort_kernel(NmsBatch nb, co
                                                                 float4* __restrict__ sorted_boxes,
                                                                 int* __restrict__ order, int* __restrict__ unsorted) {
   const int img = blockIdx.y;
-  const int n = nb.n_full[img], off = nb.box_off[img];
+  const int n = live_boxes(nb, img, nb.n_full[img]), off = nb.box_off[img];
   const int base = blockIdx.x * kRankThreads;
   if (base >= n || unsorted[nb.first_image + img] == 0) return;  // presort_kernel found the image already sorted
   __shared__ unsigned long long tile[512];
@@ -124,7 +130,7 @@ __global__ void __launch_bounds__(kTile * kMaskTilesPerCta) iou_mask_kernel(NmsB
                                                                           float thresh, int ge, const int* __restrict__ done) {
   const int img = blockIdx.y;
   if (done && done[nb.first_image + img]) return;  // full pass: settled by the prefix pass; prefix pass: image not sorted
-  const int n = nb.n[img];
+  const int n = live_boxes(nb, img, nb.n[img]);
   const int cb = ceil_div(n, kTile);
   const long long ntiles = (long long)cb * (cb + 1) / 2;
   const int grp = threadIdx.x / kTile, lane64 = threadIdx.x % kTile;
@@ -176,7 +182,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(NmsBatch nb, const
   const int img = blockIdx.x;
   if (!prefix_pass && done && done[nb.first_image + img]) return;  // settled by the prefix pass
   if (prefix_pass && unsorted[nb.first_image + img]) return;       // a prefix only answers for sorted images (done stays 0)
-  const int n = nb.n[img];
+  const int n = live_boxes(nb, img, nb.n[img]);
   const int cb = ceil_div(n, kTile);
   unsigned long long* removed = sm;
   unsigned long long* kept_sorted = removed + cb;
@@ -259,7 +265,8 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(NmsBatch nb, const
   if (prefix_pass) {
     // Only a prefix of a SORTED image was examined: the answer is final iff it already holds max_keep boxes (later
     // boxes could only add indices beyond the cut); otherwise the full pass redoes the image.
-    const bool final_answer = may_stop && kept_total >= max_keep;
+    // (or when the prefix happened to cover the whole image)
+    const bool final_answer = (may_stop && kept_total >= max_keep) || n >= live_boxes(nb, img, nb.n_full[img]);
     if (tid == 0) done[nb.first_image + img] = final_answer ? 1 : 0;
     if (!final_answer) return;
   }
@@ -345,6 +352,12 @@ static NmsLayout nms_layout(const int* offsets, int n_images) {
   return l;
 }
 
+// abr_nms_batched with an optional device-side box count per image (used by the RPN proposal path, where the number of
+// boxes that survive the small-box filter is only known on the device): offsets_host then describes capacities.
+int nms_run(const float* boxes, const float* scores, const int* offsets_host, const int* counts_dev, int n_images,
+            float thresh, int ge, int max_keep, int64_t* keep, int keep_stride, int32_t* n_keep, void* workspace,
+            size_t workspace_bytes, cudaStream_t st);
+
 }  // namespace abr
 
 using namespace abr;
@@ -359,6 +372,17 @@ size_t abr_nms_workspace_bytes(const int* offsets_host, int n_images) {
 int abr_nms_batched(const float* boxes, const float* scores, const int* offsets_host, int n_images, float thresh, int ge,
                     int max_keep, int64_t* keep, int keep_stride, int32_t* n_keep, void* workspace,
                     size_t workspace_bytes, abr_stream_t stream) {
+  return nms_run(boxes, scores, offsets_host, nullptr, n_images, thresh, ge, max_keep, keep, keep_stride, n_keep, workspace,
+                 workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"
+
+namespace abr {
+
+int nms_run(const float* boxes, const float* scores, const int* offsets_host, const int* counts_dev, int n_images,
+            float thresh, int ge, int max_keep, int64_t* keep, int keep_stride, int32_t* n_keep, void* workspace,
+            size_t workspace_bytes, cudaStream_t st) {
   ABR_REQUIRE(n_images >= 0, ABR_ERR_BAD_ARG, "nms: n_images=%d", n_images);
   if (n_images == 0) return ABR_OK;
   ABR_REQUIRE(offsets_host && keep && n_keep && keep_stride >= 0, ABR_ERR_BAD_ARG, "nms: null pointer or negative stride");
@@ -370,7 +394,6 @@ int abr_nms_batched(const float* boxes, const float* scores, const int* offsets_
     ABR_REQUIRE(keep_stride >= need, ABR_ERR_BAD_ARG, "nms: keep_stride %d < %d needed by image %d", keep_stride, need, i);
   }
   const int total = offsets_host[n_images];
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (total > 0) ABR_REQUIRE(boxes && scores, ABR_ERR_BAD_ARG, "nms: null boxes/scores");
   if (total > 0 && (reinterpret_cast<uintptr_t>(boxes) & 15))
     ABR_REQUIRE(false, ABR_ERR_BAD_ARG, "nms: boxes must be 16-byte aligned");
@@ -391,6 +414,7 @@ int abr_nms_batched(const float* boxes, const float* scores, const int* offsets_
     NmsBatch nb;
     nb.n_images = 0;
     nb.first_image = base;
+    nb.counts = counts_dev;
     int nmax = 0;
     const int lim = n_images - base < kImagesPerLaunch ? n_images - base : kImagesPerLaunch;
     for (int i = 0; i < lim; i++) {
@@ -449,4 +473,4 @@ int abr_nms_batched(const float* boxes, const float* scores, const int* offsets_
   return ABR_OK;
 }
 
-}  // extern "C"
+}  // namespace abr

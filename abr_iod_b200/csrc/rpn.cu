@@ -1,0 +1,460 @@
+// rpn.cu -- RPN proposal selection around NMS for a whole batch, entirely on the device (sm_100a).
+//
+// Semantics: RPNPostProcessor.forward_for_single_feature_map (modeling/rpn/inference.py:76-118 of the reference):
+// sigmoid -> top pre_nms_top_n per image -> gather regression + anchors -> BoxCoder.decode (modeling/box_coder.py:52-95)
+// -> clip_to_image (structures/bounding_box.py:214-219) -> remove_small_boxes (structures/boxlist_ops.py:34-48) ->
+// boxlist_nms with max_proposals = post_nms_top_n (structures/boxlist_ops.py:9-31).
+// Design (not a port).  The reference permutes and copies both head outputs, runs a library top-k, three fancy-index
+// gathers, ~25 elementwise kernels and then loops over the images in Python with a `nonzero` and an NMS round trip per
+// image.  Here the head outputs are read in place (NCHW or channels-last) and the batch is:
+//   1. rpn_hist_kernel x5   -- MSB-first radix SELECT of the pre_nms_top_n-th key on 54-bit keys
+//                              (order-preserving logit bits : 22 bits of reversed anchor index), 11 bits per pass, many
+//                              CTAs per image; a pass whose bin holds exactly the remaining count ends the search, so the
+//                              index digits only run when equal logits straddle the cut.  Ranking by logit instead of
+//                              by sigmoid(logit) is the same order (monotonic) without a transcendental in the key;
+//   2. rpn_collect_kernel   -- the selected keys, unordered, into a per-image candidate list;
+//   3. rpn_sort_decode_kernel -- one CTA per image: bitonic sort of the <= 16384 candidates in shared memory, then
+//                              decode + clip + small-box filter + ORDERED compaction (block scan) of boxes / scores;
+//   4. nms_run              -- the batched NMS of nms.cu with device-side box counts (the inputs are already sorted, so
+//                              it takes its O(N) presort path and the prefix pass);
+//   5. rpn_gather_kernel    -- kept boxes / scores / anchor indices into the padded outputs + per-image counts.
+// No host synchronisation, no allocation; the caller reads n_out once for the batch.
+#include <cfloat>
+#include <vector>
+
+#include "common.cuh"
+
+namespace abr {
+
+int nms_run(const float* boxes, const float* scores, const int* offsets_host, const int* counts_dev, int n_images,
+            float thresh, int ge, int max_keep, int64_t* keep, int keep_stride, int32_t* n_keep, void* workspace,
+            size_t workspace_bytes, cudaStream_t st);
+
+constexpr int kRpnBins = 2048;        // 11-bit digits
+constexpr int kRpnPasses = 5;         // 11 + 11 + 10 bits of logit, 11 + 11 bits of index
+constexpr int kRpnIdxBits = 22;       // anchors per image < 2^22
+constexpr int kRpnMaxCand = 16384;    // candidates one CTA sorts in shared memory
+constexpr int kRpnChunk = 2048;       // elements per CTA in the histogram / collect kernels
+constexpr int kRpnMaxImages = 64;     // images per launch group (image sizes travel as kernel arguments)
+
+__device__ __forceinline__ int rpn_shift(int pass) {
+  // digit positions inside the 54-bit key: [53:43] [42:32] [31:22] [21:11] [10:0]
+  return pass == 0 ? 43 : pass == 1 ? 32 : pass == 2 ? 22 : pass == 3 ? 11 : 0;
+}
+__device__ __forceinline__ unsigned rpn_digit_mask(int pass) { return pass == 2 ? 1023u : 2047u; }
+
+__device__ __forceinline__ unsigned ordered_bits(float s) {
+  unsigned u = __float_as_uint(s);
+  if (s != s) return 0xFFFFFFFFu;  // NaN ranks first, like torch.topk
+  if (u == 0x80000000u) u = 0u;    // -0.0 ties with +0.0
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float from_ordered_bits(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u);
+}
+__device__ __forceinline__ unsigned long long rpn_key(float logit, int anchor) {
+  return ((unsigned long long)ordered_bits(logit) << kRpnIdxBits) | (unsigned long long)(((1u << kRpnIdxBits) - 1u) - (unsigned)anchor);
+}
+
+struct RpnShape {
+  int N, A, H, W, layout, k;  // k = min(pre_nms_top_n, A*H*W)
+};
+
+// storage index of an objectness element -> anchor index in the reference's flattened (h, w, a) order
+__device__ __forceinline__ int anchor_of_storage(const RpnShape& s, int e) {
+  if (s.layout == ABR_NHWC) return e;
+  const int hw = s.H * s.W;
+  const int a = e / hw;
+  return (e - a * hw) * s.A + a;
+}
+
+struct SelectState {
+  unsigned long long prefix, mask;
+  int remaining;
+  int done;  // a bin held exactly the remaining count: everything matching the prefix is taken
+};
+
+// Replays passes [0, upto) from their finished histograms.  Block-wide; every CTA of an image derives the same state.
+__device__ void derive_state(const unsigned* __restrict__ hist_img, int upto, int k, SelectState& out_state) {
+  __shared__ SelectState st;
+  __shared__ int warp_tot[32];
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+  if (tid == 0) { st.prefix = 0; st.mask = 0; st.remaining = k; st.done = 0; }
+  __syncthreads();
+  const int per = kRpnBins / nthr;  // bins per thread, walked from the top bin down
+  for (int q = 0; q < upto; q++) {
+    if (st.done) break;
+    const unsigned* h = hist_img + q * kRpnBins;
+    const int top = kRpnBins - 1 - tid * per;  // this thread owns bins top, top-1, ..., top-per+1
+    int mine = 0;
+    for (int b = 0; b < per; b++) mine += (int)h[top - b];
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int before = 0;
+    for (int w2 = 0; w2 < warp; w2++) before += warp_tot[w2];
+    (void)nwarp;
+    incl += before;
+    const int excl = incl - mine;
+    const int remaining = st.remaining;
+    __syncthreads();  // everyone has read st.remaining and warp_tot
+    if (excl < remaining && remaining <= incl) {  // the crossing bin is one of mine (exactly one thread gets here)
+      int above = excl;
+      for (int b = 0; b < per; b++) {
+        const int c = (int)h[top - b];
+        if (above + c >= remaining) {
+          const int sh = rpn_shift(q);
+          st.prefix |= (unsigned long long)(top - b) << sh;
+          st.mask |= (unsigned long long)rpn_digit_mask(q) << sh;
+          st.remaining = remaining - above;
+          st.done = (c == remaining - above);
+          break;
+        }
+        above += c;
+      }
+    }
+    __syncthreads();
+  }
+  out_state = st;
+  __syncthreads();
+}
+
+// One radix-select pass: histogram of digit `pass` over the elements that match the prefix found so far.
+__global__ void __launch_bounds__(256) rpn_hist_kernel(RpnShape s, const float* __restrict__ objectness,
+                                                       unsigned* __restrict__ hist, int pass) {
+  __shared__ unsigned sh[kRpnBins];
+  const int img = blockIdx.y;
+  const int M = s.A * s.H * s.W;
+  unsigned* hist_img = hist + (size_t)img * kRpnPasses * kRpnBins;
+  SelectState st;
+  derive_state(hist_img, pass, s.k, st);
+  if (st.done) return;
+  for (int b = threadIdx.x; b < kRpnBins; b += blockDim.x) sh[b] = 0;
+  __syncthreads();
+  const float* obj = objectness + (size_t)img * M;
+  const int shift = rpn_shift(pass);
+  const unsigned dmask = rpn_digit_mask(pass);
+  const int e0 = blockIdx.x * kRpnChunk;
+#pragma unroll
+  for (int u = 0; u < kRpnChunk / 256; u++) {
+    const int e = e0 + u * 256 + threadIdx.x;
+    if (e < M) {
+      const unsigned long long key = rpn_key(__ldg(obj + e), anchor_of_storage(s, e));
+      if ((key & st.mask) == st.prefix) atomicAdd(&sh[(unsigned)(key >> shift) & dmask], 1u);
+    }
+  }
+  __syncthreads();
+  unsigned* g = hist_img + pass * kRpnBins;
+  for (int b = threadIdx.x; b < kRpnBins; b += blockDim.x)
+    if (sh[b]) atomicAdd(&g[b], sh[b]);
+}
+
+// The selected keys (exactly k per image) into cand[img][0..k), unordered.
+__global__ void __launch_bounds__(256) rpn_collect_kernel(RpnShape s, const float* __restrict__ objectness,
+                                                          const unsigned* __restrict__ hist,
+                                                          unsigned long long* __restrict__ cand, int* __restrict__ cand_count) {
+  __shared__ unsigned long long list[kRpnChunk];
+  __shared__ int n_local, base;
+  const int img = blockIdx.y;
+  const int M = s.A * s.H * s.W;
+  SelectState st;
+  derive_state(hist + (size_t)img * kRpnPasses * kRpnBins, kRpnPasses, s.k, st);
+  if (threadIdx.x == 0) n_local = 0;
+  __syncthreads();
+  const float* obj = objectness + (size_t)img * M;
+  const int e0 = blockIdx.x * kRpnChunk;
+#pragma unroll
+  for (int u = 0; u < kRpnChunk / 256; u++) {
+    const int e = e0 + u * 256 + threadIdx.x;
+    if (e < M) {
+      const unsigned long long key = rpn_key(__ldg(obj + e), anchor_of_storage(s, e));
+      if ((key & st.mask) >= st.prefix) list[atomicAdd(&n_local, 1)] = key;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) base = n_local ? atomicAdd(&cand_count[img], n_local) : 0;
+  __syncthreads();
+  unsigned long long* out = cand + (size_t)img * s.k;
+  for (int i = threadIdx.x; i < n_local; i += blockDim.x)
+    if (base + i < s.k) out[base + i] = list[i];
+}
+
+struct RpnDecode {
+  float wx, wy, ww, wh, clip, min_size;
+  long long anchor_image_stride;  // floats between the anchor sets of consecutive images (0 = shared)
+  int im_w[kRpnMaxImages], im_h[kRpnMaxImages];
+};
+
+constexpr int kSortThreads = 1024;
+
+// One CTA per image: sort the candidates, decode, filter, compact in rank order.
+__global__ void __launch_bounds__(kSortThreads) rpn_sort_decode_kernel(RpnShape s, RpnDecode d, int first_image,
+                                                                      const unsigned long long* __restrict__ cand,
+                                                                      const float* __restrict__ box_regression,
+                                                                      const float* __restrict__ anchors,
+                                                                      float4* __restrict__ boxes_c, float* __restrict__ scores_c,
+                                                                      int* __restrict__ anchor_c, int* __restrict__ counts,
+                                                                      int sort_size) {
+  extern __shared__ unsigned long long keys[];  // [sort_size]
+  __shared__ int warp_tot[kSortThreads / 32];
+  __shared__ int running;
+  const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int k = s.k;
+  const unsigned long long* in = cand + (size_t)img * k;
+  for (int i = tid; i < sort_size; i += kSortThreads) keys[i] = i < k ? in[i] : 0ull;  // real keys are > 0
+  __syncthreads();
+  // bitonic sort, descending
+  for (int size = 2; size <= sort_size; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < sort_size / 2; t += kSortThreads) {
+        const int i = 2 * t - (t & (stride - 1));
+        const int j = i + stride;
+        const unsigned long long a = keys[i], b = keys[j];
+        const bool desc = (i & size) == 0;
+        if ((a < b) == desc) { keys[i] = b; keys[j] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  // decode in rank order, chunk by chunk, with an ordered compaction of the boxes that pass the size filter
+  if (tid == 0) running = 0;
+  __syncthreads();
+  const int hw = s.H * s.W;
+  const int M = s.A * hw;
+  const float* reg = box_regression + (size_t)img * 4 * M;
+  const float* anc = anchors + (size_t)(first_image + img) * d.anchor_image_stride;
+  const float xmax = (float)(d.im_w[img] - 1), ymax = (float)(d.im_h[img] - 1);
+  float4* ob = boxes_c + (size_t)img * k;
+  float* os = scores_c + (size_t)img * k;
+  int* oa = anchor_c + (size_t)img * k;
+  for (int j0 = 0; j0 < k; j0 += kSortThreads) {
+    const int j = j0 + tid;
+    bool ok = false;
+    float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+    float score = 0.f;
+    int anchor = 0;
+    if (j < k) {
+      const unsigned long long key = keys[j];
+      anchor = (int)(((1u << kRpnIdxBits) - 1u) - (unsigned)(key & ((1u << kRpnIdxBits) - 1u)));
+      const float logit = from_ordered_bits((unsigned)(key >> kRpnIdxBits));
+      float r0, r1, r2, r3;
+      if (s.layout == ABR_NHWC) {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(reg) + anchor);
+        r0 = r.x; r1 = r.y; r2 = r.z; r3 = r.w;
+      } else {
+        const int p = anchor / s.A, a = anchor - p * s.A;
+        const float* rp = reg + (size_t)(a * 4) * hw + p;
+        r0 = __ldg(rp); r1 = __ldg(rp + hw); r2 = __ldg(rp + 2 * hw); r3 = __ldg(rp + 3 * hw);
+      }
+      const float4 an = __ldg(reinterpret_cast<const float4*>(anc) + anchor);
+      // BoxCoder.decode, one rounding per tensor op (no contraction)
+      const float widths = __fadd_rn(__fsub_rn(an.z, an.x), 1.f);
+      const float heights = __fadd_rn(__fsub_rn(an.w, an.y), 1.f);
+      const float ctr_x = __fadd_rn(an.x, __fmul_rn(0.5f, widths));
+      const float ctr_y = __fadd_rn(an.y, __fmul_rn(0.5f, heights));
+      const float dx = __fdiv_rn(r0, d.wx), dy = __fdiv_rn(r1, d.wy);
+      float dw = __fdiv_rn(r2, d.ww), dh = __fdiv_rn(r3, d.wh);
+      dw = dw > d.clip ? d.clip : dw;  // torch.clamp(max=): NaN stays NaN
+      dh = dh > d.clip ? d.clip : dh;
+      const float pcx = __fadd_rn(__fmul_rn(dx, widths), ctr_x);
+      const float pcy = __fadd_rn(__fmul_rn(dy, heights), ctr_y);
+      const float pw = __fmul_rn(expf(dw), widths);
+      const float ph = __fmul_rn(expf(dh), heights);
+      float x1 = __fsub_rn(pcx, __fmul_rn(0.5f, pw));
+      float y1 = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
+      float x2 = __fsub_rn(__fadd_rn(pcx, __fmul_rn(0.5f, pw)), 1.f);
+      float y2 = __fsub_rn(__fadd_rn(pcy, __fmul_rn(0.5f, ph)), 1.f);
+      // clip_to_image: clamp(min=0, max=size-1)
+      x1 = fminf(fmaxf(x1, 0.f), xmax); y1 = fminf(fmaxf(y1, 0.f), ymax);
+      x2 = fminf(fmaxf(x2, 0.f), xmax); y2 = fminf(fmaxf(y2, 0.f), ymax);
+      box = make_float4(x1, y1, x2, y2);
+      // remove_small_boxes on the xywh sides (+1 convention)
+      const float bw = __fadd_rn(__fsub_rn(x2, x1), 1.f), bh = __fadd_rn(__fsub_rn(y2, y1), 1.f);
+      ok = bw >= d.min_size && bh >= d.min_size;
+      score = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-logit)));
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) warp_tot[warp] = __popc(ballot);
+    __syncthreads();
+    int before = running;
+    for (int w2 = 0; w2 < warp; w2++) before += warp_tot[w2];
+    if (ok) {
+      const int pos = before + __popc(ballot & ((1u << lane) - 1u));
+      ob[pos] = box;
+      os[pos] = score;
+      oa[pos] = anchor;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int w2 = 0; w2 < kSortThreads / 32; w2++) t += warp_tot[w2];
+      running += t;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) counts[first_image + img] = running;
+}
+
+// kept candidates -> padded outputs.  keep == nullptr: no NMS ran (nms_thresh <= 0), every candidate is a proposal.
+__global__ void rpn_gather_kernel(int k, int first_image, const float4* __restrict__ boxes_c, const float* __restrict__ scores_c,
+                                  const int* __restrict__ anchor_c, const int* __restrict__ counts,
+                                  const long long* __restrict__ keep, int keep_stride, const int* __restrict__ n_keep,
+                                  float4* __restrict__ proposals, float* __restrict__ scores, int* __restrict__ anchor_index,
+                                  int* __restrict__ n_out, int out_stride) {
+  const int img = blockIdx.x, g = first_image + img;
+  const int n = keep ? n_keep[g] : min(counts[g], out_stride);
+  const float4* b = boxes_c + (size_t)img * k;
+  const float* sc = scores_c + (size_t)img * k;
+  const int* an = anchor_c + (size_t)img * k;
+  for (int j = threadIdx.x; j < out_stride; j += blockDim.x) {
+    float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+    float s = 0.f;
+    int a = -1;
+    if (j < n) {
+      const int src = keep ? (int)keep[(size_t)g * keep_stride + j] : j;
+      box = b[src]; s = sc[src]; a = an[src];
+    }
+    proposals[(size_t)g * out_stride + j] = box;
+    scores[(size_t)g * out_stride + j] = s;
+    if (anchor_index) anchor_index[(size_t)g * out_stride + j] = a;
+  }
+  if (threadIdx.x == 0) n_out[g] = n;
+}
+
+struct RpnLayout {
+  size_t hist, cand_count, counts, n_keep, cand, boxes, scores, anchor, keep, nms, total;
+  size_t nms_bytes;
+  int k, keep_stride;
+};
+
+static size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static RpnLayout rpn_layout(int N, int A, int H, int W, int pre_nms_top_n, int post_nms_top_n) {
+  RpnLayout l;
+  const long long M = (long long)A * H * W;
+  l.k = (int)(pre_nms_top_n < M ? pre_nms_top_n : M);
+  l.keep_stride = post_nms_top_n > 0 && post_nms_top_n < l.k ? post_nms_top_n : l.k;
+  size_t o = 0;
+  l.hist = o; o += a256((size_t)N * kRpnPasses * kRpnBins * sizeof(unsigned));
+  l.cand_count = o; o += a256((size_t)N * sizeof(int));
+  l.counts = o; o += a256((size_t)N * sizeof(int));
+  l.n_keep = o; o += a256((size_t)N * sizeof(int));
+  l.cand = o; o += a256((size_t)N * l.k * 8);
+  l.boxes = o; o += a256((size_t)N * l.k * 16);
+  l.scores = o; o += a256((size_t)N * l.k * 4);
+  l.anchor = o; o += a256((size_t)N * l.k * 4);
+  l.keep = o; o += a256((size_t)N * l.keep_stride * 8);
+  // NMS scratch for N images of capacity k
+  std::vector<int> offsets((size_t)N + 1);
+  for (int i = 0; i <= N; i++) offsets[i] = i * l.k;
+  l.nms_bytes = a256(abr_nms_workspace_bytes(offsets.data(), N));
+  l.nms = o; o += l.nms_bytes;
+  l.total = o;
+  return l;
+}
+
+}  // namespace abr
+
+using namespace abr;
+
+extern "C" {
+
+size_t abr_rpn_proposals_workspace_bytes(int N, int A, int H, int W, int pre_nms_top_n, int post_nms_top_n) {
+  if (N <= 0 || A <= 0 || H <= 0 || W <= 0 || pre_nms_top_n <= 0) return 0;
+  return rpn_layout(N, A, H, W, pre_nms_top_n, post_nms_top_n).total;
+}
+
+int abr_rpn_proposals(const float* objectness, const float* box_regression, const float* anchors,
+                      long long anchor_image_stride, const int* image_sizes_host, int N, int A, int H, int W, int layout,
+                      int pre_nms_top_n, int post_nms_top_n, float nms_thresh, int ge, float min_size,
+                      const float* weights4_host, float bbox_xform_clip, float* proposals, float* scores,
+                      int32_t* anchor_index, int32_t* n_out, int out_stride, void* workspace, size_t workspace_bytes,
+                      abr_stream_t stream) {
+  ABR_REQUIRE(N >= 0, ABR_ERR_BAD_ARG, "rpn: N=%d", N);
+  if (N == 0) return ABR_OK;
+  ABR_REQUIRE(A > 0 && H > 0 && W > 0 && pre_nms_top_n > 0, ABR_ERR_BAD_ARG, "rpn: bad sizes A=%d H=%d W=%d pre_nms_top_n=%d", A, H, W, pre_nms_top_n);
+  ABR_REQUIRE((long long)A * H * W < (1ll << kRpnIdxBits), ABR_ERR_UNSUPPORTED, "rpn: %lld anchors per image (max %d)", (long long)A * H * W, (1 << kRpnIdxBits) - 1);
+  ABR_REQUIRE(layout == ABR_NCHW || layout == ABR_NHWC, ABR_ERR_UNSUPPORTED, "rpn: layout %d not supported", layout);
+  ABR_REQUIRE(objectness && box_regression && anchors && image_sizes_host && weights4_host && proposals && scores && n_out,
+              ABR_ERR_BAD_ARG, "rpn: null pointer");
+  ABR_REQUIRE(((reinterpret_cast<uintptr_t>(anchors) | reinterpret_cast<uintptr_t>(proposals)) & 15) == 0 && anchor_image_stride % 4 == 0,
+              ABR_ERR_BAD_ARG, "rpn: anchors / proposals must be 16-byte aligned");
+  if (layout == ABR_NHWC)
+    ABR_REQUIRE((reinterpret_cast<uintptr_t>(box_regression) & 15) == 0, ABR_ERR_BAD_ARG, "rpn: channels-last box_regression must be 16-byte aligned");
+  const RpnLayout lay = rpn_layout(N, A, H, W, pre_nms_top_n, post_nms_top_n);
+  ABR_REQUIRE(lay.k <= kRpnMaxCand, ABR_ERR_UNSUPPORTED, "rpn: pre_nms_top_n %d > %d", lay.k, kRpnMaxCand);
+  const int need_stride = nms_thresh > 0.f ? lay.keep_stride : lay.k;
+  ABR_REQUIRE(out_stride >= need_stride, ABR_ERR_BAD_ARG, "rpn: out_stride %d < %d", out_stride, need_stride);
+  ABR_REQUIRE(workspace && workspace_bytes >= lay.total && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, ABR_ERR_WORKSPACE,
+              "rpn: workspace %zu B < %zu B (or not 256-byte aligned)", workspace_bytes, lay.total);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* ws = static_cast<char*>(workspace);
+  unsigned* hist = reinterpret_cast<unsigned*>(ws + lay.hist);
+  int* cand_count = reinterpret_cast<int*>(ws + lay.cand_count);
+  int* counts = reinterpret_cast<int*>(ws + lay.counts);
+  int* n_keep = reinterpret_cast<int*>(ws + lay.n_keep);
+  unsigned long long* cand = reinterpret_cast<unsigned long long*>(ws + lay.cand);
+  float4* boxes_c = reinterpret_cast<float4*>(ws + lay.boxes);
+  float* scores_c = reinterpret_cast<float*>(ws + lay.scores);
+  int* anchor_c = reinterpret_cast<int*>(ws + lay.anchor);
+  long long* keep = reinterpret_cast<long long*>(ws + lay.keep);
+  ABR_CUDA_OK(cudaMemsetAsync(ws + lay.hist, 0, lay.counts - lay.hist, st));  // histograms + candidate counters
+
+  const int M = A * H * W;
+  const int k = lay.k;
+  int sort_size = 2;
+  while (sort_size < k) sort_size <<= 1;
+  const size_t sort_smem = (size_t)sort_size * 8;
+  if (sort_smem > 48 * 1024)
+    ABR_CUDA_OK(cudaFuncSetAttribute(rpn_sort_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+  const int chunks = ceil_div(M, kRpnChunk);
+  for (int base = 0; base < N; base += kRpnMaxImages) {
+    const int n = N - base < kRpnMaxImages ? N - base : kRpnMaxImages;
+    RpnShape s;
+    s.N = n; s.A = A; s.H = H; s.W = W; s.layout = layout; s.k = k;
+    RpnDecode d;
+    d.wx = weights4_host[0]; d.wy = weights4_host[1]; d.ww = weights4_host[2]; d.wh = weights4_host[3];
+    d.clip = bbox_xform_clip; d.min_size = min_size; d.anchor_image_stride = anchor_image_stride;
+    for (int i = 0; i < n; i++) {
+      d.im_w[i] = image_sizes_host[2 * (base + i)];
+      d.im_h[i] = image_sizes_host[2 * (base + i) + 1];
+    }
+    const float* obj = objectness + (size_t)base * M;
+    const float* reg = box_regression + (size_t)base * 4 * M;
+    unsigned* h = hist + (size_t)base * kRpnPasses * kRpnBins;
+    for (int pass = 0; pass < kRpnPasses; pass++) {
+      rpn_hist_kernel<<<dim3(chunks, n), 256, 0, st>>>(s, obj, h, pass);
+      ABR_CHECK_LAUNCH("rpn_hist");
+    }
+    rpn_collect_kernel<<<dim3(chunks, n), 256, 0, st>>>(s, obj, h, cand + (size_t)base * k, cand_count + base);
+    ABR_CHECK_LAUNCH("rpn_collect");
+    rpn_sort_decode_kernel<<<n, kSortThreads, sort_smem, st>>>(s, d, base, cand + (size_t)base * k, reg, anchors,
+                                                              boxes_c + (size_t)base * k, scores_c + (size_t)base * k,
+                                                              anchor_c + (size_t)base * k, counts, sort_size);
+    ABR_CHECK_LAUNCH("rpn_sort_decode");
+  }
+  const bool run_nms = nms_thresh > 0.f;  // structures/boxlist_ops.py:22-23: otherwise the list is returned untouched
+  if (run_nms) {
+    std::vector<int> offsets((size_t)N + 1);
+    for (int i = 0; i <= N; i++) offsets[i] = i * k;
+    int rc = nms_run(reinterpret_cast<const float*>(boxes_c), scores_c, offsets.data(), counts, N, nms_thresh, ge,
+                     post_nms_top_n > 0 ? post_nms_top_n : -1, reinterpret_cast<int64_t*>(keep), lay.keep_stride, n_keep,
+                     ws + lay.nms, lay.nms_bytes, st);
+    if (rc) return rc;
+  }
+  for (int base = 0; base < N; base += kRpnMaxImages) {
+    const int n = N - base < kRpnMaxImages ? N - base : kRpnMaxImages;
+    rpn_gather_kernel<<<n, 256, 0, st>>>(k, base, boxes_c + (size_t)base * k, scores_c + (size_t)base * k,
+                                         anchor_c + (size_t)base * k, counts, run_nms ? keep : nullptr, lay.keep_stride, n_keep,
+                                         reinterpret_cast<float4*>(proposals), scores, anchor_index, n_out, out_stride);
+    ABR_CHECK_LAUNCH("rpn_gather");
+  }
+  return ABR_OK;
+}
+
+}  // extern "C"

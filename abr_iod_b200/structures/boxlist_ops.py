@@ -35,3 +35,23 @@ def boxlist_nms_batched(boxlists, nms_thresh, max_proposals=-1, score_field="sco
         for j, i in enumerate(nonempty):
             out[i] = xyxy[i][keep[j, : counts[j]]]
     return [b.convert(m) for b, m in zip(out, modes)]
+
+
+def cat_boxlist(bboxes):
+    """One BoxList out of several of the same image (same size, mode and field names): structures/boxlist_ops.py:102-128.
+    A single-element list is returned without a copy, like the reference's ``_cat``."""
+    bboxes = list(bboxes)
+    if not bboxes:
+        raise ValueError("cat_boxlist needs at least one BoxList")
+    first = bboxes[0]
+    names = set(first.fields())
+    for b in bboxes[1:]:
+        if b.size != first.size or b.mode != first.mode or set(b.fields()) != names:
+            raise ValueError("cat_boxlist: image size, mode and fields must agree")
+    join = (lambda ts: ts[0]) if len(bboxes) == 1 else (lambda ts: torch.cat(ts, dim=0))
+    from .bounding_box import BoxList
+
+    out = BoxList(join([b.bbox for b in bboxes]), first.size, first.mode)
+    for name in names:
+        out.add_field(name, join([b.get_field(name) for b in bboxes]))
+    return out

@@ -354,7 +354,38 @@ def secondary_metrics(dev):
         torch.cuda.synchronize()
         out["nms_boxes_per_s_n%d_b%d_keep%d_%s" % (n, batch, keep_n, "sorted" if is_sorted else "unsorted")] = round(
             batch * n * 10 / (s.elapsed_time(e) * 1e-3))
+    out.update(rpn_metrics(dev))
     out.update(paste_metrics(dev))
+    return out
+
+
+def rpn_metrics(dev):
+    """The RPN proposal path around NMS on config-2 shapes: batch 4, 15 anchors on a 50x76 map
+    (57,000 anchors per image), train (12000 -> 2000) and test (6000 -> 1000) settings; images/s for the whole device
+    sequence (radix select, sort + decode, NMS, gather) with resident head outputs."""
+    import torch
+
+    from abr_iod_b200.modeling.rpn import rpn_proposals
+    from inputs import make_anchors
+
+    rng = np.random.default_rng(6)
+    N, A, H, W = 4, 15, 50, 76
+    anchors = torch.from_numpy(make_anchors(H, W, 16)).to(dev)
+    obj = torch.from_numpy((rng.standard_normal((N, A, H, W)) * 2).astype(np.float32)).to(dev)
+    reg = torch.from_numpy((rng.standard_normal((N, 4 * A, H, W)) * 0.3).astype(np.float32)).to(dev)
+    sizes = [(W * 16, H * 16)] * N
+    out = {}
+    for pre, post in ((12000, 2000), (6000, 1000)):
+        for _ in range(3):
+            rpn_proposals(obj, reg, anchors, sizes, pre, post, 0.7, 0)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(10):
+            rpn_proposals(obj, reg, anchors, sizes, pre, post, 0.7, 0)
+        e.record()
+        torch.cuda.synchronize()
+        out["rpn_proposals_imgs_per_s_b4_a57000_pre%d_post%d" % (pre, post)] = round(N * 10 / (s.elapsed_time(e) * 1e-3))
     return out
 
 

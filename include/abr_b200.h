@@ -135,6 +135,33 @@ ABR_API int abr_nms_batched(const float* boxes, const float* scores, const int* 
                     float thresh, int ge, int max_keep, int64_t* keep, int keep_stride, int32_t* n_keep,
                     void* workspace, size_t workspace_bytes, abr_stream_t stream);
 
+/* ---------------------------------------------------------------- RPN proposal selection (around NMS)
+ * Replaces RPNPostProcessor.forward_for_single_feature_map (modeling/rpn/inference.py:76-118) for a
+ * whole batch with no host synchronisation: sigmoid, top pre_nms_top_n per image (inference.py:89-95),
+ * BoxCoder.decode (modeling/box_coder.py:52-95), clip_to_image (structures/bounding_box.py:214-219),
+ * remove_small_boxes (structures/boxlist_ops.py:34-48) and boxlist_nms with max_proposals =
+ * post_nms_top_n (structures/boxlist_ops.py:9-31).
+ *   objectness     [N,A,H,W] fp32 logits and box_regression [N,4A,H,W] fp32, the RPN head outputs in
+ *                  place: ABR_NCHW contiguous, or ABR_NHWC = channels-last storage of the same tensors;
+ *   anchors        [.,A*H*W,4] fp32 xyxy in the reference's (h, w, a) order; image i uses
+ *                  anchors + i*anchor_image_stride floats (0 = one set shared by all images);
+ *   image_sizes_host [N][2] HOST ints (width, height) = BoxList.size of each image's anchors;
+ *   weights4_host  HOST (wx, wy, ww, wh) and bbox_xform_clip of the BoxCoder;
+ *   proposals      [N,out_stride,4] fp32, scores [N,out_stride] fp32 (= sigmoid(logit), the
+ *                  "objectness" field), anchor_index [N,out_stride] int32 (optional, may be NULL):
+ *                  per image the surviving proposals in the reference's order, zero / -1 padded;
+ *   n_out          [N] int32 valid entries per image;  out_stride >= min(pre_nms_top_n, A*H*W,
+ *                  post_nms_top_n if > 0)  (nms_thresh <= 0 skips NMS and the cut, like boxlist_nms).
+ * Candidates are ranked by (logit descending, anchor index ascending); the reference's torch.topk
+ * leaves the order of equal scores unspecified.  pre_nms_top_n <= 16384.  `ge` as in abr_nms_batched. */
+ABR_API size_t abr_rpn_proposals_workspace_bytes(int N, int A, int H, int W, int pre_nms_top_n, int post_nms_top_n);
+ABR_API int abr_rpn_proposals(const float* objectness, const float* box_regression, const float* anchors,
+                              long long anchor_image_stride, const int* image_sizes_host, int N, int A, int H, int W,
+                              int layout, int pre_nms_top_n, int post_nms_top_n, float nms_thresh, int ge, float min_size,
+                              const float* weights4_host, float bbox_xform_clip, float* proposals, float* scores,
+                              int32_t* anchor_index, int32_t* n_out, int out_stride, void* workspace,
+                              size_t workspace_bytes, abr_stream_t stream);
+
 /* ---------------------------------------------------------------- Attentive RoI Distillation
  * Native form of calculate_attentive_roi_feature_distillation (distillation/distillation.py:86-130)
  * and of its autograd backward, in one kernel.  f_old = old model / teacher pooled features (argument 0

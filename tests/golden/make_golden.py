@@ -284,11 +284,45 @@ def gen_paste(out):
     np.savez_compressed(os.path.join(out, "paste.npz"), **d)
 
 
+def gen_rpn(out):
+    """RPNPostProcessor.forward_for_single_feature_map (modeling/rpn/inference.py:76-118) run on CPU; its NMS is the
+    reference's compiled nms_cpu (IoU >= thr flavour)."""
+    from maskrcnn_benchmark.modeling.box_coder import BoxCoder
+    from maskrcnn_benchmark.modeling.rpn.inference import RPNPostProcessor
+    from maskrcnn_benchmark.structures.bounding_box import BoxList
+    from inputs import make_anchors
+    from oracle import rpn as orpn
+
+    rng = np.random.default_rng(11)
+    N, A, H, W = 2, 15, 12, 17
+    sizes = [(272, 192), (250, 180)]  # (width, height); the second image is smaller than the padded batch
+    anchors = make_anchors(H, W, 16)
+    logits = (rng.standard_normal((N, A, H, W)) * 2).astype(np.float32)
+    reg = (rng.standard_normal((N, A * 4, H, W)) * 0.3).astype(np.float32)
+    reg[0, 2::4][rng.random((A, H, W)) < 0.01] = 6.0  # dw beyond bbox_xform_clip
+    reg[1, 3::4][rng.random((A, H, W)) < 0.01] = -5.0  # tiny boxes for the min_size filter
+    assert len(np.unique(orpn.sigmoid(logits[0]))) == logits[0].size  # no ties: topk order is unambiguous
+    assert len(np.unique(orpn.sigmoid(logits[1]))) == logits[1].size
+    d = {"objectness": logits, "box_regression": reg, "anchors": anchors, "image_sizes": np.asarray(sizes, np.int64)}
+    cases = [(1000, 150, 0.7, 0, (1.0, 1.0, 1.0, 1.0)), (600, 2000, 0.5, 8, (1.0, 1.0, 1.0, 1.0)),
+             (5000, 300, 0.7, 0, (10.0, 10.0, 5.0, 5.0))]
+    d["cases"] = np.asarray([c[:4] for c in cases], np.float64)
+    d["case_weights"] = np.asarray([c[4] for c in cases], np.float64)
+    for ci, (pre, post, thr, min_size, wts) in enumerate(cases):
+        pp = RPNPostProcessor(pre, post, thr, min_size, box_coder=BoxCoder(weights=wts))
+        boxlists = [BoxList(torch.from_numpy(anchors.copy()), s, "xyxy") for s in sizes]
+        res = pp.forward_for_single_feature_map(boxlists, torch.from_numpy(logits), torch.from_numpy(reg))
+        for n, r in enumerate(res):
+            d["c%d_i%d_boxes" % (ci, n)] = r.bbox.numpy().astype(np.float32)
+            d["c%d_i%d_scores" % (ci, n)] = r.get_field("objectness").numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(out, "rpn.npz"), **d)
+
+
 def main():
     assert os.path.isdir(REFERENCE), "the reference tree is needed to (re)generate golden vectors"
     assert oracle.ref_available(), "run `make -C oracle ref` first"
     install_reference_stubs()
-    for fn in (gen_roi_align, gen_nms, gen_ard, gen_pooler, gen_boxlist_nms, gen_paste):
+    for fn in (gen_roi_align, gen_nms, gen_ard, gen_pooler, gen_boxlist_nms, gen_paste, gen_rpn):
         fn(HERE)
         print("wrote", fn.__name__)
 

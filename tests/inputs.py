@@ -1,4 +1,6 @@
 """Seeded synthetic inputs shared by the tests, bench.py and tests/golden/make_golden.py."""
+import math
+
 import numpy as np
 
 
@@ -34,3 +36,14 @@ def make_boxes(rng, n, im_w=1000, im_h=600, unique_scores=True):
     return b, s
 
 
+def make_anchors(H, W, stride, sizes=(32, 64, 128, 256, 512), ratios=(0.5, 1.0, 2.0)):
+    """A plain anchor grid in (h, w, a) order for synthetic inputs (test data, not a restatement of anchor_generator.py)."""
+    base = []
+    for s in sizes:
+        for r in ratios:
+            w, h = s / math.sqrt(r), s * math.sqrt(r)
+            base.append([-(w - 1) / 2, -(h - 1) / 2, (w - 1) / 2, (h - 1) / 2])
+    base = np.asarray(base, np.float32)
+    ys, xs = np.meshgrid(np.arange(H, dtype=np.float32) * stride, np.arange(W, dtype=np.float32) * stride, indexing="ij")
+    shifts = np.stack([xs, ys, xs, ys], -1).reshape(-1, 1, 4)
+    return (shifts + base[None]).reshape(-1, 4).astype(np.float32)

@@ -154,3 +154,20 @@ def test_paste_bit_exact_vs_reference_python(golden):
         assert np.array_equal(og[:, :4].astype(np.float32), g[key + "_out_bbox"]), key
         assert np.array_equal(og[:, 4], g[key + "_out_labels"]), key
         assert st.boxes_index == g[key + "_index_after"].tolist(), key
+
+
+def test_rpn_proposals_oracle_matches_reference_postprocessor(golden):
+    """oracle/rpn.py against RPNPostProcessor.forward_for_single_feature_map run by make_golden.py: same proposals in the
+    same order, coordinates and scores bit for bit (the oracle calls the same torch CPU exp / sigmoid)."""
+    from oracle import rpn as orpn
+
+    g = golden("rpn.npz")
+    sizes = [tuple(int(v) for v in s) for s in g["image_sizes"]]
+    for ci, (pre, post, thr, min_size) in enumerate(g["cases"]):
+        res = orpn.rpn_proposals(g["objectness"], g["box_regression"], [g["anchors"]], sizes, int(pre), int(post), thr,
+                                 min_size, tuple(g["case_weights"][ci]), flavour="cpu")
+        for n, (boxes, scores, _) in enumerate(res):
+            assert np.array_equal(boxes, g["c%d_i%d_boxes" % (ci, n)])
+            assert np.array_equal(scores, g["c%d_i%d_scores" % (ci, n)])
+    # the three cases exercise the post-NMS cut, the min_size filter and non-unit coder weights
+    assert len(g["c0_i0_boxes"]) == 150 and len(g["c1_i0_boxes"]) < 600
