@@ -31,6 +31,8 @@ struct NmsBatch {
   int n_full[kImagesPerLaunch];         // boxes in the image
   long long mask_off[kImagesPerLaunch]; // first mask word of the image (u64 units)
   const int* counts;                    // optional, device: boxes actually present per image (<= the host-side size)
+  const unsigned long long* invalid;    // optional, device: bit i of image's words = box i (INPUT order) never takes part
+  long long invalid_off[kImagesPerLaunch];
 };
 
 // boxes of image `img` a kernel looks at: the host-side figure, cut to the device-side count when there is one
@@ -168,10 +170,11 @@ __global__ void __launch_bounds__(kTile * kMaskTilesPerCta) iou_mask_kernel(NmsB
 constexpr int kSweepThreads = 512;
 
 // One CTA per image.  Per 64-box tile: warp 0 resolves the greedy chain inside the tile from the diagonal mask words
-// (prefetched one tile ahead, suppression word and chain in registers), publishes the kept boxes, and then the WHOLE CTA
-// ORs the mask rows of the kept boxes into the shared-memory `removed` words -- (kept row, word) pairs are dealt out
-// to all threads, four independent 8-byte loads in flight per thread, merged with shared-memory atomicOr -- so a tile
-// step costs about one L2 latency instead of one per kept box.  Sorted inputs stop as soon as max_keep boxes are kept.
+// (suppression word and chain in registers, diagonal and first off-diagonal words prefetched a tile ahead) and publishes
+// the kept boxes; warps 1..15 OR the remaining mask words of the kept rows into the shared-memory `removed` words --
+// (kept row, word) pairs dealt out to all helper threads, four independent 8-byte loads in flight per thread, merged
+// with shared-memory atomicOr -- while warp 0 already runs the chain of the next tile (named barriers, see below).
+// Sorted inputs stop as soon as max_keep boxes are kept.
 // Dynamic shared memory: removed[cb], kept_sorted[cb], kept_orig[cb] (u64 each) + scan scratch.
 __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(NmsBatch nb, const unsigned long long* __restrict__ mask,
                                                              const int* __restrict__ order,
@@ -188,78 +191,139 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(NmsBatch nb, const
   unsigned long long* kept_sorted = removed + cb;
   unsigned long long* kept_orig = kept_sorted + cb;
   int* scan = reinterpret_cast<int*>(kept_orig + cb);  // [kSweepThreads/32 + 1]
-  __shared__ unsigned long long kept_now;
-  __shared__ int kept_rows[kTile];
-  __shared__ int kept_count, kept_total;
+  __shared__ int kept_rows[2][kTile];
+  __shared__ int kept_count[2], stop_flag[2], kept_total;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   long long* out = keep + (long long)(nb.first_image + img) * keep_stride;
 
-  for (int i = tid; i < cb; i += kSweepThreads) { removed[i] = 0; kept_orig[i] = 0; kept_sorted[i] = 0; }
+  // boxes flagged invalid (bitmap in INPUT order) start out suppressed
+  const unsigned long long* inv = nb.invalid ? nb.invalid + nb.invalid_off[img] : nullptr;
+  const bool reordered = unsorted[nb.first_image + img] != 0;
+  for (int i = tid; i < cb; i += kSweepThreads) {
+    unsigned long long r = 0;
+    if (inv && !reordered) r = inv[i];
+    else if (inv) {
+      const int* ord0 = order + nb.box_off[img];
+      for (int b = 0; b < kTile && i * kTile + b < n; b++) {
+        const int orig = ord0[i * kTile + b];
+        r |= ((inv[orig >> 6] >> (orig & 63)) & 1ull) << b;
+      }
+    }
+    removed[i] = r; kept_orig[i] = 0; kept_sorted[i] = 0;
+  }
   if (tid == 0) kept_total = 0;
   __syncthreads();
   const unsigned long long* m = mask + nb.mask_off[img];
   const int* ord = order + nb.box_off[img];
   const bool may_stop = max_keep > 0 && unsorted[nb.first_image + img] == 0;
 
-  // diagonal words of tile 0: lane l holds the words of boxes l and l+32
-  unsigned long long d0 = 0, d1 = 0;
-  if (warp == 0 && cb > 0) {
-    const int size = min(n, kTile);
-    d0 = lane < size ? m[(long long)lane * cb] : 0ull;
-    d1 = lane + 32 < size ? m[(long long)(lane + 32) * cb] : 0ull;
-  }
-  for (int k = 0; k < cb; k++) {
-    if (warp == 0) {
+  // Two roles, pipelined with named barriers (ids 1,2 = "kept rows of tile t published", 3,4 = "helpers finished tile
+  // t"; parity t & 1).  Warp 0 runs the serial chain: for tile t it needs removed[t] = (helper ORs of tiles <= t-2) |
+  // (word t of the rows kept in tile t-1); the latter comes from words it prefetched itself a tile ahead, so the chain
+  // of tile t+1 starts right after the chain of tile t while warps 1..15 are still ORing the far words (columns
+  // >= t+2) of tile t's kept rows into shared memory.
+  if (warp == 0) {
+    // lane l holds, for boxes l and l+32 of the current tile, the diagonal word and the first off-diagonal word
+    unsigned long long d0 = 0, d1 = 0, f0 = 0, f1 = 0;
+    if (cb > 0) {
+      const int size = min(n, kTile);
+      if (lane < size) { d0 = m[(long long)lane * cb]; f0 = cb > 1 ? m[(long long)lane * cb + 1] : 0ull; }
+      if (lane + 32 < size) { d1 = m[(long long)(lane + 32) * cb]; f1 = cb > 1 ? m[(long long)(lane + 32) * cb + 1] : 0ull; }
+    }
+    unsigned long long carry = 0;  // word t of the rows kept in tile t-1
+    int total = 0, published = 0;
+    for (int k = 0; k < cb; k++) {
       const int first = k * kTile;
       const int size = min(n - first, kTile);
-      const unsigned long long c0 = d0, c1 = d1;
-      if (k + 1 < cb) {  // prefetch the next tile's diagonal words while this tile's chain runs
+      const unsigned long long c0 = d0, c1 = d1, g0 = f0, g1 = f1;
+      if (k + 1 < cb) {  // prefetch the next tile's words while this tile's chain runs
         const int nfirst = first + kTile, nsize = min(n - nfirst, kTile);
-        d0 = lane < nsize ? m[(long long)(nfirst + lane) * cb + k + 1] : 0ull;
-        d1 = lane + 32 < nsize ? m[(long long)(nfirst + lane + 32) * cb + k + 1] : 0ull;
-      }
-      const unsigned long long valid = size == kTile ? ~0ull : ((1ull << size) - 1ull);
-      unsigned long long alive = ~removed[k] & valid;
-      unsigned long long kept = 0;
-      int cnt = 0;
-      while (alive) {  // greedy chain inside the tile (csrc/cuda/nms.cu:112-123)
-        const int b = __ffsll((long long)alive) - 1;
-        kept |= 1ull << b;
-        if (lane == 0) kept_rows[cnt] = first + b;
-        cnt++;
-        const unsigned long long lo = __shfl_sync(0xffffffffu, c0, b & 31);
-        const unsigned long long hi = __shfl_sync(0xffffffffu, c1, b & 31);
-        alive &= ~((b < 32) ? lo : hi);
-        alive &= ~(1ull << b);
-      }
-      if (lane == 0) { kept_now = kept; kept_sorted[k] = kept; kept_count = cnt; kept_total += cnt; }
-    }
-    __syncthreads();
-    if (may_stop && kept_total >= max_keep) break;  // every later box has a larger index than the max_keep-th kept one
-    const int cnt = kept_count;
-    const int nwords = cb - k - 1;
-    const int total = cnt * nwords;
-    // (kept row, later word) pairs over all threads; word index fastest so that a warp reads a contiguous run of a row
-    for (int t = tid; t < total; t += 4 * kSweepThreads) {
-      unsigned long long v[4];
-      int j[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int tt = t + u * kSweepThreads;
-        if (tt < total) {
-          const int ri = tt / nwords;
-          j[u] = k + 1 + (tt - ri * nwords);
-          v[u] = m[(long long)kept_rows[ri] * cb + j[u]];
-        } else {
-          j[u] = -1;
-          v[u] = 0;
+        const bool more = k + 2 < cb;
+        d0 = d1 = f0 = f1 = 0ull;
+        if (lane < nsize) {
+          const unsigned long long* row = m + (long long)(nfirst + lane) * cb + k + 1;
+          d0 = row[0];
+          if (more) f0 = row[1];
+        }
+        if (lane + 32 < nsize) {
+          const unsigned long long* row = m + (long long)(nfirst + lane + 32) * cb + k + 1;
+          d1 = row[0];
+          if (more) f1 = row[1];
         }
       }
+      if (k >= 2) asm volatile("bar.sync %0, %1;" ::"r"(3 + (k & 1)), "r"(kSweepThreads) : "memory");  // helpers done with tile k-2
+      const unsigned long long valid = size == kTile ? ~0ull : ((1ull << size) - 1ull);
+      unsigned long long alive = ~(removed[k] | carry) & valid;
+      // Greedy chain inside the tile (csrc/cuda/nms.cu:112-123), visiting all 64 boxes in order: box b is kept iff its
+      // bit is still set when visited; its row then clears later boxes.  Rows only hold bits > b, so a kept bit stays set
+      // and the final `alive` IS the kept set.  The row broadcasts do not depend on the chain (constant source lanes), so
+      // the dependent path per box is a bit test and a predicated AND.
+      unsigned alo = (unsigned)alive, ahi = (unsigned)(alive >> 32);
 #pragma unroll
-      for (int u = 0; u < 4; u++)
-        if (j[u] >= 0 && v[u]) atomicOr(&removed[j[u]], v[u]);
+      for (int b = 0; b < 32; b++) {
+        const unsigned rlo = __shfl_sync(0xffffffffu, (unsigned)c0, b);
+        const unsigned rhi = __shfl_sync(0xffffffffu, (unsigned)(c0 >> 32), b);
+        if ((alo >> b) & 1u) { alo &= ~rlo; ahi &= ~rhi; }
+      }
+#pragma unroll
+      for (int b = 0; b < 32; b++) {
+        const unsigned rhi = __shfl_sync(0xffffffffu, (unsigned)(c1 >> 32), b);  // rows 32..63 only reach columns > 32
+        if ((ahi >> b) & 1u) ahi &= ~rhi;
+      }
+      const unsigned long long kept = ((unsigned long long)ahi << 32) | alo;
+      const int cnt = __popcll(kept);
+      int* rows = kept_rows[k & 1];
+      if ((alo >> lane) & 1u) rows[__popc(alo & ((1u << lane) - 1u))] = first + lane;
+      if ((ahi >> lane) & 1u) rows[__popc(alo) + __popc(ahi & ((1u << lane) - 1u))] = first + 32 + lane;
+      total += cnt;
+      const bool last = (k + 1 == cb) || (may_stop && total >= max_keep);  // later boxes have larger indices than the cut
+      if (lane == 0) { kept_sorted[k] = kept; kept_count[k & 1] = cnt; stop_flag[k & 1] = last ? 1 : 0; }
+      __threadfence_block();
+      asm volatile("bar.arrive %0, %1;" ::"r"(1 + (k & 1)), "r"(kSweepThreads) : "memory");  // tile k published
+      published = k + 1;
+      if (last) break;
+      // word k+1 of the rows just kept: OR over the kept lanes' prefetched words
+      unsigned long long mine = (((kept >> lane) & 1ull) ? g0 : 0ull) | (((kept >> (lane + 32)) & 1ull) ? g1 : 0ull);
+      const unsigned lo32 = __reduce_or_sync(0xffffffffu, (unsigned)mine);
+      const unsigned hi32 = __reduce_or_sync(0xffffffffu, (unsigned)(mine >> 32));
+      carry = ((unsigned long long)hi32 << 32) | lo32;
     }
-    __syncthreads();
+    if (lane == 0) kept_total = total;
+    // helpers arrive once per tile they worked on (every published tile but the last); the loop waited for all of those
+    // except the one before the last
+    if (published >= 2) asm volatile("bar.sync %0, %1;" ::"r"(3 + ((published - 2) & 1)), "r"(kSweepThreads) : "memory");
+  } else {
+    const int htid = tid - 32, nhelp = kSweepThreads - 32;
+    for (int k = 0; k < cb; k++) {
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + (k & 1)), "r"(kSweepThreads) : "memory");  // kept rows of tile k are published
+      if (stop_flag[k & 1]) break;  // tile k was the last one: nothing further depends on its far words
+      const int cnt = kept_count[k & 1];
+      const int* rows = kept_rows[k & 1];
+      const int nwords = cb - k - 2;  // columns k+2 .. cb-1 (column k+1 travels in warp 0's registers)
+      const int total = cnt * nwords;
+      // (kept row, word) pairs dealt out to all helper threads, word index fastest, four independent loads in flight
+      for (int t = htid; t < total; t += 4 * nhelp) {
+        unsigned long long v[4];
+        int j[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int tt = t + u * nhelp;
+          if (tt < total) {
+            const int ri = tt / nwords;
+            j[u] = k + 2 + (tt - ri * nwords);
+            v[u] = m[(long long)rows[ri] * cb + j[u]];
+          } else {
+            j[u] = -1;
+            v[u] = 0;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (j[u] >= 0 && v[u]) atomicOr(&removed[j[u]], v[u]);
+      }
+      __threadfence_block();
+      asm volatile("bar.arrive %0, %1;" ::"r"(3 + (k & 1)), "r"(kSweepThreads) : "memory");  // done with tile k
+    }
   }
   __syncthreads();
   if (prefix_pass) {
@@ -354,9 +418,9 @@ static NmsLayout nms_layout(const int* offsets, int n_images) {
 
 // abr_nms_batched with an optional device-side box count per image (used by the RPN proposal path, where the number of
 // boxes that survive the small-box filter is only known on the device): offsets_host then describes capacities.
-int nms_run(const float* boxes, const float* scores, const int* offsets_host, const int* counts_dev, int n_images,
-            float thresh, int ge, int max_keep, int64_t* keep, int keep_stride, int32_t* n_keep, void* workspace,
-            size_t workspace_bytes, cudaStream_t st);
+int nms_run(const float* boxes, const float* scores, const int* offsets_host, const int* counts_dev,
+            const unsigned long long* invalid, int n_images, float thresh, int ge, int max_keep, int64_t* keep,
+            int keep_stride, int32_t* n_keep, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
 }  // namespace abr
 
@@ -372,7 +436,7 @@ size_t abr_nms_workspace_bytes(const int* offsets_host, int n_images) {
 int abr_nms_batched(const float* boxes, const float* scores, const int* offsets_host, int n_images, float thresh, int ge,
                     int max_keep, int64_t* keep, int keep_stride, int32_t* n_keep, void* workspace,
                     size_t workspace_bytes, abr_stream_t stream) {
-  return nms_run(boxes, scores, offsets_host, nullptr, n_images, thresh, ge, max_keep, keep, keep_stride, n_keep, workspace,
+  return nms_run(boxes, scores, offsets_host, nullptr, nullptr, n_images, thresh, ge, max_keep, keep, keep_stride, n_keep, workspace,
                  workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
@@ -380,9 +444,9 @@ int abr_nms_batched(const float* boxes, const float* scores, const int* offsets_
 
 namespace abr {
 
-int nms_run(const float* boxes, const float* scores, const int* offsets_host, const int* counts_dev, int n_images,
-            float thresh, int ge, int max_keep, int64_t* keep, int keep_stride, int32_t* n_keep, void* workspace,
-            size_t workspace_bytes, cudaStream_t st) {
+int nms_run(const float* boxes, const float* scores, const int* offsets_host, const int* counts_dev,
+            const unsigned long long* invalid, int n_images, float thresh, int ge, int max_keep, int64_t* keep,
+            int keep_stride, int32_t* n_keep, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   ABR_REQUIRE(n_images >= 0, ABR_ERR_BAD_ARG, "nms: n_images=%d", n_images);
   if (n_images == 0) return ABR_OK;
   ABR_REQUIRE(offsets_host && keep && n_keep && keep_stride >= 0, ABR_ERR_BAD_ARG, "nms: null pointer or negative stride");
@@ -409,12 +473,13 @@ int nms_run(const float* boxes, const float* scores, const int* offsets_host, co
   if (total > 0) ABR_CUDA_OK(cudaMemsetAsync(unsorted, 0, lay.mask - lay.unsorted, st));
   unsigned long long* mask = reinterpret_cast<unsigned long long*>(ws + lay.mask);
 
-  long long mask_cursor = 0;
+  long long mask_cursor = 0, invalid_cursor = 0;
   for (int base = 0; base < n_images; base += kImagesPerLaunch) {
     NmsBatch nb;
     nb.n_images = 0;
     nb.first_image = base;
     nb.counts = counts_dev;
+    nb.invalid = invalid;
     int nmax = 0;
     const int lim = n_images - base < kImagesPerLaunch ? n_images - base : kImagesPerLaunch;
     for (int i = 0; i < lim; i++) {
@@ -423,6 +488,8 @@ int nms_run(const float* boxes, const float* scores, const int* offsets_host, co
       nb.n[i] = nb.n_full[i] = n;
       nb.mask_off[i] = mask_cursor;
       mask_cursor += (long long)n * ceil_div(n, kTile);
+      nb.invalid_off[i] = invalid_cursor;
+      invalid_cursor += ceil_div(n, kTile);
       nmax = n > nmax ? n : nmax;
     }
     nb.n_images = lim;

@@ -13,11 +13,13 @@
 //                              index digits only run when equal logits straddle the cut.  Ranking by logit instead of
 //                              by sigmoid(logit) is the same order (monotonic) without a transcendental in the key;
 //   2. rpn_collect_kernel   -- the selected keys, unordered, into a per-image candidate list;
-//   3. rpn_sort_decode_kernel -- one CTA per image: bitonic sort of the <= 16384 candidates in shared memory, then
-//                              decode + clip + small-box filter + ORDERED compaction (block scan) of boxes / scores;
-//   4. nms_run              -- the batched NMS of nms.cu with device-side box counts (the inputs are already sorted, so
-//                              it takes its O(N) presort path and the prefix pass);
-//   5. rpn_gather_kernel    -- kept boxes / scores / anchor indices into the padded outputs + per-image counts.
+//   3. rpn_chunk_sort_kernel -- bitonic sort of 2048-key chunks in shared memory, one CTA per chunk;
+//   4. rpn_rank_decode_kernel -- one thread per candidate: rank = position in its chunk + binary searches in the other
+//                              chunks (a merge by counting), then decode + clip, written AT its rank; boxes failing the
+//                              size filter are only flagged in a bitmap (no compaction pass);
+//   5. nms_run              -- the batched NMS of nms.cu, started with the flagged boxes already suppressed (the inputs
+//                              are sorted, so it takes its O(N) presort path and the prefix pass);
+//   6. rpn_gather_kernel    -- kept boxes / scores / anchor indices into the padded outputs + per-image counts.
 // No host synchronisation, no allocation; the caller reads n_out once for the batch.
 #include <cfloat>
 #include <vector>
@@ -26,9 +28,9 @@
 
 namespace abr {
 
-int nms_run(const float* boxes, const float* scores, const int* offsets_host, const int* counts_dev, int n_images,
-            float thresh, int ge, int max_keep, int64_t* keep, int keep_stride, int32_t* n_keep, void* workspace,
-            size_t workspace_bytes, cudaStream_t st);
+int nms_run(const float* boxes, const float* scores, const int* offsets_host, const int* counts_dev,
+            const unsigned long long* invalid, int n_images, float thresh, int ge, int max_keep, int64_t* keep,
+            int keep_stride, int32_t* n_keep, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
 constexpr int kRpnBins = 2048;        // 11-bit digits
 constexpr int kRpnPasses = 5;         // 11 + 11 + 10 bits of logit, 11 + 11 bits of index
@@ -190,146 +192,199 @@ struct RpnDecode {
   int im_w[kRpnMaxImages], im_h[kRpnMaxImages];
 };
 
+constexpr int kSortChunk = 2048;   // keys one CTA sorts (two per thread)
 constexpr int kSortThreads = 1024;
+constexpr int kMaxChunks = kRpnMaxCand / kSortChunk;
 
-// One CTA per image: sort the candidates, decode, filter, compact in rank order.
-__global__ void __launch_bounds__(kSortThreads) rpn_sort_decode_kernel(RpnShape s, RpnDecode d, int first_image,
-                                                                      const unsigned long long* __restrict__ cand,
-                                                                      const float* __restrict__ box_regression,
-                                                                      const float* __restrict__ anchors,
-                                                                      float4* __restrict__ boxes_c, float* __restrict__ scores_c,
-                                                                      int* __restrict__ anchor_c, int* __restrict__ counts,
-                                                                      int sort_size) {
-  extern __shared__ unsigned long long keys[];  // [sort_size]
-  __shared__ int warp_tot[kSortThreads / 32];
-  __shared__ int running;
-  const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int k = s.k;
-  const unsigned long long* in = cand + (size_t)img * k;
-  for (int i = tid; i < sort_size; i += kSortThreads) keys[i] = i < k ? in[i] : 0ull;  // real keys are > 0
+// Stage 1 of the sort: every CTA sorts one 2048-key chunk of an image's candidates in shared memory (bitonic, descending,
+// one compare-exchange per thread and stage), in place.
+__global__ void __launch_bounds__(kSortThreads) rpn_chunk_sort_kernel(int k, unsigned long long* __restrict__ cand) {
+  __shared__ unsigned long long keys[kSortChunk];
+  const int img = blockIdx.y, tid = threadIdx.x;
+  const int c0 = blockIdx.x * kSortChunk;
+  unsigned long long* io = cand + (size_t)img * k;
+  keys[tid] = c0 + tid < k ? io[c0 + tid] : 0ull;  // real keys are > 0: the padding sorts last
+  keys[tid + kSortThreads] = c0 + tid + kSortThreads < k ? io[c0 + tid + kSortThreads] : 0ull;
   __syncthreads();
-  // bitonic sort, descending
-  for (int size = 2; size <= sort_size; size <<= 1) {
+  for (int size = 2; size <= kSortChunk; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = tid; t < sort_size / 2; t += kSortThreads) {
-        const int i = 2 * t - (t & (stride - 1));
-        const int j = i + stride;
-        const unsigned long long a = keys[i], b = keys[j];
-        const bool desc = (i & size) == 0;
-        if ((a < b) == desc) { keys[i] = b; keys[j] = a; }
-      }
+      const int i = 2 * tid - (tid & (stride - 1));
+      const int j = i + stride;
+      const unsigned long long a = keys[i], b = keys[j];
+      const bool desc = (i & size) == 0;
+      if ((a < b) == desc) { keys[i] = b; keys[j] = a; }
       __syncthreads();
     }
   }
-  // decode in rank order, chunk by chunk, with an ordered compaction of the boxes that pass the size filter
-  if (tid == 0) running = 0;
-  __syncthreads();
+  if (c0 + tid < k) io[c0 + tid] = keys[tid];
+  if (c0 + tid + kSortThreads < k) io[c0 + tid + kSortThreads] = keys[tid + kSortThreads];
+}
+
+// Stage 2: the rank of a candidate = its position in its own sorted chunk + the number of larger keys in every other
+// chunk (one binary search per chunk, all in flight together; keys are unique).  The candidate is decoded and written at
+// its rank, so the outputs are in (logit descending, anchor ascending) order without a merge pass.  Boxes that fail the
+// size filter stay in place and are flagged in `invalid` (one bit per rank) -- the NMS starts with them suppressed.
+__global__ void __launch_bounds__(256) rpn_rank_decode_kernel(RpnShape s, RpnDecode d, int first_image,
+                                                              const unsigned long long* __restrict__ cand,
+                                                              const float* __restrict__ box_regression,
+                                                              const float* __restrict__ anchors,
+                                                              float4* __restrict__ boxes_c, float* __restrict__ scores_c,
+                                                              int* __restrict__ anchor_c,
+                                                              unsigned long long* __restrict__ invalid, int invalid_words) {
+  const int img = blockIdx.y;
+  const int k = s.k;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= k) return;
+  const unsigned long long* in = cand + (size_t)img * k;
+  const unsigned long long key = in[e];
+  const int own = e / kSortChunk;
+  const int nchunks = ceil_div(k, kSortChunk);
+  int lo[kMaxChunks], hi[kMaxChunks];
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; c++) {
+    lo[c] = 0;
+    hi[c] = (c < nchunks && c != own) ? min(kSortChunk, k - c * kSortChunk) : 0;
+  }
+#pragma unroll 1
+  for (int step = 0; step < 12; step++) {  // 2^11 = chunk size; one more step to settle lo == hi
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; c++) {
+      if (lo[c] < hi[c]) {
+        const int mid = (lo[c] + hi[c]) >> 1;
+        if (in[c * kSortChunk + mid] > key) lo[c] = mid + 1;
+        else hi[c] = mid;
+      }
+    }
+  }
+  int rank = e - own * kSortChunk;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; c++) rank += lo[c];
+
+  const int anchor = (int)(((1u << kRpnIdxBits) - 1u) - (unsigned)(key & ((1u << kRpnIdxBits) - 1u)));
+  const float logit = from_ordered_bits((unsigned)(key >> kRpnIdxBits));
   const int hw = s.H * s.W;
   const int M = s.A * hw;
   const float* reg = box_regression + (size_t)img * 4 * M;
   const float* anc = anchors + (size_t)(first_image + img) * d.anchor_image_stride;
-  const float xmax = (float)(d.im_w[img] - 1), ymax = (float)(d.im_h[img] - 1);
-  float4* ob = boxes_c + (size_t)img * k;
-  float* os = scores_c + (size_t)img * k;
-  int* oa = anchor_c + (size_t)img * k;
-  for (int j0 = 0; j0 < k; j0 += kSortThreads) {
-    const int j = j0 + tid;
-    bool ok = false;
-    float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
-    float score = 0.f;
-    int anchor = 0;
-    if (j < k) {
-      const unsigned long long key = keys[j];
-      anchor = (int)(((1u << kRpnIdxBits) - 1u) - (unsigned)(key & ((1u << kRpnIdxBits) - 1u)));
-      const float logit = from_ordered_bits((unsigned)(key >> kRpnIdxBits));
-      float r0, r1, r2, r3;
-      if (s.layout == ABR_NHWC) {
-        const float4 r = __ldg(reinterpret_cast<const float4*>(reg) + anchor);
-        r0 = r.x; r1 = r.y; r2 = r.z; r3 = r.w;
-      } else {
-        const int p = anchor / s.A, a = anchor - p * s.A;
-        const float* rp = reg + (size_t)(a * 4) * hw + p;
-        r0 = __ldg(rp); r1 = __ldg(rp + hw); r2 = __ldg(rp + 2 * hw); r3 = __ldg(rp + 3 * hw);
-      }
-      const float4 an = __ldg(reinterpret_cast<const float4*>(anc) + anchor);
-      // BoxCoder.decode, one rounding per tensor op (no contraction)
-      const float widths = __fadd_rn(__fsub_rn(an.z, an.x), 1.f);
-      const float heights = __fadd_rn(__fsub_rn(an.w, an.y), 1.f);
-      const float ctr_x = __fadd_rn(an.x, __fmul_rn(0.5f, widths));
-      const float ctr_y = __fadd_rn(an.y, __fmul_rn(0.5f, heights));
-      const float dx = __fdiv_rn(r0, d.wx), dy = __fdiv_rn(r1, d.wy);
-      float dw = __fdiv_rn(r2, d.ww), dh = __fdiv_rn(r3, d.wh);
-      dw = dw > d.clip ? d.clip : dw;  // torch.clamp(max=): NaN stays NaN
-      dh = dh > d.clip ? d.clip : dh;
-      const float pcx = __fadd_rn(__fmul_rn(dx, widths), ctr_x);
-      const float pcy = __fadd_rn(__fmul_rn(dy, heights), ctr_y);
-      const float pw = __fmul_rn(expf(dw), widths);
-      const float ph = __fmul_rn(expf(dh), heights);
-      float x1 = __fsub_rn(pcx, __fmul_rn(0.5f, pw));
-      float y1 = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
-      float x2 = __fsub_rn(__fadd_rn(pcx, __fmul_rn(0.5f, pw)), 1.f);
-      float y2 = __fsub_rn(__fadd_rn(pcy, __fmul_rn(0.5f, ph)), 1.f);
-      // clip_to_image: clamp(min=0, max=size-1)
-      x1 = fminf(fmaxf(x1, 0.f), xmax); y1 = fminf(fmaxf(y1, 0.f), ymax);
-      x2 = fminf(fmaxf(x2, 0.f), xmax); y2 = fminf(fmaxf(y2, 0.f), ymax);
-      box = make_float4(x1, y1, x2, y2);
-      // remove_small_boxes on the xywh sides (+1 convention)
-      const float bw = __fadd_rn(__fsub_rn(x2, x1), 1.f), bh = __fadd_rn(__fsub_rn(y2, y1), 1.f);
-      ok = bw >= d.min_size && bh >= d.min_size;
-      score = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-logit)));
-    }
-    const unsigned ballot = __ballot_sync(0xffffffffu, ok);
-    if (lane == 0) warp_tot[warp] = __popc(ballot);
-    __syncthreads();
-    int before = running;
-    for (int w2 = 0; w2 < warp; w2++) before += warp_tot[w2];
-    if (ok) {
-      const int pos = before + __popc(ballot & ((1u << lane) - 1u));
-      ob[pos] = box;
-      os[pos] = score;
-      oa[pos] = anchor;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      int t = 0;
-      for (int w2 = 0; w2 < kSortThreads / 32; w2++) t += warp_tot[w2];
-      running += t;
-    }
-    __syncthreads();
+  float r0, r1, r2, r3;
+  if (s.layout == ABR_NHWC) {
+    const float4 r = __ldg(reinterpret_cast<const float4*>(reg) + anchor);
+    r0 = r.x; r1 = r.y; r2 = r.z; r3 = r.w;
+  } else {
+    const int p = anchor / s.A, a = anchor - p * s.A;
+    const float* rp = reg + (size_t)(a * 4) * hw + p;
+    r0 = __ldg(rp); r1 = __ldg(rp + hw); r2 = __ldg(rp + 2 * hw); r3 = __ldg(rp + 3 * hw);
   }
-  if (tid == 0) counts[first_image + img] = running;
+  const float4 an = __ldg(reinterpret_cast<const float4*>(anc) + anchor);
+  // BoxCoder.decode, one rounding per tensor op (no contraction)
+  const float widths = __fadd_rn(__fsub_rn(an.z, an.x), 1.f);
+  const float heights = __fadd_rn(__fsub_rn(an.w, an.y), 1.f);
+  const float ctr_x = __fadd_rn(an.x, __fmul_rn(0.5f, widths));
+  const float ctr_y = __fadd_rn(an.y, __fmul_rn(0.5f, heights));
+  const float dx = __fdiv_rn(r0, d.wx), dy = __fdiv_rn(r1, d.wy);
+  float dw = __fdiv_rn(r2, d.ww), dh = __fdiv_rn(r3, d.wh);
+  dw = dw > d.clip ? d.clip : dw;  // torch.clamp(max=): NaN stays NaN
+  dh = dh > d.clip ? d.clip : dh;
+  const float pcx = __fadd_rn(__fmul_rn(dx, widths), ctr_x);
+  const float pcy = __fadd_rn(__fmul_rn(dy, heights), ctr_y);
+  const float pw = __fmul_rn(expf(dw), widths);
+  const float ph = __fmul_rn(expf(dh), heights);
+  float x1 = __fsub_rn(pcx, __fmul_rn(0.5f, pw));
+  float y1 = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
+  float x2 = __fsub_rn(__fadd_rn(pcx, __fmul_rn(0.5f, pw)), 1.f);
+  float y2 = __fsub_rn(__fadd_rn(pcy, __fmul_rn(0.5f, ph)), 1.f);
+  // clip_to_image: clamp(min=0, max=size-1)
+  const float xmax = (float)(d.im_w[img] - 1), ymax = (float)(d.im_h[img] - 1);
+  x1 = fminf(fmaxf(x1, 0.f), xmax); y1 = fminf(fmaxf(y1, 0.f), ymax);
+  x2 = fminf(fmaxf(x2, 0.f), xmax); y2 = fminf(fmaxf(y2, 0.f), ymax);
+  // remove_small_boxes on the xywh sides (+1 convention)
+  const float bw = __fadd_rn(__fsub_rn(x2, x1), 1.f), bh = __fadd_rn(__fsub_rn(y2, y1), 1.f);
+  const bool ok = bw >= d.min_size && bh >= d.min_size;
+  const size_t o = (size_t)img * k + rank;
+  boxes_c[o] = make_float4(x1, y1, x2, y2);
+  scores_c[o] = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-logit)));
+  anchor_c[o] = anchor;
+  if (!ok) atomicOr(invalid + (size_t)(first_image + img) * invalid_words + (rank >> 6), 1ull << (rank & 63));
 }
 
-// kept candidates -> padded outputs.  keep == nullptr: no NMS ran (nms_thresh <= 0), every candidate is a proposal.
-__global__ void rpn_gather_kernel(int k, int first_image, const float4* __restrict__ boxes_c, const float* __restrict__ scores_c,
-                                  const int* __restrict__ anchor_c, const int* __restrict__ counts,
-                                  const long long* __restrict__ keep, int keep_stride, const int* __restrict__ n_keep,
-                                  float4* __restrict__ proposals, float* __restrict__ scores, int* __restrict__ anchor_index,
-                                  int* __restrict__ n_out, int out_stride) {
-  const int img = blockIdx.x, g = first_image + img;
-  const int n = keep ? n_keep[g] : min(counts[g], out_stride);
+// Survivors -> padded outputs.  With keep: the NMS result (indices into the ranked candidates, ascending = the
+// reference's order).  Without (nms_thresh <= 0, the reference returns the list untouched): every valid candidate in
+// rank order (ordered compaction over the validity bitmap).
+__global__ void __launch_bounds__(256) rpn_gather_kernel(int k, int first_image, const float4* __restrict__ boxes_c,
+                                                         const float* __restrict__ scores_c, const int* __restrict__ anchor_c,
+                                                         const unsigned long long* __restrict__ invalid, int invalid_words,
+                                                         const long long* __restrict__ keep, int keep_stride,
+                                                         const int* __restrict__ n_keep, float4* __restrict__ proposals,
+                                                         float* __restrict__ scores, int* __restrict__ anchor_index,
+                                                         int* __restrict__ n_out, int out_stride) {
+  __shared__ int warp_tot[8];
+  __shared__ int total;
+  const int img = blockIdx.x, g = first_image + img, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float4* b = boxes_c + (size_t)img * k;
   const float* sc = scores_c + (size_t)img * k;
   const int* an = anchor_c + (size_t)img * k;
-  for (int j = threadIdx.x; j < out_stride; j += blockDim.x) {
-    float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
-    float s = 0.f;
-    int a = -1;
-    if (j < n) {
-      const int src = keep ? (int)keep[(size_t)g * keep_stride + j] : j;
-      box = b[src]; s = sc[src]; a = an[src];
+  float4* op = proposals + (size_t)g * out_stride;
+  float* os = scores + (size_t)g * out_stride;
+  int* oa = anchor_index ? anchor_index + (size_t)g * out_stride : nullptr;
+  int n;
+  if (keep) {
+    n = n_keep[g];
+    for (int j = tid; j < n; j += blockDim.x) {
+      const int src = (int)keep[(size_t)g * keep_stride + j];
+      op[j] = b[src]; os[j] = sc[src];
+      if (oa) oa[j] = an[src];
     }
-    proposals[(size_t)g * out_stride + j] = box;
-    scores[(size_t)g * out_stride + j] = s;
-    if (anchor_index) anchor_index[(size_t)g * out_stride + j] = a;
+  } else {
+    const unsigned long long* inv = invalid + (size_t)g * invalid_words;
+    int running = 0;
+    for (int w0 = 0; w0 < invalid_words; w0 += 256) {  // one 64-candidate word per thread
+      const int w = w0 + tid;
+      unsigned long long bits = 0;
+      if (w < invalid_words) {
+        const int rem = k - w * 64;
+        const unsigned long long live = rem >= 64 ? ~0ull : (rem > 0 ? (1ull << rem) - 1ull : 0ull);
+        bits = ~inv[w] & live;
+      }
+      const int cnt = __popcll(bits);
+      int incl = cnt;
+#pragma unroll
+      for (int o2 = 1; o2 < 32; o2 <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o2);
+        if (lane >= o2) incl += t;
+      }
+      if (lane == 31) warp_tot[warp] = incl;
+      __syncthreads();
+      int pos = running + incl - cnt;
+      for (int w2 = 0; w2 < warp; w2++) pos += warp_tot[w2];
+      while (bits) {
+        const int bit = __ffsll((long long)bits) - 1;
+        bits &= bits - 1;
+        const int src = w * 64 + bit;
+        if (pos < out_stride) {
+          op[pos] = b[src]; os[pos] = sc[src];
+          if (oa) oa[pos] = an[src];
+        }
+        pos++;
+      }
+      for (int w2 = 0; w2 < 8; w2++) running += warp_tot[w2];
+      __syncthreads();
+    }
+    if (tid == 0) total = min(running, out_stride);
+    __syncthreads();
+    n = total;
   }
-  if (threadIdx.x == 0) n_out[g] = n;
+  for (int j = n + tid; j < out_stride; j += blockDim.x) {
+    op[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    os[j] = 0.f;
+    if (oa) oa[j] = -1;
+  }
+  if (tid == 0) n_out[g] = n;
 }
 
 struct RpnLayout {
-  size_t hist, cand_count, counts, n_keep, cand, boxes, scores, anchor, keep, nms, total;
+  size_t hist, cand_count, invalid, zero_end, n_keep, cand, boxes, scores, anchor, keep, nms, total;
   size_t nms_bytes;
-  int k, keep_stride;
+  int k, keep_stride, invalid_words;
 };
 
 static size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -342,7 +397,9 @@ static RpnLayout rpn_layout(int N, int A, int H, int W, int pre_nms_top_n, int p
   size_t o = 0;
   l.hist = o; o += a256((size_t)N * kRpnPasses * kRpnBins * sizeof(unsigned));
   l.cand_count = o; o += a256((size_t)N * sizeof(int));
-  l.counts = o; o += a256((size_t)N * sizeof(int));
+  l.invalid_words = ceil_div(l.k, 64);
+  l.invalid = o; o += a256((size_t)N * l.invalid_words * 8);
+  l.zero_end = o;  // [hist, zero_end) is cleared by one memset per call
   l.n_keep = o; o += a256((size_t)N * sizeof(int));
   l.cand = o; o += a256((size_t)N * l.k * 8);
   l.boxes = o; o += a256((size_t)N * l.k * 16);
@@ -396,22 +453,17 @@ int abr_rpn_proposals(const float* objectness, const float* box_regression, cons
   char* ws = static_cast<char*>(workspace);
   unsigned* hist = reinterpret_cast<unsigned*>(ws + lay.hist);
   int* cand_count = reinterpret_cast<int*>(ws + lay.cand_count);
-  int* counts = reinterpret_cast<int*>(ws + lay.counts);
+  unsigned long long* invalid = reinterpret_cast<unsigned long long*>(ws + lay.invalid);
   int* n_keep = reinterpret_cast<int*>(ws + lay.n_keep);
   unsigned long long* cand = reinterpret_cast<unsigned long long*>(ws + lay.cand);
   float4* boxes_c = reinterpret_cast<float4*>(ws + lay.boxes);
   float* scores_c = reinterpret_cast<float*>(ws + lay.scores);
   int* anchor_c = reinterpret_cast<int*>(ws + lay.anchor);
   long long* keep = reinterpret_cast<long long*>(ws + lay.keep);
-  ABR_CUDA_OK(cudaMemsetAsync(ws + lay.hist, 0, lay.counts - lay.hist, st));  // histograms + candidate counters
+  ABR_CUDA_OK(cudaMemsetAsync(ws + lay.hist, 0, lay.zero_end - lay.hist, st));  // histograms, counters, validity bitmap
 
   const int M = A * H * W;
   const int k = lay.k;
-  int sort_size = 2;
-  while (sort_size < k) sort_size <<= 1;
-  const size_t sort_smem = (size_t)sort_size * 8;
-  if (sort_smem > 48 * 1024)
-    ABR_CUDA_OK(cudaFuncSetAttribute(rpn_sort_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
   const int chunks = ceil_div(M, kRpnChunk);
   for (int base = 0; base < N; base += kRpnMaxImages) {
     const int n = N - base < kRpnMaxImages ? N - base : kRpnMaxImages;
@@ -433,16 +485,18 @@ int abr_rpn_proposals(const float* objectness, const float* box_regression, cons
     }
     rpn_collect_kernel<<<dim3(chunks, n), 256, 0, st>>>(s, obj, h, cand + (size_t)base * k, cand_count + base);
     ABR_CHECK_LAUNCH("rpn_collect");
-    rpn_sort_decode_kernel<<<n, kSortThreads, sort_smem, st>>>(s, d, base, cand + (size_t)base * k, reg, anchors,
-                                                              boxes_c + (size_t)base * k, scores_c + (size_t)base * k,
-                                                              anchor_c + (size_t)base * k, counts, sort_size);
-    ABR_CHECK_LAUNCH("rpn_sort_decode");
+    rpn_chunk_sort_kernel<<<dim3(ceil_div(k, kSortChunk), n), kSortThreads, 0, st>>>(k, cand + (size_t)base * k);
+    ABR_CHECK_LAUNCH("rpn_chunk_sort");
+    rpn_rank_decode_kernel<<<dim3(ceil_div(k, 256), n), 256, 0, st>>>(s, d, base, cand + (size_t)base * k, reg, anchors,
+                                                                     boxes_c + (size_t)base * k, scores_c + (size_t)base * k,
+                                                                     anchor_c + (size_t)base * k, invalid, lay.invalid_words);
+    ABR_CHECK_LAUNCH("rpn_rank_decode");
   }
   const bool run_nms = nms_thresh > 0.f;  // structures/boxlist_ops.py:22-23: otherwise the list is returned untouched
   if (run_nms) {
     std::vector<int> offsets((size_t)N + 1);
     for (int i = 0; i <= N; i++) offsets[i] = i * k;
-    int rc = nms_run(reinterpret_cast<const float*>(boxes_c), scores_c, offsets.data(), counts, N, nms_thresh, ge,
+    int rc = nms_run(reinterpret_cast<const float*>(boxes_c), scores_c, offsets.data(), nullptr, invalid, N, nms_thresh, ge,
                      post_nms_top_n > 0 ? post_nms_top_n : -1, reinterpret_cast<int64_t*>(keep), lay.keep_stride, n_keep,
                      ws + lay.nms, lay.nms_bytes, st);
     if (rc) return rc;
@@ -450,7 +504,8 @@ int abr_rpn_proposals(const float* objectness, const float* box_regression, cons
   for (int base = 0; base < N; base += kRpnMaxImages) {
     const int n = N - base < kRpnMaxImages ? N - base : kRpnMaxImages;
     rpn_gather_kernel<<<n, 256, 0, st>>>(k, base, boxes_c + (size_t)base * k, scores_c + (size_t)base * k,
-                                         anchor_c + (size_t)base * k, counts, run_nms ? keep : nullptr, lay.keep_stride, n_keep,
+                                         anchor_c + (size_t)base * k, invalid, lay.invalid_words, run_nms ? keep : nullptr,
+                                         lay.keep_stride, n_keep,
                                          reinterpret_cast<float4*>(proposals), scores, anchor_index, n_out, out_stride);
     ABR_CHECK_LAUNCH("rpn_gather");
   }
