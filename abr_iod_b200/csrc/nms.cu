@@ -121,6 +121,10 @@ __device__ __forceinline__ float iou_plus_one(const float4 a, const float4 b) {
   return __fdiv_rn(inter, __fsub_rn(__fadd_rn(sa, sb), inter));
 }
 
+__device__ __forceinline__ float box_area_plus_one(const float4 b) {
+  return __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.f), __fadd_rn(__fsub_rn(b.w, b.y), 1.f));
+}
+
 // Upper-triangular tile pairs only, enumerated row-major: tile t of an image with cb tile rows is (row, col >= row).
 // A 256-thread CTA takes kMaskTilesPerCta consecutive pairs, one per 64-thread group; thread i of a group owns row box
 // 64*row+i and emits the 64-bit word of column boxes it suppresses (only boxes AFTER it in score order:
@@ -138,6 +142,7 @@ __global__ void __launch_bounds__(kTile * kMaskTilesPerCta) iou_mask_kernel(NmsB
   const int grp = threadIdx.x / kTile, lane64 = threadIdx.x % kTile;
   const long long t = (long long)blockIdx.x * kMaskTilesPerCta + grp;
   __shared__ float4 cbox[kMaskTilesPerCta][kTile];
+  __shared__ float carea[kMaskTilesPerCta][kTile];
   int row = 0, col = 0;
   const bool live = t < ntiles;
   if (live) {
@@ -152,16 +157,42 @@ __global__ void __launch_bounds__(kTile * kMaskTilesPerCta) iou_mask_kernel(NmsB
   }
   const float4* bx = sorted_boxes + nb.box_off[img];
   const int col_size = live ? min(n - col * kTile, kTile) : 0, row_size = live ? min(n - row * kTile, kTile) : 0;
-  if (lane64 < col_size) cbox[grp][lane64] = bx[col * kTile + lane64];
+  if (lane64 < col_size) {
+    const float4 b = bx[col * kTile + lane64];
+    cbox[grp][lane64] = b;
+    carea[grp][lane64] = box_area_plus_one(b);
+  }
   __syncthreads();
   if (lane64 < row_size) {
     const int cur = row * kTile + lane64;
     const float4 a = bx[cur];
+    const float sa = box_area_plus_one(a);
     unsigned long long w = 0;
     const int start = (row == col) ? lane64 + 1 : 0;
+    // The decision is fl(inter / union) > thresh exactly as the reference rounds it, but the division only runs for
+    // the few pairs within 2^-20 of the threshold: pairs without intersection and pairs clearly on one side are
+    // settled by a product.  (thresh <= 0 or non-finite values take the exact path for every pair.)
+    const bool fast = thresh >= 1e-6f;  // keeps thresh * union a normal number for every union the fast path accepts
+    const float hi_k = 1.f + 9.5367431640625e-07f, lo_k = 1.f - 9.5367431640625e-07f;  // 1 +- 2^-20
     for (int i = start; i < col_size; i++) {
-      const float v = iou_plus_one(a, cbox[grp][i]);
-      if (ge ? (v >= thresh) : (v > thresh)) w |= 1ull << i;
+      const float4 b = cbox[grp][i];
+      const float width = __fadd_rn(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 1.f);
+      const float height = __fadd_rn(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 1.f);
+      bool hit;
+      if (fast && (width <= 0.f || height <= 0.f)) {
+        hit = false;  // inter = 0, IoU = 0 (or NaN for 0/0): never above a positive threshold
+      } else {
+        const float inter = __fmul_rn(fmaxf(width, 0.f), fmaxf(height, 0.f));
+        const float uni = __fsub_rn(__fadd_rn(sa, carea[grp][i]), inter);
+        const float p = __fmul_rn(thresh, uni);
+        if (fast && uni > 1e-10f && inter > __fmul_rn(p, hi_k)) hit = true;
+        else if (fast && uni > 1e-10f && inter < __fmul_rn(p, lo_k)) hit = false;
+        else {
+          const float v = __fdiv_rn(inter, uni);
+          hit = ge ? (v >= thresh) : (v > thresh);
+        }
+      }
+      if (hit) w |= 1ull << i;
     }
     mask[nb.mask_off[img] + (long long)cur * cb + col] = w;
   }
