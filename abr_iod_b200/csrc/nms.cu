@@ -324,33 +324,55 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(NmsBatch nb, const
     // except the one before the last
     if (published >= 2) asm volatile("bar.sync %0, %1;" ::"r"(3 + ((published - 2) & 1)), "r"(kSweepThreads) : "memory");
   } else {
-    const int htid = tid - 32, nhelp = kSweepThreads - 32;
+    const int htid = tid - 32;
+    constexpr int nhelp = kSweepThreads - 32;           // 480 helper threads
+    constexpr int kNear = 60, kSpec = kTile * kNear / nhelp;  // 64 rows x 60 nearest columns = 8 words per helper
+    static_assert(kTile * kNear == kSpec * nhelp, "speculative words must divide evenly over the helpers");
     for (int k = 0; k < cb; k++) {
+      // Speculative part: the 60 columns after k+1 for ALL 64 rows of tile k are fetched while warp 0 still runs the
+      // chain of tile k, so that once the kept set is published only shared-memory ORs remain.
+      unsigned long long v[kSpec];
+      const int first = k * kTile;
+#pragma unroll
+      for (int u = 0; u < kSpec; u++) {
+        const int p = htid + u * nhelp;
+        const int ri = p / kNear, col = k + 2 + (p - ri * kNear);
+        v[u] = (first + ri < n && col < cb) ? m[(long long)(first + ri) * cb + col] : 0ull;
+      }
       asm volatile("bar.sync %0, %1;" ::"r"(1 + (k & 1)), "r"(kSweepThreads) : "memory");  // kept rows of tile k are published
       if (stop_flag[k & 1]) break;  // tile k was the last one: nothing further depends on its far words
+      const unsigned long long kept = kept_sorted[k];
+#pragma unroll
+      for (int u = 0; u < kSpec; u++) {
+        const int p = htid + u * nhelp;
+        const int ri = p / kNear;
+        if (v[u] && ((kept >> ri) & 1ull)) atomicOr(&removed[k + 2 + (p - ri * kNear)], v[u]);
+      }
+      // Far part (columns beyond the speculative window; only long full passes have any): kept rows only, (row, word)
+      // pairs dealt out to all helper threads, word index fastest, four independent loads in flight.
       const int cnt = kept_count[k & 1];
       const int* rows = kept_rows[k & 1];
-      const int nwords = cb - k - 2;  // columns k+2 .. cb-1 (column k+1 travels in warp 0's registers)
-      const int total = cnt * nwords;
-      // (kept row, word) pairs dealt out to all helper threads, word index fastest, four independent loads in flight
+      const int far0 = k + 2 + kNear;
+      const int nwords = cb - far0;
+      const int total = nwords > 0 ? cnt * nwords : 0;
       for (int t = htid; t < total; t += 4 * nhelp) {
-        unsigned long long v[4];
+        unsigned long long w[4];
         int j[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
           const int tt = t + u * nhelp;
           if (tt < total) {
             const int ri = tt / nwords;
-            j[u] = k + 2 + (tt - ri * nwords);
-            v[u] = m[(long long)rows[ri] * cb + j[u]];
+            j[u] = far0 + (tt - ri * nwords);
+            w[u] = m[(long long)rows[ri] * cb + j[u]];
           } else {
             j[u] = -1;
-            v[u] = 0;
+            w[u] = 0;
           }
         }
 #pragma unroll
         for (int u = 0; u < 4; u++)
-          if (j[u] >= 0 && v[u]) atomicOr(&removed[j[u]], v[u]);
+          if (j[u] >= 0 && w[u]) atomicOr(&removed[j[u]], w[u]);
       }
       __threadfence_block();
       asm volatile("bar.arrive %0, %1;" ::"r"(3 + (k & 1)), "r"(kSweepThreads) : "memory");  // done with tile k
