@@ -200,6 +200,13 @@ __global__ void __launch_bounds__(kTile * kMaskTilesPerCta) iou_mask_kernel(NmsB
 
 constexpr int kSweepThreads = 512;
 
+// OR into a 64-bit shared-memory word as two native 32-bit atomics (the 64-bit form compiles to a CAS spin loop)
+__device__ __forceinline__ void or_shared_u64(unsigned long long* word, unsigned long long v) {
+  unsigned* h = reinterpret_cast<unsigned*>(word);
+  if ((unsigned)v) atomicOr(h, (unsigned)v);
+  if ((unsigned)(v >> 32)) atomicOr(h + 1, (unsigned)(v >> 32));
+}
+
 // One CTA per image.  Per 64-box tile: warp 0 resolves the greedy chain inside the tile from the diagonal mask words
 // (suppression word and chain in registers, diagonal and first off-diagonal words prefetched a tile ahead) and publishes
 // the kept boxes; warps 1..15 OR the remaining mask words of the kept rows into the shared-memory `removed` words --
@@ -309,7 +316,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(NmsBatch nb, const
       total += cnt;
       const bool last = (k + 1 == cb) || (may_stop && total >= max_keep);  // later boxes have larger indices than the cut
       if (lane == 0) { kept_sorted[k] = kept; kept_count[k & 1] = cnt; stop_flag[k & 1] = last ? 1 : 0; }
-      __threadfence_block();
+      __syncwarp();
       asm volatile("bar.arrive %0, %1;" ::"r"(1 + (k & 1)), "r"(kSweepThreads) : "memory");  // tile k published
       published = k + 1;
       if (last) break;
@@ -326,28 +333,33 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(NmsBatch nb, const
   } else {
     const int htid = tid - 32;
     constexpr int nhelp = kSweepThreads - 32;           // 480 helper threads
-    constexpr int kNear = 60, kSpec = kTile * kNear / nhelp;  // 64 rows x 60 nearest columns = 8 words per helper
-    static_assert(kTile * kNear == kSpec * nhelp, "speculative words must divide evenly over the helpers");
+    // Speculative window: the 60 columns after k+1.  Helper (c, g) = (htid / 8, htid % 8) owns column k+2+c for rows
+    // 8g..8g+7 of the tile; the eight row groups of a column sit in adjacent lanes, so a column's OR is three shuffles
+    // and one pair of 32-bit atomics by its g == 0 lane (a 64-bit shared-memory atomicOr is a CAS spin loop).
+    constexpr int kNear = nhelp / 8, kSpec = kTile / 8;
+    const int hc = htid >> 3, hg = htid & 7;
     for (int k = 0; k < cb; k++) {
-      // Speculative part: the 60 columns after k+1 for ALL 64 rows of tile k are fetched while warp 0 still runs the
-      // chain of tile k, so that once the kept set is published only shared-memory ORs remain.
+      // fetched for ALL rows of tile k while warp 0 still runs the chain of tile k: once the kept set is published only
+      // register work and one shared-memory word per column remain
       unsigned long long v[kSpec];
       const int first = k * kTile;
+      const int col = k + 2 + hc;
 #pragma unroll
       for (int u = 0; u < kSpec; u++) {
-        const int p = htid + u * nhelp;
-        const int ri = p / kNear, col = k + 2 + (p - ri * kNear);
-        v[u] = (first + ri < n && col < cb) ? m[(long long)(first + ri) * cb + col] : 0ull;
+        const int r = first + hg * kSpec + u;
+        v[u] = (r < n && col < cb) ? m[(long long)r * cb + col] : 0ull;
       }
       asm volatile("bar.sync %0, %1;" ::"r"(1 + (k & 1)), "r"(kSweepThreads) : "memory");  // kept rows of tile k are published
       if (stop_flag[k & 1]) break;  // tile k was the last one: nothing further depends on its far words
-      const unsigned long long kept = kept_sorted[k];
+      const unsigned kept8 = (unsigned)(kept_sorted[k] >> (hg * kSpec)) & 0xffu;
+      unsigned long long acc = 0;
 #pragma unroll
-      for (int u = 0; u < kSpec; u++) {
-        const int p = htid + u * nhelp;
-        const int ri = p / kNear;
-        if (v[u] && ((kept >> ri) & 1ull)) atomicOr(&removed[k + 2 + (p - ri * kNear)], v[u]);
-      }
+      for (int u = 0; u < kSpec; u++)
+        if ((kept8 >> u) & 1u) acc |= v[u];
+      acc |= __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc |= __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc |= __shfl_xor_sync(0xffffffffu, acc, 4);
+      if (hg == 0 && col < cb && acc) or_shared_u64(&removed[col], acc);  // helpers of adjacent tiles may overlap here
       // Far part (columns beyond the speculative window; only long full passes have any): kept rows only, (row, word)
       // pairs dealt out to all helper threads, word index fastest, four independent loads in flight.
       const int cnt = kept_count[k & 1];
@@ -372,9 +384,8 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(NmsBatch nb, const
         }
 #pragma unroll
         for (int u = 0; u < 4; u++)
-          if (j[u] >= 0 && w[u]) atomicOr(&removed[j[u]], w[u]);
+          if (j[u] >= 0 && w[u]) or_shared_u64(&removed[j[u]], w[u]);
       }
-      __threadfence_block();
       asm volatile("bar.arrive %0, %1;" ::"r"(3 + (k & 1)), "r"(kSweepThreads) : "memory");  // done with tile k
     }
   }
@@ -388,23 +399,25 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(NmsBatch nb, const
     if (!final_answer) return;
   }
 
-  // kept (sorted positions) -> bitmap over original indices
-  for (int w = tid; w < cb; w += kSweepThreads) {
-    unsigned long long bits = kept_sorted[w];
-    while (bits) {
-      const int b = __ffsll((long long)bits) - 1;
-      bits &= bits - 1;
-      const int orig = ord[w * kTile + b];
-      atomicOr(&kept_orig[orig >> 6], 1ull << (orig & 63));
+  // kept (sorted positions) -> bitmap over original indices.  Sorted inputs: the order is the identity.  Otherwise one
+  // thread per POSITION (coalesced reads of the order, independent of each other), not one per word.
+  if (!reordered) {
+    for (int w = tid; w < cb; w += kSweepThreads) kept_orig[w] = kept_sorted[w];
+  } else {
+    for (int p = tid; p < n; p += kSweepThreads) {
+      if ((kept_sorted[p >> 6] >> (p & 63)) & 1ull) {
+        const int orig = ord[p];
+        atomicOr(reinterpret_cast<unsigned*>(kept_orig) + (orig >> 5), 1u << (orig & 31));
+      }
     }
   }
   __syncthreads();
-  // ascending original indices: block-wide exclusive scan of per-word popcounts, chunk by chunk
+  // ascending original indices: block-wide exclusive scan of per-word popcounts (chunk by chunk) into word offsets ...
+  int* word_pos = reinterpret_cast<int*>(removed);  // the suppression words are no longer needed
   int running = 0;
   for (int w0 = 0; w0 < cb; w0 += kSweepThreads) {
     const int w = w0 + tid;
-    const unsigned long long bits = w < cb ? kept_orig[w] : 0ull;
-    const int cnt = __popcll(bits);
+    const int cnt = w < cb ? __popcll(kept_orig[w]) : 0;
     int incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -425,16 +438,18 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(NmsBatch nb, const
       if (lane == kSweepThreads / 32 - 1) scan[kSweepThreads / 32] = s2;
     }
     __syncthreads();
-    int pos = running + scan[warp] + incl - cnt;
-    unsigned long long b2 = bits;
-    while (b2) {
-      const int b = __ffsll((long long)b2) - 1;
-      b2 &= b2 - 1;
-      if (pos < keep_stride && (max_keep <= 0 || pos < max_keep)) out[pos] = (long long)(w * kTile + b);
-      pos++;
-    }
+    if (w < cb) word_pos[w] = running + scan[warp] + incl - cnt;
     running += scan[kSweepThreads / 32];
     __syncthreads();
+  }
+  // ... then one thread per box index writes its own slot
+  const int limit = max_keep > 0 ? min(max_keep, keep_stride) : keep_stride;
+  for (int p = tid; p < cb * kTile; p += kSweepThreads) {
+    const unsigned long long bits = kept_orig[p >> 6];
+    if ((bits >> (p & 63)) & 1ull) {
+      const int pos = word_pos[p >> 6] + __popcll(bits & ((1ull << (p & 63)) - 1ull));
+      if (pos < limit) out[pos] = (long long)p;
+    }
   }
   int total = running;
   if (max_keep > 0) total = min(total, max_keep);
