@@ -55,6 +55,9 @@ SIGNATURES = {
     "abr_rpn_proposals_workspace_bytes": (_sz, [_int] * 6),
     "abr_rpn_proposals": (_int, [_vp, _vp, _vp, ctypes.c_longlong, _vp] + [_int] * 7 + [_f, _int, _f, _vp, _f,
                                  _vp, _vp, _vp, _vp, _int, _vp, _sz, _vp]),
+    "abr_box_postprocess_workspace_bytes": (_sz, [_vp, _int, _int]),
+    "abr_box_postprocess": (_int, [_vp, _vp, _int, _int, _vp, _vp, _vp, _int, _int, _f, _f, _int, _int, _vp, _f,
+                                   _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _int, _vp, _sz, _vp]),
     "abr_ard_workspace_bytes": (_sz, [_int, _int, _int]),
     "abr_ard_forward_backward": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _f, _f, _int, _int, _vp, _sz, _vp]),
     "abr_scale_if_needed": (_int, [_vp, _sz, _vp, _f, _int, _vp]),

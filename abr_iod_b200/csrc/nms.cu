@@ -21,7 +21,7 @@
 namespace abr {
 
 constexpr int kTile = 64;          // boxes per mask word
-constexpr int kImagesPerLaunch = 32;
+constexpr int kImagesPerLaunch = 64;
 
 struct NmsBatch {
   int n_images;

@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "decode.cuh"
 
 namespace abr {
 
@@ -45,15 +46,6 @@ __device__ __forceinline__ int rpn_shift(int pass) {
 }
 __device__ __forceinline__ unsigned rpn_digit_mask(int pass) { return pass == 2 ? 1023u : 2047u; }
 
-__device__ __forceinline__ unsigned ordered_bits(float s) {
-  unsigned u = __float_as_uint(s);
-  if (s != s) return 0xFFFFFFFFu;  // NaN ranks first, like torch.topk
-  if (u == 0x80000000u) u = 0u;    // -0.0 ties with +0.0
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float from_ordered_bits(unsigned u) {
-  return __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u);
-}
 __device__ __forceinline__ unsigned long long rpn_key(float logit, int anchor) {
   return ((unsigned long long)ordered_bits(logit) << kRpnIdxBits) | (unsigned long long)(((1u << kRpnIdxBits) - 1u) - (unsigned)anchor);
 }
@@ -276,32 +268,15 @@ __global__ void __launch_bounds__(256) rpn_rank_decode_kernel(RpnShape s, RpnDec
     r0 = __ldg(rp); r1 = __ldg(rp + hw); r2 = __ldg(rp + 2 * hw); r3 = __ldg(rp + 3 * hw);
   }
   const float4 an = __ldg(reinterpret_cast<const float4*>(anc) + anchor);
-  // BoxCoder.decode, one rounding per tensor op (no contraction)
-  const float widths = __fadd_rn(__fsub_rn(an.z, an.x), 1.f);
-  const float heights = __fadd_rn(__fsub_rn(an.w, an.y), 1.f);
-  const float ctr_x = __fadd_rn(an.x, __fmul_rn(0.5f, widths));
-  const float ctr_y = __fadd_rn(an.y, __fmul_rn(0.5f, heights));
-  const float dx = __fdiv_rn(r0, d.wx), dy = __fdiv_rn(r1, d.wy);
-  float dw = __fdiv_rn(r2, d.ww), dh = __fdiv_rn(r3, d.wh);
-  dw = dw > d.clip ? d.clip : dw;  // torch.clamp(max=): NaN stays NaN
-  dh = dh > d.clip ? d.clip : dh;
-  const float pcx = __fadd_rn(__fmul_rn(dx, widths), ctr_x);
-  const float pcy = __fadd_rn(__fmul_rn(dy, heights), ctr_y);
-  const float pw = __fmul_rn(expf(dw), widths);
-  const float ph = __fmul_rn(expf(dh), heights);
-  float x1 = __fsub_rn(pcx, __fmul_rn(0.5f, pw));
-  float y1 = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
-  float x2 = __fsub_rn(__fadd_rn(pcx, __fmul_rn(0.5f, pw)), 1.f);
-  float y2 = __fsub_rn(__fadd_rn(pcy, __fmul_rn(0.5f, ph)), 1.f);
-  // clip_to_image: clamp(min=0, max=size-1)
-  const float xmax = (float)(d.im_w[img] - 1), ymax = (float)(d.im_h[img] - 1);
-  x1 = fminf(fmaxf(x1, 0.f), xmax); y1 = fminf(fmaxf(y1, 0.f), ymax);
-  x2 = fminf(fmaxf(x2, 0.f), xmax); y2 = fminf(fmaxf(y2, 0.f), ymax);
+  BoxCoderParams bc;
+  bc.wx = d.wx; bc.wy = d.wy; bc.ww = d.ww; bc.wh = d.wh; bc.clip = d.clip;
+  const float4 box = decode_and_clip(an, r0, r1, r2, r3, bc, (float)(d.im_w[img] - 1), (float)(d.im_h[img] - 1));
+  const float x1 = box.x, y1 = box.y, x2 = box.z, y2 = box.w;
   // remove_small_boxes on the xywh sides (+1 convention)
   const float bw = __fadd_rn(__fsub_rn(x2, x1), 1.f), bh = __fadd_rn(__fsub_rn(y2, y1), 1.f);
   const bool ok = bw >= d.min_size && bh >= d.min_size;
   const size_t o = (size_t)img * k + rank;
-  boxes_c[o] = make_float4(x1, y1, x2, y2);
+  boxes_c[o] = box;
   scores_c[o] = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-logit)));
   anchor_c[o] = anchor;
   if (!ok) atomicOr(invalid + (size_t)(first_image + img) * invalid_words + (rank >> 6), 1ull << (rank & 63));

@@ -378,8 +378,33 @@ def secondary_metrics(dev):
         out[key] = round(batch * n / _time_call(lambda: nms_batched(boxes, scores, 0.7, keep_n), graph=False))
         out[key + "_graph"] = round(batch * n / _time_call(lambda: nms_batched(boxes, scores, 0.7, keep_n), graph=True))
     out.update(rpn_metrics(dev))
+    out.update(box_post_metrics(dev))
     out.update(paste_metrics(dev))
     return out
+
+
+def box_post_metrics(dev):
+    """Box-head post-processing (second half) on config-2 test shapes: batch 4, 1000 proposals per
+    image, 21 classes (VOC), score 0.05, NMS 0.5, 100 detections per image; images/s with resident head outputs."""
+    import torch
+
+    from abr_iod_b200.modeling.roi_heads.box_head import box_postprocess
+
+    rng = np.random.default_rng(7)
+    N, n, C = 4, 1000, 21
+    w, h = 1216, 800
+    centers = rng.uniform([0.1 * w, 0.1 * h], [0.9 * w, 0.9 * h], (N, 12, 2))
+    which = rng.integers(0, 12, (N, n))
+    c = np.take_along_axis(centers, which[..., None].repeat(2, -1), 1) + rng.normal(0, 12, (N, n, 2))
+    wh = rng.uniform(40, 300, (N, n, 2))
+    props = np.clip(np.concatenate([c - wh / 2, c + wh / 2], -1), 0, [w - 1, h - 1, w - 1, h - 1]).astype(np.float32).reshape(-1, 4)
+    logits = rng.normal(0, 1, (N * n, C)).astype(np.float32)
+    logits[np.arange(N * n), 1 + which.reshape(-1) % (C - 1)] += rng.uniform(0, 6, N * n).astype(np.float32)
+    reg = rng.normal(0, 0.5, (N * n, 4 * C)).astype(np.float32)
+    lt, rt, pt = (torch.from_numpy(a).to(dev) for a in (logits, reg, props))
+    call = lambda: box_postprocess(lt, rt, pt, [n] * N, [(w, h)] * N, 0.05, 0.5, 100)  # noqa: E731
+    # (the wrapper reads the per-image counts once per call, so it cannot be graph-captured as a whole)
+    return {"box_post_imgs_per_s_b4_r1000_c21": round(N / _time_call(call, graph=False))}
 
 
 def rpn_metrics(dev):

@@ -162,6 +162,34 @@ ABR_API int abr_rpn_proposals(const float* objectness, const float* box_regressi
                               int32_t* anchor_index, int32_t* n_out, int out_stride, void* workspace,
                               size_t workspace_bytes, abr_stream_t stream);
 
+/* ---------------------------------------------------------------- box-head post-processing (class-batched NMS)
+ * Replaces PostProcessor.forward / filter_results (modeling/roi_heads/box_head/inference.py:42-151) for a
+ * whole batch with no host synchronisation: softmax (:56), BoxCoder.decode of the class deltas (:65-67,
+ * modeling/box_coder.py:52-95), clip_to_image (:80), score threshold (:117), per-class boxlist_nms
+ * (:119-126) as ONE batched NMS over all (image, class) pairs, concatenation of the foreground classes
+ * in class order (:139) and the detections_per_img cut (:142-149: scores >= the k-th largest, ties survive).
+ *   class_logits   [R,C] fp32; box_regression rows of reg_row_stride floats: class j's deltas at
+ *                  columns 4j..4j+3, or (cls_agnostic != 0, :63-64,68-69) the row's LAST four columns for
+ *                  every class; proposals [R,4] fp32 xyxy: the images' proposals back to back;
+ *   boxes_per_image_host [n_images], image_sizes_host [n_images][2] (width, height): HOST arrays;
+ *   det_boxes [n_images,det_stride,4] fp32, det_scores [n_images,det_stride] fp32, det_labels
+ *   [n_images,det_stride] int64, det_rows [n_images,det_stride] int32 (optional: the proposal each
+ *   detection came from, image-relative), n_det [n_images] int32: the results in the reference's order,
+ *   zero / -1 padded.  n_det[i] is the TRUE count: if it exceeds det_stride (equal scores tying at the
+ *   cut, or no cut), only det_stride entries were written and the caller re-runs with a wider stride;
+ *   bg_boxes [n_images,bg_stride,4], bg_scores [n_images,bg_stride], n_bg [n_images]: class 0 after its
+ *   own NMS (the reference returns the last image's: :82,137-138); bg_stride >= max boxes per image.
+ * nms_thresh <= 0 skips the NMS like boxlist_nms does.  `ge` as in abr_nms_batched.  Score ties inside
+ * the NMS break by ascending proposal index (see abr_nms_batched). */
+ABR_API size_t abr_box_postprocess_workspace_bytes(const int* boxes_per_image_host, int n_images, int num_classes);
+ABR_API int abr_box_postprocess(const float* class_logits, const float* box_regression, int reg_row_stride, int cls_agnostic,
+                                const float* proposals, const int* boxes_per_image_host, const int* image_sizes_host,
+                                int n_images, int num_classes, float score_thresh, float nms_thresh, int ge,
+                                int detections_per_img, const float* weights4_host, float bbox_xform_clip,
+                                float* det_boxes, float* det_scores, int64_t* det_labels, int32_t* det_rows,
+                                int32_t* n_det, int det_stride, float* bg_boxes, float* bg_scores, int32_t* n_bg,
+                                int bg_stride, void* workspace, size_t workspace_bytes, abr_stream_t stream);
+
 /* ---------------------------------------------------------------- Attentive RoI Distillation
  * Native form of calculate_attentive_roi_feature_distillation (distillation/distillation.py:86-130)
  * and of its autograd backward, in one kernel.  f_old = old model / teacher pooled features (argument 0

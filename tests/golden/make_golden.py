@@ -318,11 +318,61 @@ def gen_rpn(out):
     np.savez_compressed(os.path.join(out, "rpn.npz"), **d)
 
 
+def box_post_inputs(rng, sizes, counts, C):
+    """Clustered proposals with peaky class logits, so that the score threshold, the per-class NMS and the
+    detections_per_img cut all have something to do."""
+    props, logits, regs = [], [], []
+    for (w, h), n in zip(sizes, counts):
+        centers = rng.uniform([0.2 * w, 0.2 * h], [0.8 * w, 0.8 * h], (6, 2))
+        cls = rng.integers(1, C, 6)
+        which = rng.integers(0, 6, n)
+        c = centers[which] + rng.normal(0, 6, (n, 2))
+        wh = rng.uniform(30, 90, (n, 2))
+        b = np.stack([c[:, 0] - wh[:, 0] / 2, c[:, 1] - wh[:, 1] / 2, c[:, 0] + wh[:, 0] / 2, c[:, 1] + wh[:, 1] / 2], 1)
+        b = np.clip(b, 0, [w - 1, h - 1, w - 1, h - 1]).astype(np.float32)
+        lg = rng.normal(0, 1, (n, C)).astype(np.float32)
+        lg[np.arange(n), cls[which]] += rng.uniform(0, 5, n).astype(np.float32)
+        lg[:, 0] += rng.uniform(-1, 3, n).astype(np.float32)
+        props.append(b)
+        logits.append(lg)
+        regs.append((rng.normal(0, 0.5, (n, 4 * C))).astype(np.float32))
+    return props, np.concatenate(logits, 0), np.concatenate(regs, 0)
+
+
+def gen_box_post(out):
+    """PostProcessor.forward (modeling/roi_heads/box_head/inference.py:42-151) run on CPU; NMS = the reference's nms_cpu."""
+    from maskrcnn_benchmark.modeling.box_coder import BoxCoder
+    from maskrcnn_benchmark.modeling.roi_heads.box_head.inference import PostProcessor
+    from maskrcnn_benchmark.structures.bounding_box import BoxList
+
+    rng = np.random.default_rng(21)
+    sizes = [(320, 240), (300, 200)]
+    counts = [120, 90]
+    C = 6
+    props, logits, reg = box_post_inputs(rng, sizes, counts, C)
+    d = {"image_sizes": np.asarray(sizes, np.int64), "counts": np.asarray(counts, np.int64), "class_logits": logits,
+         "box_regression": reg, "proposals": np.concatenate(props, 0)}
+    cases = [(0.05, 0.5, 100, False), (0.05, 0.5, 12, False), (0.3, 0.3, 100, False), (0.05, 0.5, 100, True)]
+    d["cases"] = np.asarray([[c[0], c[1], c[2], float(c[3])] for c in cases], np.float64)
+    for ci, (st, nt, det, agn) in enumerate(cases):
+        pp = PostProcessor(st, nt, det, BoxCoder(weights=(10.0, 10.0, 5.0, 5.0)), agn)
+        boxlists = [BoxList(torch.from_numpy(p.copy()), s, "xyxy") for p, s in zip(props, sizes)]
+        r = reg[:, -4:] if False else reg
+        results, bg = pp((torch.from_numpy(logits), torch.from_numpy(r)), boxlists)
+        for n, res in enumerate(results):
+            d["c%d_i%d_boxes" % (ci, n)] = res.bbox.numpy().astype(np.float32)
+            d["c%d_i%d_scores" % (ci, n)] = res.get_field("scores").numpy().astype(np.float32)
+            d["c%d_i%d_labels" % (ci, n)] = res.get_field("labels").numpy().astype(np.int64)
+        d["c%d_bg_boxes" % ci] = bg.bbox.numpy().astype(np.float32)
+        d["c%d_bg_scores" % ci] = bg.get_field("scores").numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(out, "box_post.npz"), **d)
+
+
 def main():
     assert os.path.isdir(REFERENCE), "the reference tree is needed to (re)generate golden vectors"
     assert oracle.ref_available(), "run `make -C oracle ref` first"
     install_reference_stubs()
-    for fn in (gen_roi_align, gen_nms, gen_ard, gen_pooler, gen_boxlist_nms, gen_paste, gen_rpn):
+    for fn in (gen_roi_align, gen_nms, gen_ard, gen_pooler, gen_boxlist_nms, gen_paste, gen_rpn, gen_box_post):
         fn(HERE)
         print("wrote", fn.__name__)
 

@@ -1,0 +1,134 @@
+"""GPU parity of the box-head post-processing (softmax -> per-class decode -> threshold -> class-batched NMS -> detection
+cut) through the reference-shaped Python API (-> C ABI -> sm_100a kernels) against the golden vectors produced by the
+reference's own PostProcessor and against the numpy oracle.
+
+Index work (which (proposal, class) pairs survive, their order, labels) is checked exactly.  Scores are softmax values
+(expf on the device vs torch's CPU exp, and a different summation order): |a-b| <= 2e-6.  Box coordinates: 4 ulp of the
+largest decode intermediate, e^bbox_xform_clip * (largest proposal side), as in tests/test_gpu_rpn.py."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import box_post as obp
+from oracle import rpn as orpn
+
+pytestmark = pytest.mark.gpu
+
+
+def boxes_close(a, ref, proposals):
+    a, ref = np.asarray(a, np.float64), np.asarray(ref, np.float64)
+    assert a.shape == ref.shape
+    side = float(max((proposals[:, 2] - proposals[:, 0]).max(), (proposals[:, 3] - proposals[:, 1]).max())) + 1.0
+    tol = 4 * 2.0 ** -23 * np.exp(orpn.BBOX_XFORM_CLIP) * side
+    err = np.abs(a - ref)
+    assert err.size == 0 or (err <= tol).all(), "max err %g > %g" % (err.max(), tol)
+
+
+def dev(x):
+    return torch.as_tensor(x).cuda()
+
+
+def make_inputs(rng, sizes, counts, C):
+    """Clustered proposals with peaky class logits (same recipe as tests/golden/make_golden.py:box_post_inputs)."""
+    props, logits, regs = [], [], []
+    for (w, h), n in zip(sizes, counts):
+        centers = rng.uniform([0.2 * w, 0.2 * h], [0.8 * w, 0.8 * h], (6, 2))
+        cls = rng.integers(1, C, 6)
+        which = rng.integers(0, 6, n)
+        c = centers[which] + rng.normal(0, 6, (n, 2))
+        wh = rng.uniform(30, 90, (n, 2))
+        b = np.stack([c[:, 0] - wh[:, 0] / 2, c[:, 1] - wh[:, 1] / 2, c[:, 0] + wh[:, 0] / 2, c[:, 1] + wh[:, 1] / 2], 1)
+        b = np.clip(b, 0, [w - 1, h - 1, w - 1, h - 1]).astype(np.float32)
+        lg = rng.normal(0, 1, (n, C)).astype(np.float32)
+        lg[np.arange(n), cls[which]] += rng.uniform(0, 5, n).astype(np.float32)
+        lg[:, 0] += rng.uniform(-1, 3, n).astype(np.float32)
+        props.append(b)
+        logits.append(lg)
+        regs.append((rng.normal(0, 0.5, (n, 4 * C))).astype(np.float32))
+    return props, np.concatenate(logits, 0), np.concatenate(regs, 0)
+
+
+def test_post_processor_golden_vs_reference_python(golden):
+    from abr_iod_b200.modeling.roi_heads.box_head import box_postprocess
+
+    g = golden("box_post.npz")
+    counts = [int(c) for c in g["counts"]]
+    sizes = [tuple(int(v) for v in s) for s in g["image_sizes"]]
+    for ci, (st, nt, det, agn) in enumerate(g["cases"]):
+        # the golden run used the reference's CPU NMS (IoU >= thr)
+        out = box_postprocess(dev(g["class_logits"]), dev(g["box_regression"]), dev(g["proposals"]), counts, sizes, st, nt,
+                              int(det), cls_agnostic_bbox_reg=bool(agn), cpu_tie_rule=True)
+        for n in range(len(sizes)):
+            k = out["n_host"][n]
+            gb, gs, gl = g["c%d_i%d_boxes" % (ci, n)], g["c%d_i%d_scores" % (ci, n)], g["c%d_i%d_labels" % (ci, n)]
+            assert k == len(gs)
+            assert np.array_equal(out["labels"][n, :k].cpu().numpy(), gl)
+            assert np.abs(out["scores"][n, :k].cpu().numpy() - gs).max() <= 2e-6
+            boxes_close(out["boxes"][n, :k].cpu().numpy(), gb, g["proposals"])
+            assert int((out["labels"][n, k:] != -1).sum()) == 0
+        last = len(sizes) - 1
+        kb = int(out["bg_n"][last])
+        assert kb == len(g["c%d_bg_scores" % ci])
+        assert np.abs(out["bg_scores"][last, :kb].cpu().numpy() - g["c%d_bg_scores" % ci]).max() <= 2e-6
+        boxes_close(out["bg_boxes"][last, :kb].cpu().numpy(), g["c%d_bg_boxes" % ci], g["proposals"])
+
+
+@pytest.mark.parametrize("counts,C,det,agnostic", [([1000, 1000, 1000, 1000], 21, 100, False), ([300, 0, 517], 16, 40, False),
+                                                    ([64, 65], 81, 0, False), ([200, 150], 11, 100, True)])
+def test_post_processor_module_vs_oracle(counts, C, det, agnostic):
+    from abr_iod_b200.modeling.roi_heads.box_head import PostProcessor
+    from abr_iod_b200.structures.bounding_box import BoxList
+
+    rng = np.random.default_rng(sum(counts) + C)
+    sizes = [(1216 - 16 * i, 800 - 8 * i) for i in range(len(counts))]
+    props, logits, reg = make_inputs(rng, sizes, counts, C)
+    pp = PostProcessor(0.05, 0.5, det, cls_agnostic_bbox_reg=agnostic)
+    boxlists = [BoxList(dev(p.reshape(-1, 4)), s, "xyxy") for p, s in zip(props, sizes)]
+    results, bg = pp((dev(logits), dev(reg)), boxlists)
+    ref, ref_bg = obp.box_postprocess(logits, reg, props, sizes, 0.05, 0.5, det, cls_agnostic_bbox_reg=agnostic)
+    allp = np.concatenate(props, 0)
+    for n in range(len(counts)):
+        rb, rs, rl, _ = ref[n]
+        assert len(results[n]) == len(rs) and results[n].size == sizes[n]
+        assert np.array_equal(results[n].get_field("labels").cpu().numpy(), rl)
+        if len(rs):
+            assert np.abs(results[n].get_field("scores").cpu().numpy() - rs).max() <= 2e-6
+            boxes_close(results[n].bbox.cpu().numpy(), rb, allp)
+    assert len(bg) == len(ref_bg[-1][1])
+    if len(bg):
+        assert np.abs(bg.get_field("scores").cpu().numpy() - ref_bg[-1][1]).max() <= 2e-6
+
+
+def test_post_processor_ties_at_the_cut_survive_and_rows_are_exact():
+    """Equal logits rows -> equal scores: `scores >= kthvalue` keeps every tied detection (inference.py:147), so more than
+    detections_per_img come back; the wrapper widens its output and the proposal rows match the oracle exactly."""
+    from abr_iod_b200.modeling.roi_heads.box_head import box_postprocess
+
+    rng = np.random.default_rng(2)
+    C, n = 5, 400
+    w, h = 640, 480
+    xy = rng.uniform(0, [w - 60, h - 60], (n, 2))
+    props = np.concatenate([xy, xy + rng.uniform(20, 50, (n, 2))], 1).astype(np.float32)  # scattered: NMS keeps most
+    logits = np.zeros((n, C), np.float32)
+    logits[:, 2] = 3.0  # the same class-2 score for every proposal
+    reg = np.zeros((n, 4 * C), np.float32)
+    out = box_postprocess(dev(logits), dev(reg), dev(props), [n], [(w, h)], 0.05, 0.5, 10, det_stride=16)
+    ref, _ = obp.box_postprocess(logits, reg, [props], [(w, h)], 0.05, 0.5, 10)
+    k = out["n_host"][0]
+    assert k == len(ref[0][1]) and k > 100
+    assert np.array_equal(out["rows"][0, :k].cpu().numpy(), ref[0][3])
+    assert np.array_equal(out["labels"][0, :k].cpu().numpy(), ref[0][2])
+
+
+def test_post_processor_argument_errors():
+    from abr_iod_b200.modeling.roi_heads.box_head import box_postprocess
+
+    logits = torch.zeros((10, 4), device="cuda")
+    reg = torch.zeros((10, 16), device="cuda")
+    props = torch.zeros((10, 4), device="cuda")
+    with pytest.raises(RuntimeError):
+        box_postprocess(logits.cpu(), reg, props, [10], [(100, 100)])
+    with pytest.raises(RuntimeError):
+        box_postprocess(logits, reg, props, [9], [(100, 100)])
+    with pytest.raises(RuntimeError):
+        box_postprocess(logits, reg[:, :8], props, [10], [(100, 100)])

@@ -171,3 +171,23 @@ def test_rpn_proposals_oracle_matches_reference_postprocessor(golden):
             assert np.array_equal(scores, g["c%d_i%d_scores" % (ci, n)])
     # the three cases exercise the post-NMS cut, the min_size filter and non-unit coder weights
     assert len(g["c0_i0_boxes"]) == 150 and len(g["c1_i0_boxes"]) < 600
+
+
+def test_box_postprocess_oracle_matches_reference_postprocessor(golden):
+    """oracle/box_post.py against PostProcessor.forward run by make_golden.py (threshold, per-class NMS, the
+    detections_per_img cut, class-agnostic regression): boxes, scores and labels bit for bit, background of the last image."""
+    from oracle import box_post as obp
+
+    g = golden("box_post.npz")
+    counts = g["counts"]
+    props = np.split(g["proposals"], np.cumsum(counts)[:-1])
+    sizes = [tuple(int(v) for v in s) for s in g["image_sizes"]]
+    for ci, (st, nt, det, agn) in enumerate(g["cases"]):
+        res, bg = obp.box_postprocess(g["class_logits"], g["box_regression"], props, sizes, st, nt, int(det),
+                                      cls_agnostic_bbox_reg=bool(agn), flavour="cpu")
+        for n, (b, s, lab, _) in enumerate(res):
+            assert np.array_equal(b, g["c%d_i%d_boxes" % (ci, n)])
+            assert np.array_equal(s, g["c%d_i%d_scores" % (ci, n)])
+            assert np.array_equal(lab, g["c%d_i%d_labels" % (ci, n)])
+        assert np.array_equal(bg[-1][0], g["c%d_bg_boxes" % ci]) and np.array_equal(bg[-1][1], g["c%d_bg_scores" % ci])
+    assert len(g["c1_i0_scores"]) == 12  # the detections_per_img cut was exercised
