@@ -78,3 +78,74 @@ def calculate_attentive_roi_feature_distillation(f_map_s, f_map_t, gamma=1.0):
     """Drop-in for distillation/distillation.py:86-100.  Returns the scalar ``loss_afd + gamma * loss_pad``."""
     loss, _ = _AttentiveRoIDistillation.apply(_lib.as_compute_dtype(f_map_s), _lib.as_compute_dtype(f_map_t), gamma)
     return loss
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# Inclusive distillation of the box head's outputs (distillation/distillation.py:164-241 of the reference)
+def _scale_in_place(t, upstream):
+    scale = upstream.detach().to(torch.float32).reshape(1).contiguous()
+    with torch.cuda.device(t.device):
+        _lib.check(_lib.lib().abr_scale_if_needed(t.data_ptr(), t.numel(), scale.data_ptr(), 1.0, _lib.dtype_code(t),
+                                                  _lib.stream_ptr(t.device)))
+    return t
+
+
+class _RoIDistillationID(Function):
+    @staticmethod
+    def forward(ctx, soften_scores, soften_bboxes, target_scores, target_bboxes):
+        _lib.require_cuda(target_scores, "target_scores")
+        if soften_scores.requires_grad or soften_bboxes.requires_grad:
+            raise RuntimeError("roi distillation: the soften (old model) results carry no gradient in the reference "
+                               "(train_incremental.py:83-85); detach them")
+        R, Co = soften_scores.shape
+        Ct = target_scores.shape[1]
+        if target_scores.shape[0] != R or tuple(soften_bboxes.shape) != (R, Co, 4) or tuple(target_bboxes.shape) != (R, Ct, 4):
+            raise RuntimeError("roi distillation: scores [R,C] and bboxes [R,C,4] of both models must agree on R, got %s %s %s %s"
+                               % (tuple(soften_scores.shape), tuple(soften_bboxes.shape), tuple(target_scores.shape), tuple(target_bboxes.shape)))
+        f32 = lambda t: t.detach().to(torch.float32).contiguous()  # noqa: E731
+        ss, sb, ts, tb = f32(soften_scores), f32(soften_bboxes), f32(target_scores), f32(target_bboxes)
+        dev = ts.device
+        loss3 = torch.empty((3,), dtype=torch.float32, device=dev)
+        gs = torch.empty_like(ts) if target_scores.requires_grad else None
+        gb = torch.empty_like(tb) if target_bboxes.requires_grad else None
+        L = _lib.lib()
+        ws_bytes = int(L.abr_logit_loss_workspace_bytes(R))
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.abr_roi_distillation_id(ss.data_ptr(), sb.data_ptr(), ts.data_ptr(), tb.data_ptr(), R, Co, Ct, 1.0,
+                                                 gs.data_ptr() if gs is not None else None,
+                                                 gb.data_ptr() if gb is not None else None, loss3.data_ptr(), ws.data_ptr(),
+                                                 ws_bytes, _lib.stream_ptr(dev)))
+        ctx.grads = (gs, gb)
+        ctx.dtypes = (target_scores.dtype, target_bboxes.dtype)
+        ctx.mark_non_differentiable(loss3)
+        return loss3[0].clone(), loss3
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_loss, _grad_parts):
+        gs, gb = ctx.grads
+        ctx.grads = (None, None)
+        if gs is not None:
+            gs = _scale_in_place(gs, grad_loss).to(ctx.dtypes[0])
+        if gb is not None:
+            gb = _scale_in_place(gb, grad_loss).to(ctx.dtypes[1])
+        return None, None, gs, gb
+
+
+def roi_distillation_id_terms(soften_results, target_results):
+    """Device tensor ``[class term + box term, class term, box term]`` of the 'id' distillation, with autograd into the
+    target (student) results through the first element."""
+    soften_scores, soften_bboxes = soften_results
+    target_scores, target_bboxes = target_results
+    return _RoIDistillationID.apply(soften_scores, soften_bboxes, target_scores, target_bboxes)
+
+
+def calculate_roi_distillation_losses(soften_results, target_results, dist="l2", soften_proposal=None):
+    """Drop-in for distillation/distillation.py:220-241 with ``dist='id'`` (inclusive distillation: unbiased cross-entropy
+    + L2 box term), the setting the ABR runs use (scripts/run_SI.sh).  One fused forward+backward kernel.
+    The legacy ``dist='l2'`` branch (mean-normalised logits, Faster-ILOD) is outside this path."""
+    if dist != "id":
+        raise NotImplementedError("calculate_roi_distillation_losses: only dist='id' is part of the accelerated path")
+    loss, _ = roi_distillation_id_terms(soften_results, target_results)
+    return loss

@@ -207,6 +207,33 @@ ABR_API int abr_ard_forward_backward(const void* f_old, const void* f_new, void*
 ABR_API int abr_scale_if_needed(void* data, size_t n, const float* scale_dev, float expected, int dtype,
                         abr_stream_t stream);
 
+/* ---------------------------------------------------------------- logit-level losses (forward + backward)
+ * abr_roi_distillation_id replaces calculate_roi_distillation_losses(dist='id')
+ * (distillation/distillation.py:164-241) and its autograd backward:
+ *   soften_scores [R,C_old] / soften_bboxes [R,C_old,4]: the TEACHER's class logits and box deltas (no grad);
+ *   target_scores [R,C_total] / target_bboxes [R,C_total,4]: the STUDENT's, C_total > C_old;
+ *   loss3 = {class term + box term, class term, box term}: unbiased cross-entropy (:191-201) and the L2 box term
+ *   over the old foreground classes 1..C_old-1 (:206-211);
+ *   grad_scores [R,C_total] / grad_bboxes [R,C_total,4] (either may be NULL): grad_scale * d(total)/d(student).
+ * abr_fastrcnn_loss replaces FastRCNNLossComputation.__call__ (modeling/roi_heads/box_head/loss.py:122-184):
+ *   class_logits [R,C], box_regression rows of reg_row_stride floats, labels [R] int64 (-100 = ignored row, as
+ *   F.nll_loss), regression_targets [R,4];  n_old >= 0: inclusive classification loss (:151-159), n_old < 0:
+ *   F.cross_entropy (:162);  box term: smooth-L1 (layers/smooth_l1_loss.py:6-18, `beta`) on columns 4*label..+3 of
+ *   the rows with label > 0 (columns 4..7 when cls_agnostic), summed and divided by R (:166-180);
+ *   loss2 = {classification_loss, box_loss};  grad_logits [R,C] = grad_scale_cls * d(cls)/d(logits), grad_regression
+ *   [R,reg_row_stride] = grad_scale_box * d(box)/d(regression) (either may be NULL).
+ * workspace: abr_logit_loss_workspace_bytes(R).  Row sums are reduced in fixed order (deterministic). */
+ABR_API size_t abr_logit_loss_workspace_bytes(int R);
+ABR_API int abr_roi_distillation_id(const float* soften_scores, const float* soften_bboxes, const float* target_scores,
+                                    const float* target_bboxes, int R, int C_old, int C_total, float grad_scale,
+                                    float* grad_scores, float* grad_bboxes, float* loss3, void* workspace,
+                                    size_t workspace_bytes, abr_stream_t stream);
+ABR_API int abr_fastrcnn_loss(const float* class_logits, const float* box_regression, int reg_row_stride,
+                              const int64_t* labels, const float* regression_targets, int R, int num_classes, int n_old,
+                              int cls_agnostic, float beta, float grad_scale_cls, float grad_scale_box,
+                              float* grad_logits, float* grad_regression, float* loss2, void* workspace,
+                              size_t workspace_bytes, abr_stream_t stream);
+
 /* ---------------------------------------------------------------- ABR paste (mixup / mosaic)
  * Pixel part of PascalVOCDataset_ABR._start_mixup / _start_boxes_mosaic
  * (data/datasets/voc_abr.py:659-678 and :744-763) for a whole batch in one launch.  All images are

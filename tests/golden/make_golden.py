@@ -368,11 +368,65 @@ def gen_box_post(out):
     np.savez_compressed(os.path.join(out, "box_post.npz"), **d)
 
 
+def gen_logit_losses(out):
+    """calculate_roi_distillation_losses(dist='id') (distillation/distillation.py:164-241) and
+    FastRCNNLossComputation.__call__ (modeling/roi_heads/box_head/loss.py:122-184), fp32 and fp64, autograd gradients."""
+    from maskrcnn_benchmark.distillation.distillation import calculate_roi_distillation_losses
+    from maskrcnn_benchmark.modeling.roi_heads.box_head.loss import FastRCNNLossComputation
+    from maskrcnn_benchmark.structures.bounding_box import BoxList
+
+    rng = np.random.default_rng(31)
+    d = {}
+    # --- inclusive distillation: teacher 16 classes (15 + bg), student 21; and a 11 -> 21 case
+    for tag, (R, Co, Ct) in {"a": (96, 16, 21), "b": (40, 11, 21), "c": (7, 2, 5)}.items():
+        ss = (rng.standard_normal((R, Co)) * 3).astype(np.float32)
+        sb = rng.standard_normal((R, Co, 4)).astype(np.float32)
+        ts = (rng.standard_normal((R, Ct)) * 3).astype(np.float32)
+        tb = rng.standard_normal((R, Ct, 4)).astype(np.float32)
+        d["id_%s_ss" % tag], d["id_%s_sb" % tag], d["id_%s_ts" % tag], d["id_%s_tb" % tag] = ss, sb, ts, tb
+        for dt, name in ((torch.float32, "32"), (torch.float64, "64")):
+            t_s = torch.from_numpy(ts).to(dt).requires_grad_(True)
+            t_b = torch.from_numpy(tb).to(dt).requires_grad_(True)
+            loss = calculate_roi_distillation_losses((torch.from_numpy(ss).to(dt), torch.from_numpy(sb).to(dt)), (t_s, t_b), dist="id")
+            loss.backward()
+            d["id_%s_loss%s" % (tag, name)] = loss.detach().numpy()
+            d["id_%s_gs%s" % (tag, name)] = t_s.grad.numpy()
+            d["id_%s_gb%s" % (tag, name)] = t_b.grad.numpy()
+    # --- box-head loss: 'id' (15 old classes) and plain cross-entropy, class-specific and class-agnostic regression
+    for tag, (R, C, n_old, dist, agn) in {"a": (128, 21, 15, "id", False), "b": (64, 21, 15, "none", False),
+                                          "c": (50, 11, 5, "id", True), "d": (9, 4, 0, "id", False)}.items():
+        logits = (rng.standard_normal((R, C)) * 2).astype(np.float32)
+        reg = rng.standard_normal((R, 8 if agn else 4 * C)).astype(np.float32) * 0.8
+        allowed = np.asarray([0] + list(range(n_old + 1, C))) if dist == "id" else np.arange(C)
+        labels = allowed[rng.integers(0, len(allowed), R)].astype(np.int64)
+        labels[rng.random(R) < 0.5] = 0
+        targets = (rng.standard_normal((R, 4)) * 0.9).astype(np.float32)
+        d["frcnn_%s_logits" % tag], d["frcnn_%s_reg" % tag], d["frcnn_%s_labels" % tag], d["frcnn_%s_targets" % tag] = logits, reg, labels, targets
+        d["frcnn_%s_cfg" % tag] = np.asarray([n_old if dist == "id" else -1, int(agn)], np.int64)
+        for dt, name in ((torch.float32, "32"), (torch.float64, "64")):
+            ev = FastRCNNLossComputation(None, None, None, agn, dist, old_classes=list(range(n_old)))
+            half = R // 2
+            props = []
+            for a, b in ((0, half), (half, R)):
+                bl = BoxList(torch.zeros((b - a, 4)), (100, 100), "xyxy")
+                bl.add_field("labels", torch.from_numpy(labels[a:b]))
+                bl.add_field("regression_targets", torch.from_numpy(targets[a:b]).to(dt))
+                props.append(bl)
+            ev._proposals = props
+            t_l = torch.from_numpy(logits).to(dt).requires_grad_(True)
+            t_r = torch.from_numpy(reg).to(dt).requires_grad_(True)
+            cls, box = ev([t_l], [t_r])
+            (2.0 * cls + 3.0 * box).backward()  # distinct upstream gradients for the two outputs
+            d["frcnn_%s_cls%s" % (tag, name)], d["frcnn_%s_box%s" % (tag, name)] = cls.detach().numpy(), box.detach().numpy()
+            d["frcnn_%s_gl%s" % (tag, name)], d["frcnn_%s_gr%s" % (tag, name)] = t_l.grad.numpy(), t_r.grad.numpy()
+    np.savez_compressed(os.path.join(out, "logit_losses.npz"), **d)
+
+
 def main():
     assert os.path.isdir(REFERENCE), "the reference tree is needed to (re)generate golden vectors"
     assert oracle.ref_available(), "run `make -C oracle ref` first"
     install_reference_stubs()
-    for fn in (gen_roi_align, gen_nms, gen_ard, gen_pooler, gen_boxlist_nms, gen_paste, gen_rpn, gen_box_post):
+    for fn in (gen_roi_align, gen_nms, gen_ard, gen_pooler, gen_boxlist_nms, gen_paste, gen_rpn, gen_box_post, gen_logit_losses):
         fn(HERE)
         print("wrote", fn.__name__)
 

@@ -191,3 +191,33 @@ def test_box_postprocess_oracle_matches_reference_postprocessor(golden):
             assert np.array_equal(lab, g["c%d_i%d_labels" % (ci, n)])
         assert np.array_equal(bg[-1][0], g["c%d_bg_boxes" % ci]) and np.array_equal(bg[-1][1], g["c%d_bg_scores" % ci])
     assert len(g["c1_i0_scores"]) == 12  # the detections_per_img cut was exercised
+
+
+def test_logit_loss_oracles_match_reference_python(golden):
+    """oracle/logit_losses.py against calculate_roi_distillation_losses(dist='id') and FastRCNNLossComputation.__call__
+    run by make_golden.py: losses and autograd gradients bit for bit in fp32 and fp64."""
+    import torch
+
+    from oracle import logit_losses as oll
+
+    g = golden("logit_losses.npz")
+    for tag in "abc":
+        for name, dt in (("32", torch.float32), ("64", torch.float64)):
+            ts = torch.from_numpy(g["id_%s_ts" % tag]).to(dt).requires_grad_(True)
+            tb = torch.from_numpy(g["id_%s_tb" % tag]).to(dt).requires_grad_(True)
+            tot, _, _ = oll.roi_distillation_id(torch.from_numpy(g["id_%s_ss" % tag]).to(dt), torch.from_numpy(g["id_%s_sb" % tag]).to(dt), ts, tb)
+            tot.backward()
+            assert tot.item() == g["id_%s_loss%s" % (tag, name)]
+            assert np.array_equal(ts.grad.numpy(), g["id_%s_gs%s" % (tag, name)])
+            assert np.array_equal(tb.grad.numpy(), g["id_%s_gb%s" % (tag, name)])
+    for tag in "abcd":
+        n_old, agn = (int(v) for v in g["frcnn_%s_cfg" % tag])
+        for name, dt in (("32", torch.float32), ("64", torch.float64)):
+            lg = torch.from_numpy(g["frcnn_%s_logits" % tag]).to(dt).requires_grad_(True)
+            rg = torch.from_numpy(g["frcnn_%s_reg" % tag]).to(dt).requires_grad_(True)
+            cls, box = oll.fastrcnn_loss(lg, rg, torch.from_numpy(g["frcnn_%s_labels" % tag]),
+                                         torch.from_numpy(g["frcnn_%s_targets" % tag]).to(dt), n_old, bool(agn))
+            (2 * cls + 3 * box).backward()
+            assert cls.item() == g["frcnn_%s_cls%s" % (tag, name)] and box.item() == g["frcnn_%s_box%s" % (tag, name)]
+            assert np.array_equal(lg.grad.numpy(), g["frcnn_%s_gl%s" % (tag, name)])
+            assert np.array_equal(rg.grad.numpy(), g["frcnn_%s_gr%s" % (tag, name)])
