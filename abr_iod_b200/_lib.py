@@ -60,6 +60,8 @@ SIGNATURES = {
                                    _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _int, _vp, _sz, _vp]),
     "abr_ard_workspace_bytes": (_sz, [_int, _int, _int]),
     "abr_ard_forward_backward": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _f, _f, _int, _int, _vp, _sz, _vp]),
+    "abr_match_proposals": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _f, _f, _vp, _vp, _vp, _vp, _vp]),
+    "abr_box_iou": (_int, [_vp, _int, _vp, _int, _vp, _vp]),
     "abr_logit_loss_workspace_bytes": (_sz, [_int]),
     "abr_roi_distillation_id": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
     "abr_fastrcnn_loss": (_int, [_vp, _vp, _int, _vp, _vp, _int, _int, _int, _int, _f, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -5,8 +5,47 @@ import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
+import ctypes
+
 from .... import _lib
 from ....distillation.distillation import _scale_in_place
+from ....structures.bounding_box import BoxList
+
+
+def match_proposals(proposals, targets, matcher, box_coder):
+    """Device matching of a batch (``abr_match_proposals``).  proposals / targets: list[BoxList] (targets carry a
+    ``labels`` field).  Returns three lists of per-image tensors: labels [n] int64, regression_targets [n,4], matched_idxs [n]."""
+    if getattr(matcher, "allow_low_quality_matches", False):
+        raise NotImplementedError("match_proposals: allow_low_quality_matches (the RPN loss setting) is outside this path")
+    n_images = len(proposals)
+    if n_images != len(targets) or n_images == 0:
+        raise RuntimeError("match_proposals: need one target BoxList per proposal BoxList")
+    dev = proposals[0].bbox.device
+    _lib.require_cuda(proposals[0].bbox, "proposals")
+    for p, t in zip(proposals, targets):
+        if p.size != t.size:
+            raise RuntimeError("boxlists should have same image size, got {}, {}".format(t, p))  # boxlist_ops.py:67-69
+        if len(t) == 0:
+            raise ValueError("No ground-truth boxes available for one of the images during training")  # matcher.py:55-58
+        if len(p) == 0:
+            raise ValueError("No proposal boxes available for one of the images during training")  # matcher.py:59-62
+    counts = [len(p) for p in proposals]
+    gcounts = [len(t) for t in targets]
+    cat = lambda ts: ts[0] if len(ts) == 1 else torch.cat(ts, 0)  # noqa: E731
+    boxes = cat([p.convert("xyxy").bbox for p in proposals]).detach().to(torch.float32).contiguous()
+    gt = cat([t.convert("xyxy").bbox.to(dev) for t in targets]).detach().to(torch.float32).contiguous()
+    gl = cat([t.get_field("labels").to(dev) for t in targets]).to(torch.int64).contiguous()
+    R = boxes.shape[0]
+    matched = torch.empty((R,), dtype=torch.int64, device=dev)
+    labels = torch.empty((R,), dtype=torch.int64, device=dev)
+    reg = torch.empty((R, 4), dtype=torch.float32, device=dev)
+    wts = (ctypes.c_float * 4)(*[float(w) for w in box_coder.weights])
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().abr_match_proposals(
+            boxes.data_ptr(), (ctypes.c_int * n_images)(*counts), gt.data_ptr(), gl.data_ptr(), (ctypes.c_int * n_images)(*gcounts),
+            n_images, float(matcher.high_threshold), float(matcher.low_threshold), wts, matched.data_ptr(), labels.data_ptr(),
+            reg.data_ptr(), _lib.stream_ptr(dev)))
+    return list(labels.split(counts)), list(reg.split(counts)), list(matched.split(counts))
 
 
 class _FastRCNNLoss(Function):
@@ -56,9 +95,9 @@ def fastrcnn_loss(class_logits, box_regression, labels, regression_targets, n_ol
 
 
 class FastRCNNLossComputation(object):
-    """Computes the loss for Faster R-CNN (same constructor and ``__call__`` as the reference's class).  ``subsample`` --
-    matching + random fg/bg sampling, SURVEY 8f rank 2 -- is not part of this library: set ``_proposals`` (BoxLists
-    with ``labels`` and ``regression_targets`` fields), e.g. from the reference's own ``subsample``."""
+    """Computes the loss for Faster R-CNN (same constructor, ``subsample`` and ``__call__`` as the reference's class).
+    ``prepare_targets`` is ONE device launch for the whole batch (``abr_match_proposals``: IoU, Matcher, labels, box
+    encoding); the fg/bg sampling keeps the reference's ``torch.randperm`` stream (see the sampler's docstring)."""
 
     def __init__(self, proposal_matcher, fg_bg_sampler, box_coder, cls_agnostic_bbox_reg=False, dist_type=None, old_classes=[]):
         self.proposal_matcher = proposal_matcher
@@ -68,8 +107,33 @@ class FastRCNNLossComputation(object):
         self.dist_type = dist_type
         self.n_old_cl = len(old_classes)
 
+    def prepare_targets(self, proposals, targets):
+        """loss.py:57-84 for the batch: per image the int64 labels (0 background, -1 ignored) and the regression targets.
+        Also returns the matched ground-truth indices (``matched_idxs`` of loss.py:43-55)."""
+        return match_proposals(proposals, targets, self.proposal_matcher, self.box_coder)
+
+    def match_targets_to_proposals(self, proposal, target):
+        """loss.py:43-55 for one image: the matched targets with ``labels`` and ``matched_idxs`` fields."""
+        _, _, matched = match_proposals([proposal], [target], self.proposal_matcher, self.box_coder)
+        idx = matched[0].clamp(min=0)
+        out = BoxList(target.bbox[idx], target.size, target.mode)
+        out.add_field("labels", target.get_field("labels")[idx])
+        out.add_field("matched_idxs", matched[0])
+        return out
+
     def subsample(self, proposals, targets):
-        raise NotImplementedError("FastRCNNLossComputation.subsample is outside the accelerated path (SURVEY 8f rank 2)")
+        """loss.py:86-120: positive/negative sampling; returns the sampled proposals with ``labels`` and
+        ``regression_targets`` fields and remembers them for ``__call__``."""
+        labels, regression_targets, _ = self.prepare_targets(proposals, targets)
+        sampled_pos_inds, sampled_neg_inds = self.fg_bg_sampler(labels)
+        proposals = list(proposals)
+        for lab, tgt, per_image in zip(labels, regression_targets, proposals):
+            per_image.add_field("labels", lab)
+            per_image.add_field("regression_targets", tgt)
+        for i, (pos, neg) in enumerate(zip(sampled_pos_inds, sampled_neg_inds)):
+            proposals[i] = proposals[i][torch.nonzero(pos | neg).squeeze(1)]
+        self._proposals = proposals
+        return proposals
 
     def __call__(self, class_logits, box_regression):
         """

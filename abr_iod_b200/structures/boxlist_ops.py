@@ -55,3 +55,19 @@ def cat_boxlist(bboxes):
     for name in names:
         out.add_field(name, join([b.get_field(name) for b in bboxes]))
     return out
+
+
+def boxlist_iou(boxlist1, boxlist2):
+    """IoU of two BoxLists of the same image, [N,M] (structures/boxlist_ops.py:53-88; +1 pixel convention), one kernel."""
+    from .. import _lib
+
+    if boxlist1.size != boxlist2.size:
+        raise RuntimeError("boxlists should have same image size, got {}, {}".format(boxlist1, boxlist2))
+    b1 = boxlist1.convert("xyxy").bbox.detach().to(torch.float32).contiguous()
+    b2 = boxlist2.convert("xyxy").bbox.detach().to(torch.float32).contiguous()
+    _lib.require_cuda(b1, "boxlist1")
+    out = torch.empty((b1.shape[0], b2.shape[0]), dtype=torch.float32, device=b1.device)
+    with torch.cuda.device(b1.device):
+        _lib.check(_lib.lib().abr_box_iou(b1.data_ptr(), b1.shape[0], b2.data_ptr(), b2.shape[0], out.data_ptr(),
+                                          _lib.stream_ptr(b1.device)))
+    return out

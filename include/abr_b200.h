@@ -207,6 +207,24 @@ ABR_API int abr_ard_forward_backward(const void* f_old, const void* f_new, void*
 ABR_API int abr_scale_if_needed(void* data, size_t n, const float* scale_dev, float expected, int dtype,
                         abr_stream_t stream);
 
+/* ---------------------------------------------------------------- proposal <-> ground-truth matching
+ * abr_match_proposals replaces FastRCNNLossComputation.match_targets_to_proposals + prepare_targets
+ * (modeling/roi_heads/box_head/loss.py:43-84) for a whole batch: boxlist_iou (structures/boxlist_ops.py:53-88),
+ * Matcher without low-quality matches (modeling/matcher.py:52-81), labels and BoxCoder.encode
+ * (modeling/box_coder.py:22-50).
+ *   proposals [R,4] fp32 xyxy, the images' proposals back to back (boxes_per_image_host [n_images]);
+ *   gt_boxes [G,4] fp32 xyxy + gt_labels [G] int64, likewise (gt_per_image_host [n_images], each > 0);
+ *   matched_idxs [R] int64: index of the best ground-truth box inside its image (first maximum wins), -1 below
+ *   low_threshold, -2 in [low_threshold, high_threshold);  labels [R] int64: the matched box's label, 0 for -1,
+ *   -1 (ignored by the sampler) for -2;  regression_targets [R,4] fp32: encode(matched box, proposal), for
+ *   unmatched proposals against ground-truth box 0 like the reference's clamp(min=0).
+ * abr_box_iou is boxlist_iou itself: iou [N,M] of boxes1 [N,4] x boxes2 [M,4], +1 pixel convention. */
+ABR_API int abr_match_proposals(const float* proposals, const int* boxes_per_image_host, const float* gt_boxes,
+                                const int64_t* gt_labels, const int* gt_per_image_host, int n_images,
+                                float high_threshold, float low_threshold, const float* weights4_host,
+                                int64_t* matched_idxs, int64_t* labels, float* regression_targets, abr_stream_t stream);
+ABR_API int abr_box_iou(const float* boxes1, int N, const float* boxes2, int M, float* iou, abr_stream_t stream);
+
 /* ---------------------------------------------------------------- logit-level losses (forward + backward)
  * abr_roi_distillation_id replaces calculate_roi_distillation_losses(dist='id')
  * (distillation/distillation.py:164-241) and its autograd backward:

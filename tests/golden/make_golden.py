@@ -422,11 +422,60 @@ def gen_logit_losses(out):
     np.savez_compressed(os.path.join(out, "logit_losses.npz"), **d)
 
 
+def match_inputs(rng, size, n, G):
+    """Ground-truth boxes and proposals scattered around them (so that all three Matcher outcomes occur)."""
+    w, h = size
+    c = rng.uniform([0.2 * w, 0.2 * h], [0.8 * w, 0.8 * h], (G, 2))
+    wh = rng.uniform(30, 160, (G, 2))
+    gt = np.clip(np.concatenate([c - wh / 2, c + wh / 2], 1), 0, [w - 1, h - 1, w - 1, h - 1]).astype(np.float32)
+    which = rng.integers(0, G, n)
+    jitter = rng.normal(0, 1, (n, 4)) * rng.choice([3.0, 15.0, 60.0], (n, 1))
+    props = np.clip(gt[which] + jitter, 0, [w - 1, h - 1, w - 1, h - 1])
+    props = np.stack([np.minimum(props[:, 0], props[:, 2]), np.minimum(props[:, 1], props[:, 3]),
+                      np.maximum(props[:, 0], props[:, 2]) + 1, np.maximum(props[:, 1], props[:, 3]) + 1], 1).astype(np.float32)
+    props[: min(G, n)] = gt[: min(G, n)]  # add_gt_proposals: exact copies of the ground truth (IoU = 1)
+    return props, gt, rng.integers(1, 21, G).astype(np.int64)
+
+
+def gen_match(out):
+    """FastRCNNLossComputation.prepare_targets (modeling/roi_heads/box_head/loss.py:57-84) with the reference's Matcher,
+    boxlist_iou and BoxCoder, on CPU."""
+    from maskrcnn_benchmark.modeling.box_coder import BoxCoder
+    from maskrcnn_benchmark.modeling.matcher import Matcher
+    from maskrcnn_benchmark.modeling.roi_heads.box_head.loss import FastRCNNLossComputation
+    from maskrcnn_benchmark.structures.bounding_box import BoxList
+
+    rng = np.random.default_rng(41)
+    sizes = [(640, 480), (500, 375), (320, 200)]
+    d = {"image_sizes": np.asarray(sizes, np.int64)}
+    props, gts, labs = [], [], []
+    for (n, G), size in zip([(300, 5), (257, 1), (64, 12)], sizes):
+        p, g, l = match_inputs(rng, size, n, G)
+        props.append(p); gts.append(g); labs.append(l)
+    d["n"], d["g"] = np.asarray([len(p) for p in props]), np.asarray([len(g) for g in gts])
+    d["proposals"], d["gt_boxes"], d["gt_labels"] = np.concatenate(props), np.concatenate(gts), np.concatenate(labs)
+    for ci, (high, low, wts) in enumerate([(0.5, 0.5, (10.0, 10.0, 5.0, 5.0)), (0.7, 0.3, (1.0, 1.0, 1.0, 1.0))]):
+        ev = FastRCNNLossComputation(Matcher(high, low, allow_low_quality_matches=False), None, BoxCoder(weights=wts))
+        pl = [BoxList(torch.from_numpy(p.copy()), s, "xyxy") for p, s in zip(props, sizes)]
+        tl = []
+        for g, l, s in zip(gts, labs, sizes):
+            t = BoxList(torch.from_numpy(g.copy()), s, "xyxy")
+            t.add_field("labels", torch.from_numpy(l))
+            tl.append(t)
+        labels, targets = ev.prepare_targets(pl, tl)
+        matched = [ev.match_targets_to_proposals(p, t).get_field("matched_idxs") for p, t in zip(pl, tl)]
+        d["c%d_cfg" % ci] = np.asarray([high, low] + list(wts), np.float64)
+        d["c%d_labels" % ci] = torch.cat(labels).numpy()
+        d["c%d_targets" % ci] = torch.cat(targets).numpy()
+        d["c%d_matched" % ci] = torch.cat(matched).numpy()
+    np.savez_compressed(os.path.join(out, "match.npz"), **d)
+
+
 def main():
     assert os.path.isdir(REFERENCE), "the reference tree is needed to (re)generate golden vectors"
     assert oracle.ref_available(), "run `make -C oracle ref` first"
     install_reference_stubs()
-    for fn in (gen_roi_align, gen_nms, gen_ard, gen_pooler, gen_boxlist_nms, gen_paste, gen_rpn, gen_box_post, gen_logit_losses):
+    for fn in (gen_roi_align, gen_nms, gen_ard, gen_pooler, gen_boxlist_nms, gen_paste, gen_rpn, gen_box_post, gen_logit_losses, gen_match):
         fn(HERE)
         print("wrote", fn.__name__)
 

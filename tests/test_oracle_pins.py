@@ -221,3 +221,24 @@ def test_logit_loss_oracles_match_reference_python(golden):
             assert cls.item() == g["frcnn_%s_cls%s" % (tag, name)] and box.item() == g["frcnn_%s_box%s" % (tag, name)]
             assert np.array_equal(lg.grad.numpy(), g["frcnn_%s_gl%s" % (tag, name)])
             assert np.array_equal(rg.grad.numpy(), g["frcnn_%s_gr%s" % (tag, name)])
+
+
+def test_match_oracle_matches_reference_prepare_targets(golden):
+    """oracle/match.py against FastRCNNLossComputation.prepare_targets / match_targets_to_proposals run by
+    make_golden.py (reference Matcher, boxlist_iou, BoxCoder.encode): matched indices, labels and targets bit for bit."""
+    from oracle import match as om
+
+    g = golden("match.npz")
+    ro = np.concatenate([[0], np.cumsum(g["n"])])
+    go = np.concatenate([[0], np.cumsum(g["g"])])
+    seen = set()
+    for ci in range(2):
+        high, low, *wts = g["c%d_cfg" % ci]
+        for i in range(len(g["n"])):
+            m, lab, t = om.prepare_targets(g["proposals"][ro[i]:ro[i + 1]], g["gt_boxes"][go[i]:go[i + 1]],
+                                           g["gt_labels"][go[i]:go[i + 1]], high, low, wts)
+            sl = slice(ro[i], ro[i + 1])
+            assert np.array_equal(m, g["c%d_matched" % ci][sl]) and np.array_equal(lab, g["c%d_labels" % ci][sl])
+            assert np.array_equal(t, g["c%d_targets" % ci][sl])
+            seen |= set(np.minimum(m, 0).tolist())
+    assert seen == {0, -1, -2}  # matched, background and ignored proposals all occur
