@@ -4,8 +4,10 @@
 
 * registers :mod:`abr_iod_b200._C` as ``maskrcnn_benchmark._C`` (the native extension the reference's
   ``layers/*.py`` import), so ``layers.ROIAlign / ROIPool / nms`` and everything above them run on libabr_b200;
-* after the reference modules are imported, ``patch_loaded()`` swaps the Python-level hot-path functions
-  (``Pooler``, ``boxlist_nms``, ``calculate_attentive_roi_feature_distillation``) for the fused versions.
+* after the reference modules are imported, ``patch_loaded()`` swaps the Python-level hot-path entry points (``Pooler``,
+  ``boxlist_nms`` / ``boxlist_iou``, ``RPNPostProcessor``, the box head's ``PostProcessor`` and
+  ``FastRCNNLossComputation``, ``calculate_attentive_roi_feature_distillation``,
+  ``calculate_roi_distillation_losses``) for the fused versions, including every ``from ... import`` alias of them.
 """
 import sys
 
@@ -20,24 +22,62 @@ def install():
     return _C
 
 
+def _swap(module_name, attr, new, done):
+    """Rebind ``module.attr`` and every other loaded module's name that still points at the old object (the reference
+    binds hot-path functions with ``from x import f``, e.g. tools/train_incremental.py:36-38)."""
+    m = sys.modules.get(module_name)
+    if m is None or not hasattr(m, attr):
+        return
+    old = getattr(m, attr)
+    if old is new:
+        return
+    setattr(m, attr, new)
+    for name, other in list(sys.modules.items()):
+        if other is None or not (name == "__main__" or name.startswith("maskrcnn_benchmark") or name.startswith("tools")):
+            continue
+        for k, v in list(vars(other).items()):
+            if v is old:
+                setattr(other, k, new)
+    done.append("%s.%s" % (module_name.replace("maskrcnn_benchmark.", ""), attr))
+
+
 def patch_loaded():
-    """Replace the Python hot-path entry points of already-imported reference modules."""
-    from .distillation import distillation as ard
+    """Replace the Python hot-path entry points of already-imported reference modules (and every ``from ... import``
+    alias of them).  Returns the list of names that were swapped."""
+    from .distillation import distillation as dist
     from .modeling import poolers
+    from .modeling.roi_heads.box_head import inference as box_inference
+    from .modeling.roi_heads.box_head import loss as box_loss
+    from .modeling.rpn import inference as rpn_inference
     from .structures import boxlist_ops
 
     done = []
-    m = sys.modules.get("maskrcnn_benchmark.distillation.distillation")
+    ref = "maskrcnn_benchmark."
+    _swap(ref + "distillation.distillation", "calculate_attentive_roi_feature_distillation",
+          dist.calculate_attentive_roi_feature_distillation, done)
+    m = sys.modules.get(ref + "distillation.distillation")
+    if m is not None and hasattr(m, "calculate_roi_distillation_losses"):
+        original = m.calculate_roi_distillation_losses
+
+        def calculate_roi_distillation_losses(soften_results, target_results, dist="l2", soften_proposal=None, _orig=original):
+            # the 'id' setting runs fused; the legacy Faster-ILOD branch keeps the reference's own code
+            if dist == "id":
+                return dist_mod.calculate_roi_distillation_losses(soften_results, target_results, dist, soften_proposal)
+            return _orig(soften_results, target_results, dist, soften_proposal)
+
+        dist_mod = dist
+        if getattr(original, "__module__", "").startswith("maskrcnn_benchmark"):
+            _swap(ref + "distillation.distillation", "calculate_roi_distillation_losses", calculate_roi_distillation_losses, done)
+    _swap(ref + "structures.boxlist_ops", "boxlist_nms", boxlist_ops.boxlist_nms, done)
+    _swap(ref + "structures.boxlist_ops", "boxlist_iou", boxlist_ops.boxlist_iou, done)
+    m = sys.modules.get(ref + "structures.boxlist_ops")
     if m is not None:
-        m.calculate_attentive_roi_feature_distillation = ard.calculate_attentive_roi_feature_distillation
-        done.append("distillation.calculate_attentive_roi_feature_distillation")
-    m = sys.modules.get("maskrcnn_benchmark.structures.boxlist_ops")
-    if m is not None:
-        m.boxlist_nms = boxlist_ops.boxlist_nms
         m.boxlist_nms_batched = boxlist_ops.boxlist_nms_batched
-        done.append("structures.boxlist_ops.boxlist_nms")
-    m = sys.modules.get("maskrcnn_benchmark.modeling.poolers")
-    if m is not None:
-        m.Pooler, m.LevelMapper, m.make_pooler = poolers.Pooler, poolers.LevelMapper, poolers.make_pooler
-        done.append("modeling.poolers.Pooler")
+    for attr in ("Pooler", "LevelMapper", "make_pooler"):
+        _swap(ref + "modeling.poolers", attr, getattr(poolers, attr), done)
+    for attr in ("RPNPostProcessor", "make_rpn_postprocessor"):
+        _swap(ref + "modeling.rpn.inference", attr, getattr(rpn_inference, attr), done)
+    for attr in ("PostProcessor", "make_roi_box_post_processor"):
+        _swap(ref + "modeling.roi_heads.box_head.inference", attr, getattr(box_inference, attr), done)
+    _swap(ref + "modeling.roi_heads.box_head.loss", "FastRCNNLossComputation", box_loss.FastRCNNLossComputation, done)
     return done
