@@ -65,6 +65,8 @@ SIGNATURES = {
     "abr_logit_loss_workspace_bytes": (_sz, [_int]),
     "abr_roi_distillation_id": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
     "abr_fastrcnn_loss": (_int, [_vp, _vp, _int, _vp, _vp, _int, _int, _int, _int, _f, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "abr_channel_mean": (_int, [_vp, _int, _int, _int, _int, _int, _vp, _vp]),
+    "abr_prototype_distances": (_int, [_vp, _int, _int, _vp, _vp, _vp]),
     "abr_scale_if_needed": (_int, [_vp, _sz, _vp, _f, _int, _vp]),
     "abr_paste_batch": (_int, [_vp, _vp, _int, _vp, _int, _vp, _int, _vp]),
 }

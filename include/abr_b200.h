@@ -252,6 +252,16 @@ ABR_API int abr_fastrcnn_loss(const float* class_logits, const float* box_regres
                               float* grad_logits, float* grad_regression, float* loss2, void* workspace,
                               size_t workspace_bytes, abr_stream_t stream);
 
+/* ---------------------------------------------------------------- Prototype Box Selection (scoring)
+ * abr_channel_mean: out[r][p] = mean over channels of pooled[r][:, p] -- the per-RoI descriptor of
+ * tools/prototype_box_selection.py:96-101 (torch.mean(roi_align_features.cpu(), dim=1)); pooled is
+ * [R,C,HW] (ABR_NCHW) or [R,HW,C] (ABR_NHWC), fp32 or bf16; out [R,HW] fp32.
+ * abr_prototype_distances: Mem.mean_feature_sampling's scoring (tools/extract_memory.py:125-141) for one
+ * class in float64: features [n,F] fp32 (F = 49); mean_out [F] = normalised class mean; dist [n] = distance
+ * of each descriptor / |all descriptors|_F to it.  The n smallest-distance boxes (ascending) are the prototypes. */
+ABR_API int abr_channel_mean(const void* pooled, int R, int C, int HW, int dtype, int layout, float* out, abr_stream_t stream);
+ABR_API int abr_prototype_distances(const float* features, int n, int F, double* mean_out, double* dist, abr_stream_t stream);
+
 /* ---------------------------------------------------------------- ABR paste (mixup / mosaic)
  * Pixel part of PascalVOCDataset_ABR._start_mixup / _start_boxes_mosaic
  * (data/datasets/voc_abr.py:659-678 and :744-763) for a whole batch in one launch.  All images are

@@ -471,11 +471,49 @@ def gen_match(out):
     np.savez_compressed(os.path.join(out, "match.npz"), **d)
 
 
+def gen_prototype(out):
+    """Mem.mean_feature_sampling (tools/extract_memory.py:111-161) of the reference, loaded by file path with the config
+    import stubbed, run on a hand-built Mem object; creat_and_save_box_image is replaced by a recorder."""
+    cfgmod = types.ModuleType("maskrcnn_benchmark.config")
+    cfgmod.cfg = None
+    sys.modules["maskrcnn_benchmark.config"] = cfgmod
+    spec = importlib.util.spec_from_file_location("ref_extract_memory", os.path.join(REFERENCE, "tools", "extract_memory.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    import tempfile
+
+    rng = np.random.default_rng(51)
+    d = {}
+    counts = [40, 3, 17]     # the middle class has fewer boxes than num_bbox_per_cls: the top-up path
+    per_cls = 6
+    pooled = [(rng.standard_normal((n, 32, 7, 7)) + rng.uniform(0, 2, (1, 1, 7, 7))).astype(np.float32) for n in counts]
+    saved = []
+    mem = mod.Mem.__new__(mod.Mem)
+    mem.num_current_classes = len(counts)
+    mem.num_bbox_per_cls = per_cls
+    mem.mem_size = 0
+    mem.current_mem_path = tempfile.mkdtemp()
+    mem.creat_and_save_box_image = lambda info, ind: saved.append((info["cls"], info["idx"], ind))
+    mem.current_mem_info, mem.current_features, mem.current_logits = [], [], []
+    for c, x in enumerate(pooled):
+        desc = torch.mean(torch.from_numpy(x), dim=1).tolist()  # prototype_box_selection.py:97
+        mem.current_mem_info.append([{"cls": c, "idx": i} for i in range(len(desc))])
+        mem.current_features.append(list(desc))
+        mem.current_logits.append([0] * len(desc))
+        d["pooled_%d" % c] = x
+        d["desc_%d" % c] = torch.mean(torch.from_numpy(x), dim=1).numpy()
+    mem.mean_feature_sampling()
+    d["per_cls"] = np.asarray(per_cls)
+    for c in range(len(counts)):
+        d["selected_%d" % c] = np.asarray([idx for cls, idx, _ in saved if cls == c], np.int64)
+    np.savez_compressed(os.path.join(out, "prototype.npz"), **d)
+
+
 def main():
     assert os.path.isdir(REFERENCE), "the reference tree is needed to (re)generate golden vectors"
     assert oracle.ref_available(), "run `make -C oracle ref` first"
     install_reference_stubs()
-    for fn in (gen_roi_align, gen_nms, gen_ard, gen_pooler, gen_boxlist_nms, gen_paste, gen_rpn, gen_box_post, gen_logit_losses, gen_match):
+    for fn in (gen_roi_align, gen_nms, gen_ard, gen_pooler, gen_boxlist_nms, gen_paste, gen_rpn, gen_box_post, gen_logit_losses, gen_match, gen_prototype):
         fn(HERE)
         print("wrote", fn.__name__)
 

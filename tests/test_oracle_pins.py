@@ -242,3 +242,16 @@ def test_match_oracle_matches_reference_prepare_targets(golden):
             assert np.array_equal(t, g["c%d_targets" % ci][sl])
             seen |= set(np.minimum(m, 0).tolist())
     assert seen == {0, -1, -2}  # matched, background and ignored proposals all occur
+
+
+def test_prototype_oracle_matches_reference_mem_sampling(golden):
+    """oracle/prototype.py against Mem.mean_feature_sampling (tools/extract_memory.py) run by make_golden.py, including a
+    class that has to be topped up with copies; descriptors bit for bit (same torch CPU mean)."""
+    from oracle import prototype as op
+
+    g = golden("prototype.npz")
+    for c in range(3):
+        assert np.array_equal(op.descriptors(g["pooled_%d" % c]), g["desc_%d" % c])
+        order, _, source = op.mean_feature_ranking(list(g["desc_%d" % c]), int(g["per_cls"]))
+        assert np.array_equal(source[order], g["selected_%d" % c])
+    assert sorted(g["selected_1"].tolist()) == [0, 0, 1, 1, 2, 2]
