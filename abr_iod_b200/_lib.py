@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libabr_b200.so")
 
 ABR_F32, ABR_BF16 = 0, 1
-ABR_NCHW, ABR_NHWC = 0, 1
+ABR_NCHW, ABR_NHWC, ABR_NCHW_MAPS_NHWC_POOLED = 0, 1, 2
 ABR_MAX_LEVELS = 8
 
 _vp, _int, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
@@ -43,6 +43,7 @@ SIGNATURES = {
     "abr_launch_count": (ctypes.c_uint64, []),
     "abr_roi_align_workspace_bytes": (_sz, [_int, _int, _int, _int]),
     "abr_roi_align_workspace_bytes_nchw": (_sz, [_int, _int, _int, _int, _int, _int, ctypes.c_longlong, _int]),
+    "abr_roi_align_workspace_bytes_layout": (_sz, [_int, _int, _int, _int, _int, _int, ctypes.c_longlong, _int, _int]),
     "abr_roi_align_forward": (_int, [_vp, _vp, _vp] + [_int] * 7 + [_f, _int, _int, _int, _vp, _sz, _vp]),
     "abr_roi_align_backward": (_int, [_vp, _vp, _vp] + [_int] * 7 + [_f, _int, _int, _int, _int, _vp, _sz, _int, _vp]),
     "abr_roi_align_multilevel_forward": (_int, [_vp, _vp, _vp, _vp, _int, _vp, _vp, _vp] + [_int] * 8 + [_vp, _sz, _vp]),
@@ -123,15 +124,32 @@ def is_channels_last(t: torch.Tensor) -> bool:
 
 
 NCHW_STAGING = True  # run contiguous-NCHW ROIAlign calls through the channels-last kernels (costs scratch memory)
+# Contiguous feature maps, but channels-last RoI features (same logical [R,C,P,P] tensor, channels_last strides): saves the
+# two passes over the pooled tensor that a contiguous result costs (1.6x on the RoI path of a contiguous model).  Off by
+# default because a consumer that calls ``.view(R, -1)`` on the pooled tensor (the FPN MLP head) needs ``.reshape``.
+POOLED_CHANNELS_LAST = False
 
 
-def roi_align_workspace(R, PH, PW, max_h, device, channels_last=True, nchw_staging=None):
+def roi_align_layout(x: torch.Tensor) -> int:
+    """Layout code of a ROIAlign call on feature map ``x``."""
+    if is_channels_last(x):
+        return ABR_NHWC
+    return ABR_NCHW_MAPS_NHWC_POOLED if POOLED_CHANNELS_LAST else ABR_NCHW
+
+
+def roi_align_workspace(R, PH, PW, max_h, device, channels_last=True, nchw_staging=None, layout=None):
     """Scratch for ROIAlign (caller-owned, per call): the per-RoI plans of the channels-last kernels and, for a
     contiguous-NCHW call (``nchw_staging=(B, C, sum_hw, dtype_code)``), room for channels-last copies of the maps and
-    of the pooled tensor.  Returns (tensor|None, bytes)."""
+    of the pooled tensor.  ``layout`` (a code of ``roi_align_layout``) overrides ``channels_last``.
+    Returns (tensor|None, bytes)."""
     if R == 0:
         return None, 0
-    if channels_last:
+    if layout is not None:
+        channels_last = layout == ABR_NHWC
+    if layout == ABR_NCHW_MAPS_NHWC_POOLED:
+        B, C, sum_hw, code = nchw_staging
+        n = int(lib().abr_roi_align_workspace_bytes_layout(R, PH, PW, max_h, B, C, sum_hw, code, layout))
+    elif channels_last:
         n = int(lib().abr_roi_align_workspace_bytes(R, PH, PW, max_h))
     elif nchw_staging is not None and NCHW_STAGING:
         B, C, sum_hw, code = nchw_staging

@@ -1297,6 +1297,59 @@ __global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ sr
   }
 }
 
+// Pooled tensors ([R][C][HW] <-> [R][HW][C], HW = 49 or 196): a CTA moves one RoI's chunk of 64 channels.  The NCHW side
+// of the chunk is one contiguous run (64*HW elements), the NHWC side is HW runs of 64 channels; the chunk sits in
+// shared memory as [c][HW | 1] (odd pitch: conflict-free in both directions).
+constexpr int kPoolChunk = 64;
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_pooled_kernel(const T* __restrict__ src, T* __restrict__ dst, int C, int HW, int to_nhwc) {
+  extern __shared__ float chunk[];
+  const int r = blockIdx.y, c0 = blockIdx.x * kPoolChunk;
+  const int nC = min(kPoolChunk, C - c0), pitch = HW | 1, total = nC * HW;
+  const size_t nchw = ((size_t)r * C + c0) * HW, nhwc = (size_t)r * HW * C + c0;
+  if (to_nhwc) {
+    for (int i = threadIdx.x; i < total; i += 256) {
+      const int c = i / HW, p2 = i - c * HW;
+      float v[1];
+      VecIO<T, 1>::load(src + nchw + i, v);
+      chunk[c * pitch + p2] = v[0];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < total; i += 256) {
+      const int p2 = i / nC, c = i - p2 * nC;
+      const float v[1] = {chunk[c * pitch + p2]};
+      VecIO<T, 1>::store(dst + nhwc + (size_t)p2 * C + c, v);
+    }
+  } else {
+    for (int i = threadIdx.x; i < total; i += 256) {
+      const int p2 = i / nC, c = i - p2 * nC;
+      float v[1];
+      VecIO<T, 1>::load(src + nhwc + (size_t)p2 * C + c, v);
+      chunk[c * pitch + p2] = v[0];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < total; i += 256) {
+      const int c = i / HW, p2 = i - c * HW;
+      const float v[1] = {chunk[c * pitch + p2]};
+      VecIO<T, 1>::store(dst + nchw + i, v);
+    }
+  }
+}
+
+// [R][C][HW] -> [R][HW][C] (to_nhwc) or back
+static int transpose_pooled(const void* src, void* dst, int R, int C, int HW, int to_nhwc, int dtype, cudaStream_t st) {
+  if (R <= 0) return ABR_OK;
+  const size_t smem = (size_t)kPoolChunk * (HW | 1) * sizeof(float);
+  ABR_REQUIRE(smem <= 48 * 1024 && R <= 65535, ABR_ERR_UNSUPPORTED, "roi_align: pooled transpose of %d RoIs x %d positions", R, HW);
+  const dim3 grid(ceil_div(C, kPoolChunk), R);
+  if (dtype == ABR_F32)
+    transpose_pooled_kernel<float><<<grid, 256, smem, st>>>(static_cast<const float*>(src), static_cast<float*>(dst), C, HW, to_nhwc);
+  else
+    transpose_pooled_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), C, HW, to_nhwc);
+  ABR_CHECK_LAUNCH("roi_align_transpose_pooled");
+  return ABR_OK;
+}
+
 template <typename T>
 static int launch_transpose(const void* src, void* dst, int rows, int cols, long long batch, int add, cudaStream_t st) {
   if (rows <= 0 || cols <= 0 || batch <= 0) return ABR_OK;
@@ -1316,7 +1369,8 @@ static int check_common(const void* a, const float* rois, const void* b, int B, 
   ABR_REQUIRE(B >= 0 && C > 0 && R >= 0 && PH > 0 && PW > 0, ABR_ERR_BAD_ARG,
               "roi_align: bad sizes B=%d C=%d R=%d PH=%d PW=%d", B, C, R, PH, PW);
   ABR_REQUIRE(dtype == ABR_F32 || dtype == ABR_BF16, ABR_ERR_UNSUPPORTED, "roi_align: dtype %d not supported", dtype);
-  ABR_REQUIRE(layout == ABR_NCHW || layout == ABR_NHWC, ABR_ERR_UNSUPPORTED, "roi_align: layout %d not supported", layout);
+  ABR_REQUIRE(layout == ABR_NCHW || layout == ABR_NHWC || layout == ABR_NCHW_MAPS_NHWC_POOLED, ABR_ERR_UNSUPPORTED,
+              "roi_align: layout %d not supported", layout);
   if (R > 0) ABR_REQUIRE(a && rois && b, ABR_ERR_BAD_ARG, "roi_align: null pointer");
   return ABR_OK;
 }
@@ -1554,8 +1608,10 @@ static size_t elem_size(int dtype) { return dtype == ABR_F32 ? 4 : 2; }
 // NCHW callers can be run through the channels-last kernels when the workspace also has room for a channels-last copy
 // of every level's map and of the pooled tensor (after the plans, 256-byte aligned).
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
-static size_t staging_need(int B, int C, long long sum_hw, int R, int PH, int PW, int dtype) {
-  return align256((size_t)B * C * sum_hw * (dtype == ABR_F32 ? 4 : 2)) + align256((size_t)R * C * PH * PW * (dtype == ABR_F32 ? 4 : 2));
+static size_t staging_need(int B, int C, long long sum_hw, int R, int PH, int PW, int dtype, int layout = ABR_NCHW) {
+  const size_t maps = align256((size_t)B * C * sum_hw * (dtype == ABR_F32 ? 4 : 2));
+  if (layout == ABR_NCHW_MAPS_NHWC_POOLED) return maps;  // the pooled tensor already is channels-last
+  return maps + align256((size_t)R * C * PH * PW * (dtype == ABR_F32 ? 4 : 2));
 }
 
 // The plans are only used by the NHWC kernels; a workspace that is absent or too small selects the self-contained path.
@@ -1581,6 +1637,12 @@ size_t abr_roi_align_workspace_bytes_nchw(int R, int PH, int PW, int max_h, int 
   return align256(workspace_need(R, PW, max_h)) + staging_need(B, C, sum_hw, R, PH, PW, dtype);
 }
 
+size_t abr_roi_align_workspace_bytes_layout(int R, int PH, int PW, int max_h, int B, int C, long long sum_hw, int dtype, int layout) {
+  if (layout == ABR_NHWC) return abr_roi_align_workspace_bytes(R, PH, PW, max_h);
+  if (R <= 0 || PW <= 0 || PH <= 0 || max_h <= 0 || B <= 0 || C <= 0 || sum_hw <= 0) return 0;
+  return align256(workspace_need(R, PW, max_h)) + staging_need(B, C, sum_hw, R, PH, PW, dtype, layout);
+}
+
 int abr_roi_align_multilevel_forward(const void* const* inputs_host, const int* hs_host, const int* ws_host,
                                      const float* scales_host, int L, const float* rois, const int32_t* levels,
                                      void* output, int B, int C, int R, int PH, int PW, int sampling_ratio, int dtype,
@@ -1602,9 +1664,13 @@ int abr_roi_align_multilevel_forward(const void* const* inputs_host, const int* 
   long long sum_hw = 0;
   for (int l = 0; l < L; l++) sum_hw += (long long)hs_host[l] * ws_host[l];
   const size_t plan_bytes = align256(workspace_need(R, PW, c.Hs));
-  if (layout == ABR_NCHW && workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 &&
-      workspace_bytes >= plan_bytes + staging_need(B, C, sum_hw, R, PH, PW, dtype)) {
-    // NCHW caller with staging room: channels-last copies of the maps, channels-last kernels, transposed result
+  const bool mixed = layout == ABR_NCHW_MAPS_NHWC_POOLED;
+  const bool staged_ok = workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 &&
+                         workspace_bytes >= plan_bytes + staging_need(B, C, sum_hw, R, PH, PW, dtype, layout);
+  ABR_REQUIRE(!mixed || staged_ok, ABR_ERR_WORKSPACE, "roi_align: layout %d needs a 256-byte aligned workspace of %zu B", layout,
+              plan_bytes + staging_need(B, C, sum_hw, R, PH, PW, dtype, layout));
+  if (layout != ABR_NHWC && staged_ok) {
+    // NCHW maps with staging room: channels-last copies of the maps, channels-last kernels, transposed result
     const size_t es = elem_size(dtype);
     char* stage = static_cast<char*>(workspace) + plan_bytes;
     for (int l = 0; l < L; l++) {
@@ -1617,8 +1683,11 @@ int abr_roi_align_multilevel_forward(const void* const* inputs_host, const int* 
     void* pooled = static_cast<char*>(workspace) + plan_bytes + align256((size_t)B * C * sum_hw * es);
     c.layout = ABR_NHWC;
     c.plans = static_cast<int*>(workspace);
+    if (mixed) return dispatch_fwd(c, output, dtype);  // the caller's pooled tensor is channels-last already
     rc = dispatch_fwd(c, pooled, dtype);
     if (rc) return rc;
+    if ((size_t)kPoolChunk * ((PH * PW) | 1) * sizeof(float) <= 48 * 1024 && R <= 65535)
+      return transpose_pooled(pooled, output, R, C, PH * PW, 0, dtype, c.st);
     return transpose_any(pooled, output, PH * PW, C, R, 0, dtype, c.st);
   }
   c.plans = usable_workspace(workspace, workspace_bytes, R, PW, c.Hs, layout);
@@ -1648,15 +1717,26 @@ int abr_roi_align_multilevel_backward(const void* grad_output, const float* rois
   long long sum_hw = 0;
   for (int l = 0; l < L; l++) sum_hw += (long long)hs_host[l] * ws_host[l];
   const size_t plan_bytes = align256(workspace_need(R, PW, c.Hs));
-  if (layout == ABR_NCHW && workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 &&
-      workspace_bytes >= plan_bytes + staging_need(B, C, sum_hw, R, PH, PW, dtype)) {
-    // NCHW caller with staging room: channels-last copy of the upstream gradient, channels-last kernels into zeroed
+  const bool mixed = layout == ABR_NCHW_MAPS_NHWC_POOLED;
+  const bool staged_ok = workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 &&
+                         workspace_bytes >= plan_bytes + staging_need(B, C, sum_hw, R, PH, PW, dtype, layout);
+  ABR_REQUIRE(!mixed || staged_ok, ABR_ERR_WORKSPACE, "roi_align: layout %d needs a 256-byte aligned workspace of %zu B", layout,
+              plan_bytes + staging_need(B, C, sum_hw, R, PH, PW, dtype, layout));
+  if (layout != ABR_NHWC && staged_ok) {
+    // NCHW maps with staging room: channels-last copy of the upstream gradient, channels-last kernels into zeroed
     // channels-last maps, then transposed (added when zero_init == 0) into the caller's gradient maps
     const size_t es = elem_size(dtype);
     char* stage0 = static_cast<char*>(workspace) + plan_bytes;
-    void* pooled = stage0 + align256((size_t)B * C * sum_hw * es);
-    rc = transpose_any(grad_output, pooled, C, PH * PW, R, 0, dtype, c.st);
-    if (rc) return rc;
+    const void* pooled = grad_output;  // mixed layout: already channels-last
+    if (!mixed) {
+      void* staged = stage0 + align256((size_t)B * C * sum_hw * es);
+      if ((size_t)kPoolChunk * ((PH * PW) | 1) * sizeof(float) <= 48 * 1024 && R <= 65535)
+        rc = transpose_pooled(grad_output, staged, R, C, PH * PW, 1, dtype, c.st);
+      else
+        rc = transpose_any(grad_output, staged, C, PH * PW, R, 0, dtype, c.st);
+      if (rc) return rc;
+      pooled = staged;
+    }
     ABR_CUDA_OK(cudaMemsetAsync(stage0, 0, (size_t)B * C * sum_hw * es, c.st));
     void* user[ABR_MAX_LEVELS];
     char* stage = stage0;

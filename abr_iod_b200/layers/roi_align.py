@@ -22,38 +22,42 @@ def _prep_rois(rois, device):
 
 def roi_align_forward(input, rois, spatial_scale, pooled_h, pooled_w, sampling_ratio, return_plan=False):
     """``_C.roi_align_forward`` (csrc/ROIAlign.h:11-25).  With ``return_plan`` also returns the workspace holding the
-    per-RoI plans, which ``roi_align_backward(..., plan=...)`` of the same RoIs can reuse."""
+    per-RoI plans, which ``roi_align_backward(..., plan=...)`` of the same RoIs can reuse.  The result is channels-last
+    for a channels-last ``input`` (and for a contiguous one when ``_lib.POOLED_CHANNELS_LAST`` is set)."""
     _lib.require_cuda(input, "input")
     rois = _prep_rois(rois, input.device)
-    nhwc = _lib.is_channels_last(input)
-    x = input if nhwc else input.contiguous()
+    layout = _lib.roi_align_layout(input)
+    x = input if layout == _lib.ABR_NHWC else input.contiguous()
     B, C, H, W = x.shape
     R = rois.size(0)
     out = torch.empty((R, C, pooled_h, pooled_w), dtype=x.dtype, device=x.device,
-                      memory_format=torch.channels_last if nhwc else torch.contiguous_format)
+                      memory_format=torch.contiguous_format if layout == _lib.ABR_NCHW else torch.channels_last)
     if out.numel() == 0:
         return (out, None) if return_plan else out
     with torch.cuda.device(x.device):
-        ws, ws_bytes = _lib.roi_align_workspace(R, pooled_h, pooled_w, H, x.device, nhwc,
+        ws, ws_bytes = _lib.roi_align_workspace(R, pooled_h, pooled_w, H, x.device, layout=layout,
                                                 nchw_staging=(B, C, H * W, _lib.dtype_code(x)))
         _lib.check(_lib.lib().abr_roi_align_forward(
             x.data_ptr(), rois.data_ptr(), out.data_ptr(), B, C, H, W, R, pooled_h, pooled_w,
-            float(spatial_scale), int(sampling_ratio), _lib.dtype_code(x),
-            _lib.ABR_NHWC if nhwc else _lib.ABR_NCHW, ws.data_ptr() if ws is not None else None, ws_bytes,
-            _lib.stream_ptr(x.device)))
+            float(spatial_scale), int(sampling_ratio), _lib.dtype_code(x), layout,
+            ws.data_ptr() if ws is not None else None, ws_bytes, _lib.stream_ptr(x.device)))
     return (out, ws) if return_plan else out
 
 
 def roi_align_backward(grad, rois, spatial_scale, pooled_h, pooled_w, batch_size, channels, height, width,
-                       sampling_ratio, channels_last=None, plan=None):
-    """``_C.roi_align_backward`` (csrc/ROIAlign.h:27-46).  ``channels_last=None`` follows ``grad``'s layout; ``plan`` is
-    the workspace a forward over the same RoIs returned (skips re-planning)."""
+                       sampling_ratio, channels_last=None, plan=None, layout=None):
+    """``_C.roi_align_backward`` (csrc/ROIAlign.h:27-46).  ``channels_last=None`` follows ``grad``'s layout; ``layout``
+    (a code of ``_lib.roi_align_layout``) overrides it; ``plan`` is the workspace a forward over the same RoIs returned
+    (skips re-planning)."""
     _lib.require_cuda(grad, "grad")
     rois = _prep_rois(rois, grad.device)
-    nhwc = _lib.is_channels_last(grad) if channels_last is None else bool(channels_last)
-    g = grad.contiguous(memory_format=torch.channels_last) if nhwc else grad.contiguous()
-    gin = torch.empty((batch_size, channels, height, width), dtype=g.dtype, device=g.device,
-                      memory_format=torch.channels_last if nhwc else torch.contiguous_format)
+    if layout is None:
+        nhwc = _lib.is_channels_last(grad) if channels_last is None else bool(channels_last)
+        layout = _lib.ABR_NHWC if nhwc else _lib.ABR_NCHW
+    pooled_fmt = torch.contiguous_format if layout == _lib.ABR_NCHW else torch.channels_last
+    map_fmt = torch.channels_last if layout == _lib.ABR_NHWC else torch.contiguous_format
+    g = grad.contiguous(memory_format=pooled_fmt)
+    gin = torch.empty((batch_size, channels, height, width), dtype=g.dtype, device=g.device, memory_format=map_fmt)
     if gin.numel() == 0:
         return gin
     with torch.cuda.device(g.device):
@@ -61,13 +65,12 @@ def roi_align_backward(grad, rois, spatial_scale, pooled_h, pooled_w, batch_size
         if has_plan:
             ws, ws_bytes = plan, plan.numel()
         else:
-            ws, ws_bytes = _lib.roi_align_workspace(rois.size(0), pooled_h, pooled_w, height, g.device, nhwc,
+            ws, ws_bytes = _lib.roi_align_workspace(rois.size(0), pooled_h, pooled_w, height, g.device, layout=layout,
                                                     nchw_staging=(batch_size, channels, height * width, _lib.dtype_code(g)))
         _lib.check(_lib.lib().abr_roi_align_backward(
             g.data_ptr(), rois.data_ptr(), gin.data_ptr(), batch_size, channels, height, width, rois.size(0),
-            pooled_h, pooled_w, float(spatial_scale), int(sampling_ratio), _lib.dtype_code(g),
-            _lib.ABR_NHWC if nhwc else _lib.ABR_NCHW, 1, ws.data_ptr() if ws is not None else None, ws_bytes, has_plan,
-            _lib.stream_ptr(g.device)))
+            pooled_h, pooled_w, float(spatial_scale), int(sampling_ratio), _lib.dtype_code(g), layout, 1,
+            ws.data_ptr() if ws is not None else None, ws_bytes, has_plan, _lib.stream_ptr(g.device)))
     return gin
 
 
@@ -79,7 +82,7 @@ class _ROIAlign(Function):
         ctx.spatial_scale = spatial_scale
         ctx.sampling_ratio = sampling_ratio
         ctx.input_shape = input.size()
-        ctx.channels_last = _lib.is_channels_last(input)
+        ctx.layout = _lib.roi_align_layout(input)
         out, ctx.plan = roi_align_forward(input, roi, spatial_scale, ctx.output_size[0], ctx.output_size[1], sampling_ratio,
                                           return_plan=True)
         return out
@@ -90,7 +93,7 @@ class _ROIAlign(Function):
         (rois,) = ctx.saved_tensors
         bs, ch, h, w = ctx.input_shape
         grad_input = roi_align_backward(grad_output, rois, ctx.spatial_scale, ctx.output_size[0], ctx.output_size[1],
-                                        bs, ch, h, w, ctx.sampling_ratio, channels_last=ctx.channels_last, plan=ctx.plan)
+                                        bs, ch, h, w, ctx.sampling_ratio, layout=ctx.layout, plan=ctx.plan)
         return grad_input, None, None, None, None
 
 

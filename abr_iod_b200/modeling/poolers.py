@@ -65,25 +65,26 @@ def _level_arrays(feats, scales):
 class _MultiLevelROIAlign(Function):
     @staticmethod
     def forward(ctx, rois, levels, output_size, scales, sampling_ratio, *feats):
-        nhwc = _lib.is_channels_last(feats[0])
-        fmt = torch.channels_last if nhwc else torch.contiguous_format
+        layout = _lib.roi_align_layout(feats[0])
+        fmt = torch.channels_last if layout == _lib.ABR_NHWC else torch.contiguous_format
         feats = [f.contiguous(memory_format=fmt) for f in feats]
         B, C = feats[0].shape[:2]
         R = rois.size(0)
         PH, PW = output_size
-        out = torch.empty((R, C, PH, PW), dtype=feats[0].dtype, device=feats[0].device, memory_format=fmt)
+        out = torch.empty((R, C, PH, PW), dtype=feats[0].dtype, device=feats[0].device,
+                          memory_format=torch.contiguous_format if layout == _lib.ABR_NCHW else torch.channels_last)
         ctx.save_for_backward(rois, levels)
-        ctx.meta = (output_size, tuple(scales), sampling_ratio, [tuple(f.shape) for f in feats], nhwc)
+        ctx.meta = (output_size, tuple(scales), sampling_ratio, [tuple(f.shape) for f in feats], layout)
         ctx.plan = None
         if out.numel():
             ptrs, hs, ws, sc = _level_arrays(feats, scales)
             with torch.cuda.device(out.device):
                 wk, wk_bytes = _lib.roi_align_workspace(
-                    R, PH, PW, max(f.shape[2] for f in feats), out.device, nhwc,
+                    R, PH, PW, max(f.shape[2] for f in feats), out.device, layout=layout,
                     nchw_staging=(B, C, sum(f.shape[2] * f.shape[3] for f in feats), _lib.dtype_code(out)))
                 _lib.check(_lib.lib().abr_roi_align_multilevel_forward(
                     ptrs, hs, ws, sc, len(feats), rois.data_ptr(), levels.data_ptr(), out.data_ptr(), B, C, R, PH, PW,
-                    int(sampling_ratio), _lib.dtype_code(out), _lib.ABR_NHWC if nhwc else _lib.ABR_NCHW,
+                    int(sampling_ratio), _lib.dtype_code(out), layout,
                     wk.data_ptr() if wk is not None else None, wk_bytes, _lib.stream_ptr(out.device)))
                 ctx.plan = wk
         return out
@@ -92,9 +93,9 @@ class _MultiLevelROIAlign(Function):
     @once_differentiable
     def backward(ctx, grad_output):
         rois, levels = ctx.saved_tensors
-        (PH, PW), scales, sampling_ratio, shapes, nhwc = ctx.meta
-        fmt = torch.channels_last if nhwc else torch.contiguous_format
-        g = grad_output.contiguous(memory_format=fmt)
+        (PH, PW), scales, sampling_ratio, shapes, layout = ctx.meta
+        fmt = torch.channels_last if layout == _lib.ABR_NHWC else torch.contiguous_format
+        g = grad_output.contiguous(memory_format=torch.contiguous_format if layout == _lib.ABR_NCHW else torch.channels_last)
         grads = [torch.empty(s, dtype=g.dtype, device=g.device, memory_format=fmt) for s in shapes]
         B, C = shapes[0][:2]
         ptrs, hs, ws, sc = _level_arrays(grads, scales)
@@ -104,11 +105,11 @@ class _MultiLevelROIAlign(Function):
                 wk, wk_bytes = ctx.plan, ctx.plan.numel()
             else:
                 wk, wk_bytes = _lib.roi_align_workspace(
-                    rois.size(0), PH, PW, max(s[2] for s in shapes), g.device, nhwc,
+                    rois.size(0), PH, PW, max(s[2] for s in shapes), g.device, layout=layout,
                     nchw_staging=(B, C, sum(s[2] * s[3] for s in shapes), _lib.dtype_code(g)))
             _lib.check(_lib.lib().abr_roi_align_multilevel_backward(
                 g.data_ptr(), rois.data_ptr(), levels.data_ptr(), ptrs, hs, ws, sc, len(grads), B, C, rois.size(0),
-                PH, PW, int(sampling_ratio), _lib.dtype_code(g), _lib.ABR_NHWC if nhwc else _lib.ABR_NCHW, 1,
+                PH, PW, int(sampling_ratio), _lib.dtype_code(g), layout, 1,
                 wk.data_ptr() if wk is not None else None, wk_bytes, has_plan, _lib.stream_ptr(g.device)))
         return (None, None, None, None, None) + tuple(grads)
 

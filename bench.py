@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- the reference's headline metric on B200: ROIAlign+ARD RoIs/s, forward+backward.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--layout nhwc|nchw]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--layout nhwc|nchw|nchw_cl]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
 
 A "step" is one pass of the RoI hot path over one batch of synthetic input at the shapes of BASELINE.json
@@ -176,6 +176,7 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank) if rank == 0 else None  # started early: nvidia-smi needs a second to warm up
     w = WORKLOAD
     nhwc = args.layout == "nhwc"
+    _lib.POOLED_CHANNELS_LAST = args.layout == "nchw_cl"  # contiguous maps, channels-last RoI features
     fmt = torch.channels_last if nhwc else torch.contiguous_format
     teacher_np, student_np, rois_np = make_workload(seed=rank)
     R = rois_np.shape[0]
@@ -200,7 +201,7 @@ def run_ours(args, rank, world, local_rank):
         mark()
         loss3, g = _ard_launch(f_old, f_new, 1.0, True)
         mark()
-        gin = roi_align_backward(g, rois, scale, P, P, w["B"], w["C"], w["H"], w["W"], ratio, channels_last=nhwc, plan=plan)
+        gin = roi_align_backward(g, rois, scale, P, P, w["B"], w["C"], w["H"], w["W"], ratio, layout=_lib.roi_align_layout(student), plan=plan)
         mark()
         if ev is not None:
             ev.append(marks)
@@ -482,7 +483,9 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--layout", default="nhwc", choices=["nhwc", "nchw"])
+    ap.add_argument("--layout", default="nhwc", choices=["nhwc", "nchw", "nchw_cl"],
+                    help="nhwc: channels-last maps (default); nchw: contiguous maps and RoI features (an unmodified reference "
+                         "model); nchw_cl: contiguous maps, channels-last RoI features (_lib.POOLED_CHANNELS_LAST)")
     ap.add_argument("--cpu-rois", type=int, default=192, help="RoIs in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")

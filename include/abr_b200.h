@@ -13,6 +13,9 @@
  *   - return value: ABR_OK or an ABR_ERR_* code; abr_last_error() gives the thread-local text;
  *   - `dtype`  : element type of feature maps / pooled tensors / gradients (rois are always fp32);
  *   - `layout` : ABR_NCHW = the reference's contiguous [B,C,H,W] -> [R,C,PH,PW];
+ *                ABR_NCHW_MAPS_NHWC_POOLED (ROIAlign only) = contiguous feature / gradient maps,
+ *                channels-last pooled tensors: what a contiguous model gets when it accepts
+ *                channels-last RoI features (saves both passes over the pooled tensor);
  *                ABR_NHWC = channels-last storage of the same logical tensors,
  *                [B,H,W,C] -> [R,PH,PW,C] (torch.channels_last), the vectorised fast path.
  *   - rois are [R,5] fp32 rows (batch_index, x1, y1, x2, y2) in image pixels, exactly the
@@ -47,7 +50,7 @@ enum abr_status {
 };
 
 enum abr_dtype { ABR_F32 = 0, ABR_BF16 = 1 };
-enum abr_layout { ABR_NCHW = 0, ABR_NHWC = 1 };
+enum abr_layout { ABR_NCHW = 0, ABR_NHWC = 1, ABR_NCHW_MAPS_NHWC_POOLED = 2 };
 
 ABR_API int abr_version(void);
 ABR_API const char* abr_last_error(void);
@@ -68,6 +71,10 @@ ABR_API size_t abr_roi_align_workspace_bytes(int R, int PH, int PW, int max_h);
  * channels-last copy of every level's map (sum_hw = sum over levels of H*W) + one of the pooled tensor.  With less, an
  * NCHW call uses the direct NCHW kernels. */
 ABR_API size_t abr_roi_align_workspace_bytes_nchw(int R, int PH, int PW, int max_h, int B, int C, long long sum_hw, int dtype);
+/* The same for any layout: ABR_NHWC -> the plans only, ABR_NCHW -> as above, ABR_NCHW_MAPS_NHWC_POOLED -> plans + the
+ * channels-last copies of the maps (required for that layout: there is no direct kernel for it). */
+ABR_API size_t abr_roi_align_workspace_bytes_layout(int R, int PH, int PW, int max_h, int B, int C, long long sum_hw, int dtype,
+                                                    int layout);
 ABR_API int abr_roi_align_forward(const void* input, const float* rois, void* output,
                           int B, int C, int H, int W, int R, int PH, int PW,
                           float spatial_scale, int sampling_ratio,

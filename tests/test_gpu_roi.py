@@ -297,3 +297,48 @@ def test_roi_align_nchw_staged_accumulates_when_not_zero_init():
             g.data_ptr(), r.data_ptr(), gin.data_ptr(), B, C, H, W, R, P, P, 1 / 16, 0, 0, _lib.ABR_NCHW, 0,
             ws.data_ptr() if ws is not None else None, n, 0, _lib.stream_ptr(g.device)))
         close(gin.cpu().numpy(), gref)
+
+
+def test_roi_align_contiguous_maps_channels_last_pooled(monkeypatch):
+    """_lib.POOLED_CHANNELS_LAST: contiguous feature maps in, channels-last RoI features out (same logical tensor), the
+    gradient map contiguous again -- single level through ROIAlign and four levels through the Pooler."""
+    from abr_iod_b200 import _lib
+    from abr_iod_b200.layers import roi_align
+    from abr_iod_b200.modeling.poolers import Pooler
+    from abr_iod_b200.structures.bounding_box import BoxList
+    from oracle import pooler as opooler
+
+    monkeypatch.setattr(_lib, "POOLED_CHANNELS_LAST", True)
+    rng = np.random.default_rng(12)
+    B, C, H, W, P = 2, 40, 25, 38, 7
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    rois = make_rois(rng, 50, B, W * 16, H * 16)
+    gout = rng.standard_normal((50, C, P, P)).astype(np.float32)
+    xt = dev(x).requires_grad_(True)
+    out = roi_align(xt, dev(rois), (P, P), 1 / 16, 2)
+    assert out.is_contiguous(memory_format=torch.channels_last) and not out.is_contiguous()
+    close(out.detach().cpu().numpy(), oracle.roi_align_forward(x, rois, 1 / 16, P, P, 2))
+    out.backward(dev(gout))  # a contiguous upstream gradient is accepted
+    assert xt.grad.is_contiguous()
+    close(xt.grad.cpu().numpy(), oracle.roi_align_backward(gout, rois, 1 / 16, P, P, B, C, H, W, 2))
+    # four levels
+    scales = (0.25, 0.125, 0.0625, 0.03125)
+    im_w, im_h = 320, 256
+    feats_np = [rng.standard_normal((B, 16, int(im_h * s), int(im_w * s))).astype(np.float32) for s in scales]
+    boxes_np = []
+    for b in range(B):
+        x1, y1 = rng.uniform(0, im_w - 8, 25), rng.uniform(0, im_h - 8, 25)
+        side = np.exp(rng.uniform(np.log(6), np.log(300), 25))
+        boxes_np.append(np.stack([x1, y1, np.minimum(x1 + side, im_w - 1), np.minimum(y1 + side, im_h - 1)], 1).astype(np.float32))
+    feats = [dev(f).requires_grad_(True) for f in feats_np]
+    out = Pooler((7, 7), scales, 2)(feats, [BoxList(dev(b), (im_w, im_h), "xyxy") for b in boxes_np])
+    assert out.is_contiguous(memory_format=torch.channels_last)
+    close(out.detach().cpu().numpy(), opooler.pooler(feats_np, boxes_np, 7, scales, 2))
+    g2 = rng.standard_normal(out.shape).astype(np.float32)
+    out.backward(dev(g2))
+    rois2 = opooler.to_roi_format(boxes_np)
+    levels = opooler.map_levels(rois2[:, 1:], 2.0, 5.0)
+    for lvl in range(4):
+        idx = np.nonzero(levels == lvl)[0]
+        assert feats[lvl].grad.is_contiguous()
+        close(feats[lvl].grad.cpu().numpy(), oracle.roi_align_backward(g2[idx], rois2[idx], scales[lvl], 7, 7, *feats_np[lvl].shape, 2))
