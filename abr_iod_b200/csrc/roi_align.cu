@@ -172,7 +172,7 @@ __device__ __forceinline__ void build_inverse_ranges(const Tables& t, int PH, in
 // THIN    = thinner bins and PH <= 8;  GENERIC = anything else (columns wider than kPlanNx pixels, thin bins with
 // PH > 8): those RoIs are left to the table-in-shared-memory kernels below;  EMPTY = no sample inside the map.
 constexpr int kPlanNx = 16;
-constexpr int kTileMaxPx = 32;  // widest footprint row the TMA-staged kernel holds in one ring slot
+constexpr int kTileMaxPx = 64;  // widest footprint row the TMA-staged kernel holds in one ring slot
 constexpr int kPlanHdr = 16;
 constexpr int kPlanCol = 4 + kPlanNx;
 constexpr int kPlanRow = 8;
@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(256) roi_align_bwd_sweep_kernel(LevelTable lv,
 //     form t = sum_x Wx*v and add Wy[p][y]*t to one register accumulator per bin, then hand the slot back.
 // Every distinct footprint pixel leaves L2 exactly once per (RoI, slice) -- the columns share the staged row -- the
 // loads are asynchronous and kRing rows deep, and no thread ever waits on a dependent global load.  PH <= 8.
-constexpr int kRing = 4;  // power of two: slot = it & (kRing - 1)
+constexpr int kRing = 2;  // 32 KB slots: one being filled while the other is consumed
 constexpr int kMaxBins = 8;
 
 __device__ __forceinline__ unsigned s_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -614,6 +614,18 @@ __device__ __forceinline__ void mb_wait(unsigned long long* b, unsigned parity) 
       "{\n\t.reg .pred p;\n\tW_%=:\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
       "@p bra D_%=;\n\tbra W_%=;\n\tD_%=:\n\t}" ::"r"(s_u32(b)), "r"(parity) : "memory");
+}
+// Producer-side wait: the producer warp is never on the critical path, so it backs off between polls instead of
+// taking issue slots from the consumer warps of its SM sub-partition.
+__device__ __forceinline__ void mb_wait_backoff(unsigned long long* b, unsigned parity) {
+  const unsigned a = s_u32(b);
+  unsigned done;
+  for (;;) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    if (done) break;
+    __nanosleep(40);
+  }
 }
 __device__ __forceinline__ void mb_wait_a(unsigned addr, unsigned parity) {
   asm volatile(
@@ -636,14 +648,14 @@ __device__ __forceinline__ void tma_g2s(void* dst, const void* src, unsigned byt
 }
 
 // One TMA tensor op: a box of bh rows x bw pixels x 512 bytes of the [B*H rows][W pixels][C channels] view of a map
-// (bw * bh = kTileMaxPx, so every box is one 16 KB ring slot).
+// (bw * bh = kTileMaxPx, so every box is one 32 KB ring slot).
 __device__ __forceinline__ void tma_box_g2s(void* dst, const CUtensorMap* map, int c0, int x, int row, unsigned long long* b) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(s_u32(dst)),
                "l"(map), "r"(c0), "r"(x), "r"(row), "r"(s_u32(b))
                : "memory");
 }
 constexpr int kTmaLevels = 4;  // feature levels the tensor-map path carries (kernel parameter space)
-constexpr int kTmaBoxes = 5;   // boxes of 2x16, 4x8, 8x4, 16x2, 32x1 (pixels x rows)
+constexpr int kTmaBoxes = 6;   // boxes of 2x32, 4x16, 8x8, 16x4, 32x2, 64x1 (pixels x rows)
 struct TmaMaps {
   CUtensorMap m[kTmaLevels][kTmaBoxes];
 };
@@ -703,7 +715,7 @@ __global__ void __launch_bounds__(256, 3) roi_align_fwd_tma_kernel(const __grid_
       const int mode = h0.x, batch = h0.y, level = h0.z, Y0 = h0.w, nrows = h1.x - h0.w + 1, H = h1.z, W = h1.w;
       const int X0 = h2.x, wf = h2.y - h2.x + 1;
       const int pb = ti & 1;
-      mb_wait(&pempty[pb], ((ti >> 1) & 1) ^ 1);
+      mb_wait_backoff(&pempty[pb], ((ti >> 1) & 1) ^ 1);
       int* dst = planbuf + (size_t)pb * planw;
       const bool live = mode == PLAN_ROLLING || mode == PLAN_THIN;
       if (lane == 0) {
@@ -723,7 +735,7 @@ __global__ void __launch_bounds__(256, 3) roi_align_fwd_tma_kernel(const __grid_
       int grow = batch * H + Y0;
       for (int row = 0; row < nrows; row += bh, it++, grow += bh) {
         const int slot = it % kRing;
-        mb_wait(&empty[slot], ((it / kRing) & 1) ^ 1);
+        mb_wait_backoff(&empty[slot], ((it / kRing) & 1) ^ 1);
         if (lane == 0) {
           mb_expect_tx(&full[slot], (unsigned)kTileMaxPx * 512u);
           tma_box_g2s(ring + (size_t)slot * kTileMaxPx * 32, map, c0, X0, grow, &full[slot]);
@@ -809,8 +821,9 @@ __global__ void __launch_bounds__(256, 3) roi_align_fwd_tma_kernel(const __grid_
           mb_wait_a(full_a + slot * 8, (it / kRing) & 1);
           const int rows_here = min(bh, nrows - row0);
           unsigned ra = ring_a + (unsigned)slot * (kTileMaxPx * 512u);
-          for (int rr = 0; rr < rows_here; rr++, ra += rowbytes) {
-            const uint4 info = lds128(rec_a + (unsigned)(row0 + rr) * 32u);
+          unsigned rec = rec_a + (unsigned)row0 * 32u;
+          for (int rr = 0; rr < rows_here; rr++, ra += rowbytes, rec += 32u) {
+            const uint4 info = lds128(rec);
             const int ia = (int)info.x;
             if (ia < 0) continue;  // a map row between two bins' supports (sparse fixed-ratio sampling)
             float tr[V];
@@ -917,7 +930,7 @@ __global__ void __launch_bounds__(256, 4) roi_align_bwd_tma_kernel(const __grid_
       const int4 h1 = __ldg(reinterpret_cast<const int4*>(plan) + 1);
       const int mode = h0.x, nrows = h1.x - h0.w + 1;
       const int pb = ti & 1;
-      mb_wait(&pempty[pb], ((ti >> 1) & 1) ^ 1);
+      mb_wait_backoff(&pempty[pb], ((ti >> 1) & 1) ^ 1);
       const bool live = mode == PLAN_ROLLING || mode == PLAN_THIN;
       if (lane == 0) {
         const unsigned rowbytes = live ? (unsigned)nrows * (kPlanRow * 4u) : 0u;
