@@ -44,9 +44,9 @@ SIGNATURES = {
     "abr_roi_align_workspace_bytes": (_sz, [_int, _int, _int, _int]),
     "abr_roi_align_workspace_bytes_nchw": (_sz, [_int, _int, _int, _int, _int, _int, ctypes.c_longlong, _int]),
     "abr_roi_align_workspace_bytes_layout": (_sz, [_int, _int, _int, _int, _int, _int, ctypes.c_longlong, _int, _int]),
-    "abr_roi_align_forward": (_int, [_vp, _vp, _vp] + [_int] * 7 + [_f, _int, _int, _int, _vp, _sz, _vp]),
+    "abr_roi_align_forward": (_int, [_vp, _vp, _vp] + [_int] * 7 + [_f, _int, _int, _int, _vp, _sz, _int, _vp]),
     "abr_roi_align_backward": (_int, [_vp, _vp, _vp] + [_int] * 7 + [_f, _int, _int, _int, _int, _vp, _sz, _int, _vp]),
-    "abr_roi_align_multilevel_forward": (_int, [_vp, _vp, _vp, _vp, _int, _vp, _vp, _vp] + [_int] * 8 + [_vp, _sz, _vp]),
+    "abr_roi_align_multilevel_forward": (_int, [_vp, _vp, _vp, _vp, _int, _vp, _vp, _vp] + [_int] * 8 + [_vp, _sz, _int, _vp]),
     "abr_roi_align_multilevel_backward": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _int] + [_int] * 9 + [_vp, _sz, _int, _vp]),
     "abr_fpn_map_levels": (_int, [_vp, _vp, _int, _f, _f, _f, _f, _f, _vp]),
     "abr_roi_pool_forward": (_int, [_vp, _vp, _vp, _vp] + [_int] * 7 + [_f, _int, _int, _vp]),

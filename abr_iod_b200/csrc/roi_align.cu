@@ -1659,7 +1659,8 @@ size_t abr_roi_align_workspace_bytes_layout(int R, int PH, int PW, int max_h, in
 int abr_roi_align_multilevel_forward(const void* const* inputs_host, const int* hs_host, const int* ws_host,
                                      const float* scales_host, int L, const float* rois, const int32_t* levels,
                                      void* output, int B, int C, int R, int PH, int PW, int sampling_ratio, int dtype,
-                                     int layout, void* workspace, size_t workspace_bytes, abr_stream_t stream) {
+                                     int layout, void* workspace, size_t workspace_bytes, int workspace_has_plan,
+                                     abr_stream_t stream) {
   ABR_REQUIRE(inputs_host && hs_host && ws_host && scales_host, ABR_ERR_BAD_ARG, "roi_align: null level arrays");
   int rc = check_common(inputs_host, rois, output, B, C, R, PH, PW, dtype, layout);
   if (rc) return rc;
@@ -1672,7 +1673,7 @@ int abr_roi_align_multilevel_forward(const void* const* inputs_host, const int* 
   c.rois = rois; c.levels = L == 1 ? nullptr : levels;
   c.B = B; c.L = L;
   c.C = C; c.R = R; c.PH = PH; c.PW = PW; c.ratio = sampling_ratio; c.layout = layout;
-  c.plan_ready = false;
+  c.plan_ready = false;  // set below once the plans' location is known
   c.st = static_cast<cudaStream_t>(stream);
   long long sum_hw = 0;
   for (int l = 0; l < L; l++) sum_hw += (long long)hs_host[l] * ws_host[l];
@@ -1696,6 +1697,7 @@ int abr_roi_align_multilevel_forward(const void* const* inputs_host, const int* 
     void* pooled = static_cast<char*>(workspace) + plan_bytes + align256((size_t)B * C * sum_hw * es);
     c.layout = ABR_NHWC;
     c.plans = static_cast<int*>(workspace);
+    c.plan_ready = workspace_has_plan != 0;
     if (mixed) return dispatch_fwd(c, output, dtype);  // the caller's pooled tensor is channels-last already
     rc = dispatch_fwd(c, pooled, dtype);
     if (rc) return rc;
@@ -1704,6 +1706,7 @@ int abr_roi_align_multilevel_forward(const void* const* inputs_host, const int* 
     return transpose_any(pooled, output, PH * PW, C, R, 0, dtype, c.st);
   }
   c.plans = usable_workspace(workspace, workspace_bytes, R, PW, c.Hs, layout);
+  c.plan_ready = c.plans != nullptr && workspace_has_plan != 0;
   return dispatch_fwd(c, output, dtype);
 }
 
@@ -1780,12 +1783,12 @@ int abr_roi_align_multilevel_backward(const void* grad_output, const float* rois
 
 int abr_roi_align_forward(const void* input, const float* rois, void* output, int B, int C, int H, int W, int R, int PH,
                           int PW, float spatial_scale, int sampling_ratio, int dtype, int layout, void* workspace,
-                          size_t workspace_bytes, abr_stream_t stream) {
+                          size_t workspace_bytes, int workspace_has_plan, abr_stream_t stream) {
   if (R > 0) ABR_REQUIRE(input && H > 0 && W > 0, ABR_ERR_BAD_ARG, "roi_align_forward: null or empty input");
   if (R == 0) return check_common(&input, rois, output, B, C, R, PH, PW, dtype, layout);
   const void* ptrs[1] = {input};
   return abr_roi_align_multilevel_forward(ptrs, &H, &W, &spatial_scale, 1, rois, nullptr, output, B, C, R, PH, PW,
-                                          sampling_ratio, dtype, layout, workspace, workspace_bytes, stream);
+                                          sampling_ratio, dtype, layout, workspace, workspace_bytes, workspace_has_plan, stream);
 }
 
 int abr_roi_align_backward(const void* grad_output, const float* rois, void* grad_input, int B, int C, int H, int W,

@@ -20,9 +20,10 @@ def _prep_rois(rois, device):
     return rois.detach().to(dtype=torch.float32).contiguous()
 
 
-def roi_align_forward(input, rois, spatial_scale, pooled_h, pooled_w, sampling_ratio, return_plan=False):
+def roi_align_forward(input, rois, spatial_scale, pooled_h, pooled_w, sampling_ratio, return_plan=False, plan=None):
     """``_C.roi_align_forward`` (csrc/ROIAlign.h:11-25).  With ``return_plan`` also returns the workspace holding the
-    per-RoI plans, which ``roi_align_backward(..., plan=...)`` of the same RoIs can reuse.  The result is channels-last
+    per-RoI plans, which ``roi_align_backward(..., plan=...)`` -- or another forward over the SAME RoIs, output size,
+    sampling ratio, scale and map shape (the teacher / student pair of the distillation step), via ``plan=`` -- can reuse.  The result is channels-last
     for a channels-last ``input`` (and for a contiguous one when ``_lib.POOLED_CHANNELS_LAST`` is set)."""
     _lib.require_cuda(input, "input")
     rois = _prep_rois(rois, input.device)
@@ -35,12 +36,15 @@ def roi_align_forward(input, rois, spatial_scale, pooled_h, pooled_w, sampling_r
     if out.numel() == 0:
         return (out, None) if return_plan else out
     with torch.cuda.device(x.device):
-        ws, ws_bytes = _lib.roi_align_workspace(R, pooled_h, pooled_w, H, x.device, layout=layout,
-                                                nchw_staging=(B, C, H * W, _lib.dtype_code(x)))
+        if plan is not None:
+            ws, ws_bytes = plan, plan.numel()
+        else:
+            ws, ws_bytes = _lib.roi_align_workspace(R, pooled_h, pooled_w, H, x.device, layout=layout,
+                                                    nchw_staging=(B, C, H * W, _lib.dtype_code(x)))
         _lib.check(_lib.lib().abr_roi_align_forward(
             x.data_ptr(), rois.data_ptr(), out.data_ptr(), B, C, H, W, R, pooled_h, pooled_w,
             float(spatial_scale), int(sampling_ratio), _lib.dtype_code(x), layout,
-            ws.data_ptr() if ws is not None else None, ws_bytes, _lib.stream_ptr(x.device)))
+            ws.data_ptr() if ws is not None else None, ws_bytes, int(plan is not None), _lib.stream_ptr(x.device)))
     return (out, ws) if return_plan else out
 
 

@@ -85,7 +85,7 @@ class _MultiLevelROIAlign(Function):
                 _lib.check(_lib.lib().abr_roi_align_multilevel_forward(
                     ptrs, hs, ws, sc, len(feats), rois.data_ptr(), levels.data_ptr(), out.data_ptr(), B, C, R, PH, PW,
                     int(sampling_ratio), _lib.dtype_code(out), layout,
-                    wk.data_ptr() if wk is not None else None, wk_bytes, _lib.stream_ptr(out.device)))
+                    wk.data_ptr() if wk is not None else None, wk_bytes, 0, _lib.stream_ptr(out.device)))
                 ctx.plan = wk
         return out
 

@@ -195,9 +195,9 @@ def run_ours(args, rank, world, local_rank):
                 e.record()
                 marks.append(e)
         mark()
-        f_old = roi_align_forward(teacher, rois, scale, P, P, ratio)
+        f_old, plan = roi_align_forward(teacher, rois, scale, P, P, ratio, return_plan=True)
         mark()
-        f_new, plan = roi_align_forward(student, rois, scale, P, P, ratio, return_plan=True)
+        f_new = roi_align_forward(student, rois, scale, P, P, ratio, plan=plan)  # same RoIs and map shape: plans reused
         mark()
         loss3, g = _ard_launch(f_old, f_new, 1.0, True)
         mark()

@@ -64,7 +64,8 @@ ABR_API uint64_t abr_launch_count(void);
  * R == 0 is a no-op (ROIAlign_cuda.cu:278-281).
  * `workspace` (optional, 16-byte aligned, abr_roi_align_workspace_bytes(R, PH, PW, max H over levels) bytes) holds the
  * per-RoI interpolation plans of the fast NHWC kernels; with NULL (or the NCHW layout) the self-contained kernels run.
- * The forward leaves the plans of its RoIs in the workspace; a backward for the SAME rois / levels / geometry may be
+ * A call leaves the plans of its RoIs in the workspace; a later call -- the backward, or another forward such as the
+ * student's after the teacher's -- for the SAME rois / levels / output size / sampling ratio / scales / map shapes may be
  * handed that workspace with workspace_has_plan != 0 and then skips planning (0: contents are treated as scratch). */
 ABR_API size_t abr_roi_align_workspace_bytes(int R, int PH, int PW, int max_h);
 /* Workspace that additionally lets an ABR_NCHW call run through the channels-last kernels (256-byte aligned): plans + a
@@ -78,7 +79,8 @@ ABR_API size_t abr_roi_align_workspace_bytes_layout(int R, int PH, int PW, int m
 ABR_API int abr_roi_align_forward(const void* input, const float* rois, void* output,
                           int B, int C, int H, int W, int R, int PH, int PW,
                           float spatial_scale, int sampling_ratio,
-                          int dtype, int layout, void* workspace, size_t workspace_bytes, abr_stream_t stream);
+                          int dtype, int layout, void* workspace, size_t workspace_bytes, int workspace_has_plan,
+        abr_stream_t stream);
 
 /* grad_input [B,C,H,W] is zero-filled first when zero_init != 0 (the reference always does,
  * ROIAlign_cuda.cu:316); pass 0 to accumulate into an existing gradient. */
@@ -98,8 +100,8 @@ ABR_API int abr_roi_align_multilevel_forward(const void* const* inputs_host, con
                                      const float* scales_host, int L,
                                      const float* rois, const int32_t* levels, void* output,
                                      int B, int C, int R, int PH, int PW, int sampling_ratio,
-                                     int dtype, int layout, void* workspace, size_t workspace_bytes,
-                                     abr_stream_t stream);
+                                     int dtype, int layout, void* workspace, size_t workspace_bytes, int workspace_has_plan,
+        abr_stream_t stream);
 ABR_API int abr_roi_align_multilevel_backward(const void* grad_output, const float* rois, const int32_t* levels,
                                       void* const* grad_inputs_host, const int* hs_host, const int* ws_host,
                                       const float* scales_host, int L,

@@ -342,3 +342,20 @@ def test_roi_align_contiguous_maps_channels_last_pooled(monkeypatch):
         idx = np.nonzero(levels == lvl)[0]
         assert feats[lvl].grad.is_contiguous()
         close(feats[lvl].grad.cpu().numpy(), oracle.roi_align_backward(g2[idx], rois2[idx], scales[lvl], 7, 7, *feats_np[lvl].shape, 2))
+
+
+def test_roi_align_forward_plan_shared_between_two_maps():
+    """The teacher / student pair pools the same RoIs from maps of the same shape: the second forward reuses the first's
+    plans (workspace_has_plan) and must give the same result as planning afresh."""
+    from abr_iod_b200.layers.roi_align import roi_align_forward
+
+    rng = np.random.default_rng(21)
+    B, C, H, W, P = 2, 32, 25, 38, 7
+    a = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    b = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    rois = make_rois(rng, 60, B, W * 16, H * 16)
+    for cl in (True, False):
+        fa, plan = roi_align_forward(dev(a, cl), dev(rois), 1 / 16, P, P, 0, return_plan=True)
+        fb = roi_align_forward(dev(b, cl), dev(rois), 1 / 16, P, P, 0, plan=plan)
+        close(fa.cpu().numpy(), oracle.roi_align_forward(a, rois, 1 / 16, P, P, 0))
+        close(fb.cpu().numpy(), oracle.roi_align_forward(b, rois, 1 / 16, P, P, 0))
