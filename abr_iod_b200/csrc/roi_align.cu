@@ -624,7 +624,7 @@ __device__ __forceinline__ void mb_wait_backoff(unsigned long long* b, unsigned 
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(done) : "r"(a), "r"(parity) : "memory");
     if (done) break;
-    __nanosleep(40);
+    __nanosleep(100);
   }
 }
 __device__ __forceinline__ void mb_wait_a(unsigned addr, unsigned parity) {
@@ -700,14 +700,15 @@ __global__ void __launch_bounds__(256, 3) roi_align_fwd_tma_kernel(const __grid_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const long long ntasks = (long long)R * nslices;
+  const int dr = (int)(gridDim.x / (unsigned)nslices), dslice = (int)(gridDim.x % (unsigned)nslices);
   unsigned it = 0;  // rows streamed so far by this CTA (ring position), identical in every warp
   int ti = 0;       // tasks done so far (plan buffer position)
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
-    for (long long task = blockIdx.x; task < ntasks; task += gridDim.x, ti++) {
-      const int r = (int)(task / nslices), slice = (int)(task - (long long)r * nslices);
+    // task = r * nslices + slice walks blockIdx.x, blockIdx.x + gridDim.x, ...: (r, slice) advance without a division
+    for (int r = (int)(blockIdx.x / (unsigned)nslices), slice = (int)(blockIdx.x % (unsigned)nslices); r < R; ti++, slice += dslice, r += dr) {
+      if (slice >= nslices) { slice -= nslices; r++; if (r >= R) break; }
       const int* plan = plans + (size_t)r * stride;
       const int4 h0 = __ldg(reinterpret_cast<const int4*>(plan));
       const int4 h1 = __ldg(reinterpret_cast<const int4*>(plan) + 1);
@@ -746,8 +747,9 @@ __global__ void __launch_bounds__(256, 3) roi_align_fwd_tma_kernel(const __grid_
     // ------------------------------------------------------------------ consumers: warp w owns bin column w-1
     const int pw = warp - 1;
     const unsigned ring_a = s_u32(ring) + lane * 16, full_a = s_u32(full), empty_a = s_u32(empty);
-    for (long long task = blockIdx.x; task < ntasks; task += gridDim.x, ti++) {
-      const int r = (int)(task / nslices), slice = (int)(task - (long long)r * nslices);
+    // task = r * nslices + slice walks blockIdx.x, blockIdx.x + gridDim.x, ...: (r, slice) advance without a division
+    for (int r = (int)(blockIdx.x / (unsigned)nslices), slice = (int)(blockIdx.x % (unsigned)nslices); r < R; ti++, slice += dslice, r += dr) {
+      if (slice >= nslices) { slice -= nslices; r++; if (r >= R) break; }
       const int pb = ti & 1;
       mb_wait(&pfull[pb], (ti >> 1) & 1);
       const int* pl = planbuf + (size_t)pb * planw;
@@ -816,6 +818,7 @@ __global__ void __launch_bounds__(256, 3) roi_align_fwd_tma_kernel(const __grid_
 #pragma unroll
         for (int i = 0; i < V; i++) accA[i] = accB[i] = 0.f;
         int a = 0;
+        T* oa = o;  // output address of bin a of this column
         for (int row0 = 0; row0 < nrows; row0 += bh, it++) {
           const int slot = it % kRing;
           mb_wait_a(full_a + slot * 8, (it / kRing) & 1);
@@ -832,7 +835,8 @@ __global__ void __launch_bounds__(256, 3) roi_align_fwd_tma_kernel(const __grid_
               do {
 #pragma unroll
                 for (int i = 0; i < V; i++) accA[i] *= inv_count;
-                if (active) VecIO<T, V>::store(o + (size_t)a * binstride, accA);
+                if (active) VecIO<T, V>::store(oa, accA);
+                oa += binstride;
 #pragma unroll
                 for (int i = 0; i < V; i++) { accA[i] = accB[i]; accB[i] = 0.f; }
               } while (++a < ia);
@@ -846,10 +850,10 @@ __global__ void __launch_bounds__(256, 3) roi_align_fwd_tma_kernel(const __grid_
           }
           mb_arrive_a(empty_a + slot * 8);
         }
-        for (; a < PH; a++) {
+        for (; a < PH; a++, oa += binstride) {
 #pragma unroll
           for (int i = 0; i < V; i++) accA[i] *= inv_count;
-          if (active) VecIO<T, V>::store(o + (size_t)a * binstride, accA);
+          if (active) VecIO<T, V>::store(oa, accA);
 #pragma unroll
           for (int i = 0; i < V; i++) { accA[i] = accB[i]; accB[i] = 0.f; }
         }
@@ -919,12 +923,13 @@ __global__ void __launch_bounds__(256, 4) roi_align_bwd_tma_kernel(const __grid_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const long long ntasks = (long long)R * nslices;
+  const int dr = (int)(gridDim.x / (unsigned)nslices), dslice = (int)(gridDim.x % (unsigned)nslices);
   int ti = 0;
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
-    for (long long task = blockIdx.x; task < ntasks; task += gridDim.x, ti++) {
-      const int r = (int)(task / nslices), slice = (int)(task - (long long)r * nslices);
+    // task = r * nslices + slice walks blockIdx.x, blockIdx.x + gridDim.x, ...: (r, slice) advance without a division
+    for (int r = (int)(blockIdx.x / (unsigned)nslices), slice = (int)(blockIdx.x % (unsigned)nslices); r < R; ti++, slice += dslice, r += dr) {
+      if (slice >= nslices) { slice -= nslices; r++; if (r >= R) break; }
       const int* plan = plans + (size_t)r * stride;
       const int4 h0 = __ldg(reinterpret_cast<const int4*>(plan));
       const int4 h1 = __ldg(reinterpret_cast<const int4*>(plan) + 1);
@@ -946,8 +951,9 @@ __global__ void __launch_bounds__(256, 4) roi_align_bwd_tma_kernel(const __grid_
   } else if (warp <= PW) {
     // ------------------------------------------------------------------ consumers: warp w owns bin column w-1
     const int pw = warp - 1;
-    for (long long task = blockIdx.x; task < ntasks; task += gridDim.x, ti++) {
-      const int r = (int)(task / nslices), slice = (int)(task - (long long)r * nslices);
+    // task = r * nslices + slice walks blockIdx.x, blockIdx.x + gridDim.x, ...: (r, slice) advance without a division
+    for (int r = (int)(blockIdx.x / (unsigned)nslices), slice = (int)(blockIdx.x % (unsigned)nslices); r < R; ti++, slice += dslice, r += dr) {
+      if (slice >= nslices) { slice -= nslices; r++; if (r >= R) break; }
       (void)r;
       const int pb = ti & 1;
       mb_wait(&pfull[pb], (ti >> 1) & 1);
