@@ -132,3 +132,23 @@ def test_post_processor_argument_errors():
         box_postprocess(logits, reg, props, [9], [(100, 100)])
     with pytest.raises(RuntimeError):
         box_postprocess(logits, reg[:, :8], props, [10], [(100, 100)])
+
+
+def test_post_processor_many_images():
+    """70 images x 9 classes = 630 (image, class) NMS segments: several launch groups of every kernel."""
+    from abr_iod_b200.modeling.roi_heads.box_head import box_postprocess
+
+    rng = np.random.default_rng(71)
+    counts = [int(c) for c in rng.integers(5, 40, 70)]
+    counts[3] = 0
+    sizes = [(320 - (i % 7), 240 - (i % 5)) for i in range(70)]
+    props, logits, reg = make_inputs(rng, sizes, counts, 9)
+    allp = np.concatenate([p.reshape(-1, 4) for p in props], 0)
+    out = box_postprocess(dev(logits), dev(reg), dev(allp), counts, sizes, 0.05, 0.5, 20)
+    ref, ref_bg = obp.box_postprocess(logits, reg, props, sizes, 0.05, 0.5, 20)
+    for n in range(70):
+        k = out["n_host"][n]
+        assert k == len(ref[n][1])
+        assert np.array_equal(out["labels"][n, :k].cpu().numpy(), ref[n][2])
+        assert np.array_equal(out["rows"][n, :k].cpu().numpy(), ref[n][3])
+        assert int(out["bg_n"][n]) == len(ref_bg[n][1])

@@ -151,3 +151,26 @@ def test_rpn_argument_errors():
         big = torch.zeros((1, 3, 100, 100), device="cuda")
         rpn_proposals(big, torch.zeros((1, 12, 100, 100), device="cuda"), torch.zeros((30000, 4), device="cuda"), [(1600, 1600)],
                       20000, 5, 0.7, 0)
+
+
+def test_rpn_many_images_and_per_image_anchors():
+    """70 images (more than one launch group of the selection kernels and of the batched NMS), every image with its own
+    anchor tensor (anchor_image_stride != 0) and its own size."""
+    from abr_iod_b200.modeling.rpn import RPNPostProcessor
+    from abr_iod_b200.structures.bounding_box import BoxList
+
+    rng = np.random.default_rng(70)
+    N, A, H, W = 70, 3, 6, 8
+    base = make_anchors(H, W, 16, sizes=(48,), ratios=(0.5, 1.0, 2.0))
+    anchors = [base + rng.uniform(-2, 2, base.shape).astype(np.float32) for _ in range(N)]
+    logits = (rng.standard_normal((N, A, H, W)) * 2).astype(np.float32)
+    reg = (rng.standard_normal((N, 4 * A, H, W)) * 0.3).astype(np.float32)
+    sizes = [(W * 16 - (i % 5), H * 16 - (i % 3)) for i in range(N)]
+    pp = RPNPostProcessor(100, 30, 0.7, 0)
+    res = pp.forward_for_single_feature_map([BoxList(dev(a), s, "xyxy") for a, s in zip(anchors, sizes)], dev(logits), dev(reg))
+    ref = orpn.rpn_proposals(logits, reg, anchors, sizes, 100, 30, 0.7, 0)
+    assert len(res) == N
+    for n in range(N):
+        assert len(res[n]) == len(ref[n][0])
+        boxes_close(res[n].bbox.cpu().numpy(), ref[n][0], base)
+        assert np.abs(res[n].get_field("objectness").cpu().numpy() - ref[n][1]).max() <= 1e-6
