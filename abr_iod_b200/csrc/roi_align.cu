@@ -23,6 +23,8 @@
 
 #include <cstdlib>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace abr {
@@ -1316,38 +1318,81 @@ __global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ sr
   }
 }
 
-// Pooled tensors ([R][C][HW] <-> [R][HW][C], HW = 49 or 196): a CTA moves one RoI's chunk of 64 channels.  The NCHW side
-// of the chunk is one contiguous run (64*HW elements), the NHWC side is HW runs of 64 channels; the chunk sits in
-// shared memory as [c][HW | 1] (odd pitch: conflict-free in both directions).
-constexpr int kPoolChunk = 64;
-template <typename T>
-__global__ void __launch_bounds__(256) transpose_pooled_kernel(const T* __restrict__ src, T* __restrict__ dst, int C, int HW, int to_nhwc) {
+// Pooled tensors ([R][C][HW] <-> [R][HW][C], HW = 49 or 196): a CTA moves one RoI's chunk of CH channels (as many as
+// ~100 KB of shared memory hold, two CTAs per SM).  The NCHW side of the chunk is one contiguous run (CH*HW elements),
+// the NHWC side is HW runs of CH channels (2 KB each for CH = 512); the chunk sits in shared memory as [c][HW | 1]
+// (odd pitch: conflict-free in both directions).
+constexpr int kPoolThreads = 512;
+template <typename T, int CH>
+__global__ void __launch_bounds__(kPoolThreads) transpose_pooled_kernel(const T* __restrict__ src, T* __restrict__ dst, int C, int HW, int to_nhwc) {
   extern __shared__ float chunk[];
-  const int r = blockIdx.y, c0 = blockIdx.x * kPoolChunk;
-  const int nC = min(kPoolChunk, C - c0), pitch = HW | 1, total = nC * HW;
+  const int r = blockIdx.y, c0 = blockIdx.x * CH;
+  const int nC = min(CH, C - c0), pitch = HW | 1, total = nC * HW;
   const size_t nchw = ((size_t)r * C + c0) * HW, nhwc = (size_t)r * HW * C + c0;
+  if constexpr (std::is_same<T, float>::value) {
+    // full fp32 chunks move as 16-byte vectors on both global sides (the shared-memory side stays scalar)
+    if (nC == CH && C % 4 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+      const int total4 = total / 4;
+      if (to_nhwc) {
+        const float4* s4 = reinterpret_cast<const float4*>(src + nchw);
+        for (int i4 = threadIdx.x; i4 < total4; i4 += kPoolThreads) {
+          const float4 v = __ldg(s4 + i4);
+          const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int i = i4 * 4 + k, c = i / HW;
+            chunk[c * pitch + (i - c * HW)] = e[k];
+          }
+        }
+        __syncthreads();
+        for (int i4 = threadIdx.x; i4 < total4; i4 += kPoolThreads) {
+          const int p2 = i4 / (CH / 4), c = (i4 - p2 * (CH / 4)) * 4;
+          const float4 v = make_float4(chunk[c * pitch + p2], chunk[(c + 1) * pitch + p2], chunk[(c + 2) * pitch + p2], chunk[(c + 3) * pitch + p2]);
+          *reinterpret_cast<float4*>(dst + nhwc + (size_t)p2 * C + c) = v;
+        }
+      } else {
+        for (int i4 = threadIdx.x; i4 < total4; i4 += kPoolThreads) {
+          const int p2 = i4 / (CH / 4), c = (i4 - p2 * (CH / 4)) * 4;
+          const float4 v = __ldg(reinterpret_cast<const float4*>(src + nhwc + (size_t)p2 * C + c));
+          chunk[c * pitch + p2] = v.x; chunk[(c + 1) * pitch + p2] = v.y; chunk[(c + 2) * pitch + p2] = v.z; chunk[(c + 3) * pitch + p2] = v.w;
+        }
+        __syncthreads();
+        float4* d4 = reinterpret_cast<float4*>(dst + nchw);
+        for (int i4 = threadIdx.x; i4 < total4; i4 += kPoolThreads) {
+          float e[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int i = i4 * 4 + k, c = i / HW;
+            e[k] = chunk[c * pitch + (i - c * HW)];
+          }
+          d4[i4] = make_float4(e[0], e[1], e[2], e[3]);
+        }
+      }
+      return;
+    }
+  }
   if (to_nhwc) {
-    for (int i = threadIdx.x; i < total; i += 256) {
+    for (int i = threadIdx.x; i < total; i += kPoolThreads) {
       const int c = i / HW, p2 = i - c * HW;
       float v[1];
       VecIO<T, 1>::load(src + nchw + i, v);
       chunk[c * pitch + p2] = v[0];
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < total; i += 256) {
+    for (int i = threadIdx.x; i < total; i += kPoolThreads) {
       const int p2 = i / nC, c = i - p2 * nC;
       const float v[1] = {chunk[c * pitch + p2]};
       VecIO<T, 1>::store(dst + nhwc + (size_t)p2 * C + c, v);
     }
   } else {
-    for (int i = threadIdx.x; i < total; i += 256) {
+    for (int i = threadIdx.x; i < total; i += kPoolThreads) {
       const int p2 = i / nC, c = i - p2 * nC;
       float v[1];
       VecIO<T, 1>::load(src + nhwc + (size_t)p2 * C + c, v);
       chunk[c * pitch + p2] = v[0];
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < total; i += 256) {
+    for (int i = threadIdx.x; i < total; i += kPoolThreads) {
       const int c = i / HW, p2 = i - c * HW;
       const float v[1] = {chunk[c * pitch + p2]};
       VecIO<T, 1>::store(dst + nchw + i, v);
@@ -1355,18 +1400,32 @@ __global__ void __launch_bounds__(256) transpose_pooled_kernel(const T* __restri
   }
 }
 
-// [R][C][HW] -> [R][HW][C] (to_nhwc) or back
-static int transpose_pooled(const void* src, void* dst, int R, int C, int HW, int to_nhwc, int dtype, cudaStream_t st) {
-  if (R <= 0) return ABR_OK;
-  const size_t smem = (size_t)kPoolChunk * (HW | 1) * sizeof(float);
-  ABR_REQUIRE(smem <= 48 * 1024 && R <= 65535, ABR_ERR_UNSUPPORTED, "roi_align: pooled transpose of %d RoIs x %d positions", R, HW);
-  const dim3 grid(ceil_div(C, kPoolChunk), R);
-  if (dtype == ABR_F32)
-    transpose_pooled_kernel<float><<<grid, 256, smem, st>>>(static_cast<const float*>(src), static_cast<float*>(dst), C, HW, to_nhwc);
-  else
-    transpose_pooled_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), C, HW, to_nhwc);
+constexpr size_t kPoolSmem = 101 * 1024;  // per CTA: two CTAs per SM
+static bool pooled_transpose_fits(int HW, int R) { return (size_t)64 * (HW | 1) * sizeof(float) <= kPoolSmem && R <= 65535; }
+
+template <typename T, int CH>
+static int launch_transpose_pooled(const void* src, void* dst, int R, int C, int HW, int to_nhwc, cudaStream_t st) {
+  const size_t smem = (size_t)CH * (HW | 1) * sizeof(float);
+  auto kern = transpose_pooled_kernel<T, CH>;
+  if (smem > 48 * 1024) ABR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<dim3(ceil_div(C, CH), R), kPoolThreads, smem, st>>>(static_cast<const T*>(src), static_cast<T*>(dst), C, HW, to_nhwc);
   ABR_CHECK_LAUNCH("roi_align_transpose_pooled");
   return ABR_OK;
+}
+
+// [R][C][HW] -> [R][HW][C] (to_nhwc) or back
+template <typename T>
+static int transpose_pooled_t(const void* src, void* dst, int R, int C, int HW, int to_nhwc, cudaStream_t st) {
+  const size_t per_ch = (size_t)(HW | 1) * sizeof(float);
+  if (C >= 512 && 512 * per_ch <= kPoolSmem) return launch_transpose_pooled<T, 512>(src, dst, R, C, HW, to_nhwc, st);
+  if (C >= 128 && 128 * per_ch <= kPoolSmem) return launch_transpose_pooled<T, 128>(src, dst, R, C, HW, to_nhwc, st);
+  return launch_transpose_pooled<T, 64>(src, dst, R, C, HW, to_nhwc, st);
+}
+static int transpose_pooled(const void* src, void* dst, int R, int C, int HW, int to_nhwc, int dtype, cudaStream_t st) {
+  if (R <= 0) return ABR_OK;
+  ABR_REQUIRE(pooled_transpose_fits(HW, R), ABR_ERR_UNSUPPORTED, "roi_align: pooled transpose of %d RoIs x %d positions", R, HW);
+  return dtype == ABR_F32 ? transpose_pooled_t<float>(src, dst, R, C, HW, to_nhwc, st)
+                          : transpose_pooled_t<__nv_bfloat16>(src, dst, R, C, HW, to_nhwc, st);
 }
 
 template <typename T>
@@ -1707,8 +1766,7 @@ int abr_roi_align_multilevel_forward(const void* const* inputs_host, const int* 
     if (mixed) return dispatch_fwd(c, output, dtype);  // the caller's pooled tensor is channels-last already
     rc = dispatch_fwd(c, pooled, dtype);
     if (rc) return rc;
-    if ((size_t)kPoolChunk * ((PH * PW) | 1) * sizeof(float) <= 48 * 1024 && R <= 65535)
-      return transpose_pooled(pooled, output, R, C, PH * PW, 0, dtype, c.st);
+    if (pooled_transpose_fits(PH * PW, R)) return transpose_pooled(pooled, output, R, C, PH * PW, 0, dtype, c.st);
     return transpose_any(pooled, output, PH * PW, C, R, 0, dtype, c.st);
   }
   c.plans = usable_workspace(workspace, workspace_bytes, R, PW, c.Hs, layout);
@@ -1752,7 +1810,7 @@ int abr_roi_align_multilevel_backward(const void* grad_output, const float* rois
     const void* pooled = grad_output;  // mixed layout: already channels-last
     if (!mixed) {
       void* staged = stage0 + align256((size_t)B * C * sum_hw * es);
-      if ((size_t)kPoolChunk * ((PH * PW) | 1) * sizeof(float) <= 48 * 1024 && R <= 65535)
+      if (pooled_transpose_fits(PH * PW, R))
         rc = transpose_pooled(grad_output, staged, R, C, PH * PW, 1, dtype, c.st);
       else
         rc = transpose_any(grad_output, staged, C, PH * PW, R, 0, dtype, c.st);
