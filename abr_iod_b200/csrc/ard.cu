@@ -566,7 +566,7 @@ __global__ void scale_if_needed_kernel(T* data, size_t n, const float* __restric
 template <typename T, int V>
 static int launch_nhwc(const ArdParams& p, const void* fo, const void* fn, void* g, cudaStream_t st) {
   const size_t smem = (size_t)5 * p.HW * sizeof(float);
-  static const int threads = getenv("ABR_ARD_THREADS") ? atoi(getenv("ABR_ARD_THREADS")) : 1024;
+  const int threads = 1024;  // one CTA per SM: the RoIs in flight stay L2-resident between the two passes
   const int per_sm = 2048 / threads;
   const int grid = p.N < num_sms() * per_sm ? p.N : num_sms() * per_sm;
   if (g) ard_nhwc_kernel<T, V, true><<<grid, threads, smem, st>>>(p, static_cast<const T*>(fo), static_cast<const T*>(fn), static_cast<T*>(g));
