@@ -401,10 +401,11 @@ static int launch_nhwc_cluster(const ArdParams& p, const void* fo, const void* f
 
 // ------------------------------------------------------------------------------------------ NCHW cluster kernel
 // [N][C][HW]: a RoI is the same contiguous C*HW*4 bytes as in NHWC, so the CTAs of a cluster take contiguous channel
-// ranges with 1-D bulk copies.  Thread (g, p) of the first G*HW threads owns position p and walks the channels
-// g, g+G, ... of the tile (consecutive threads -> consecutive shared-memory words and consecutive global words in the
-// gradient pass).  Per-position sums are partial per CTA: every CTA stores its three partial rows into every peer's
-// table and each CTA adds them up in rank order (deterministic).
+// ranges with 1-D bulk copies.  The first T = HW*G threads (G = 512 / HW) each own the four consecutive floats
+// 4t .. 4t+3 of every sweep of S = 4*T floats through the tile: S is a multiple of HW, so a thread's four floats
+// always belong to the same four positions (4t+j) mod HW -- 16-byte shared-memory loads and global stores, per-thread
+// accumulators for its four positions.  Per-position sums are partial per CTA: every CTA stores its three partial rows
+// into every peer's table and each CTA adds them up in rank order (deterministic).
 template <bool GRAD>
 __global__ void __launch_bounds__(kArdClusterThreads, 1) ard_nchw_cluster_kernel(ArdParams p, const float* __restrict__ f_old,
                                                                               const float* __restrict__ f_new,
@@ -412,11 +413,13 @@ __global__ void __launch_bounds__(kArdClusterThreads, 1) ard_nchw_cluster_kernel
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int HW = p.HW, C = p.C;
   const unsigned rank = cluster_ctarank(), csize = cluster_nctarank();
+  const int T = HW * G, S = 4 * T;                                  // owning threads, floats per sweep
   float* t_old = reinterpret_cast<float*>(smem_raw);                 // [ch_per_cta][HW]
   float* t_new = t_old + (size_t)ch_per_cta * HW;
   float* ex = t_new + (size_t)ch_per_cta * HW;                       // [2 parities][3][csize][HW]
-  float* part = ex + (size_t)6 * csize * HW;                         // [3][G][HW]
-  float* tot = part + (size_t)3 * G * HW;                            // [3][HW]
+  float* part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ex + (size_t)6 * csize * HW) + 15) & ~(uintptr_t)15);  // [3][S], 16-byte aligned:
+                                                                     // entry e = group (e / HW), position (e % HW)
+  float* tot = part + (size_t)3 * S;                                 // [3][HW]
   float* a_old = tot + 3 * HW;
   float* kk = a_old + HW;
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(
@@ -425,10 +428,14 @@ __global__ void __launch_bounds__(kArdClusterThreads, 1) ard_nchw_cluster_kernel
   const int tid = threadIdx.x;
   const int c0 = rank * ch_per_cta;
   const int nch = max(0, min(ch_per_cta, C - c0));
+  const int nfl = nch * HW;                                          // floats of this CTA's tile (a multiple of 4)
   const int chunk_ch = max(1, ceil_div(ch_per_cta, kArdChunks));
+  const int chunk_fl = chunk_ch * HW;                                // floats per chunk (a multiple of 4)
   const int nchunks = ceil_div(nch, chunk_ch);
-  const bool active = tid < G * HW;
-  const int g = tid / HW, pos = tid - g * HW;
+  const bool active = tid < T;
+  int pos[4];
+#pragma unroll
+  for (int j2 = 0; j2 < 4; j2++) pos[j2] = (4 * tid + j2) % HW;
   if (tid == 0) {
     for (int i = 0; i < kArdChunks; i++) mbar_init(&bars[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -449,35 +456,31 @@ __global__ void __launch_bounds__(kArdClusterThreads, 1) ard_nchw_cluster_kernel
         tma_load_1d(t_new + (size_t)r0 * HW, f_new + base + (size_t)r0 * HW, bytes, &bars[ch]);
       }
     }
-    float so = 0.f, sn = 0.f, sd = 0.f;
-    for (int ch = 0; ch < nchunks; ch++) {
-      mbar_wait(&bars[ch], parity);
-      if (active) {
-        const int cend = min((ch + 1) * chunk_ch, nch);
-        // this thread's channels of the chunk: c == g (mod G)
-        int c = ch * chunk_ch;
-        c += (g - c % G + G) % G;
-#pragma unroll 4
-        for (; c < cend; c += G) {
-          const float a = t_old[c * HW + pos], b = t_new[c * HW + pos];
-          so = fmaf(a, a, so);
-          sn = fmaf(b, b, sn);
-          const float d = b - a;
-          sd = fmaf(d, d, sd);
-        }
+    float so[4] = {0.f, 0.f, 0.f, 0.f}, sn[4] = {0.f, 0.f, 0.f, 0.f}, sd[4] = {0.f, 0.f, 0.f, 0.f};
+    int ready = -1;  // chunks 0..ready have landed
+    if (active) {
+      for (int e = 4 * tid; e < nfl; e += S) {
+        const int ch = e / chunk_fl;
+        while (ready < ch) mbar_wait(&bars[++ready], parity);
+        const float4 a = *reinterpret_cast<const float4*>(t_old + e), b = *reinterpret_cast<const float4*>(t_new + e);
+        so[0] = fmaf(a.x, a.x, so[0]); so[1] = fmaf(a.y, a.y, so[1]); so[2] = fmaf(a.z, a.z, so[2]); so[3] = fmaf(a.w, a.w, so[3]);
+        sn[0] = fmaf(b.x, b.x, sn[0]); sn[1] = fmaf(b.y, b.y, sn[1]); sn[2] = fmaf(b.z, b.z, sn[2]); sn[3] = fmaf(b.w, b.w, sn[3]);
+        const float d0 = b.x - a.x, d1 = b.y - a.y, d2 = b.z - a.z, d3 = b.w - a.w;
+        sd[0] = fmaf(d0, d0, sd[0]); sd[1] = fmaf(d1, d1, sd[1]); sd[2] = fmaf(d2, d2, sd[2]); sd[3] = fmaf(d3, d3, sd[3]);
       }
     }
+    while (ready < nchunks - 1) mbar_wait(&bars[++ready], parity);  // every thread observes every chunk's phase
     if (active) {
-      part[(0 * G + g) * HW + pos] = so;
-      part[(1 * G + g) * HW + pos] = sn;
-      part[(2 * G + g) * HW + pos] = sd;
+      *reinterpret_cast<float4*>(part + 4 * tid) = make_float4(so[0], so[1], so[2], so[3]);
+      *reinterpret_cast<float4*>(part + S + 4 * tid) = make_float4(sn[0], sn[1], sn[2], sn[3]);
+      *reinterpret_cast<float4*>(part + 2 * S + 4 * tid) = make_float4(sd[0], sd[1], sd[2], sd[3]);
     }
     __syncthreads();
     float* ex_par = ex + (size_t)parity * 3 * csize * HW;
     for (int t = tid; t < 3 * HW; t += kArdClusterThreads) {
       const int q = t / HW, pp = t - q * HW;
       float v = 0.f;
-      for (int gg = 0; gg < G; gg++) v += part[(q * G + gg) * HW + pp];
+      for (int gg = 0; gg < 4 * G; gg++) v += part[q * S + gg * HW + pp];
       for (unsigned r = 0; r < csize; r++) dsmem_store(ex_par + ((size_t)q * csize + rank) * HW + pp, r, v);
     }
     cluster_sync_all();  // every CTA's partial rows are in every CTA's table
@@ -492,11 +495,17 @@ __global__ void __launch_bounds__(kArdClusterThreads, 1) ard_nchw_cluster_kernel
     __syncthreads();
     if (GRAD && active) {
       float* gp = grad + base;
-      const float ka = a_old[pos], kb = kk[pos];
-#pragma unroll 4
-      for (int c = g; c < nch; c += G) {
-        const float a = t_old[c * HW + pos], b = t_new[c * HW + pos];
-        gp[c * HW + pos] = fmaf(ka, b - a, kb * b);
+      const float ka0 = a_old[pos[0]], ka1 = a_old[pos[1]], ka2 = a_old[pos[2]], ka3 = a_old[pos[3]];
+      const float kb0 = kk[pos[0]], kb1 = kk[pos[1]], kb2 = kk[pos[2]], kb3 = kk[pos[3]];
+#pragma unroll 2
+      for (int e = 4 * tid; e < nfl; e += S) {
+        const float4 a = *reinterpret_cast<const float4*>(t_old + e), b = *reinterpret_cast<const float4*>(t_new + e);
+        float4 o;
+        o.x = fmaf(ka0, b.x - a.x, kb0 * b.x);
+        o.y = fmaf(ka1, b.y - a.y, kb1 * b.y);
+        o.z = fmaf(ka2, b.z - a.z, kb2 * b.z);
+        o.w = fmaf(ka3, b.w - a.w, kb3 * b.w);
+        *reinterpret_cast<float4*>(gp + e) = o;
       }
     }
     __syncthreads();  // tiles, part, tot, a_old / kk are free for the next RoI
@@ -512,17 +521,13 @@ static int ard_nchw_cluster_size(int C, int HW, size_t& smem_bytes, int& ch_per_
   for (int cs = 1; cs <= 8; cs *= 2) {
     if (cs > C) break;
     ch_per_cta = ceil_div(C, cs);
-    if (((size_t)ch_per_cta * HW) % 4 != 0) continue;  // 16-byte bulk copies
+    if (((size_t)ch_per_cta * HW) % 4 != 0) continue;  // 16-byte bulk copies and vector accesses
     // every chunk of channels must be a 16-byte multiple as well
     const int chunk_ch = ceil_div(ch_per_cta, kArdChunks) > 0 ? ceil_div(ch_per_cta, kArdChunks) : 1;
     if (((size_t)chunk_ch * HW) % 4 != 0) continue;
-    const int g = G < ch_per_cta ? G : ch_per_cta;
-    smem_bytes = ((size_t)2 * ch_per_cta * HW + (size_t)6 * cs * HW + (size_t)3 * g * HW + 5 * HW) * sizeof(float) + 8 +
+    smem_bytes = ((size_t)2 * ch_per_cta * HW + (size_t)6 * cs * HW + (size_t)12 * G * HW + 5 * HW) * sizeof(float) + 16 + 8 +
                  kArdChunks * 8 + 128;
-    if (smem_bytes <= 227 * 1024) {
-      G = g;
-      return cs;
-    }
+    if (smem_bytes <= 227 * 1024) return cs;
   }
   return 0;
 }
