@@ -168,21 +168,23 @@ __device__ __forceinline__ void build_inverse_ranges(const Tables& t, int PH, in
 // kernels, which therefore need no shared memory, no barriers and no per-CTA setup:
 //   hdr  [16 words]         mode, batch index, level, Y0, Y1, 1/count, H, W, X0, X1, (6 spare)
 //   col  [PW][4 + kPlanNx]  x0, nx, -, -, then the nx column weights Wx[pw][x0 ..] zero-padded to kPlanNx
-//   row  [Y1-Y0+1][8]       ROLLING: first bin a holding the row (-1: none), Wy[a][y], Wy[a+1][y] (0 if not shared)
-//                           THIN:    Wy[0..7][y]
+//   row  [Y1-Y0+1][8 | 16]  ROLLING: first bin a holding the row (-1: none), Wy[a][y], Wy[a+1][y] (0 if not shared)
+//                           THIN:    Wy[0..PH-1][y]   (8 words per row when PH <= 8, else 16)
 // ROLLING = every map row feeds at most two vertically adjacent bins (bins at least ~1 map pixel tall);
-// THIN    = thinner bins and PH <= 8;  GENERIC = anything else (columns wider than kPlanNx pixels, thin bins with
-// PH > 8): those RoIs are left to the table-in-shared-memory kernels below;  EMPTY = no sample inside the map.
+// THIN    = thinner bins and PH <= 16;  GENERIC = anything else (columns wider than kPlanNx pixels, thin bins with
+// PH > 16): those RoIs are left to the table-in-shared-memory kernels below;  EMPTY = no sample inside the map.
 constexpr int kPlanNx = 16;
 constexpr int kTileMaxPx = 64;  // widest footprint row the TMA-staged kernel holds in one ring slot
 constexpr int kPlanHdr = 16;
 constexpr int kPlanCol = 4 + kPlanNx;
-constexpr int kPlanRow = 8;
-constexpr int kThinBins = 8;
+constexpr int kPlanRow = 8;      // words of a row record when PH <= 8 (the TMA-staged kernels' format)
+constexpr int kThinBins = 8;     // bins a THIN row record holds in that format
+constexpr int kThinBinsMax = 16; // PH <= 16 (the framework's default 14x14 pooling): 16-word row records, sweep kernels only
+__host__ __device__ inline int plan_row_words(int PH) { return PH <= kThinBins ? kPlanRow : kThinBinsMax; }
 enum PlanMode { PLAN_EMPTY = 0, PLAN_ROLLING = 1, PLAN_THIN = 2, PLAN_GENERIC = 3 };
 
-__host__ __device__ inline size_t plan_stride_words(int PW, int Hs) {
-  return (size_t)kPlanHdr + (size_t)PW * kPlanCol + (size_t)Hs * kPlanRow;
+__host__ __device__ inline size_t plan_stride_words(int PW, int Hs, int PH) {
+  return (size_t)kPlanHdr + (size_t)PW * kPlanCol + (size_t)Hs * plan_row_words(PH);
 }
 
 __global__ void __launch_bounds__(128) plan_kernel(LevelTable lv, const float* __restrict__ rois,
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(128) plan_kernel(LevelTable lv, const float* _
     } else {
       bool wide = fp[3] - fp[2] + 1 > kTileMaxPx;  // footprint wider than the staged row tile
       for (int p = 0; p < PW; p++) wide |= (t.xhi[p] - t.xlo[p] + 1 > kPlanNx);
-      mode = wide ? PLAN_GENERIC : (fp[4] <= 1 ? PLAN_ROLLING : (PH <= kThinBins ? PLAN_THIN : PLAN_GENERIC));
+      mode = wide ? PLAN_GENERIC : (fp[4] <= 1 ? PLAN_ROLLING : (PH <= kThinBinsMax ? PLAN_THIN : PLAN_GENERIC));
     }
     s_mode = mode;
     plan[0] = mode; plan[1] = g.batch; plan[2] = g.level; plan[3] = Y0; plan[4] = Y1;
@@ -239,8 +241,9 @@ __global__ void __launch_bounds__(128) plan_kernel(LevelTable lv, const float* _
   }
   int* row = col + PW * kPlanCol;
   const int nrows = Y1 - Y0 + 1;
-  for (int i = threadIdx.x; i < nrows * kPlanRow; i += blockDim.x) {
-    const int y = Y0 + i / kPlanRow, k = i % kPlanRow;
+  const int rw = plan_row_words(PH);
+  for (int i = threadIdx.x; i < nrows * rw; i += blockDim.x) {
+    const int y = Y0 + i / rw, k = i % rw;
     int v = 0;
     if (mode == PLAN_ROLLING) {
       const int p0 = plo[y], p1 = phi[y];
@@ -260,11 +263,12 @@ struct SweepTask {
   bool active;
   const int* col;
   const int4* rows;
+  int rw4;  // int4 units per row record
 };
 
 // Decodes the warp's task = (RoI, bin column pw, slice of 32*V channels).  Returns false when there is nothing to do.
 template <int V>
-__device__ __forceinline__ bool sweep_task(SweepTask& k, const int* __restrict__ plans, size_t stride, int C, int PW,
+__device__ __forceinline__ bool sweep_task(SweepTask& k, const int* __restrict__ plans, size_t stride, int C, int PH, int PW,
                                            int nslices, long long ntasks, int& r) {
   const long long task = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (task >= ntasks) return false;
@@ -284,6 +288,7 @@ __device__ __forceinline__ bool sweep_task(SweepTask& k, const int* __restrict__
   if (!k.active) k.c = 0;  // idle lanes of a ragged last slice shadow channel 0 and never store
   k.col = plan + kPlanHdr + k.pw * kPlanCol;
   k.rows = reinterpret_cast<const int4*>(plan + kPlanHdr + PW * kPlanCol);
+  k.rw4 = plan_row_words(PH) / 4;
   k.x0 = k.col[0];
   k.nx = k.mode == PLAN_EMPTY ? 0 : k.col[1];
   return true;
@@ -319,13 +324,13 @@ __device__ __forceinline__ void row_dot(float (&tr)[V], const T* q0, const T* q1
 // ONCE: for every row y it forms  t = sum_x Wx[pw][x] * v[y][x]  and adds  Wy[ph][y] * t  to the (at most two)
 // vertically adjacent bins the row belongs to, held in two rolling register accumulators.  Every distinct pixel of
 // the column's footprint is loaded once per RoI, not once per bin or per sample tap.
-template <typename T, int V>
+template <typename T, int V, int NB>
 __global__ void __launch_bounds__(256) roi_align_fwd_sweep_kernel(LevelTable lv, const int* __restrict__ plans,
                                                                  size_t stride, T* __restrict__ out, int C, int PH,
                                                                  int PW, int nslices, long long ntasks) {
   SweepTask k;
   int r;
-  if (!sweep_task<V>(k, plans, stride, C, PW, nslices, ntasks, r)) return;
+  if (!sweep_task<V>(k, plans, stride, C, PH, PW, nslices, ntasks, r)) return;
   const size_t pix = (size_t)C, binstride = (size_t)PW * C;
   T* o = out + ((size_t)r * PH * PW + k.pw) * C + k.c;
   if (k.nx == 0) {  // no sample of this column (or of the whole RoI) falls inside the map
@@ -352,7 +357,7 @@ __global__ void __launch_bounds__(256) roi_align_fwd_sweep_kernel(LevelTable lv,
     int4 info_next = __ldg(rr);
     for (int n = k.nrows; n > 0; n--, q0 += rowstride, q1 += rowstride, q2 += rowstride, q3 += rowstride) {
       const int4 info = info_next;
-      rr += 2;
+      rr += k.rw4;
       if (n > 1) info_next = __ldg(rr);  // row records are fetched one row ahead
       if (info.x < 0) continue;
       float tr[V];
@@ -380,25 +385,28 @@ __global__ void __launch_bounds__(256) roi_align_fwd_sweep_kernel(LevelTable lv,
 #pragma unroll
       for (int i = 0; i < V; i++) { accA[i] = accB[i]; accB[i] = 0.f; }
     }
-  } else {  // PLAN_THIN: one statically indexed accumulator per bin; rows carry all PH weights
-    float acc[kThinBins][V];
+  } else {  // PLAN_THIN: one statically indexed accumulator per bin; rows carry all PH weights (NB = 8 or 16 of them)
+    float acc[NB][V];
 #pragma unroll
-    for (int p = 0; p < kThinBins; p++)
+    for (int p = 0; p < NB; p++)
 #pragma unroll
       for (int i = 0; i < V; i++) acc[p][i] = 0.f;
-    for (int n = k.nrows; n > 0; n--, rr += 2, q0 += rowstride, q1 += rowstride, q2 += rowstride, q3 += rowstride) {
-      const int4 wlo = __ldg(rr), whi = __ldg(rr + 1);
+    for (int n = k.nrows; n > 0; n--, rr += NB / 4, q0 += rowstride, q1 += rowstride, q2 += rowstride, q3 += rowstride) {
+      int4 wv[NB / 4];
+#pragma unroll
+      for (int i = 0; i < NB / 4; i++) wv[i] = __ldg(rr + i);
       float tr[V];
       row_dot<T, V>(tr, q0, q1, q2, q3, w, k.nx, pix, k.col);
-      const float wy[kThinBins] = {__int_as_float(wlo.x), __int_as_float(wlo.y), __int_as_float(wlo.z), __int_as_float(wlo.w),
-                                   __int_as_float(whi.x), __int_as_float(whi.y), __int_as_float(whi.z), __int_as_float(whi.w)};
 #pragma unroll
-      for (int p = 0; p < kThinBins; p++)
+      for (int p = 0; p < NB; p++) {
+        const int4 q4 = wv[p / 4];
+        const float wy = __int_as_float((p & 3) == 0 ? q4.x : (p & 3) == 1 ? q4.y : (p & 3) == 2 ? q4.z : q4.w);
 #pragma unroll
-        for (int i = 0; i < V; i++) acc[p][i] = fmaf(wy[p], tr[i], acc[p][i]);
+        for (int i = 0; i < V; i++) acc[p][i] = fmaf(wy, tr[i], acc[p][i]);
+      }
     }
 #pragma unroll
-    for (int p = 0; p < kThinBins; p++) {
+    for (int p = 0; p < NB; p++) {
       if (p < PH && k.active) {
 #pragma unroll
         for (int i = 0; i < V; i++) acc[p][i] *= inv_count;
@@ -451,13 +459,13 @@ __device__ __forceinline__ void row_scatter(T* q0, const float (&s)[V], const fl
   }
 }
 
-template <typename T, int V>
+template <typename T, int V, int NB>
 __global__ void __launch_bounds__(256) roi_align_bwd_sweep_kernel(LevelTable lv, const int* __restrict__ plans,
                                                                  size_t stride, const T* __restrict__ gout, int C, int PH,
                                                                  int PW, int nslices, long long ntasks) {
   SweepTask k;
   int r;
-  if (!sweep_task<V>(k, plans, stride, C, PW, nslices, ntasks, r)) return;
+  if (!sweep_task<V>(k, plans, stride, C, PH, PW, nslices, ntasks, r)) return;
   if (k.nx == 0) return;  // warp-uniform
   const bool active = k.active;  // idle lanes of a ragged last slice shadow channel 0 and never reduce
   const size_t pix = (size_t)C, binstride = (size_t)PW * C;
@@ -494,7 +502,7 @@ __global__ void __launch_bounds__(256) roi_align_bwd_sweep_kernel(LevelTable lv,
     const int lane = threadIdx.x & 31;
     for (int base = 0; base < k.nrows; base += 32) {  // row records: one coalesced fetch per 32 rows, then shuffles
       const int cnt = min(32, k.nrows - base);
-      const int4 mine = lane < cnt ? __ldg(rr + 2 * (base + lane)) : make_int4(-1, 0, 0, 0);
+      const int4 mine = lane < cnt ? __ldg(rr + k.rw4 * (base + lane)) : make_int4(-1, 0, 0, 0);
       for (int j = 0; j < cnt; j++, q0 += rowstride) {
         int4 info;
         info.x = __shfl_sync(0xffffffffu, mine.x, j);
@@ -561,9 +569,9 @@ __global__ void __launch_bounds__(256) roi_align_bwd_sweep_kernel(LevelTable lv,
       }
     }
   } else {  // PLAN_THIN
-    float g[kThinBins][V];
+    float g[NB][V];
 #pragma unroll
-    for (int p = 0; p < kThinBins; p++) {
+    for (int p = 0; p < NB; p++) {
       if (p < PH) {
         VecIO<T, V>::load(go + (size_t)p * binstride, g[p]);
       } else {
@@ -571,17 +579,20 @@ __global__ void __launch_bounds__(256) roi_align_bwd_sweep_kernel(LevelTable lv,
         for (int i = 0; i < V; i++) g[p][i] = 0.f;
       }
     }
-    for (int n = k.nrows; n > 0; n--, rr += 2, q0 += rowstride) {
-      const int4 wlo = __ldg(rr), whi = __ldg(rr + 1);
-      const float wy[kThinBins] = {__int_as_float(wlo.x), __int_as_float(wlo.y), __int_as_float(wlo.z), __int_as_float(wlo.w),
-                                   __int_as_float(whi.x), __int_as_float(whi.y), __int_as_float(whi.z), __int_as_float(whi.w)};
+    for (int n = k.nrows; n > 0; n--, rr += NB / 4, q0 += rowstride) {
+      int4 wv[NB / 4];
+#pragma unroll
+      for (int i = 0; i < NB / 4; i++) wv[i] = __ldg(rr + i);
       float s[V];
 #pragma unroll
       for (int i = 0; i < V; i++) s[i] = 0.f;
 #pragma unroll
-      for (int p = 0; p < kThinBins; p++)
+      for (int p = 0; p < NB; p++) {
+        const int4 q4 = wv[p / 4];
+        const float wy = __int_as_float((p & 3) == 0 ? q4.x : (p & 3) == 1 ? q4.y : (p & 3) == 2 ? q4.z : q4.w);
 #pragma unroll
-        for (int i = 0; i < V; i++) s[i] = fmaf(wy[p], g[p][i], s[i]);
+        for (int i = 0; i < V; i++) s[i] = fmaf(wy, g[p][i], s[i]);
+      }
 #pragma unroll
       for (int i = 0; i < V; i++) s[i] *= inv_count;
       if (active) row_scatter<T, V>(q0, s, w, k.nx, pix, k.col);
@@ -1510,7 +1521,7 @@ struct Call {
   cudaStream_t st;
 };
 
-static size_t workspace_need(int R, int PW, int Hs) { return (size_t)R * plan_stride_words(PW, Hs) * sizeof(int); }
+static size_t workspace_need(int R, int PW, int Hs, int PH) { return (size_t)R * plan_stride_words(PW, Hs, PH) * sizeof(int); }
 
 // Tensor maps of every level's [B*H rows][W pixels][C channels] view, one per box shape.  False when the driver entry point is
 // missing or a map cannot be encoded (the caller then uses the sweep kernel).
@@ -1540,7 +1551,7 @@ static int run_plan(const Call& c) {
   const size_t smem = tables_bytes(c.PH, c.PW, c.Hs, c.Ws, true);
   int rc = set_smem(plan_kernel, smem, "roi_align plan");
   if (rc) return rc;
-  plan_kernel<<<c.R, 128, smem, c.st>>>(c.lv, c.rois, c.levels, c.plans, plan_stride_words(c.PW, c.Hs), c.PH, c.PW, c.ratio, c.Hs, c.Ws);
+  plan_kernel<<<c.R, 128, smem, c.st>>>(c.lv, c.rois, c.levels, c.plans, plan_stride_words(c.PW, c.Hs, c.PH), c.PH, c.PW, c.ratio, c.Hs, c.Ws);
   ABR_CHECK_LAUNCH("roi_align_plan");
   return ABR_OK;
 }
@@ -1549,7 +1560,7 @@ template <typename T, int V>
 static int launch_fwd(const Call& c, void* out) {
   const size_t smem = tables_bytes(c.PH, c.PW, c.Hs, c.Ws, false);
   if (c.layout == ABR_NHWC) {
-    const size_t stride = plan_stride_words(c.PW, c.Hs);
+    const size_t stride = plan_stride_words(c.PW, c.Hs, c.PH);
     if (c.plans) {
       int rc = run_plan(c);
       if (rc) return rc;
@@ -1576,7 +1587,10 @@ static int launch_fwd(const Call& c, void* out) {
         const long long ntasks = (long long)c.R * c.PW * nslices;
         const long long blocks = ceil_div<long long>(ntasks, 8);
         ABR_REQUIRE(blocks <= 0x7fffffffLL, ABR_ERR_UNSUPPORTED, "roi_align_forward: too many tasks");
-        roi_align_fwd_sweep_kernel<T, V><<<(unsigned)blocks, 256, 0, c.st>>>(c.lv, c.plans, stride, static_cast<T*>(out), c.C, c.PH, c.PW, nslices, ntasks);
+        if (c.PH <= kThinBins)
+          roi_align_fwd_sweep_kernel<T, V, kThinBins><<<(unsigned)blocks, 256, 0, c.st>>>(c.lv, c.plans, stride, static_cast<T*>(out), c.C, c.PH, c.PW, nslices, ntasks);
+        else
+          roi_align_fwd_sweep_kernel<T, V, kThinBinsMax><<<(unsigned)blocks, 256, 0, c.st>>>(c.lv, c.plans, stride, static_cast<T*>(out), c.C, c.PH, c.PW, nslices, ntasks);
         ABR_CHECK_LAUNCH("roi_align_forward_sweep");
       }
     }
@@ -1601,7 +1615,7 @@ template <typename T, int V>
 static int launch_bwd(const Call& c, const void* gout) {
   const size_t smem = tables_bytes(c.PH, c.PW, c.Hs, c.Ws, true);
   if (c.layout == ABR_NHWC) {
-    const size_t stride = plan_stride_words(c.PW, c.Hs);
+    const size_t stride = plan_stride_words(c.PW, c.Hs, c.PH);
     if (c.plans) {
       int rc = run_plan(c);
       if (rc) return rc;
@@ -1642,7 +1656,10 @@ static int launch_bwd(const Call& c, const void* gout) {
         const long long ntasks = (long long)c.R * c.PW * nslices;
         const long long blocks = ceil_div<long long>(ntasks, 8);
         ABR_REQUIRE(blocks <= 0x7fffffffLL, ABR_ERR_UNSUPPORTED, "roi_align_backward: too many tasks");
-        roi_align_bwd_sweep_kernel<T, V><<<(unsigned)blocks, 256, 0, c.st>>>(c.lv, c.plans, stride, static_cast<const T*>(gout), c.C, c.PH, c.PW, nslices, ntasks);
+        if (c.PH <= kThinBins)
+          roi_align_bwd_sweep_kernel<T, V, kThinBins><<<(unsigned)blocks, 256, 0, c.st>>>(c.lv, c.plans, stride, static_cast<const T*>(gout), c.C, c.PH, c.PW, nslices, ntasks);
+        else
+          roi_align_bwd_sweep_kernel<T, V, kThinBinsMax><<<(unsigned)blocks, 256, 0, c.st>>>(c.lv, c.plans, stride, static_cast<const T*>(gout), c.C, c.PH, c.PW, nslices, ntasks);
         ABR_CHECK_LAUNCH("roi_align_backward_sweep");
       }
     }
@@ -1693,9 +1710,9 @@ static size_t staging_need(int B, int C, long long sum_hw, int R, int PH, int PW
 }
 
 // The plans are only used by the NHWC kernels; a workspace that is absent or too small selects the self-contained path.
-static int* usable_workspace(void* ws, size_t bytes, int R, int PW, int Hs, int layout) {
+static int* usable_workspace(void* ws, size_t bytes, int R, int PH, int PW, int Hs, int layout) {
   if (!ws || layout != ABR_NHWC || (reinterpret_cast<uintptr_t>(ws) & 15)) return nullptr;
-  return bytes >= workspace_need(R, PW, Hs) ? static_cast<int*>(ws) : nullptr;
+  return bytes >= workspace_need(R, PW, Hs, PH) ? static_cast<int*>(ws) : nullptr;
 }
 
 }  // namespace abr
@@ -1705,20 +1722,19 @@ using namespace abr;
 extern "C" {
 
 size_t abr_roi_align_workspace_bytes(int R, int PH, int PW, int max_h) {
-  (void)PH;
   if (R <= 0 || PW <= 0 || max_h <= 0) return 0;
-  return workspace_need(R, PW, max_h);
+  return workspace_need(R, PW, max_h, PH);
 }
 
 size_t abr_roi_align_workspace_bytes_nchw(int R, int PH, int PW, int max_h, int B, int C, long long sum_hw, int dtype) {
   if (R <= 0 || PW <= 0 || PH <= 0 || max_h <= 0 || B <= 0 || C <= 0 || sum_hw <= 0) return 0;
-  return align256(workspace_need(R, PW, max_h)) + staging_need(B, C, sum_hw, R, PH, PW, dtype);
+  return align256(workspace_need(R, PW, max_h, PH)) + staging_need(B, C, sum_hw, R, PH, PW, dtype);
 }
 
 size_t abr_roi_align_workspace_bytes_layout(int R, int PH, int PW, int max_h, int B, int C, long long sum_hw, int dtype, int layout) {
   if (layout == ABR_NHWC) return abr_roi_align_workspace_bytes(R, PH, PW, max_h);
   if (R <= 0 || PW <= 0 || PH <= 0 || max_h <= 0 || B <= 0 || C <= 0 || sum_hw <= 0) return 0;
-  return align256(workspace_need(R, PW, max_h)) + staging_need(B, C, sum_hw, R, PH, PW, dtype, layout);
+  return align256(workspace_need(R, PW, max_h, PH)) + staging_need(B, C, sum_hw, R, PH, PW, dtype, layout);
 }
 
 int abr_roi_align_multilevel_forward(const void* const* inputs_host, const int* hs_host, const int* ws_host,
@@ -1742,7 +1758,7 @@ int abr_roi_align_multilevel_forward(const void* const* inputs_host, const int* 
   c.st = static_cast<cudaStream_t>(stream);
   long long sum_hw = 0;
   for (int l = 0; l < L; l++) sum_hw += (long long)hs_host[l] * ws_host[l];
-  const size_t plan_bytes = align256(workspace_need(R, PW, c.Hs));
+  const size_t plan_bytes = align256(workspace_need(R, PW, c.Hs, PH));
   const bool mixed = layout == ABR_NCHW_MAPS_NHWC_POOLED;
   const bool staged_ok = workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 &&
                          workspace_bytes >= plan_bytes + staging_need(B, C, sum_hw, R, PH, PW, dtype, layout);
@@ -1769,7 +1785,7 @@ int abr_roi_align_multilevel_forward(const void* const* inputs_host, const int* 
     if (pooled_transpose_fits(PH * PW, R)) return transpose_pooled(pooled, output, R, C, PH * PW, 0, dtype, c.st);
     return transpose_any(pooled, output, PH * PW, C, R, 0, dtype, c.st);
   }
-  c.plans = usable_workspace(workspace, workspace_bytes, R, PW, c.Hs, layout);
+  c.plans = usable_workspace(workspace, workspace_bytes, R, PH, PW, c.Hs, layout);
   c.plan_ready = c.plans != nullptr && workspace_has_plan != 0;
   return dispatch_fwd(c, output, dtype);
 }
@@ -1796,7 +1812,7 @@ int abr_roi_align_multilevel_backward(const void* grad_output, const float* rois
   c.C = C; c.R = R; c.PH = PH; c.PW = PW; c.ratio = sampling_ratio; c.layout = layout;
   long long sum_hw = 0;
   for (int l = 0; l < L; l++) sum_hw += (long long)hs_host[l] * ws_host[l];
-  const size_t plan_bytes = align256(workspace_need(R, PW, c.Hs));
+  const size_t plan_bytes = align256(workspace_need(R, PW, c.Hs, PH));
   const bool mixed = layout == ABR_NCHW_MAPS_NHWC_POOLED;
   const bool staged_ok = workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 &&
                          workspace_bytes >= plan_bytes + staging_need(B, C, sum_hw, R, PH, PW, dtype, layout);
@@ -1840,7 +1856,7 @@ int abr_roi_align_multilevel_backward(const void* grad_output, const float* rois
     }
     return ABR_OK;
   }
-  c.plans = usable_workspace(workspace, workspace_bytes, R, PW, c.Hs, layout);
+  c.plans = usable_workspace(workspace, workspace_bytes, R, PH, PW, c.Hs, layout);
   c.plan_ready = c.plans != nullptr && workspace_has_plan != 0;
   return dispatch_bwd(c, grad_output, dtype);
 }
