@@ -375,11 +375,35 @@ static int ard_cluster_size(int C, int HW, size_t& smem_bytes, int& rows_per_cta
   return 0;
 }
 
+// Clusters of `cs` CTAs that can be resident at once (a cluster must fit inside one GPC, so this can be fewer than
+// SMs / cs): a persistent grid larger than that would leave late clusters to run after the others have finished.
+template <typename K>
+static int resident_clusters(K kern, int cs, size_t smem) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(num_sms() / cs * cs);
+  cfg.blockDim = dim3(kArdClusterThreads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) {
+    cudaGetLastError();
+    n = num_sms() / cs;
+  }
+  return n < num_sms() / cs ? n : num_sms() / cs;
+}
+
 static int launch_nhwc_cluster(const ArdParams& p, const void* fo, const void* fn, void* g, cudaStream_t st, int cs,
                                size_t smem, int rows_per_cta) {
   auto kern = g ? ard_nhwc_cluster_kernel<true> : ard_nhwc_cluster_kernel<false>;
   ABR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int clusters = num_sms() / cs;
+  if (cs > 8) ABR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  int clusters = resident_clusters(kern, cs, smem);
   if (clusters > p.N) clusters = p.N;
   if (clusters < 1) clusters = 1;
   cudaLaunchConfig_t cfg = {};
@@ -536,7 +560,8 @@ static int launch_nchw_cluster(const ArdParams& p, const void* fo, const void* f
                                size_t smem, int ch_per_cta, int G) {
   auto kern = g ? ard_nchw_cluster_kernel<true> : ard_nchw_cluster_kernel<false>;
   ABR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int clusters = num_sms() / cs;
+  if (cs > 8) ABR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  int clusters = resident_clusters(kern, cs, smem);
   if (clusters > p.N) clusters = p.N;
   if (clusters < 1) clusters = 1;
   cudaLaunchConfig_t cfg = {};
