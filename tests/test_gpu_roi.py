@@ -359,3 +359,26 @@ def test_roi_align_forward_plan_shared_between_two_maps():
         fb = roi_align_forward(dev(b, cl), dev(rois), 1 / 16, P, P, 0, plan=plan)
         close(fa.cpu().numpy(), oracle.roi_align_forward(a, rois, 1 / 16, P, P, 0))
         close(fb.cpu().numpy(), oracle.roi_align_forward(b, rois, 1 / 16, P, P, 0))
+
+
+def test_roi_align_wide_rois_on_the_staged_path():
+    """RoIs whose footprint is 33..64 map pixels wide (the ring slots of the TMA-staged kernels hold rows of up to 64
+    pixels) and a few wider ones (left to the generic kernel), channels-last, forward and backward against the oracle."""
+    from abr_iod_b200.layers import roi_align
+
+    rng = np.random.default_rng(64)
+    B, C, H, W, P = 2, 16, 50, 76, 7
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    n = 40
+    w = np.concatenate([rng.uniform(520, 1000, n - 6), rng.uniform(1030, 1215, 6)])
+    h = rng.uniform(40, 790, n)
+    x1 = rng.uniform(0, 1215 - w)
+    y1 = rng.uniform(0, 799 - h)
+    rois = np.stack([rng.integers(0, B, n), x1, y1, x1 + w, y1 + h], 1).astype(np.float32)
+    gout = rng.standard_normal((n, C, P, P)).astype(np.float32)
+    for ratio in (0, 2):
+        xt = dev(x, True).requires_grad_(True)
+        out = roi_align(xt, dev(rois), (P, P), 1 / 16, ratio)
+        close(out.detach().cpu().numpy(), oracle.roi_align_forward(x, rois, 1 / 16, P, P, ratio))
+        out.backward(dev(gout, True))
+        close(xt.grad.cpu().numpy(), oracle.roi_align_backward(gout, rois, 1 / 16, P, P, B, C, H, W, ratio))
