@@ -166,7 +166,8 @@ __device__ __forceinline__ void build_inverse_ranges(const Tables& t, int PH, in
 // A "plan" is the compact form of one RoI's two interpolation tables, written once per call by plan_kernel (a small
 // CTA per RoI) into caller-provided workspace and then read, warp-uniformly and straight out of L1/L2, by the sweep
 // kernels, which therefore need no shared memory, no barriers and no per-CTA setup:
-//   hdr  [16 words]         mode, batch index, level, Y0, Y1, 1/count, H, W, X0, X1, (6 spare)
+//   hdr  [16 words]         mode, batch index, level, Y0, Y1, 1/count, H, W, X0, X1, backward scheme (1 column pairs,
+//                           2 pixel records, 0 neither), (5 spare)
 //   col  [PW][4 + kPlanNx]  x0, nx, -, -, then the nx column weights Wx[pw][x0 ..] zero-padded to kPlanNx
 //   row  [Y1-Y0+1][8 | 16]  ROLLING: first bin a holding the row (-1: none), Wy[a][y], Wy[a+1][y] (0 if not shared)
 //                           THIN:    Wy[0..PH-1][y]   (8 words per row when PH <= 8, else 16)
@@ -181,10 +182,15 @@ constexpr int kPlanRow = 8;      // words of a row record when PH <= 8 (the TMA-
 constexpr int kThinBins = 8;     // bins a THIN row record holds in that format
 constexpr int kThinBinsMax = 16; // PH <= 16 (the framework's default 14x14 pooling): 16-word row records, sweep kernels only
 __host__ __device__ inline int plan_row_words(int PH) { return PH <= kThinBins ? kPlanRow : kThinBinsMax; }
+// Backward only, narrow RoIs (bins thinner than a map pixel in x, so a pixel lies in three or more bin columns and the
+// column-pair scheme below does not apply): one record per footprint pixel -- first covering column, number of covering
+// columns (<= kPixCols), their weights -- so that the TMA-staged backward reduces such a pixel once instead of once per
+// covering column.  Footprints of up to kPixMax pixels; the area sits after the row records.
+constexpr int kPixMax = 16, kPixCols = 7, kPixRec = 8, kPlanPix = kPixMax * kPixRec;  // record: first column | count << 8, 7 weights
 enum PlanMode { PLAN_EMPTY = 0, PLAN_ROLLING = 1, PLAN_THIN = 2, PLAN_GENERIC = 3 };
 
 __host__ __device__ inline size_t plan_stride_words(int PW, int Hs, int PH) {
-  return (size_t)kPlanHdr + (size_t)PW * kPlanCol + (size_t)Hs * plan_row_words(PH);
+  return (size_t)kPlanHdr + (size_t)PW * kPlanCol + (size_t)Hs * plan_row_words(PH) + kPlanPix;
 }
 
 __global__ void __launch_bounds__(128) plan_kernel(LevelTable lv, const float* __restrict__ rois,
@@ -217,7 +223,11 @@ __global__ void __launch_bounds__(128) plan_kernel(LevelTable lv, const float* _
     plan[0] = mode; plan[1] = g.batch; plan[2] = g.level; plan[3] = Y0; plan[4] = Y1;
     plan[5] = __float_as_int(1.f / g.count); plan[6] = H; plan[7] = W;
     plan[8] = fp[2]; plan[9] = fp[3];
-    for (int i = 10; i < kPlanHdr; i++) plan[i] = 0;
+    int scheme = 0;
+    if (mode == PLAN_ROLLING && fp[5] <= 1) scheme = 1;
+    else if (mode == PLAN_ROLLING && fp[5] < kPixCols && fp[3] - fp[2] + 1 <= kPixMax && PH <= kThinBins) scheme = 2;
+    plan[10] = scheme;
+    for (int i = 11; i < kPlanHdr; i++) plan[i] = 0;
   }
   __syncthreads();
   const int mode = s_mode;
@@ -254,6 +264,20 @@ __global__ void __launch_bounds__(128) plan_kernel(LevelTable lv, const float* _
       v = k < PH ? __float_as_int(t.Wy[(size_t)k * Hs + y]) : 0;
     }
     row[i] = v;
+  }
+  if (mode == PLAN_ROLLING && fp[5] > 1 && fp[5] < kPixCols && fp[3] - fp[2] + 1 <= kPixMax && PH <= kThinBins) {
+    const int* qlo = phi + Hs;
+    const int* qhi = qlo + Ws;
+    int* pixrec = plan + kPlanHdr + PW * kPlanCol + (size_t)Hs * rw;
+    const int X0 = fp[2], npx = fp[3] - fp[2] + 1;
+    for (int i = threadIdx.x; i < npx * kPixRec; i += blockDim.x) {
+      const int x = X0 + i / kPixRec, k = i % kPixRec;
+      const int lo = qlo[x], cnt = qhi[x] - lo + 1;
+      int v = 0;
+      if (k == 0) v = cnt > 0 ? (lo | (cnt << 8)) : 0;
+      else if (k - 1 < cnt) v = __float_as_int(t.Wx[(size_t)(lo + k - 1) * Ws + x]);
+      pixrec[i] = v;
+    }
   }
 }
 
@@ -649,6 +673,11 @@ __device__ __forceinline__ void mb_wait_a(unsigned addr, unsigned parity) {
 __device__ __forceinline__ void mb_arrive_a(unsigned addr) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
 }
+__device__ __forceinline__ unsigned lds32(unsigned addr) {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ uint4 lds128(unsigned addr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -924,7 +953,8 @@ __global__ void __launch_bounds__(256, 4) roi_align_bwd_tma_kernel(const __grid_
   const unsigned gbytes = (unsigned)nbin * 512u;             // one stage of bin gradients
   const unsigned gstage = (gbytes + 127u) & ~127u;
   const int headw = kPlanHdr + PW * kPlanCol;
-  const int planw = headw + Hs * kPlanRow;
+  const int rowsw = Hs * kPlanRow;
+  const int planw = headw + rowsw + kPlanPix;  // header + columns | row records | pixel records
   uint4* gtile = reinterpret_cast<uint4*>(smem_raw);         // [2][nbin][32 lanes]
   int* planbuf = reinterpret_cast<int*>(smem_raw + 2 * (size_t)gstage);
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(planbuf + 2 * (size_t)planw);
@@ -946,15 +976,19 @@ __global__ void __launch_bounds__(256, 4) roi_align_bwd_tma_kernel(const __grid_
       const int* plan = plans + (size_t)r * stride;
       const int4 h0 = __ldg(reinterpret_cast<const int4*>(plan));
       const int4 h1 = __ldg(reinterpret_cast<const int4*>(plan) + 1);
+      const int4 h2 = __ldg(reinterpret_cast<const int4*>(plan) + 2);
       const int mode = h0.x, nrows = h1.x - h0.w + 1;
+      const bool pixels = h2.z == 2;  // narrow RoI: per-pixel records follow the row records
       const int pb = ti & 1;
       mb_wait_backoff(&pempty[pb], ((ti >> 1) & 1) ^ 1);
       const bool live = mode == PLAN_ROLLING || mode == PLAN_THIN;
       if (lane == 0) {
         const unsigned rowbytes = live ? (unsigned)nrows * (kPlanRow * 4u) : 0u;
-        mb_expect_tx(&pfull[pb], (unsigned)headw * 4u + rowbytes + (live ? gbytes : 0u));
+        const unsigned pixbytes = (live && pixels) ? (unsigned)(h2.y - h2.x + 1) * (kPixRec * 4u) : 0u;
+        mb_expect_tx(&pfull[pb], (unsigned)headw * 4u + rowbytes + pixbytes + (live ? gbytes : 0u));
         int* dst = planbuf + (size_t)pb * planw;
         tma_g2s(dst, plan, (unsigned)headw * 4u, &pfull[pb]);
+        if (pixbytes) tma_g2s(dst + headw + rowsw, plan + headw + rowsw, pixbytes, &pfull[pb]);
         if (live) {
           tma_g2s(dst + headw, plan + headw, rowbytes, &pfull[pb]);
           tma_box_g2s(smem_raw + (size_t)pb * gstage, &gmap, slice * 32 * V, 0, r, &pfull[pb]);
@@ -973,8 +1007,54 @@ __global__ void __launch_bounds__(256, 4) roi_align_bwd_tma_kernel(const __grid_
       const int* pl = planbuf + (size_t)pb * planw;
       const int mode = pl[0];
       const int* col = pl + kPlanHdr + pw * kPlanCol;
-      const int nx = (mode == PLAN_ROLLING || mode == PLAN_THIN) ? col[1] : 0;
       const int c = (slice * 32 + lane) * V;
+      if (mode == PLAN_ROLLING && pl[10] == 2) {
+        // Narrow RoI, pixel by pixel: this warp owns the footprint pixels X0 + pw, X0 + pw + PW, ... and reduces each of
+        // them ONCE per row, adding up the (<= kPixCols) bin columns that cover it from the pixel's record.
+        if (c < C) {
+          const int X0 = pl[8], X1 = pl[9], Y0p = pl[3], nrows_p = pl[4] - pl[3] + 1;
+          const float inv_cnt = __int_as_float(pl[5]);
+          const size_t rowstride_p = (size_t)pl[7] * C;
+          const unsigned g0 = s_u32(smem_raw + (size_t)pb * gstage) + lane * 16;  // bin (0, 0)
+          const unsigned binrow_p = (unsigned)PW * 512u;
+          const unsigned rec_p = s_u32(pl + headw);
+          const unsigned pix_p = s_u32(pl + headw + rowsw);
+          T* qrow = static_cast<T*>(lv.ptr[pl[2]]) + ((size_t)pl[1] * pl[6] + Y0p) * rowstride_p + c;
+          for (int row = 0; row < nrows_p; row++, qrow += rowstride_p) {
+            const uint4 info = lds128(rec_p + (unsigned)row * 32u);
+            const int a = (int)info.x;
+            if (a < 0) continue;
+            const float wa = __uint_as_float(info.y) * inv_cnt, wb = (a + 1 < PH) ? __uint_as_float(info.z) * inv_cnt : 0.f;
+            const unsigned ga = g0 + (unsigned)a * binrow_p, gb = ga + ((a + 1 < PH) ? binrow_p : 0u);
+            for (int x = X0 + pw; x <= X1; x += PW) {
+              const unsigned ra = pix_p + (unsigned)(x - X0) * (kPixRec * 4u);
+              const uint4 r0 = lds128(ra), r1 = lds128(ra + 16u);
+              const int clo = (int)(r0.x & 255u), cnt = (int)(r0.x >> 8);
+              const float wx[kPixCols] = {__uint_as_float(r0.y), __uint_as_float(r0.z), __uint_as_float(r0.w), __uint_as_float(r1.x),
+                                          __uint_as_float(r1.y), __uint_as_float(r1.z), __uint_as_float(r1.w)};
+              float v[V];
+#pragma unroll
+              for (int i = 0; i < V; i++) v[i] = 0.f;
+#pragma unroll
+              for (int j = 0; j < kPixCols; j++) {
+                if (j < cnt && wx[j] != 0.f) {
+                  const unsigned off = (unsigned)(clo + j) * 512u;
+                  float gA[V], gB[V];
+                  unpack16<T, V>(lds128(ga + off), gA);
+                  unpack16<T, V>(lds128(gb + off), gB);
+                  const float ka = wx[j] * wa, kb = wx[j] * wb;
+#pragma unroll
+                  for (int i = 0; i < V; i++) v[i] = fmaf(kb, gB[i], fmaf(ka, gA[i], v[i]));
+                }
+              }
+              if (cnt > 0) VecIO<T, V>::red_add(qrow + (size_t)x * C, v);
+            }
+          }
+        }
+        mb_arrive(&pempty[pb]);
+        continue;
+      }
+      const int nx = (mode == PLAN_ROLLING || mode == PLAN_THIN) ? col[1] : 0;
       if (nx == 0 || c >= C) {  // nothing to reduce (EMPTY / GENERIC RoI, column outside the map, idle lane of a ragged slice)
         mb_arrive(&pempty[pb]);
         continue;
@@ -1625,7 +1705,7 @@ static int launch_bwd(const Call& c, const void* gout) {
         static const bool use_tma = getenv("ABR_BWD_TMA") ? atoi(getenv("ABR_BWD_TMA")) != 0 : true;
         const int nbin = c.PH * c.PW;
         const size_t gstage = ((size_t)nbin * 512 + 127) & ~(size_t)127;
-        const size_t planw = (size_t)kPlanHdr + (size_t)c.PW * kPlanCol + (size_t)c.Hs * kPlanRow;
+        const size_t planw = (size_t)kPlanHdr + (size_t)c.PW * kPlanCol + (size_t)c.Hs * kPlanRow + kPlanPix;
         const size_t tma_smem = 2 * gstage + 2 * planw * 4 + 4 * 8;
         EncodeTiledFn enc = encode_tiled_fn();
         CUtensorMap gmap;

@@ -18,7 +18,7 @@ x = torch.from_numpy(s).cuda().contiguous(memory_format=torch.channels_last)
 out, plan = roi_align_forward(x, torch.from_numpy(rois).cuda(), w["scale"], w["P"], w["P"], w["sampling_ratio"], return_plan=True)
 torch.cuda.synchronize()
 PW, Hs = w["P"], w["H"]
-stride = 16 + PW * 20 + Hs * 8
+stride = 16 + PW * 20 + Hs * 8 + 128
 R = rois.shape[0]
 p = plan.cpu().numpy().view(np.int32)[: R * stride].reshape(R, stride)
 names = {0: "EMPTY", 1: "ROLLING", 2: "THIN", 3: "GENERIC"}
@@ -33,8 +33,10 @@ for r in range(R):
     rows = p[r, 16 + PW * 20:16 + PW * 20 + nrows * 8].reshape(nrows, 8)
     live_rows = int((rows[:, 0] >= 0).sum()) if mode == 1 else nrows
     emitted = int((cols[:, 1] - cols[:, 2]).sum()) if mode == 1 else int(cols[:, 1].sum())
-    paired = bool(cols[:, 2].any() or cols[:, 3].any())
-    key = names[int(mode)] + ("" if mode != 1 else ("+pair" if paired else "+nopair"))
+    scheme = int(p[r, 10])
+    if scheme == 2:
+        emitted = int(X1 - X0 + 1)  # pixel records: one reduction per footprint pixel
+    key = names[int(mode)] + {1: "+pair", 2: "+pixel records", 0: "+neither"}[scheme]
     d = tot.setdefault(key, [0, 0, 0, 0])
     d[0] += 1
     d[1] += live_rows * emitted              # reductions issued per 32*V-channel slice
