@@ -15,7 +15,7 @@ WANT = [
     "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
     "launch__waves_per_multiprocessor", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
     "launch__occupancy_limit_warps", "smsp__cycles_active.avg", "sm__cycles_elapsed.max", "launch__grid_size", "launch__block_size",
-    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lts__t_sectors_op_red.sum", "lts__t_sectors_op_atom.sum",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lts__t_sectors_op_red.sum", "lts__t_sectors_op_atom.sum", "l1tex__m_l1tex2xbar_write_sectors_mem_global_op_red.sum",
 ]
 
 
