@@ -632,7 +632,8 @@ __global__ void __launch_bounds__(256) roi_align_bwd_sweep_kernel(LevelTable lv,
 //   * warps 1..PW (consumers, one per bin column) wait for a row, take their column's pixels out of shared memory,
 //     form t = sum_x Wx*v and add Wy[p][y]*t to one register accumulator per bin, then hand the slot back.
 // Every distinct footprint pixel leaves L2 exactly once per (RoI, slice) -- the columns share the staged row -- the
-// loads are asynchronous and kRing rows deep, and no thread ever waits on a dependent global load.  PH <= 8.
+// loads are asynchronous (kRing slots of up to 64 pixels x rows), and no thread ever waits on a dependent global load.
+// PH <= 8.
 constexpr int kRing = 2;  // 32 KB slots: one being filled while the other is consumed
 constexpr int kMaxBins = 8;
 
