@@ -626,14 +626,15 @@ __global__ void __launch_bounds__(256) roi_align_bwd_sweep_kernel(LevelTable lv,
 
 // ------------------------------------------------------------------------------------------ forward, NHWC, TMA-staged
 // Warp-specialised, persistent.  A CTA owns (RoI, slice of 32*V channels = 512 bytes per pixel) at a time:
-//   * warp 0 (producer) streams the RoI's footprint, one map row per ring slot, with TMA bulk copies (one 512-byte
-//     cp.async.bulk per footprint pixel, issued by 32 lanes in parallel, completion counted on the slot's mbarrier),
-//     and the RoI's plan (column records + per-row bin weights) into a double-buffered plan area;
-//   * warps 1..PW (consumers, one per bin column) wait for a row, take their column's pixels out of shared memory,
-//     form t = sum_x Wx*v and add Wy[p][y]*t to one register accumulator per bin, then hand the slot back.
-// Every distinct footprint pixel leaves L2 exactly once per (RoI, slice) -- the columns share the staged row -- the
-// loads are asynchronous (kRing slots of up to 64 pixels x rows), and no thread ever waits on a dependent global load.
-// PH <= 8.
+//   * warp 0 (producer) streams the RoI's footprint into a ring of shared-memory slots, ONE TMA tensor op per slot
+//     (cp.async.bulk.tensor.3d: a box of bw pixels x bh rows x 512 bytes of the map, bw the narrowest power of two that
+//     covers the footprint width, bw * bh = 64; completion counted on the slot's mbarrier), and the RoI's plan (column
+//     records + per-row bin weights, cp.async.bulk) into a double-buffered plan area;
+//   * warps 1..PW (consumers, one per bin column) wait for a slot, take their column's pixels of each staged row out of
+//     shared memory, form t = sum_x Wx*v and add Wy[p][y]*t into two rolling register accumulators (or one per bin for
+//     thin bins), then hand the slot back.
+// Every distinct footprint pixel leaves L2 once per (RoI, slice) -- the columns share the staged rows -- the loads are
+// asynchronous and no thread ever waits on a dependent global load.  PH <= 8, PW <= 7.
 constexpr int kRing = 2;  // 32 KB slots: one being filled while the other is consumed
 constexpr int kMaxBins = 8;
 
