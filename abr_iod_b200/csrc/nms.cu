@@ -174,23 +174,21 @@ __global__ void __launch_bounds__(kTile * kMaskTilesPerCta) iou_mask_kernel(NmsB
     // settled by a product.  (thresh <= 0 or non-finite values take the exact path for every pair.)
     const bool fast = thresh >= 1e-6f;  // keeps thresh * union a normal number for every union the fast path accepts
     const float hi_k = 1.f + 9.5367431640625e-07f, lo_k = 1.f - 9.5367431640625e-07f;  // 1 +- 2^-20
+#pragma unroll 4
     for (int i = start; i < col_size; i++) {
       const float4 b = cbox[grp][i];
-      const float width = __fadd_rn(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 1.f);
-      const float height = __fadd_rn(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 1.f);
-      bool hit;
-      if (fast && (width <= 0.f || height <= 0.f)) {
-        hit = false;  // inter = 0, IoU = 0 (or NaN for 0/0): never above a positive threshold
-      } else {
-        const float inter = __fmul_rn(fmaxf(width, 0.f), fmaxf(height, 0.f));
-        const float uni = __fsub_rn(__fadd_rn(sa, carea[grp][i]), inter);
-        const float p = __fmul_rn(thresh, uni);
-        if (fast && uni > 1e-10f && inter > __fmul_rn(p, hi_k)) hit = true;
-        else if (fast && uni > 1e-10f && inter < __fmul_rn(p, lo_k)) hit = false;
-        else {
-          const float v = __fdiv_rn(inter, uni);
-          hit = ge ? (v >= thresh) : (v > thresh);
-        }
+      const float width = fmaxf(__fadd_rn(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 1.f), 0.f);
+      const float height = fmaxf(__fadd_rn(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 1.f), 0.f);
+      const float inter = __fmul_rn(width, height);
+      const float uni = __fsub_rn(__fadd_rn(sa, carea[grp][i]), inter);
+      const float p = __fmul_rn(thresh, uni);
+      // branch-free for all but the pairs within 2^-20 of the threshold (a pair without intersection has inter = 0 < p)
+      const bool usable = fast && uni > 1e-10f;
+      bool hit = usable && inter > __fmul_rn(p, hi_k);
+      const bool settled = usable && (hit || inter < __fmul_rn(p, lo_k));
+      if (!settled) {
+        const float v = __fdiv_rn(inter, uni);
+        hit = ge ? (v >= thresh) : (v > thresh);
       }
       if (hit) w |= 1ull << i;
     }
