@@ -123,47 +123,37 @@ class RPNPostProcessor(torch.nn.Module):
         return result
 
     def forward(self, anchors, objectness, box_regression, targets=None):
-        """
-        Arguments:
-            anchors: list[list[BoxList]]
-            objectness: list[tensor]
-            box_regression: list[tensor]
-        Returns:
-            boxlists (list[BoxList]): the post-processed anchors, after applying box decoding and NMS
-        """
-        sampled_boxes = []
-        num_levels = len(objectness)
-        anchors = list(zip(*anchors))
-        for a, o, b in zip(anchors, objectness, box_regression):
-            sampled_boxes.append(self.forward_for_single_feature_map(a, o, b))
-        boxlists = list(zip(*sampled_boxes))
-        boxlists = [cat_boxlist(boxlist) for boxlist in boxlists]
-        if num_levels > 1:
-            boxlists = self.select_over_all_levels(boxlists)
+        """anchors: per image, per level BoxLists; objectness / box_regression: one tensor per level.
+        Returns one BoxList of proposals per image (decoded, clipped, NMS-filtered; with the ground truth appended while
+        training, inference.py:120-147)."""
+        levels = len(objectness)
+        per_level_anchors = list(zip(*anchors))  # level -> the images' anchor BoxLists
+        per_level = [self.forward_for_single_feature_map(per_level_anchors[lvl], objectness[lvl], box_regression[lvl])
+                     for lvl in range(levels)]
+        proposals = [cat_boxlist([per_level[lvl][img] for lvl in range(levels)]) for img in range(len(per_level[0]))]
+        if levels > 1:
+            proposals = self.select_over_all_levels(proposals)
         if self.training and targets is not None:
-            boxlists = self.add_gt_proposals(boxlists, targets)
-        return boxlists
+            proposals = self.add_gt_proposals(proposals, targets)
+        return proposals
 
     def select_over_all_levels(self, boxlists):
-        """inference.py:149-178 (FPN only; a handful of tiny tensors per batch, kept as tensor glue)."""
-        num_images = len(boxlists)
+        """FPN only (inference.py:149-178; a handful of small tensors per batch, kept as tensor glue).  Training with
+        ``fpn_post_nms_per_batch``: the best ``fpn_post_nms_top_n`` proposals of the WHOLE batch survive, each image
+        keeping its own order; otherwise every image keeps its best ``fpn_post_nms_top_n``, best first."""
+        budget = self.fpn_post_nms_top_n
         if self.training and self.fpn_post_nms_per_batch:
-            objectness = torch.cat([boxlist.get_field("objectness") for boxlist in boxlists], dim=0)
-            box_sizes = [len(boxlist) for boxlist in boxlists]
-            post_nms_top_n = min(self.fpn_post_nms_top_n, len(objectness))
-            _, inds_sorted = torch.topk(objectness, post_nms_top_n, dim=0, sorted=True)
-            inds_mask = torch.zeros_like(objectness, dtype=torch.bool)
-            inds_mask[inds_sorted] = 1
-            inds_mask = inds_mask.split(box_sizes)
-            for i in range(num_images):
-                boxlists[i] = boxlists[i][inds_mask[i]]
-        else:
-            for i in range(num_images):
-                objectness = boxlists[i].get_field("objectness")
-                post_nms_top_n = min(self.fpn_post_nms_top_n, len(objectness))
-                _, inds_sorted = torch.topk(objectness, post_nms_top_n, dim=0, sorted=True)
-                boxlists[i] = boxlists[i][inds_sorted]
-        return boxlists
+            counts = [len(b) for b in boxlists]
+            scores = torch.cat([b.get_field("objectness") for b in boxlists], dim=0)
+            winners = torch.topk(scores, min(budget, scores.numel()), dim=0, sorted=True)[1]
+            keep = torch.zeros(scores.shape, dtype=torch.bool, device=scores.device)
+            keep[winners] = True
+            return [b[m] for b, m in zip(boxlists, keep.split(counts))]
+        out = []
+        for b in boxlists:
+            scores = b.get_field("objectness")
+            out.append(b[torch.topk(scores, min(budget, scores.numel()), dim=0, sorted=True)[1]])
+        return out
 
 
 def make_rpn_postprocessor(config, rpn_box_coder, is_train):
