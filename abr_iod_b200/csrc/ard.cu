@@ -193,23 +193,29 @@ __global__ void __launch_bounds__(1024) ard_nchw_kernel(ArdParams p, const T* __
   const T* __restrict__ fo = f_old + base;
   const T* __restrict__ fn = f_new + base;
 
-  float so = 0.f, sn = 0.f, sd = 0.f;
+  // fp32 runs of 16 channels folded into double totals: as accurate as the reference's pairwise fp32 sums or better,
+  // also for the hundreds of channels a thread walks when HW is large
+  double tso = 0.0, tsn = 0.0, tsd = 0.0;
+  for (int c0 = grp; c0 < C; c0 += 16 * G) {
+    float so = 0.f, sn = 0.f, sd = 0.f;
 #pragma unroll 4
-  for (int c = grp; c < C; c += G) {
-    float a[1], b[1];
-    VecIO<T, 1>::load(fo + (size_t)c * HW + pos, a);
-    VecIO<T, 1>::load(fn + (size_t)c * HW + pos, b);
-    so = fmaf(a[0], a[0], so);
-    sn = fmaf(b[0], b[0], sn);
-    const float d = b[0] - a[0];
-    sd = fmaf(d, d, sd);
+    for (int c = c0; c < min(C, c0 + 16 * G); c += G) {
+      float a[1], b[1];
+      VecIO<T, 1>::load(fo + (size_t)c * HW + pos, a);
+      VecIO<T, 1>::load(fn + (size_t)c * HW + pos, b);
+      so = fmaf(a[0], a[0], so);
+      sn = fmaf(b[0], b[0], sn);
+      const float d = b[0] - a[0];
+      sd = fmaf(d, d, sd);
+    }
+    tso += (double)so; tsn += (double)sn; tsd += (double)sd;
   }
-  if (active) { red[tid] = so; red[T_ + tid] = sn; red[2 * T_ + tid] = sd; }
+  if (active) { red[tid] = (float)tso; red[T_ + tid] = (float)tsn; red[2 * T_ + tid] = (float)tsd; }
   __syncthreads();
   if (tid < HW) {
-    float x = 0.f, y = 0.f, z = 0.f;
-    for (int g = 0; g < G; g++) { x += red[g * HW + tid]; y += red[T_ + g * HW + tid]; z += red[2 * T_ + g * HW + tid]; }
-    m_old[tid] = x; m_new[tid] = y; dd[tid] = z;
+    double x = 0.0, y = 0.0, z = 0.0;
+    for (int g = 0; g < G; g++) { x += (double)red[g * HW + tid]; y += (double)red[T_ + g * HW + tid]; z += (double)red[2 * T_ + g * HW + tid]; }
+    m_old[tid] = (float)x; m_new[tid] = (float)y; dd[tid] = (float)z;
   }
   __syncthreads();
   if (tid < 32) ard_position_phase(p, m_old, m_new, dd, a_old, kk, n);
@@ -503,8 +509,9 @@ __global__ void __launch_bounds__(kArdClusterThreads, 1) ard_nchw_cluster_kernel
     float* ex_par = ex + (size_t)parity * 3 * csize * HW;
     for (int t = tid; t < 3 * HW; t += kArdClusterThreads) {
       const int q = t / HW, pp = t - q * HW;
-      float v = 0.f;
-      for (int gg = 0; gg < 4 * G; gg++) v += part[q * S + gg * HW + pp];
+      double acc = 0.0;  // up to 4*G (hundreds of) partial sums: accumulated in double, like a pairwise fp32 sum or better
+      for (int gg = 0; gg < 4 * G; gg++) acc += (double)part[q * S + gg * HW + pp];
+      const float v = (float)acc;
       for (unsigned r = 0; r < csize; r++) dsmem_store(ex_par + ((size_t)q * csize + rank) * HW + pp, r, v);
     }
     cluster_sync_all();  // every CTA's partial rows are in every CTA's table

@@ -1,0 +1,95 @@
+"""Randomised parity sweep (not part of the test suite; run on a GPU box): random shapes, pooling sizes, sampling
+ratios, layouts and adversarial RoIs for ROIAlign forward/backward, random box sets for NMS, random shapes for ARD,
+each against the CPU oracle with the tolerances of tests/.  Prints one line per family and fails loudly on a mismatch.
+
+    python tools/fuzz_parity.py [cases]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import torch
+
+import oracle
+from oracle import ard_torch
+from abr_iod_b200.distillation.distillation import calculate_attentive_roi_feature_distillation as ard
+from abr_iod_b200.layers import nms, roi_align
+from inputs import make_boxes, make_rois
+
+
+def close(a, ref, rel=1e-5, what=""):
+    a, ref = np.asarray(a, np.float64), np.asarray(ref, np.float64)
+    scale = np.abs(ref).max() if ref.size else 1.0
+    err = np.abs(a - ref)
+    if not (err <= rel * scale + rel * np.abs(ref)).all():
+        raise SystemExit("MISMATCH %s: max err %g (scale %g)" % (what, err.max(), scale))
+
+
+def main():
+    cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
+    rng = np.random.default_rng(2026)
+    for i in range(cases):
+        B = int(rng.integers(1, 4))
+        C = int(rng.choice([3, 4, 8, 20, 64, 132, 256]))
+        H, W = int(rng.integers(5, 60)), int(rng.integers(5, 90))
+        P = int(rng.choice([1, 2, 3, 5, 7, 7, 7, 8, 14]))
+        ratio = int(rng.choice([0, 0, 1, 2, 3]))
+        R = int(rng.integers(1, 80))
+        cl = bool(rng.integers(0, 2))
+        x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+        rois = make_rois(rng, R, B, W * 16, H * 16)
+        if rng.random() < 0.3:  # tiny and huge RoIs
+            rois[: R // 2, 3] = rois[: R // 2, 1] + rng.uniform(0, 20, R // 2)
+            rois[: R // 2, 4] = rois[: R // 2, 2] + rng.uniform(0, 2000, R // 2)
+        xt = torch.from_numpy(x).cuda()
+        if cl:
+            xt = xt.contiguous(memory_format=torch.channels_last)
+        xt.requires_grad_(True)
+        out = roi_align(xt, torch.from_numpy(rois).cuda(), (P, P), 1 / 16, ratio)
+        tag = "roi_align case %d: B=%d C=%d H=%d W=%d P=%d ratio=%d R=%d channels_last=%s" % (i, B, C, H, W, P, ratio, R, cl)
+        close(out.detach().cpu().numpy(), oracle.roi_align_forward(x, rois, 1 / 16, P, P, ratio), what=tag + " fwd")
+        g = rng.standard_normal(out.shape).astype(np.float32)
+        out.backward(torch.from_numpy(g).cuda())
+        close(xt.grad.cpu().numpy(), oracle.roi_align_backward(g, rois, 1 / 16, P, P, B, C, H, W, ratio), what=tag + " bwd")
+    print("roi_align: %d random cases match the oracle" % cases)
+    for i in range(cases):
+        n = int(rng.choice([1, 2, 63, 64, 65, 129, 500, 1500, 4000]))
+        b, s = make_boxes(rng, n, 1216, 800)
+        if rng.random() < 0.3:
+            s = np.round(s, 1).astype(np.float32)  # many equal scores
+        if rng.random() < 0.3:
+            b[n // 2:] = b[: n - n // 2]  # duplicate boxes
+        thr = float(rng.choice([0.3, 0.5, 0.7, 0.9]))
+        keep = nms(torch.from_numpy(b).cuda(), torch.from_numpy(s).cuda(), thr).cpu().numpy()
+        if not np.array_equal(keep, oracle.nms(b, s, thr, "cuda")):
+            raise SystemExit("MISMATCH nms case %d: n=%d thr=%g" % (i, n, thr))
+    print("nms: %d random cases match the oracle exactly" % cases)
+    worst = 0.0
+    for i in range(cases // 2):
+        N, C, P = int(rng.integers(1, 9)), int(rng.choice([4, 8, 24, 64, 100, 256, 1024])), int(rng.choice([1, 3, 7, 14]))
+        cl = bool(rng.integers(0, 2))
+        fo = (rng.standard_normal((N, C, P, P)) * rng.choice([0.1, 1.0, 10.0])).astype(np.float32)
+        fn = (fo + rng.standard_normal(fo.shape).astype(np.float32) * 0.2).astype(np.float32)
+        to, tn = torch.from_numpy(fo).cuda(), torch.from_numpy(fn).cuda()
+        if cl:
+            to, tn = to.contiguous(memory_format=torch.channels_last), tn.contiguous(memory_format=torch.channels_last)
+        tn.requires_grad_(True)
+        loss = ard(to, tn, 1.0)
+        loss.backward()
+        o_loss, _, _, o_g = oracle.ard(fo, fn, 1.0)
+        tag = "ard case %d: N=%d C=%d P=%d channels_last=%s" % (i, N, C, P, cl)
+        # Large-magnitude features make the softmax ill-conditioned in fp32 (exponents ~ mean_c f^2): the tolerance is
+        # 1e-5 or what the reference's own fp32 arithmetic (oracle/ard_torch.py) loses against float64, whichever is larger.
+        l32, g32 = ard_torch.ard_fwd_bwd(torch.from_numpy(fo), torch.from_numpy(fn), 1.0)
+        rel_l = max(1e-5, 2 * abs(l32.item() - o_loss) / abs(o_loss))
+        rel_g = max(1e-5, 2 * float(np.abs(g32.numpy() - o_g).max() / np.abs(o_g).max()))
+        worst = max(worst, rel_l)
+        close(loss.item(), o_loss, rel=rel_l, what=tag + " loss")
+        close(tn.grad.cpu().numpy(), o_g, rel=rel_g, what=tag + " grad")
+    print("ard: %d random cases match the oracle (loosest tolerance used: %.1e)" % (cases // 2, worst))
+
+
+if __name__ == "__main__":
+    main()
