@@ -66,7 +66,7 @@ def main():
         if not np.array_equal(keep, oracle.nms(b, s, thr, "cuda")):
             raise SystemExit("MISMATCH nms case %d: n=%d thr=%g" % (i, n, thr))
     print("nms: %d random cases match the oracle exactly" % cases)
-    worst = 0.0
+    worst, skipped = 0.0, 0
     for i in range(cases // 2):
         N, C, P = int(rng.integers(1, 9)), int(rng.choice([4, 8, 24, 64, 100, 256, 1024])), int(rng.choice([1, 3, 7, 14]))
         cl = bool(rng.integers(0, 2))
@@ -87,8 +87,20 @@ def main():
         rel_g = max(1e-5, 2 * float(np.abs(g32.numpy() - o_g).max() / np.abs(o_g).max()))
         worst = max(worst, rel_l)
         close(loss.item(), o_loss, rel=rel_l, what=tag + " loss")
-        close(tn.grad.cpu().numpy(), o_g, rel=rel_g, what=tag + " grad")
-    print("ard: %d random cases match the oracle (loosest tolerance used: %.1e)" % (cases // 2, worst))
+        # The PAD term's gradient carries sign(A_new - A_old): where the two attentions agree to within fp32 noise the sign
+        # is numerically undetermined (a measure-zero discontinuity of the loss itself), and it couples into every position
+        # of that RoI through the softmax Jacobian -- such RoIs are left out of the gradient comparison.
+        def att(f):
+            m = (f.astype(np.float64) ** 2).mean(1).reshape(N, -1)
+            e = np.exp(m - m.max(1, keepdims=True))
+            return e / e.sum(1, keepdims=True) * m.shape[1]
+        dd = np.abs(att(fn) - att(fo))
+        ok_rois = ~((dd > 0) & (dd < 1e-6)).any(1)  # an exact 0 (one position per RoI) has sign 0 in every arithmetic
+        skipped += int((~ok_rois).sum())
+        if ok_rois.any():
+            close(tn.grad.cpu().numpy()[ok_rois], o_g[ok_rois], rel=rel_g, what=tag + " grad")
+    print("ard: %d random cases match the oracle (loosest tolerance used: %.1e; %d RoIs with an undetermined sign left out of the gradient check)"
+          % (cases // 2, worst, skipped))
 
 
 if __name__ == "__main__":
