@@ -67,6 +67,42 @@ def main():
         out.backward(dev(g))
         close(xt.grad.cpu().numpy(), oracle.roi_pool_backward(g, arg, rois, B, C, H, W), 1e-5, "roi_pool backward case %d" % i)
     print("roi_pool: %d random cases match the oracle (forward exactly)" % cases)
+    # ---- multi-level Pooler (FPN), all ROIAlign layouts
+    from abr_iod_b200 import _lib
+    from abr_iod_b200.modeling.poolers import Pooler
+    from oracle import pooler as opooler
+
+    for i in range(cases):
+        B, C = int(rng.integers(1, 3)), int(rng.choice([4, 8, 36, 128]))
+        L = int(rng.integers(2, 5))
+        scales = tuple(0.25 / 2 ** l for l in range(L))
+        im_w, im_h = int(rng.integers(8, 40)) * 32, int(rng.integers(8, 30)) * 32
+        P, ratio = int(rng.choice([3, 7, 7, 14])), int(rng.choice([0, 2]))
+        feats_np = [rng.standard_normal((B, C, int(im_h * sc), int(im_w * sc))).astype(np.float32) for sc in scales]
+        boxes_np = []
+        for _ in range(B):
+            n = int(rng.integers(1, 40))
+            x1, y1 = rng.uniform(0, im_w - 8, n), rng.uniform(0, im_h - 8, n)
+            side = np.exp(rng.uniform(np.log(4), np.log(1200), n))
+            boxes_np.append(np.stack([x1, y1, np.minimum(x1 + side, im_w - 1), np.minimum(y1 + side * rng.uniform(0.3, 3, n), im_h - 1)], 1).astype(np.float32))
+        route = int(rng.integers(0, 4))  # channels-last | contiguous staged | contiguous direct | contiguous + channels-last pooled
+        _lib.NCHW_STAGING = route != 2
+        _lib.POOLED_CHANNELS_LAST = route == 3
+        feats = [dev(f).contiguous(memory_format=torch.channels_last) if route == 0 else dev(f) for f in feats_np]
+        feats = [f.requires_grad_(True) for f in feats]
+        out = Pooler((P, P), scales, ratio)(feats, [BoxList(dev(b), (im_w, im_h), "xyxy") for b in boxes_np])
+        close(out.detach().cpu().numpy(), opooler.pooler(feats_np, boxes_np, P, scales, ratio), 1e-5, "pooler case %d route %d forward" % (i, route))
+        g = rng.standard_normal(out.shape).astype(np.float32)
+        out.backward(dev(g))
+        rois = opooler.to_roi_format(boxes_np)
+        k_min, k_max = -np.log2(np.float32(scales[0])), -np.log2(np.float32(scales[-1]))
+        levels = opooler.map_levels(rois[:, 1:], k_min, k_max)
+        for lvl in range(L):
+            sel = np.nonzero(levels == lvl)[0]
+            gref = oracle.roi_align_backward(g[sel], rois[sel], scales[lvl], P, P, *feats_np[lvl].shape, ratio)
+            close(feats[lvl].grad.cpu().numpy(), gref, 1e-5, "pooler case %d route %d backward level %d" % (i, route, lvl))
+    _lib.NCHW_STAGING, _lib.POOLED_CHANNELS_LAST = True, False
+    print("pooler: %d random multi-level cases (all four layout routes) match the oracle" % cases)
     # ---- matching
     for i in range(cases):
         n_img = int(rng.integers(1, 5))
