@@ -207,6 +207,42 @@ def main():
             if int(n_out[n]) != len(ref[n][0]):
                 flips += 1  # an IoU within an ulp of the threshold (decode differs by ulps from torch's CPU exp)
     print("rpn: %d random cases; candidate selection exact; %d near-threshold flips in the size filter / NMS" % (cases, flips))
+    # ---- ABR paste: whole batches in one launch against the numpy restatement of the reference's three methods
+    import random
+
+    from PIL import Image
+
+    from abr_iod_b200.data.abr_paste import BoxRehearsalPaster
+    from oracle import paste as opaste
+
+    kinds_seen = {}
+    for i in range(max(4, cases // 6)):
+        protos = []
+        for j in range(int(rng.integers(6, 40))):
+            h, w = int(rng.integers(8, 320)), int(rng.integers(8, 320))
+            protos.append(("%d_%05d.jpg" % (int(rng.integers(1, 16)), j), rng.integers(0, 256, (h, w, 3), dtype=np.uint8)))
+        bs = int(rng.choice([2, 4, 8]))
+        paster = BoxRehearsalPaster([(n, a) for n, a in protos], bs)
+        st = opaste.BoxRehearsalState([(n, opaste.as_pil(a)) for n, a in protos], bs)
+        images, targets = [], []
+        for _ in range(int(rng.integers(1, 12))):
+            h, w = int(rng.integers(60, 420)), int(rng.integers(60, 520))
+            images.append(Image.fromarray(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)))
+            ng = int(rng.integers(1, 5))
+            x1, y1 = rng.uniform(0, w * 0.6, ng), rng.uniform(0, h * 0.6, ng)
+            targets.append(np.stack([x1, y1, x1 + rng.uniform(5, w * 0.4, ng), y1 + rng.uniform(5, h * 0.4, ng), rng.integers(16, 21, ng)], 1))
+        seed = int(rng.integers(0, 1 << 30))
+        random.seed(seed); torch.manual_seed(seed)
+        ref = [opaste.transform_current_data_with_abr(st, im, t) for im, t in zip(images, targets)]
+        random.seed(seed); torch.manual_seed(seed)
+        outs, gts, kinds = paster.paste_batch(images, targets)
+        if kinds != [r[0] for r in ref] or paster.boxes_index != st.boxes_index:
+            fail("paste round %d: decisions or rehearsal index differ" % i)
+        for k, (o, gt, (kind, rimg, rgt)) in enumerate(zip(outs, gts, ref)):
+            kinds_seen[kind] = kinds_seen.get(kind, 0) + 1
+            if not (np.array_equal(o.cpu().numpy(), rimg) and np.array_equal(gt, rgt)):
+                fail("paste round %d image %d (%s): pixels or boxes differ" % (i, k, kind))
+    print("paste: %d random batches bit-exact (%s)" % (max(4, cases // 6), ", ".join("%s x%d" % kv for kv in sorted(kinds_seen.items()))))
     # ---- box-head post-processing
     flips = 0
     for i in range(cases):
