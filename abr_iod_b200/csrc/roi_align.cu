@@ -1628,12 +1628,13 @@ static bool build_tma_maps(const Call& c, TmaMaps& maps) {
   return true;
 }
 
+constexpr int kPlanThreads = 64;  // per RoI: the table builds are barrier-bound, two warps measured best (32: 0.2258, 64: 0.2255, 128: 0.2280 ms per teacher forward)
 static int run_plan(const Call& c) {
   if (c.plan_ready) return ABR_OK;
   const size_t smem = tables_bytes(c.PH, c.PW, c.Hs, c.Ws, true);
   int rc = set_smem(plan_kernel, smem, "roi_align plan");
   if (rc) return rc;
-  plan_kernel<<<c.R, 128, smem, c.st>>>(c.lv, c.rois, c.levels, c.plans, plan_stride_words(c.PW, c.Hs, c.PH), c.PH, c.PW, c.ratio, c.Hs, c.Ws);
+  plan_kernel<<<c.R, kPlanThreads, smem, c.st>>>(c.lv, c.rois, c.levels, c.plans, plan_stride_words(c.PW, c.Hs, c.PH), c.PH, c.PW, c.ratio, c.Hs, c.Ws);
   ABR_CHECK_LAUNCH("roi_align_plan");
   return ABR_OK;
 }
