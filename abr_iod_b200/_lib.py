@@ -41,6 +41,7 @@ SIGNATURES = {
     "abr_version": (_int, []),
     "abr_last_error": (ctypes.c_char_p, []),
     "abr_launch_count": (ctypes.c_uint64, []),
+    "abr_set_option": (_int, [ctypes.c_char_p, _int]),
     "abr_roi_align_workspace_bytes": (_sz, [_int, _int, _int, _int]),
     "abr_roi_align_workspace_bytes_nchw": (_sz, [_int, _int, _int, _int, _int, _int, ctypes.c_longlong, _int]),
     "abr_roi_align_workspace_bytes_layout": (_sz, [_int, _int, _int, _int, _int, _int, ctypes.c_longlong, _int, _int]),
@@ -61,6 +62,8 @@ SIGNATURES = {
                                    _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _int, _vp, _sz, _vp]),
     "abr_ard_workspace_bytes": (_sz, [_int, _int, _int]),
     "abr_ard_forward_backward": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _f, _f, _int, _int, _vp, _sz, _vp]),
+    "abr_roi_ard_fused_workspace_bytes": (_sz, [_int, _int, _int, _int]),
+    "abr_roi_ard_fused": (_int, [_vp] * 7 + [_int] * 7 + [_f, _int, _f, _f, _int, _int, _int, _vp, _sz, _int, _vp]),
     "abr_match_proposals": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     "abr_box_iou": (_int, [_vp, _int, _vp, _int, _vp, _vp]),
     "abr_logit_loss_workspace_bytes": (_sz, [_int]),
@@ -157,6 +160,11 @@ def roi_align_workspace(R, PH, PW, max_h, device, channels_last=True, nchw_stagi
     else:
         return None, 0
     return torch.empty((n,), dtype=torch.uint8, device=device), n
+
+
+def set_option(key: str, value: int) -> None:
+    """``abr_set_option``: kernel-family switches for measurements and tests ("roi_v2", "v2_prefetch", "fwd_tma", ...)."""
+    check(lib().abr_set_option(key.encode(), int(value)))
 
 
 def launch_count() -> int:

@@ -15,6 +15,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "roi_v2.h"
 
 namespace abr {
 
@@ -588,6 +589,52 @@ static int launch_nchw_cluster(const ArdParams& p, const void* fo, const void* f
   return ABR_OK;
 }
 
+// ------------------------------------------------------------------------------------------ ARD from channel sums
+// The pooling kernel of the fused step (roi_v2.cu, v2_fwd_kernel<NT = 2>) leaves, per RoI and channel slice, the three
+// channel sums of every position.  One small CTA per RoI folds the slices in fixed order (double), runs the same
+// position phase as the kernels above and writes the two per-position coefficients of
+//     dL/df_new = ka * (f_new - f_old) + kb * f_new
+// which the fused backward applies on the fly; the loss partials are reduced by the last CTA (ard_finish).
+__global__ void __launch_bounds__(256) ard_coeff_kernel(ArdParams p, const float* __restrict__ sums, int nslices,
+                                                       float2* __restrict__ coef) {
+  extern __shared__ float sm[];
+  const int HW = p.HW, n = blockIdx.x;
+  float* m_old = sm;
+  float* m_new = m_old + HW;
+  float* dd = m_new + HW;
+  float* a_old = dd + HW;
+  float* kk = a_old + HW;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    double so = 0.0, sn = 0.0, sd = 0.0;
+    for (int s = 0; s < nslices; s++) {
+      const float* q = sums + (((size_t)n * nslices + s) * HW + i) * 3;
+      so += (double)__ldg(q); sn += (double)__ldg(q + 1); sd += (double)__ldg(q + 2);
+    }
+    m_old[i] = (float)so; m_new[i] = (float)sn; dd[i] = (float)sd;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) ard_position_phase(p, m_old, m_new, dd, a_old, kk, n);
+  __syncthreads();
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) coef[(size_t)n * HW + i] = make_float2(a_old[i], kk[i]);
+  ard_finish(p);
+}
+
+size_t ard_coeff_workspace_bytes(int N) { return 256 + (size_t)(N > 0 ? N : 0) * 2 * sizeof(float); }
+
+int ard_coeff_run(const float* sums, int nslices, float2* coef, float* loss3, int N, int C, int HW, float gamma, float grad_scale,
+                  void* ws, cudaStream_t st) {
+  ArdParams p;
+  p.N = N; p.C = C; p.HW = HW; p.gamma = gamma; p.grad_scale = grad_scale;
+  p.counter = static_cast<unsigned int*>(ws);
+  p.partials = reinterpret_cast<float*>(static_cast<char*>(ws) + 256);
+  p.loss3 = loss3;
+  ABR_CUDA_OK(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), st));
+  const int threads = HW >= 192 ? 256 : (HW >= 96 ? 128 : 64);
+  ard_coeff_kernel<<<N, threads, (size_t)5 * HW * sizeof(float), st>>>(p, sums, nslices, coef);
+  ABR_CHECK_LAUNCH("ard_coefficients");
+  return ABR_OK;
+}
+
 template <typename T>
 __global__ void scale_if_needed_kernel(T* data, size_t n, const float* __restrict__ scale, float expected) {
   const float s = *scale;
@@ -658,7 +705,7 @@ int abr_ard_forward_backward(const void* f_old, const void* f_new, void* grad_ne
   ABR_CUDA_OK(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), st));
   if (layout == ABR_NHWC) {
     if (dtype == ABR_F32 && C % 4 == 0) {
-      static const bool use_cluster = getenv("ABR_ARD_CLUSTER") ? atoi(getenv("ABR_ARD_CLUSTER")) != 0 : true;
+      const bool use_cluster = options().ard_cluster != 0;
       size_t smem = 0;
       int rows = 0;
       const int cs = use_cluster ? ard_cluster_size(C, HW, smem, rows) : 0;
@@ -669,7 +716,7 @@ int abr_ard_forward_backward(const void* f_old, const void* f_new, void* grad_ne
     return (C % 8 == 0) ? launch_nhwc<__nv_bfloat16, 8>(p, f_old, f_new, grad_new, st) : launch_nhwc<__nv_bfloat16, 1>(p, f_old, f_new, grad_new, st);
   }
   if (dtype == ABR_F32) {
-    static const bool use_cluster = getenv("ABR_ARD_CLUSTER") ? atoi(getenv("ABR_ARD_CLUSTER")) != 0 : true;
+    const bool use_cluster = options().ard_cluster != 0;
     size_t smem = 0;
     int cpc = 0, G = 0;
     const bool aligned = ((reinterpret_cast<uintptr_t>(f_old) | reinterpret_cast<uintptr_t>(f_new)) & 15) == 0;

@@ -26,44 +26,10 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "roi_v2.cuh"
+#include "roi_v2.h"
 
 namespace abr {
-
-struct LevelTable {
-  void* ptr[ABR_MAX_LEVELS];
-  int H[ABR_MAX_LEVELS];
-  int W[ABR_MAX_LEVELS];
-  float scale[ABR_MAX_LEVELS];
-};
-
-struct RoiGeom {
-  int batch, level;
-  float start_h, start_w, bin_h, bin_w;
-  int grid_h, grid_w;
-  float count;
-};
-
-// ROIAlign_cuda.cu:78-104.  No rounding of the scaled corners; RoI size floor is 1 feature pixel.
-__device__ __forceinline__ RoiGeom roi_geometry(const float* __restrict__ rois, const int32_t* __restrict__ levels,
-                                                const LevelTable& lv, int r, int PH, int PW, int ratio) {
-  RoiGeom g;
-  const float* roi = rois + 5 * (size_t)r;
-  g.level = levels ? levels[r] : 0;
-  const float scale = lv.scale[g.level];
-  g.batch = (int)roi[0];
-  g.start_w = __fmul_rn(roi[1], scale);
-  g.start_h = __fmul_rn(roi[2], scale);
-  float end_w = __fmul_rn(roi[3], scale);
-  float end_h = __fmul_rn(roi[4], scale);
-  float roi_w = fmaxf(__fsub_rn(end_w, g.start_w), 1.f);
-  float roi_h = fmaxf(__fsub_rn(end_h, g.start_h), 1.f);
-  g.bin_h = __fdiv_rn(roi_h, (float)PH);
-  g.bin_w = __fdiv_rn(roi_w, (float)PW);
-  g.grid_h = ratio > 0 ? ratio : (int)ceilf(__fdiv_rn(roi_h, (float)PH));
-  g.grid_w = ratio > 0 ? ratio : (int)ceilf(__fdiv_rn(roi_w, (float)PW));
-  g.count = (float)(g.grid_h * g.grid_w);
-  return g;
-}
 
 // Builds one axis table:  Wt[p*stride + i] (zero elsewhere) and the closed support range [lo[p], hi[p]]
 // (lo > hi when bin p has no sample inside the map).  Every thread of the CTA must call this.
@@ -1603,7 +1569,21 @@ struct Call {
   cudaStream_t st;
 };
 
-static size_t workspace_need(int R, int PW, int Hs, int PH) { return (size_t)R * plan_stride_words(PW, Hs, PH) * sizeof(int); }
+// Which plan format / kernel family serves an NHWC call: the gather-form v2 kernels (roi_v2.cu: any output size up to
+// 16x16) or the TMA-staged / sweep kernels of this file (the staged ones need PH <= 8, PW <= 7).  Depends only on the output
+// size, so a forward and the backward that reuses its plans always agree.  abr_set_option("roi_v2", 0 / 1) overrides (measurements, tests).
+static bool use_v2(int PH, int PW) {
+  const int forced = options().roi_v2;
+  if (!v2_supported(PH, PW) || forced == 0) return false;
+  if (forced == 1) return true;
+  return !(PH <= kMaxBins && PW <= 7);
+}
+
+static size_t workspace_need(int R, int PW, int Hs, int PH) {
+  const size_t v1 = (size_t)R * plan_stride_words(PW, Hs, PH) * sizeof(int);
+  const size_t v2 = v2_supported(PH, PW) ? v2_workspace_bytes(R, PH, PW) : 0;
+  return v1 > v2 ? v1 : v2;
+}
 
 // Tensor maps of every level's [B*H rows][W pixels][C channels] view, one per box shape.  False when the driver entry point is
 // missing or a map cannot be encoded (the caller then uses the sweep kernel).
@@ -1644,13 +1624,21 @@ static int launch_fwd(const Call& c, void* out) {
   const size_t smem = tables_bytes(c.PH, c.PW, c.Hs, c.Ws, false);
   if (c.layout == ABR_NHWC) {
     const size_t stride = plan_stride_words(c.PW, c.Hs, c.PH);
+    if (c.plans && use_v2(c.PH, c.PW)) {
+      if (!c.plan_ready) {
+        int rc = v2_plan(c.lv, c.rois, c.levels, c.plans, c.R, c.PH, c.PW, c.ratio, c.st);
+        if (rc) return rc;
+      }
+      return v2_forward(c.lv, c.plans, c.rois, c.levels, out, c.C, c.R, c.PH, c.PW, c.ratio,
+                        std::is_same<T, float>::value ? ABR_F32 : ABR_BF16, c.st);
+    }
     if (c.plans) {
       int rc = run_plan(c);
       if (rc) return rc;
       const int nslices = ceil_div(c.C, 32 * V);
       bool staged = false;
       if constexpr (V * sizeof(T) == 16) {
-        static const bool use_tma = getenv("ABR_FWD_TMA") ? atoi(getenv("ABR_FWD_TMA")) != 0 : true;
+        const bool use_tma = options().fwd_tma != 0;
         const size_t planw = (size_t)kPlanHdr + (size_t)c.PW * kPlanCol + (size_t)c.Hs * 8;
         const size_t tma_smem = (size_t)kRing * kTileMaxPx * 32 * 16 + 2 * planw * 4 + (2 * kRing + 4) * 8;
         TmaMaps maps;
@@ -1699,13 +1687,21 @@ static int launch_bwd(const Call& c, const void* gout) {
   const size_t smem = tables_bytes(c.PH, c.PW, c.Hs, c.Ws, true);
   if (c.layout == ABR_NHWC) {
     const size_t stride = plan_stride_words(c.PW, c.Hs, c.PH);
+    if (c.plans && use_v2(c.PH, c.PW)) {
+      if (!c.plan_ready) {
+        int rc = v2_plan(c.lv, c.rois, c.levels, c.plans, c.R, c.PH, c.PW, c.ratio, c.st);
+        if (rc) return rc;
+      }
+      return v2_backward(c.lv, c.plans, c.rois, c.levels, gout, c.C, c.R, c.PH, c.PW, c.ratio,
+                         std::is_same<T, float>::value ? ABR_F32 : ABR_BF16, c.st);
+    }
     if (c.plans) {
       int rc = run_plan(c);
       if (rc) return rc;
       const int nslices = ceil_div(c.C, 32 * V);
       bool staged = false;
       if constexpr (V * sizeof(T) == 16) {
-        static const bool use_tma = getenv("ABR_BWD_TMA") ? atoi(getenv("ABR_BWD_TMA")) != 0 : true;
+        const bool use_tma = options().bwd_tma != 0;
         const int nbin = c.PH * c.PW;
         const size_t gstage = ((size_t)nbin * 512 + 127) & ~(size_t)127;
         const size_t planw = (size_t)kPlanHdr + (size_t)c.PW * kPlanCol + (size_t)c.Hs * kPlanRow + kPlanPix;

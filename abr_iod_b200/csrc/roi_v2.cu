@@ -1,0 +1,264 @@
+// roi_v2.cu -- kernels and launchers of the gather-form ROIAlign (device logic and design notes: roi_v2.cuh), and the
+// fused Attentive-RoI-Distillation step built on them (abr_roi_ard_fused):
+//     v2_plan_kernel      one warp per RoI -> per-RoI records
+//     v2_fwd_kernel<NT>   CTA = (RoI, slice of 32*V channels), one warp per bin column; NT = 2 pools the teacher and the
+//                         student map in one pass and emits the ARD channel sums of every position
+//     ard_coeff_kernel    (ard.cu) softmaxes + per-position gradient coefficients + the loss, one small CTA per RoI
+//     v2_bwd_kernel<F>    CTA = (RoI, slice), warps walk the footprint's pixel columns; F = fused: the pooled gradient is
+//                         formed on the fly from the two pooled tensors and the coefficients
+// Reference semantics: csrc/cuda/ROIAlign_cuda.cu:64-346, distillation/distillation.py:86-130,
+// tools/train_incremental.py:84-115 (teacher pooling, student pooling, ARD loss, backward into the student's map).
+#include <cstdlib>
+
+#include "roi_v2.cuh"
+#include "roi_v2.h"
+
+namespace abr {
+
+__global__ void __launch_bounds__(128) v2_plan_kernel(LevelTable lv, const float* __restrict__ rois,
+                                                     const int32_t* __restrict__ levels, int* __restrict__ plans, size_t stride,
+                                                     int R, int PH, int PW, int ratio) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const RoiGeom g = roi_geometry(rois, levels, lv, r, PH, PW, ratio);
+  const int H = lv.H[g.level], W = lv.W[g.level];
+  int* plan = plans + (size_t)r * stride;
+  v2_plan_axes(plan, g, H, W, PH, PW, lane, 32);
+  __syncwarp();
+  if (lane == 0) v2_plan_header(plan, g, H, W, PH, PW);
+  __syncwarp();
+  v2_plan_pix(plan, PH, PW, lane, 32);
+}
+
+template <typename T, int NT>
+struct V2FwdArgs {
+  LevelTable lv[NT];
+  const int* plans;
+  size_t stride;
+  const float* rois;
+  const int32_t* levels;
+  T* out[NT];
+  float* sums;  // [R][nslices][PH*PW][3] (NT == 2)
+  int C, PH, PW, ratio, nslices;
+};
+
+template <typename T, int V, int NT>
+__global__ void __launch_bounds__(256, NT == 2 ? 2 : 3) v2_fwd_kernel(const __grid_constant__ V2FwdArgs<T, NT> a) {
+  const int r = blockIdx.x / a.nslices, slice = blockIdx.x - r * a.nslices;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int* plan = a.plans + (size_t)r * a.stride;
+  const int4 h0 = __ldg(reinterpret_cast<const int4*>(plan));
+  const int mode = h0.x, level = h0.z;
+  int c = (slice * 32 + lane) * V;
+  const bool active = c < a.C;
+  if (!active) c = 0;  // idle lanes of a ragged last slice shadow channel 0 and never store
+  const T* maps[NT];
+  T* outs[NT];
+#pragma unroll
+  for (int t = 0; t < NT; t++) {
+    maps[t] = static_cast<const T*>(a.lv[t].ptr[level]);
+    outs[t] = a.out[t];
+  }
+  float* srs = NT == 2 ? a.sums + ((size_t)r * a.nslices + slice) * a.PH * a.PW * 3 : nullptr;
+  if (mode == V2_GENERIC) {
+    const RoiGeom g = roi_geometry(a.rois, a.levels, a.lv[0], r, a.PH, a.PW, a.ratio);
+    for (int pw = warp; pw < a.PW; pw += nw)
+      v2_generic_fwd_column<T, V, NT>(g, a.lv[0].H[g.level], a.lv[0].W[g.level], maps, outs, srs, r, pw, c, active, a.C, a.PH,
+                                      a.PW, lane);
+    return;
+  }
+  for (int pw = warp; pw < a.PW; pw += nw)
+    v2_fwd_column<T, V, NT>(plan, maps, outs, srs, r, pw, c, active, a.C, a.PH, a.PW, lane);
+}
+
+template <typename T>
+struct V2BwdArgs {
+  LevelTable lv;  // gradient maps
+  const int* plans;
+  size_t stride;
+  const float* rois;
+  const int32_t* levels;
+  const T* a;          // upstream gradient [R][PH][PW][C], or the teacher's pooled tensor (fused)
+  const T* b;          // the student's pooled tensor (fused)
+  const float2* coef;  // [R][PH*PW] (fused)
+  int C, PH, PW, ratio, nslices, prefetch;
+};
+
+template <typename T, int V, bool FUSED>
+__global__ void __launch_bounds__(256, FUSED ? 2 : 3) v2_bwd_kernel(const __grid_constant__ V2BwdArgs<T> a) {
+  const int r = blockIdx.x / a.nslices, slice = blockIdx.x - r * a.nslices;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int* plan = a.plans + (size_t)r * a.stride;
+  const int4 h0 = __ldg(reinterpret_cast<const int4*>(plan));
+  const int mode = h0.x, level = h0.z;
+  if (mode == V2_EMPTY) return;
+  const int nbin = a.PH * a.PW;
+  const size_t tile = ((size_t)r * nbin) * a.C + (size_t)slice * 32 * V;
+  if (a.prefetch) {
+    // The pixel-column warps of this CTA read the same bins in the same order, so without help the CTA pays one exposed
+    // DRAM latency per bin row: start the whole (RoI, slice) tile towards L2 now (one 128-byte line per thread and step).
+    const int lines_per_bin = (32 * V * (int)sizeof(T)) / 128;
+    const int nlines = nbin * lines_per_bin;
+    for (int i = threadIdx.x; i < nlines; i += blockDim.x) {
+      const int bin = i / lines_per_bin, q = i - bin * lines_per_bin;
+      const size_t off = tile + (size_t)bin * a.C + (size_t)q * (128 / sizeof(T));
+      if ((slice * 32 * V + q * (int)(128 / sizeof(T))) < a.C) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.a + off));
+        if (FUSED) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.b + off));
+      }
+    }
+  }
+  const int c = (slice * 32 + lane) * V;
+  if (c >= a.C) return;  // idle lane of a ragged last slice (no warp-level primitive below)
+  V2Grad<T, V, FUSED> src;
+  src.a = a.a + (size_t)r * nbin * a.C + c;
+  src.b = FUSED ? a.b + (size_t)r * nbin * a.C + c : nullptr;
+  src.coef = FUSED ? a.coef + (size_t)r * nbin : nullptr;
+  T* gmap = static_cast<T*>(a.lv.ptr[level]);
+  if (mode == V2_GENERIC) {
+    const RoiGeom g = roi_geometry(a.rois, a.levels, a.lv, r, a.PH, a.PW, a.ratio);
+    for (int pw = warp; pw < a.PW; pw += nw)
+      v2_generic_bwd_column<T, V, FUSED>(g, a.lv.H[g.level], a.lv.W[g.level], gmap, src, pw, c, a.C, a.PH, a.PW);
+    return;
+  }
+  const int FW = __ldg(plan + 7);
+  for (int k = warp; k < FW; k += nw) v2_bwd_pixcol<T, V, FUSED>(plan, gmap, src, k, c, a.C, a.PH, a.PW);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+bool v2_supported(int PH, int PW) { return PH >= 1 && PW >= 1 && PH <= 16 && PW <= 16; }
+
+size_t v2_workspace_bytes(int R, int PH, int PW) { return (size_t)R * v2_plan_words(PH, PW) * sizeof(int); }
+
+int v2_plan(const LevelTable& lv, const float* rois, const int32_t* levels, int* plans, int R, int PH, int PW, int ratio,
+            cudaStream_t st) {
+  v2_plan_kernel<<<ceil_div(R, 4), 128, 0, st>>>(lv, rois, levels, plans, v2_plan_words(PH, PW), R, PH, PW, ratio);
+  ABR_CHECK_LAUNCH("roi_align_plan (v2)");
+  return ABR_OK;
+}
+
+static int fwd_warps(int PW) { return PW <= 8 ? PW : ceil_div(PW, ceil_div(PW, 8)); }
+
+template <typename T, int V, int NT>
+static int launch_fwd2(const LevelTable* lv, const int* plans, const float* rois, const int32_t* levels, void* const* outs,
+                       float* sums, int C, int R, int PH, int PW, int ratio, cudaStream_t st) {
+  V2FwdArgs<T, NT> a;
+  for (int t = 0; t < NT; t++) { a.lv[t] = lv[t]; a.out[t] = static_cast<T*>(outs[t]); }
+  a.plans = plans; a.stride = v2_plan_words(PH, PW); a.rois = rois; a.levels = levels; a.sums = sums;
+  a.C = C; a.PH = PH; a.PW = PW; a.ratio = ratio; a.nslices = ceil_div(C, 32 * V);
+  const long long blocks = (long long)R * a.nslices;
+  ABR_REQUIRE(blocks <= 0x7fffffffLL, ABR_ERR_UNSUPPORTED, "roi_align_forward: too many (RoI, slice) tasks");
+  v2_fwd_kernel<T, V, NT><<<(unsigned)blocks, 32 * fwd_warps(PW), 0, st>>>(a);
+  ABR_CHECK_LAUNCH(NT == 2 ? "roi_align_forward (v2, teacher+student)" : "roi_align_forward (v2)");
+  return ABR_OK;
+}
+
+int v2_forward(const LevelTable& lv, const int* plans, const float* rois, const int32_t* levels, void* out, int C, int R, int PH,
+               int PW, int ratio, int dtype, cudaStream_t st) {
+  void* outs[1] = {out};
+  if (dtype == ABR_F32) {
+    if (C % 4 == 0) return launch_fwd2<float, 4, 1>(&lv, plans, rois, levels, outs, nullptr, C, R, PH, PW, ratio, st);
+    return launch_fwd2<float, 1, 1>(&lv, plans, rois, levels, outs, nullptr, C, R, PH, PW, ratio, st);
+  }
+  if (C % 8 == 0) return launch_fwd2<__nv_bfloat16, 8, 1>(&lv, plans, rois, levels, outs, nullptr, C, R, PH, PW, ratio, st);
+  return launch_fwd2<__nv_bfloat16, 1, 1>(&lv, plans, rois, levels, outs, nullptr, C, R, PH, PW, ratio, st);
+}
+
+template <typename T, int V, bool FUSED>
+static int launch_bwd2(const LevelTable& lv, const int* plans, const float* rois, const int32_t* levels, const void* a_, const void* b_,
+                       const float2* coef, int C, int R, int PH, int PW, int ratio, cudaStream_t st) {
+  const bool prefetch = options().v2_prefetch != 0;  // A/B switch for measurements
+  V2BwdArgs<T> a;
+  a.lv = lv; a.plans = plans; a.stride = v2_plan_words(PH, PW); a.rois = rois; a.levels = levels;
+  a.a = static_cast<const T*>(a_); a.b = static_cast<const T*>(b_); a.coef = coef;
+  a.C = C; a.PH = PH; a.PW = PW; a.ratio = ratio; a.nslices = ceil_div(C, 32 * V);
+  a.prefetch = (prefetch && (32 * V * sizeof(T)) % 128 == 0 && (C * sizeof(T)) % 128 == 0) ? 1 : 0;
+  const long long blocks = (long long)R * a.nslices;
+  ABR_REQUIRE(blocks <= 0x7fffffffLL, ABR_ERR_UNSUPPORTED, "roi_align_backward: too many (RoI, slice) tasks");
+  v2_bwd_kernel<T, V, FUSED><<<(unsigned)blocks, 256, 0, st>>>(a);
+  ABR_CHECK_LAUNCH(FUSED ? "roi_align_backward (v2, fused ARD gradient)" : "roi_align_backward (v2)");
+  return ABR_OK;
+}
+
+int v2_backward(const LevelTable& lv, const int* plans, const float* rois, const int32_t* levels, const void* gout, int C, int R,
+                int PH, int PW, int ratio, int dtype, cudaStream_t st) {
+  if (dtype == ABR_F32) {
+    if (C % 4 == 0) return launch_bwd2<float, 4, false>(lv, plans, rois, levels, gout, nullptr, nullptr, C, R, PH, PW, ratio, st);
+    return launch_bwd2<float, 1, false>(lv, plans, rois, levels, gout, nullptr, nullptr, C, R, PH, PW, ratio, st);
+  }
+  if (C % 8 == 0) return launch_bwd2<__nv_bfloat16, 8, false>(lv, plans, rois, levels, gout, nullptr, nullptr, C, R, PH, PW, ratio, st);
+  return launch_bwd2<__nv_bfloat16, 1, false>(lv, plans, rois, levels, gout, nullptr, nullptr, C, R, PH, PW, ratio, st);
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct FusedLayout {
+  size_t plans, sums, coef, ard, total;
+};
+static FusedLayout fused_layout(int R, int C, int PH, int PW) {
+  const int V = C % 4 == 0 ? 4 : 1;
+  const size_t nslices = ceil_div(C, 32 * V), HW = (size_t)PH * PW;
+  FusedLayout f;
+  f.plans = 0;
+  f.sums = align256(v2_workspace_bytes(R, PH, PW));
+  f.coef = f.sums + align256((size_t)R * nslices * HW * 3 * sizeof(float));
+  f.ard = f.coef + align256((size_t)R * HW * sizeof(float2));
+  f.total = f.ard + align256(ard_coeff_workspace_bytes(R));
+  return f;
+}
+
+}  // namespace abr
+
+using namespace abr;
+
+extern "C" {
+
+size_t abr_roi_ard_fused_workspace_bytes(int R, int C, int PH, int PW) {
+  if (R <= 0 || C <= 0 || !v2_supported(PH, PW)) return 0;
+  return fused_layout(R, C, PH, PW).total;
+}
+
+int abr_roi_ard_fused(const void* teacher_map, const void* student_map, const float* rois, void* pooled_old, void* pooled_new,
+                      void* grad_student_map, float* loss3, int B, int C, int H, int W, int R, int PH, int PW,
+                      float spatial_scale, int sampling_ratio, float gamma, float grad_scale, int dtype, int layout,
+                      int zero_init, void* workspace, size_t workspace_bytes, int workspace_has_plan, abr_stream_t stream) {
+  ABR_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && R > 0, ABR_ERR_BAD_ARG,
+              "roi_ard_fused: bad sizes B=%d C=%d H=%d W=%d R=%d (the reference's mean over zero RoIs is NaN)", B, C, H, W, R);
+  ABR_REQUIRE(teacher_map && student_map && rois && pooled_old && pooled_new && loss3, ABR_ERR_BAD_ARG, "roi_ard_fused: null pointer");
+  ABR_REQUIRE(dtype == ABR_F32 && layout == ABR_NHWC, ABR_ERR_UNSUPPORTED,
+              "roi_ard_fused: fp32 channels-last only (dtype %d, layout %d); use the separate ops otherwise", dtype, layout);
+  ABR_REQUIRE(v2_supported(PH, PW) && PH * PW <= 1024, ABR_ERR_UNSUPPORTED, "roi_ard_fused: output size %dx%d (max 16x16)", PH, PW);
+  const FusedLayout f = fused_layout(R, C, PH, PW);
+  ABR_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 && workspace_bytes >= f.total, ABR_ERR_WORKSPACE,
+              "roi_ard_fused: needs a 256-byte aligned workspace of %zu B (got %zu)", f.total, workspace_bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* ws = static_cast<char*>(workspace);
+  int* plans = reinterpret_cast<int*>(ws + f.plans);
+  float* sums = reinterpret_cast<float*>(ws + f.sums);
+  float2* coef = reinterpret_cast<float2*>(ws + f.coef);
+  LevelTable lv[2];
+  for (int t = 0; t < 2; t++) {
+    for (int l = 0; l < ABR_MAX_LEVELS; l++) { lv[t].ptr[l] = nullptr; lv[t].H[l] = lv[t].W[l] = 0; lv[t].scale[l] = 0.f; }
+    lv[t].ptr[0] = const_cast<void*>(t == 0 ? teacher_map : student_map);
+    lv[t].H[0] = H; lv[t].W[0] = W; lv[t].scale[0] = spatial_scale;
+  }
+  int rc;
+  if (!workspace_has_plan) {
+    rc = v2_plan(lv[0], rois, nullptr, plans, R, PH, PW, sampling_ratio, st);
+    if (rc) return rc;
+  }
+  void* outs[2] = {pooled_old, pooled_new};
+  if (C % 4 == 0) rc = launch_fwd2<float, 4, 2>(lv, plans, rois, nullptr, outs, sums, C, R, PH, PW, sampling_ratio, st);
+  else rc = launch_fwd2<float, 1, 2>(lv, plans, rois, nullptr, outs, sums, C, R, PH, PW, sampling_ratio, st);
+  if (rc) return rc;
+  rc = ard_coeff_run(sums, ceil_div(C, 32 * (C % 4 == 0 ? 4 : 1)), coef, loss3, R, C, PH * PW, gamma, grad_scale, ws + f.ard, st);
+  if (rc) return rc;
+  if (!grad_student_map) return ABR_OK;
+  if (zero_init) ABR_CUDA_OK(cudaMemsetAsync(grad_student_map, 0, (size_t)B * C * H * W * sizeof(float), st));
+  LevelTable gl = lv[1];
+  gl.ptr[0] = grad_student_map;
+  if (C % 4 == 0) return launch_bwd2<float, 4, true>(gl, plans, rois, nullptr, pooled_old, pooled_new, coef, C, R, PH, PW, sampling_ratio, st);
+  return launch_bwd2<float, 1, true>(gl, plans, rois, nullptr, pooled_old, pooled_new, coef, C, R, PH, PW, sampling_ratio, st);
+}
+
+}  // extern "C"

@@ -54,6 +54,11 @@ enum abr_layout { ABR_NCHW = 0, ABR_NHWC = 1, ABR_NCHW_MAPS_NHWC_POOLED = 2 };
 
 ABR_API int abr_version(void);
 ABR_API const char* abr_last_error(void);
+/* Tuning switches for measurements and tests (process-wide; initial values from the environment variables ABR_ROI_V2,
+ * ABR_V2_PREFETCH, ABR_FWD_TMA, ABR_BWD_TMA, ABR_ARD_CLUSTER).  Keys: "roi_v2" (-1 automatic, 0 never, 1 whenever the
+ * output is at most 16x16: gather-form ROIAlign kernels instead of the TMA-staged ones), "v2_prefetch", "fwd_tma",
+ * "bwd_tma", "ard_cluster" (0 / 1).  They select between kernels that compute the same results. */
+ABR_API int abr_set_option(const char* key, int value);
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 ABR_API uint64_t abr_launch_count(void);
 
@@ -211,6 +216,28 @@ ABR_API int abr_ard_forward_backward(const void* f_old, const void* f_new, void*
                              int N, int C, int HW, float gamma, float grad_scale,
                              int dtype, int layout, void* workspace, size_t workspace_bytes,
                              abr_stream_t stream);
+/* ---------------------------------------------------------------- fused ARD step (pool teacher + student, loss, backward)
+ * One call for the RoI part of the distillation step of tools/train_incremental.py:84-115: the teacher's and the
+ * student's ROIAlign over the SAME RoIs (generalized_rcnn.py:121-167 -> roi_box_feature_extractors.py:44-48 for the
+ * teacher, train_incremental.py:93-95 for the student), the ARD loss (distillation/distillation.py:86-130) and the
+ * backward of the ARD loss through the student's ROIAlign (csrc/cuda/ROIAlign_cuda.cu:177-254).  Three kernels:
+ * both maps are pooled in one pass that also emits the per-position channel sums, a per-RoI kernel
+ * turns them into the loss and two coefficients per position, and the backward forms
+ * dL/df_new = ka*(f_new - f_old) + kb*f_new on the fly while scattering -- the ARD gradient tensor is never written
+ * or re-read and the pooled tensors are read once instead of three times.
+ *   teacher_map / student_map [B,H,W,C] and pooled_old / pooled_new [R,PH,PW,C]: ABR_NHWC, ABR_F32 only (other
+ *   combinations: ABR_ERR_UNSUPPORTED -- use the separate ops); the pooled tensors are written (the box head consumes them);
+ *   grad_student_map [B,H,W,C] (may be NULL: loss only) receives grad_scale * dL/d(student_map), zero-filled first
+ *   when zero_init != 0;  loss3 as in abr_ard_forward_backward;  PH, PW <= 16;  R > 0.
+ * workspace: 256-byte aligned, abr_roi_ard_fused_workspace_bytes(R, C, PH, PW) bytes (plans, channel sums, coefficients);
+ * workspace_has_plan != 0: the workspace was last used by this function for the SAME rois / sizes / scale (skips planning). */
+ABR_API size_t abr_roi_ard_fused_workspace_bytes(int R, int C, int PH, int PW);
+ABR_API int abr_roi_ard_fused(const void* teacher_map, const void* student_map, const float* rois, void* pooled_old,
+                              void* pooled_new, void* grad_student_map, float* loss3, int B, int C, int H, int W, int R,
+                              int PH, int PW, float spatial_scale, int sampling_ratio, float gamma, float grad_scale,
+                              int dtype, int layout, int zero_init, void* workspace, size_t workspace_bytes,
+                              int workspace_has_plan, abr_stream_t stream);
+
 /* data[i] *= (*scale_dev / expected) unless *scale_dev == expected (then no memory is touched):
  * lets the autograd backward apply an upstream gradient that differs from the grad_scale baked in. */
 ABR_API int abr_scale_if_needed(void* data, size_t n, const float* scale_dev, float expected, int dtype,
