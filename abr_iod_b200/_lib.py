@@ -163,7 +163,7 @@ def roi_align_workspace(R, PH, PW, max_h, device, channels_last=True, nchw_stagi
 
 
 def set_option(key: str, value: int) -> None:
-    """``abr_set_option``: kernel-family switches for measurements and tests ("roi_v2", "v2_prefetch", "fwd_tma", ...)."""
+    """``abr_set_option``: kernel-family switches for measurements and tests ("roi_v2", "fwd_tma", ...)."""
     check(lib().abr_set_option(key.encode(), int(value)))
 
 

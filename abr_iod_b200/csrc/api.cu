@@ -17,13 +17,13 @@ void set_error(const char* fmt, ...) {
 }
 
 // Tuning switches (abr_set_option): kernel-family selection for A/B measurements and tests.  Initial values come from
-// the environment once (ABR_ROI_V2, ABR_V2_PREFETCH, ABR_FWD_TMA, ABR_BWD_TMA, ABR_ARD_CLUSTER); -1 = automatic.
+// the environment once (ABR_ROI_V2, ABR_FWD_TMA, ABR_BWD_TMA, ABR_ARD_CLUSTER); -1 = automatic.
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
 }
 Options& options() {
-  static Options o = {env_int("ABR_ROI_V2", -1), env_int("ABR_V2_PREFETCH", 1), env_int("ABR_FWD_TMA", 1), env_int("ABR_BWD_TMA", 1),
+  static Options o = {env_int("ABR_ROI_V2", -1), env_int("ABR_FWD_TMA", 1), env_int("ABR_BWD_TMA", 1),
                       env_int("ABR_ARD_CLUSTER", 1)};
   return o;
 }
@@ -35,7 +35,6 @@ int abr_set_option(const char* key, int value) {
   ABR_REQUIRE(key, ABR_ERR_BAD_ARG, "set_option: null key");
   abr::Options& o = abr::options();
   if (!strcmp(key, "roi_v2")) o.roi_v2 = value;
-  else if (!strcmp(key, "v2_prefetch")) o.v2_prefetch = value;
   else if (!strcmp(key, "fwd_tma")) o.fwd_tma = value;
   else if (!strcmp(key, "bwd_tma")) o.bwd_tma = value;
   else if (!strcmp(key, "ard_cluster")) o.ard_cluster = value;

@@ -47,7 +47,6 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::mem
 // Process-wide tuning switches (api.cu: abr_set_option; initial values from the environment).
 struct Options {
   int roi_v2;       // -1: v2 kernels where the staged ones do not apply (output larger than 8x7); 0: never; 1: whenever supported
-  int v2_prefetch;  // L2 prefetch of the pooled tile in the v2 backward
   int fwd_tma, bwd_tma, ard_cluster;  // 0 disables the TMA-staged ROIAlign kernels / the cluster ARD kernels
 };
 Options& options();

@@ -1,11 +1,12 @@
 // roi_v2.cu -- kernels and launchers of the gather-form ROIAlign (device logic and design notes: roi_v2.cuh), and the
 // fused Attentive-RoI-Distillation step built on them (abr_roi_ard_fused):
 //     v2_plan_kernel      one warp per RoI -> per-RoI records
-//     v2_fwd_kernel<NT>   CTA = (RoI, slice of 32*V channels), one warp per bin column; NT = 2 pools the teacher and the
-//                         student map in one pass and emits the ARD channel sums of every position
+//     v2_fwd_kernel<NT>   CTA = (RoI, slice of 32*V channels), one warp per bin column (two for outputs wider than 8), each
+//                         with a private strip of shared memory; NT = 2 pools the teacher and the student map in one
+//                         pass and emits the ARD channel sums of every position
 //     ard_coeff_kernel    (ard.cu) softmaxes + per-position gradient coefficients + the loss, one small CTA per RoI
-//     v2_bwd_kernel<F>    CTA = (RoI, slice), warps walk the footprint's pixel columns; F = fused: the pooled gradient is
-//                         formed on the fly from the two pooled tensors and the coefficients
+//     v2_bwd_kernel<F>    CTA = (RoI, slice): the pooled-gradient tile goes to shared memory (F = fused: formed on the fly
+//                         from the two pooled tensors and the coefficients), then warps walk the footprint's pixel columns
 // Reference semantics: csrc/cuda/ROIAlign_cuda.cu:64-346, distillation/distillation.py:86-130,
 // tools/train_incremental.py:84-115 (teacher pooling, student pooling, ARD loss, backward into the student's map).
 #include <cstdlib>
@@ -43,7 +44,8 @@ struct V2FwdArgs {
 };
 
 template <typename T, int V, int NT>
-__global__ void __launch_bounds__(256, NT == 2 ? 2 : 3) v2_fwd_kernel(const __grid_constant__ V2FwdArgs<T, NT> a) {
+__global__ void __launch_bounds__(256, 2) v2_fwd_kernel(const __grid_constant__ V2FwdArgs<T, NT> a) {
+  extern __shared__ __align__(16) float v2_smem[];
   const int r = blockIdx.x / a.nslices, slice = blockIdx.x - r * a.nslices;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int* plan = a.plans + (size_t)r * a.stride;
@@ -67,8 +69,9 @@ __global__ void __launch_bounds__(256, NT == 2 ? 2 : 3) v2_fwd_kernel(const __gr
                                       a.PW, lane);
     return;
   }
+  float* strip = v2_smem + (size_t)warp * v2_strip_floats(V, NT);
   for (int pw = warp; pw < a.PW; pw += nw)
-    v2_fwd_column<T, V, NT>(plan, maps, outs, srs, r, pw, c, active, a.C, a.PH, a.PW, lane);
+    v2_fwd_column<T, V, NT>(plan, maps, outs, srs, strip, r, pw, c, active, a.C, a.PH, a.PW, lane);
 }
 
 template <typename T>
@@ -81,48 +84,38 @@ struct V2BwdArgs {
   const T* a;          // upstream gradient [R][PH][PW][C], or the teacher's pooled tensor (fused)
   const T* b;          // the student's pooled tensor (fused)
   const float2* coef;  // [R][PH*PW] (fused)
-  int C, PH, PW, ratio, nslices, prefetch;
+  int C, PH, PW, ratio, nslices;
 };
 
 template <typename T, int V, bool FUSED>
-__global__ void __launch_bounds__(256, FUSED ? 2 : 3) v2_bwd_kernel(const __grid_constant__ V2BwdArgs<T> a) {
+__global__ void __launch_bounds__(256, 2) v2_bwd_kernel(const __grid_constant__ V2BwdArgs<T> a) {
+  extern __shared__ __align__(16) float v2_smem[];
   const int r = blockIdx.x / a.nslices, slice = blockIdx.x - r * a.nslices;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int* plan = a.plans + (size_t)r * a.stride;
   const int4 h0 = __ldg(reinterpret_cast<const int4*>(plan));
   const int mode = h0.x, level = h0.z;
-  if (mode == V2_EMPTY) return;
+  if (mode == V2_EMPTY) return;  // (the whole CTA)
   const int nbin = a.PH * a.PW;
-  const size_t tile = ((size_t)r * nbin) * a.C + (size_t)slice * 32 * V;
-  if (a.prefetch) {
-    // The pixel-column warps of this CTA read the same bins in the same order, so without help the CTA pays one exposed
-    // DRAM latency per bin row: start the whole (RoI, slice) tile towards L2 now (one 128-byte line per thread and step).
-    const int lines_per_bin = (32 * V * (int)sizeof(T)) / 128;
-    const int nlines = nbin * lines_per_bin;
-    for (int i = threadIdx.x; i < nlines; i += blockDim.x) {
-      const int bin = i / lines_per_bin, q = i - bin * lines_per_bin;
-      const size_t off = tile + (size_t)bin * a.C + (size_t)q * (128 / sizeof(T));
-      if ((slice * 32 * V + q * (int)(128 / sizeof(T))) < a.C) {
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.a + off));
-        if (FUSED) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.b + off));
-      }
-    }
-  }
-  const int c = (slice * 32 + lane) * V;
-  if (c >= a.C) return;  // idle lane of a ragged last slice (no warp-level primitive below)
+  int c = (slice * 32 + lane) * V;
+  const bool active = c < a.C;
+  if (!active) c = 0;
   V2Grad<T, V, FUSED> src;
   src.a = a.a + (size_t)r * nbin * a.C + c;
   src.b = FUSED ? a.b + (size_t)r * nbin * a.C + c : nullptr;
   src.coef = FUSED ? a.coef + (size_t)r * nbin : nullptr;
+  v2_bwd_fill_tile<T, V, FUSED>(v2_smem, src, nbin, a.C, warp, nw, lane, active);
+  __syncthreads();
+  if (!active) return;  // idle lane of a ragged last slice (no warp-level primitive below)
   T* gmap = static_cast<T*>(a.lv.ptr[level]);
   if (mode == V2_GENERIC) {
     const RoiGeom g = roi_geometry(a.rois, a.levels, a.lv, r, a.PH, a.PW, a.ratio);
     for (int pw = warp; pw < a.PW; pw += nw)
-      v2_generic_bwd_column<T, V, FUSED>(g, a.lv.H[g.level], a.lv.W[g.level], gmap, src, pw, c, a.C, a.PH, a.PW);
+      v2_generic_bwd_column<T, V>(g, a.lv.H[g.level], a.lv.W[g.level], gmap, v2_smem, pw, c, a.C, a.PH, a.PW, lane);
     return;
   }
   const int FW = __ldg(plan + 7);
-  for (int k = warp; k < FW; k += nw) v2_bwd_pixcol<T, V, FUSED>(plan, gmap, src, k, c, a.C, a.PH, a.PW);
+  for (int k = warp; k < FW; k += nw) v2_bwd_pixcol<T, V>(plan, gmap, v2_smem, k, c, a.C, a.PH, a.PW, lane);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -148,7 +141,14 @@ static int launch_fwd2(const LevelTable* lv, const int* plans, const float* rois
   a.C = C; a.PH = PH; a.PW = PW; a.ratio = ratio; a.nslices = ceil_div(C, 32 * V);
   const long long blocks = (long long)R * a.nslices;
   ABR_REQUIRE(blocks <= 0x7fffffffLL, ABR_ERR_UNSUPPORTED, "roi_align_forward: too many (RoI, slice) tasks");
-  v2_fwd_kernel<T, V, NT><<<(unsigned)blocks, 32 * fwd_warps(PW), 0, st>>>(a);
+  const int nw = fwd_warps(PW);
+  const size_t smem = (size_t)nw * v2_strip_floats(V, NT) * sizeof(float);
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    ABR_CUDA_OK(cudaFuncSetAttribute(v2_fwd_kernel<T, V, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (int)v2_strip_floats(V, NT) * (int)sizeof(float)));
+    attr_set = true;
+  }
+  v2_fwd_kernel<T, V, NT><<<(unsigned)blocks, 32 * nw, smem, st>>>(a);
   ABR_CHECK_LAUNCH(NT == 2 ? "roi_align_forward (v2, teacher+student)" : "roi_align_forward (v2)");
   return ABR_OK;
 }
@@ -167,15 +167,19 @@ int v2_forward(const LevelTable& lv, const int* plans, const float* rois, const 
 template <typename T, int V, bool FUSED>
 static int launch_bwd2(const LevelTable& lv, const int* plans, const float* rois, const int32_t* levels, const void* a_, const void* b_,
                        const float2* coef, int C, int R, int PH, int PW, int ratio, cudaStream_t st) {
-  const bool prefetch = options().v2_prefetch != 0;  // A/B switch for measurements
   V2BwdArgs<T> a;
   a.lv = lv; a.plans = plans; a.stride = v2_plan_words(PH, PW); a.rois = rois; a.levels = levels;
   a.a = static_cast<const T*>(a_); a.b = static_cast<const T*>(b_); a.coef = coef;
   a.C = C; a.PH = PH; a.PW = PW; a.ratio = ratio; a.nslices = ceil_div(C, 32 * V);
-  a.prefetch = (prefetch && (32 * V * sizeof(T)) % 128 == 0 && (C * sizeof(T)) % 128 == 0) ? 1 : 0;
   const long long blocks = (long long)R * a.nslices;
   ABR_REQUIRE(blocks <= 0x7fffffffLL, ABR_ERR_UNSUPPORTED, "roi_align_backward: too many (RoI, slice) tasks");
-  v2_bwd_kernel<T, V, FUSED><<<(unsigned)blocks, 256, 0, st>>>(a);
+  const size_t smem = (size_t)PH * PW * 32 * V * sizeof(float);  // the (RoI, slice) gradient tile
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    ABR_CUDA_OK(cudaFuncSetAttribute(v2_bwd_kernel<T, V, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  v2_bwd_kernel<T, V, FUSED><<<(unsigned)blocks, 256, smem, st>>>(a);
   ABR_CHECK_LAUNCH(FUSED ? "roi_align_backward (v2, fused ARD gradient)" : "roi_align_backward (v2)");
   return ABR_OK;
 }
@@ -186,7 +190,8 @@ int v2_backward(const LevelTable& lv, const int* plans, const float* rois, const
     if (C % 4 == 0) return launch_bwd2<float, 4, false>(lv, plans, rois, levels, gout, nullptr, nullptr, C, R, PH, PW, ratio, st);
     return launch_bwd2<float, 1, false>(lv, plans, rois, levels, gout, nullptr, nullptr, C, R, PH, PW, ratio, st);
   }
-  if (C % 8 == 0) return launch_bwd2<__nv_bfloat16, 8, false>(lv, plans, rois, levels, gout, nullptr, nullptr, C, R, PH, PW, ratio, st);
+  if (C % 8 == 0 && (size_t)PH * PW * 32 * 8 * sizeof(float) <= 227 * 1024)  // the tile of 8-channel lanes must fit shared memory
+    return launch_bwd2<__nv_bfloat16, 8, false>(lv, plans, rois, levels, gout, nullptr, nullptr, C, R, PH, PW, ratio, st);
   return launch_bwd2<__nv_bfloat16, 1, false>(lv, plans, rois, levels, gout, nullptr, nullptr, C, R, PH, PW, ratio, st);
 }
 

@@ -8,17 +8,21 @@
 //        out[ph][pw] = (1/count) * sum_y Wy[ph][y] * sum_x Wx[pw][x] * V[y][x]            (exactly)
 //     with per-axis tables Wy / Wx that depend on the RoI only.  plan kernel: one 16-word record per bin row, per bin
 //     column and per footprint pixel column:  { first index | count << 16, up to 15 weights }.
-//   * FORWARD, a warp owns (RoI, bin column pw, 32*V channels): it walks the bins ph = 0..PH-1; a bin needs the rows
-//     ylo .. ylo+ny-1 of  T[y] = sum_x Wx[pw][x] * V[y][x]  (nx coalesced 512-byte loads per row).  Sample rows grow
-//     monotonically with ph, and a bin's first row is never more than one row behind the previous bin's last one, so a
-//     register cache of the LAST TWO rows of T serves every re-use: each footprint pixel of the column is loaded once,
-//     for thin bins (several bins inside one map pixel, the P=14 case) as well as for fat ones -- no per-bin
-//     accumulators, no shared memory.
-//   * BACKWARD is the transposed gather: a warp owns (RoI, footprint PIXEL column x, 32*V channels).  For every bin row
-//     it forms  G = sum_{pw covering x} Wx[pw][x] * g[ph][pw]  (the bins are read, L1-resident across the warps of the
-//     CTA), adds Wy[ph][y] * G into a two-row cache of pixel sums and, when a row leaves the cache, issues ONE vector
-//     reduction for that pixel: every footprint pixel of a RoI is reduced exactly once per channel slice (the reference
-//     issues 4*g*g scalar atomicAdds per output element; round 1 issued one reduction per pixel per covering column).
+//   * FORWARD, a warp owns (RoI, bin column pw, 32*V channels).  It works in STRIPS of up to kV2Rows map rows: phase 1
+//     computes  T[y] = sum_x Wx[pw][x] * V[y][x]  for the strip's rows -- four rows at a time, all of their loads
+//     (nx coalesced 512-byte requests per row) issued before the first is used, so a warp keeps up to 16 requests in
+//     flight instead of one dependent gather after another -- into a lane-private strip of shared memory (every lane
+//     reads back only what it wrote: no barrier); phase 2 emits every bin whose rows lie inside the strip,
+//     out[ph] = sum_y Wy[ph][y] * T[y].  Sample rows grow monotonically with ph, so the next strip starts at the first
+//     row of the first bin not yet emitted; each footprint pixel of the column is loaded once (plus a few rows where
+//     strips overlap), for thin bins (several bins inside one map pixel, the P=14 case) as well as for fat ones.
+//   * BACKWARD is the transposed gather.  A CTA owns (RoI, 32*V channels): phase 1 streams the RoI's pooled-gradient
+//     tile [PH*PW][32*V] into shared memory with independent coalesced loads (FUSED: forms it on the fly, see below);
+//     phase 2: a warp owns a footprint PIXEL column x; for every bin row it forms
+//     G = sum_{pw covering x} Wx[pw][x] * g[ph][pw]  from the tile, adds Wy[ph][y] * G into a two-row cache of pixel
+//     sums and, when a row leaves the cache, issues ONE vector reduction for that pixel: every footprint pixel of a RoI
+//     is reduced exactly once per channel slice (the reference issues 4*g*g scalar atomicAdds per output element;
+//     round 1 issued one reduction per pixel per covering column).
 //   * NT = 2 forward pools the teacher and the student map with the same plan in one pass and emits the three
 //     per-position channel sums the ARD loss needs (sum f_old^2, sum f_new^2, sum (f_new - f_old)^2); the FUSED
 //     backward reads both pooled tensors, forms dL/df_new = ka*(f_new - f_old) + kb*f_new on the fly from per-position
@@ -258,13 +262,48 @@ ABR_DEV void v2_emit_bin(float (&acc)[NT][V], float inv_count, T* const (&o)[NT]
   }
 }
 
+// Lane-private / CTA-shared fp32 staging in shared memory: V consecutive floats of one lane, 16-byte accesses when V % 4 == 0.
+template <int V>
+ABR_DEV void v2_sm_store(float* p, const float (&v)[V]) {
+#ifndef ABR_EMU
+  if (V % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < V / 4; i++) reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    return;
+  }
+#endif
+#pragma unroll
+  for (int i = 0; i < V; i++) p[i] = v[i];
+}
+template <int V>
+ABR_DEV void v2_sm_load(const float* p, float (&v)[V]) {
+#ifndef ABR_EMU
+  if (V % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < V / 4; i++) {
+      const float4 t = reinterpret_cast<const float4*>(p)[i];
+      v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+    return;
+  }
+#endif
+#pragma unroll
+  for (int i = 0; i < V; i++) v[i] = p[i];
+}
+
+constexpr int kV2Rows = 16;  // map rows per strip (>= kV2Sup + 1, so the widest bin always fits one strip)
+
+// Floats of shared memory one forward warp needs: [NT][kV2Rows][32 lanes][V].
+ABR_HOSTDEV size_t v2_strip_floats(int V, int NT) { return (size_t)NT * kV2Rows * 32 * V; }
+
 // One bin column of one RoI from its plan.  maps[t]: the level's map of tensor t ([B][H][W][C]); outs[t]: pooled tensor
-// ([R][PH][PW][C]); c: first channel of this lane; sums_rs: &sums[(r * nslices + slice) * PH*PW * 3] (NT == 2).
+// ([R][PH][PW][C]); c: first channel of this lane; sums_rs: &sums[(r * nslices + slice) * PH*PW * 3] (NT == 2);
+// strip: this WARP's v2_strip_floats(V, NT) floats of shared memory.
 template <typename T, int V, int NT>
 ABR_DEV void v2_fwd_column(const int* __restrict__ plan, const T* const (&maps)[NT], T* const (&outs)[NT], float* sums_rs,
-                           int r, int pw, int c, bool active, int C, int PH, int PW, int lane) {
-  const int4 h0 = ABR_LDG4I(plan), h1 = ABR_LDG4I(plan + 4);
-  const int mode = h0.x, batch = h0.y, H = h0.w, W = h1.x;
+                           float* strip, int r, int pw, int c, bool active, int C, int PH, int PW, int lane) {
+  const int4 h0 = ABR_LDG4I(plan), h1 = ABR_LDG4I(plan + 4), h2 = ABR_LDG4I(plan + 8);
+  const int mode = h0.x, batch = h0.y, H = h0.w, W = h1.x, Y1 = h2.y;
   const float inv_count = __int_as_float(h1.y);
   const size_t pix = (size_t)C, binstride = (size_t)PW * C;
   T* o[NT];
@@ -273,8 +312,17 @@ ABR_DEV void v2_fwd_column(const int* __restrict__ plan, const T* const (&maps)[
   float* sb = NT == 2 ? sums_rs + (size_t)pw * 3 : nullptr;
   const V2Rec col = v2_load_rec(v2_col_rec(plan, pw));
   const int nx = mode == V2_PLAN ? col.n : 0;
-  if (nx == 0) {  // no sample of this column (or of the whole RoI) falls inside the map
-    for (int ph = 0; ph < PH; ph++) {
+  const size_t rowstride = (size_t)W * C;
+  const T* base[NT];
+#pragma unroll
+  for (int t = 0; t < NT; t++) base[t] = maps[t] + ((size_t)batch * H * W + col.lo) * C + c;
+  float* mine = strip + (size_t)lane * V;  // [t][row] at (t * kV2Rows + row) * 32 * V
+  constexpr int RB = V >= 8 ? 2 : 4;       // rows whose loads are in flight together (register budget)
+
+  int ph = 0;
+  while (ph < PH) {
+    V2Rec bin = v2_load_rec(v2_bin_rec(plan, PW, ph));
+    if (nx == 0 || bin.n == 0) {  // no sample of this bin (column, RoI) falls inside the map
       float z[NT][V];
 #pragma unroll
       for (int t = 0; t < NT; t++)
@@ -284,79 +332,82 @@ ABR_DEV void v2_fwd_column(const int* __restrict__ plan, const T* const (&maps)[
 #pragma unroll
       for (int t = 0; t < NT; t++) o[t] += binstride;
       if (NT == 2) sb += (size_t)PW * 3;
+      ph++;
+      continue;
     }
-    return;
-  }
-  const size_t rowstride = (size_t)W * C;
-  const T* base[NT];
+    // ---- phase 1: T of the rows ystart .. ystart + nrows - 1
+    const int ystart = bin.lo;
+    const int nrows = Y1 - ystart + 1 < kV2Rows ? Y1 - ystart + 1 : kV2Rows;
 #pragma unroll
-  for (int t = 0; t < NT; t++) base[t] = maps[t] + ((size_t)batch * H * W + col.lo) * C + c;
-  const float w3 = nx > 3 ? v2_rec_w(col, 3) : 0.f;
-
-  float Ta[NT][V], Tb[NT][V];  // T of rows ya (older) and yb (newest)
-  int ya = -1, yb = -1;
+    for (int t = 0; t < NT; t++) {
+      const T* colbase = base[t] + (size_t)ystart * rowstride;
+      for (int i0 = 0; i0 < nrows; i0 += RB) {
+        float Tacc[RB][V];
 #pragma unroll
-  for (int t = 0; t < NT; t++)
+        for (int j = 0; j < RB; j++)
 #pragma unroll
-    for (int k = 0; k < V; k++) Ta[t][k] = Tb[t][k] = 0.f;
-
-  for (int ph = 0; ph < PH; ph++) {
-    const V2Rec bin = v2_load_rec(v2_bin_rec(plan, PW, ph));
-    float acc[NT][V];
+          for (int k = 0; k < V; k++) Tacc[j][k] = 0.f;
+        for (int kg = 0; kg < nx; kg += 4) {  // warp-uniform; one trip unless the column is wider than four map pixels
+          float v[RB][4][V];
 #pragma unroll
-    for (int t = 0; t < NT; t++)
+          for (int j = 0; j < RB; j++) {
+            if (i0 + j < nrows) {
+              const T* p = colbase + (size_t)(i0 + j) * rowstride + (size_t)kg * pix;
+              VecIO<T, V>::load(p, v[j][0]);
+              if (kg + 1 < nx) VecIO<T, V>::load(p + pix, v[j][1]);
+              if (kg + 2 < nx) VecIO<T, V>::load(p + 2 * pix, v[j][2]);
+              if (kg + 3 < nx) VecIO<T, V>::load(p + 3 * pix, v[j][3]);
+            }
+          }
+          const float w0 = v2_rec_w(col, kg);
+          const float w1 = kg + 1 < nx ? v2_rec_w(col, kg + 1) : 0.f;
+          const float w2 = kg + 2 < nx ? v2_rec_w(col, kg + 2) : 0.f;
+          const float w3 = kg + 3 < nx ? v2_rec_w(col, kg + 3) : 0.f;
 #pragma unroll
-      for (int k = 0; k < V; k++) acc[t][k] = 0.f;
-    for (int i = 0; i < bin.n; i++) {
-      const float wy = v2_rec_w(bin, i);
-      if (wy == 0.f) continue;  // e.g. the upper tap of a sample that sits exactly on a map row
-      const int y = bin.lo + i;
-      if (y != yb && y != ya) {
-        // a row not in the cache: it is newer than both (rows only grow), the older one is never needed again
-        float v[NT][4][V];
+          for (int j = 0; j < RB; j++) {
+            if (i0 + j < nrows) {
 #pragma unroll
-        for (int t = 0; t < NT; t++) {
-          const T* p = base[t] + (size_t)y * rowstride;
-          VecIO<T, V>::load(p, v[t][0]);
-          if (nx > 1) VecIO<T, V>::load(p + pix, v[t][1]);
-          if (nx > 2) VecIO<T, V>::load(p + 2 * pix, v[t][2]);
-          if (nx > 3) VecIO<T, V>::load(p + 3 * pix, v[t][3]);
-        }
-#pragma unroll
-        for (int t = 0; t < NT; t++) {
-#pragma unroll
-          for (int k = 0; k < V; k++) {
-            Ta[t][k] = Tb[t][k];
-            float s = col.w0 * v[t][0][k];
-            if (nx > 1) s = fmaf(col.w1, v[t][1][k], s);
-            if (nx > 2) s = fmaf(col.w2, v[t][2][k], s);
-            if (nx > 3) s = fmaf(w3, v[t][3][k], s);
-            Tb[t][k] = s;
+              for (int k = 0; k < V; k++) {
+                float s = fmaf(w0, v[j][0][k], Tacc[j][k]);
+                if (kg + 1 < nx) s = fmaf(w1, v[j][1][k], s);
+                if (kg + 2 < nx) s = fmaf(w2, v[j][2][k], s);
+                if (kg + 3 < nx) s = fmaf(w3, v[j][3][k], s);
+                Tacc[j][k] = s;
+              }
+            }
           }
         }
-        for (int j = 4; j < nx; j++) {  // warp-uniform: columns wider than four map pixels
-          const float wj = v2_rec_w(col, j);
 #pragma unroll
-          for (int t = 0; t < NT; t++) {
-            float x[V];
-            VecIO<T, V>::load(base[t] + (size_t)y * rowstride + (size_t)j * pix, x);
-#pragma unroll
-            for (int k = 0; k < V; k++) Tb[t][k] = fmaf(wj, x[k], Tb[t][k]);
-          }
-        }
-        ya = yb;
-        yb = y;
+        for (int j = 0; j < RB; j++)
+          if (i0 + j < nrows) v2_sm_store<V>(mine + (size_t)(t * kV2Rows + i0 + j) * 32 * V, Tacc[j]);
       }
-      const bool newest = y == yb;
+    }
+    // ---- phase 2: every bin whose rows lie inside the strip (at least the one that started it: n <= kV2Sup < kV2Rows)
+    while (true) {
+      float acc[NT][V];
 #pragma unroll
       for (int t = 0; t < NT; t++)
 #pragma unroll
-        for (int k = 0; k < V; k++) acc[t][k] = fmaf(wy, newest ? Tb[t][k] : Ta[t][k], acc[t][k]);
-    }
-    v2_emit_bin<T, V, NT>(acc, inv_count, o, active, sb, lane);
+        for (int k = 0; k < V; k++) acc[t][k] = 0.f;
+      const int off = bin.lo - ystart;
+      for (int i = 0; i < bin.n; i++) {
+        const float wy = v2_rec_w(bin, i);
 #pragma unroll
-    for (int t = 0; t < NT; t++) o[t] += binstride;
-    if (NT == 2) sb += (size_t)PW * 3;
+        for (int t = 0; t < NT; t++) {
+          float x[V];
+          v2_sm_load<V>(mine + (size_t)(t * kV2Rows + off + i) * 32 * V, x);
+#pragma unroll
+          for (int k = 0; k < V; k++) acc[t][k] = fmaf(wy, x[k], acc[t][k]);
+        }
+      }
+      v2_emit_bin<T, V, NT>(acc, inv_count, o, active, sb, lane);
+#pragma unroll
+      for (int t = 0; t < NT; t++) o[t] += binstride;
+      if (NT == 2) sb += (size_t)PW * 3;
+      if (++ph >= PH) break;
+      bin = v2_load_rec(v2_bin_rec(plan, PW, ph));
+      if (bin.n == 0 || bin.lo + bin.n > ystart + nrows) break;  // an empty bin or one that needs a new strip: outer loop
+    }
   }
 }
 
@@ -435,10 +486,30 @@ struct V2Grad {
   }
 };
 
-// One footprint pixel column x = X0 + k of one RoI.  gmap: the level's gradient map [B][H][W][C].
+// Phase 1 of the backward: warp `warp` of `nw` brings the bins warp, warp + nw, ... of this (RoI, slice) gradient tile into
+// shared memory -- tile[(bin * 32 + lane) * V .. + V) -- four bins' loads in flight at a time.  Lanes of a ragged last
+// slice (inactive) store zeros.
 template <typename T, int V, bool FUSED>
-ABR_DEV void v2_bwd_pixcol(const int* __restrict__ plan, T* gmap, const V2Grad<T, V, FUSED>& src, int k, int c, int C, int PH,
-                           int PW) {
+ABR_DEV void v2_bwd_fill_tile(float* tile, const V2Grad<T, V, FUSED>& src, int nbin, int C, int warp, int nw, int lane, bool active) {
+  float* mine = tile + (size_t)lane * V;
+  for (int b0 = warp; b0 < nbin; b0 += 4 * nw) {
+    float g[4][V];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+#pragma unroll
+      for (int k = 0; k < V; k++) g[j][k] = 0.f;
+      if (active && b0 + j * nw < nbin) src.load(b0 + j * nw, (size_t)C, g[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (b0 + j * nw < nbin) v2_sm_store<V>(mine + (size_t)(b0 + j * nw) * 32 * V, g[j]);
+  }
+}
+
+// Phase 2: one footprint pixel column x = X0 + k of one RoI.  gmap: the level's gradient map [B][H][W][C]; tile: the
+// (RoI, slice) gradient tile in shared memory.
+template <typename T, int V>
+ABR_DEV void v2_bwd_pixcol(const int* __restrict__ plan, T* gmap, const float* tile, int k, int c, int C, int PH, int PW, int lane) {
   const int4 h0 = ABR_LDG4I(plan), h1 = ABR_LDG4I(plan + 4);
   const int batch = h0.y, H = h0.w, W = h1.x, X0 = h1.z;
   const float inv_count = __int_as_float(h1.y);
@@ -448,6 +519,7 @@ ABR_DEV void v2_bwd_pixcol(const int* __restrict__ plan, T* gmap, const V2Grad<T
   const float wq3 = nq > 3 ? v2_rec_w(px, 3) : 0.f;
   const size_t rowstride = (size_t)W * C;
   T* gin = gmap + ((size_t)batch * H * W + (X0 + k)) * C + c;
+  const float* mine = tile + (size_t)lane * V;
   float Sa[V], Sb[V];
   int ya = -1, yb = -1;
 #pragma unroll
@@ -459,11 +531,11 @@ ABR_DEV void v2_bwd_pixcol(const int* __restrict__ plan, T* gmap, const V2Grad<T
     float G[V];
     {
       float g0[V], g1[V], g2[V], g3[V];
-      const int b0 = ph * PW + px.lo;
-      src.load(b0, (size_t)C, g0);
-      if (nq > 1) src.load(b0 + 1, (size_t)C, g1);
-      if (nq > 2) src.load(b0 + 2, (size_t)C, g2);
-      if (nq > 3) src.load(b0 + 3, (size_t)C, g3);
+      const float* t0 = mine + (size_t)(ph * PW + px.lo) * 32 * V;
+      v2_sm_load<V>(t0, g0);
+      if (nq > 1) v2_sm_load<V>(t0 + 32 * V, g1);
+      if (nq > 2) v2_sm_load<V>(t0 + 2 * 32 * V, g2);
+      if (nq > 3) v2_sm_load<V>(t0 + 3 * 32 * V, g3);
 #pragma unroll
       for (int i = 0; i < V; i++) {
         float s = px.w0 * g0[i];
@@ -475,7 +547,7 @@ ABR_DEV void v2_bwd_pixcol(const int* __restrict__ plan, T* gmap, const V2Grad<T
       for (int j = 4; j < nq; j++) {
         const float wj = v2_rec_w(px, j);
         float gj[V];
-        src.load(b0 + j, (size_t)C, gj);
+        v2_sm_load<V>(t0 + (size_t)j * 32 * V, gj);
 #pragma unroll
         for (int i = 0; i < V; i++) G[i] = fmaf(wj, gj[i], G[i]);
       }
@@ -504,15 +576,15 @@ ABR_DEV void v2_bwd_pixcol(const int* __restrict__ plan, T* gmap, const V2Grad<T
   if (yb >= 0) VecIO<T, V>::red_add(gin + (size_t)yb * rowstride, Sb);
 }
 
-// Per-sample backward of one bin column (ROIAlign_cuda.cu:177-254) for GENERIC RoIs.
-template <typename T, int V, bool FUSED>
-ABR_DEV void v2_generic_bwd_column(const RoiGeom& g, int H, int W, T* gmap, const V2Grad<T, V, FUSED>& src, int pw, int c,
-                                   int C, int PH, int PW) {
+// Per-sample backward of one bin column (ROIAlign_cuda.cu:177-254) for GENERIC RoIs, gradients from the tile.
+template <typename T, int V>
+ABR_DEV void v2_generic_bwd_column(const RoiGeom& g, int H, int W, T* gmap, const float* tile, int pw, int c, int C, int PH, int PW,
+                                   int lane) {
   const float fH = (float)H, fW = (float)W;
   T* img = gmap + (size_t)g.batch * H * W * C + c;
   for (int ph = 0; ph < PH; ph++) {
     float top[V];
-    src.load(ph * PW + pw, (size_t)C, top);
+    v2_sm_load<V>(tile + ((size_t)(ph * PW + pw) * 32 + lane) * V, top);
     for (int iy = 0; iy < g.grid_h; iy++) {
       float y = v2_sample_coord(g.start_h, g.bin_h, ph, iy, g.grid_h);
       if (y < -1.0f || y > fH) continue;

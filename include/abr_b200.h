@@ -55,8 +55,8 @@ enum abr_layout { ABR_NCHW = 0, ABR_NHWC = 1, ABR_NCHW_MAPS_NHWC_POOLED = 2 };
 ABR_API int abr_version(void);
 ABR_API const char* abr_last_error(void);
 /* Tuning switches for measurements and tests (process-wide; initial values from the environment variables ABR_ROI_V2,
- * ABR_V2_PREFETCH, ABR_FWD_TMA, ABR_BWD_TMA, ABR_ARD_CLUSTER).  Keys: "roi_v2" (-1 automatic, 0 never, 1 whenever the
- * output is at most 16x16: gather-form ROIAlign kernels instead of the TMA-staged ones), "v2_prefetch", "fwd_tma",
+ * ABR_FWD_TMA, ABR_BWD_TMA, ABR_ARD_CLUSTER).  Keys: "roi_v2" (-1 automatic, 0 never, 1 whenever the
+ * output is at most 16x16: gather-form ROIAlign kernels instead of the TMA-staged ones), "fwd_tma",
  * "bwd_tma", "ard_cluster" (0 / 1).  They select between kernels that compute the same results. */
 ABR_API int abr_set_option(const char* key, int value);
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */

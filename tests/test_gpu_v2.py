@@ -262,6 +262,33 @@ def test_fused_upstream_scale_head_gradient_and_no_grad():
     assert torch.equal(g1, ss.grad)
 
 
+def ard_sign_allowance(f_old, f_new, sl, gamma, thr=3e-5):
+    """The pad term of ARD has sign(A_new - A_old) in its gradient (distillation.py:115-116: L1 loss).  Where that
+    difference is below what fp32 resolves (|d| < thr * A_old; the attention values carry ~1e-6..1e-5 relative error in
+    ANY fp32 evaluation, the reference's included), either sign is a correct fp32 answer.  Returns, for the channel slice
+    ``sl``, the exact bound [R,c,P,P] on how much dL/df_new changes when those signs flip:
+        |delta dF[c,j]| <= (4*gamma*|F[c,j]| / (C*N)) * s_j * ([j ambiguous] + sum_{i ambiguous} s_i)
+    (from dF = (2F/C)*HW*s_j*(g_j - sum_k g_k s_k), g = gamma*sign(d)/(N*HW)).  float64 torch is the checker here."""
+    N, C, PH, PW = f_new.shape
+    HW = PH * PW
+    mo = (f_old.double() ** 2).mean(1).flatten(1)
+    mn = (f_new.double() ** 2).mean(1).flatten(1)
+    a_old = HW * torch.softmax(mo, 1)
+    s_new = torch.softmax(mn, 1)
+    amb = ((HW * s_new - a_old).abs() < thr * a_old).double()
+    factor = s_new * (amb + (amb * s_new).sum(1, keepdim=True))  # [N, HW]
+    allow = (4.0 * gamma / (C * N)) * f_new[:, sl].double().abs() * factor.view(N, 1, PH, PW)
+    return allow.float().cpu().numpy(), int(amb.sum().item())
+
+
+def close_allow(a, ref, allow, rel):
+    a, ref = np.asarray(a, np.float64), np.asarray(ref, np.float64)
+    scale = np.abs(ref).max()
+    err = np.abs(a - ref)
+    ok = err <= rel * scale + rel * np.abs(ref) + 1.01 * np.asarray(allow, np.float64)
+    assert ok.all(), "max err %g (scale %g) at %s" % (err[~ok].max(), scale, np.unravel_index(np.argmax(err * ~ok), err.shape))
+
+
 @pytest.mark.parametrize("P", [14, 7])
 def test_fused_full_size_config1(P):
     """configs[0] at full size through the fused call; compared with (a) the separate ops of this library over all
@@ -289,5 +316,9 @@ def test_fused_full_size_config1(P):
     assert abs(loss - rl) <= 1e-5 * abs(rl), (loss, rl)
     sl = slice(96, 160)
     rg = oracle.roi_align_backward(np.ascontiguousarray(dfn[:, sl]), rois, 1 / 16, P, P, B, sl.stop - sl.start, H, W, 0)
-    close(grad[:, sl].cpu().numpy(), rg, 2e-5)
-    close(st.grad[:, sl].cpu().numpy(), rg, 2e-5)
+    # positions whose sign(A_new - A_old) fp32 cannot resolve: their exact effect on the map gradient is allowed on top
+    allow, n_amb = ard_sign_allowance(u_old.detach(), u_new.detach(), sl, 1.0)
+    assert n_amb < 0.01 * R * P * P
+    allow_map = oracle.roi_align_backward(allow, rois, 1 / 16, P, P, B, sl.stop - sl.start, H, W, 0)
+    close_allow(grad[:, sl].cpu().numpy(), rg, allow_map, 2e-5)
+    close_allow(st.grad[:, sl].cpu().numpy(), rg, allow_map, 2e-5)

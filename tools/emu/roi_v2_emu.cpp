@@ -48,6 +48,7 @@ static void fwd_t(const int* plans, const float* rois, const float* m0, const fl
   float* outs[NT];
   maps[0] = m0; outs[0] = o0;
   if (NT == 2) { maps[NT - 1] = m1; outs[NT - 1] = o1; }
+  float* strip = new float[v2_strip_floats(V, NT)];  // one warp's strip (lanes run one after the other, each in its own columns)
   for (int r = 0; r < R; r++)
     for (int slice = 0; slice < nslices; slice++)
       for (int pw = 0; pw < PW; pw++)
@@ -61,9 +62,10 @@ static void fwd_t(const int* plans, const float* rois, const float* m0, const fl
             const RoiGeom g = roi_geometry(rois, nullptr, lv, r, PH, PW, ratio);
             v2_generic_fwd_column<float, V, NT>(g, H, W, maps, outs, srs, r, pw, c, active, C, PH, PW, lane);
           } else {
-            v2_fwd_column<float, V, NT>(plan, maps, outs, srs, r, pw, c, active, C, PH, PW, lane);
+            v2_fwd_column<float, V, NT>(plan, maps, outs, srs, strip, r, pw, c, active, C, PH, PW, lane);
           }
         }
+  delete[] strip;
 }
 
 extern "C" __attribute__((visibility("default"))) void emu_fwd(const int* plans, const float* rois, const float* m0, const float* m1, float* o0,
@@ -86,27 +88,38 @@ static void bwd_t(const int* plans, const float* rois, float* gmap, const float*
   const LevelTable lv = one_level(nullptr, H, W, scale);
   const size_t stride = v2_plan_words(PH, PW);
   const int nslices = (C + 32 * V - 1) / (32 * V);
-  const int nwarps = 8;
+  const int nwarps = 8, nbin = PH * PW;
+  float* tile = new float[(size_t)nbin * 32 * V];
   for (int r = 0; r < R; r++)
-    for (int slice = 0; slice < nslices; slice++)
-      for (int warp = 0; warp < nwarps; warp++)
-        for (int lane = 0; lane < 32; lane++) {
-          const int* plan = plans + (size_t)r * stride;
-          const int c = (slice * 32 + lane) * V;
-          if (c >= C) continue;
-          V2Grad<float, V, FUSED> src;
-          src.a = a + (size_t)r * PH * PW * C + c;
-          src.b = FUSED ? b + (size_t)r * PH * PW * C + c : nullptr;
-          src.coef = FUSED ? reinterpret_cast<const float2*>(coef) + (size_t)r * PH * PW : nullptr;
-          const int mode = plan[0];
-          if (mode == V2_GENERIC) {
-            const RoiGeom g = roi_geometry(rois, nullptr, lv, r, PH, PW, ratio);
-            for (int pw = warp; pw < PW; pw += nwarps) v2_generic_bwd_column<float, V, FUSED>(g, H, W, gmap, src, pw, c, C, PH, PW);
-          } else if (mode == V2_PLAN) {
-            const int FW = plan[7];
-            for (int k = warp; k < FW; k += nwarps) v2_bwd_pixcol<float, V, FUSED>(plan, gmap, src, k, c, C, PH, PW);
+    for (int slice = 0; slice < nslices; slice++) {
+      const int* plan = plans + (size_t)r * stride;
+      const int mode = plan[0];
+      if (mode == V2_EMPTY) continue;
+      for (int phase = 0; phase < 2; phase++)  // __syncthreads() between filling the tile and walking the pixel columns
+        for (int warp = 0; warp < nwarps; warp++)
+          for (int lane = 0; lane < 32; lane++) {
+            int c = (slice * 32 + lane) * V;
+            const bool active = c < C;
+            if (!active) c = 0;
+            V2Grad<float, V, FUSED> src;
+            src.a = a + (size_t)r * nbin * C + c;
+            src.b = FUSED ? b + (size_t)r * nbin * C + c : nullptr;
+            src.coef = FUSED ? reinterpret_cast<const float2*>(coef) + (size_t)r * nbin : nullptr;
+            if (phase == 0) {
+              v2_bwd_fill_tile<float, V, FUSED>(tile, src, nbin, C, warp, nwarps, lane, active);
+              continue;
+            }
+            if (!active) continue;
+            if (mode == V2_GENERIC) {
+              const RoiGeom g = roi_geometry(rois, nullptr, lv, r, PH, PW, ratio);
+              for (int pw = warp; pw < PW; pw += nwarps) v2_generic_bwd_column<float, V>(g, H, W, gmap, tile, pw, c, C, PH, PW, lane);
+            } else {
+              const int FW = plan[7];
+              for (int k = warp; k < FW; k += nwarps) v2_bwd_pixcol<float, V>(plan, gmap, tile, k, c, C, PH, PW, lane);
+            }
           }
-        }
+    }
+  delete[] tile;
 }
 
 extern "C" __attribute__((visibility("default"))) void emu_bwd(const int* plans, const float* rois, float* gmap, const float* a, const float* b,

@@ -59,11 +59,8 @@ def run(tag, B, C, H, W, R, P, im_w, im_h):
         g = torch.randn_like(f_new)
         res[key + "_fwd_with_plan_ms"] = timeit(lambda: roi_align_forward(t, rois, scale, P, P, 0))
         res[key + "_fwd_ms"] = timeit(lambda: roi_align_forward(s, rois, scale, P, P, 0, plan=plan))
-        for pf in ((1, 0) if v2 else (1,)):
-            _lib.set_option("v2_prefetch", pf)
-            res[key + "_bwd_ms" + ("" if pf else "_noprefetch")] = timeit(
-                lambda: roi_align_backward(g, rois, scale, P, P, B, C, H, W, 0, layout=_lib.ABR_NHWC, plan=plan))
-        _lib.set_option("v2_prefetch", 1)
+        res[key + "_bwd_ms"] = timeit(
+            lambda: roi_align_backward(g, rois, scale, P, P, B, C, H, W, 0, layout=_lib.ABR_NHWC, plan=plan))
         res["ard_ms"] = timeit(lambda: _ard_launch(f_old, f_new, 1.0, True))
         del f_old, f_new, g
     _lib.set_option("roi_v2", -1)
@@ -84,9 +81,6 @@ def run(tag, B, C, H, W, R, P, im_w, im_h):
     res["fused_total_ms"] = timeit(fused)
     res["fused_plan_reused_ms"] = timeit(lambda: fused(True, 1))
     res["fused_forward_only_ms"] = timeit(lambda: fused(False, 1))
-    _lib.set_option("v2_prefetch", 0)
-    res["fused_total_noprefetch_ms"] = timeit(fused)
-    _lib.set_option("v2_prefetch", 1)
     pooled = R * C * P * P * 4
     fmap = B * C * H * W * 4
     res["algorithmic_bytes_composite"] = 3 * fmap + 60 * R + 6 * pooled
