@@ -41,6 +41,19 @@ def _swap(module_name, attr, new, done):
     done.append("%s.%s" % (module_name.replace("maskrcnn_benchmark.", ""), attr))
 
 
+def _by_device(cuda_fn, reference_fn):
+    """Dispatch on the device of the first BoxList argument."""
+    def dispatch(boxlist, *args, **kwargs):
+        if boxlist.bbox.is_cuda:
+            return cuda_fn(boxlist, *args, **kwargs)
+        return reference_fn(boxlist, *args, **kwargs)
+
+    dispatch.__name__ = getattr(reference_fn, "__name__", "dispatch")
+    dispatch.__doc__ = cuda_fn.__doc__
+    dispatch._abr_dispatch = True
+    return dispatch
+
+
 def patch_loaded():
     """Replace the Python hot-path entry points of already-imported reference modules (and every ``from ... import``
     alias of them).  Returns the list of names that were swapped."""
@@ -68,8 +81,21 @@ def patch_loaded():
         dist_mod = dist
         if getattr(original, "__module__", "").startswith("maskrcnn_benchmark"):
             _swap(ref + "distillation.distillation", "calculate_roi_distillation_losses", calculate_roi_distillation_losses, done)
-    _swap(ref + "structures.boxlist_ops", "boxlist_nms", boxlist_ops.boxlist_nms, done)
-    _swap(ref + "structures.boxlist_ops", "boxlist_iou", boxlist_ops.boxlist_iou, done)
+    # CUDA BoxLists take the kernels; CPU BoxLists keep the reference's own functions (its evaluation calls boxlist_iou on
+    # CPU BoxLists built from numpy: data/datasets/evaluation/voc/voc_eval.py:125, coco_eval.py:316 -- this package has no
+    # CPU path of its own and does not add one)
+    m = sys.modules.get(ref + "structures.boxlist_ops")
+    if m is not None:
+        for attr in ("boxlist_nms", "boxlist_iou"):
+            original = getattr(m, attr, None)
+            if original is None or getattr(original, "_abr_dispatch", False):
+                continue
+            _swap(ref + "structures.boxlist_ops", attr, _by_device(getattr(boxlist_ops, attr), original), done)
+    rb = sys.modules.get(ref + "structures.bounding_box")
+    if rb is not None and hasattr(rb, "BoxList"):
+        from .structures import bounding_box as our_boxes
+
+        our_boxes.OUTPUT_CLASS = rb.BoxList  # the fused ops hand the reference's own BoxList type downstream
     m = sys.modules.get(ref + "structures.boxlist_ops")
     if m is not None:
         m.boxlist_nms_batched = boxlist_ops.boxlist_nms_batched

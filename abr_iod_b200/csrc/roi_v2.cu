@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(128) v2_plan_kernel(LevelTable lv, const float
   __syncwarp();
   if (lane == 0) v2_plan_header(plan, g, H, W, PH, PW);
   __syncwarp();
-  v2_plan_pix(plan, PH, PW, lane, 32);
+  v2_plan_transposed(plan, PH, PW, lane, 32);
 }
 
 template <typename T, int NT>
@@ -40,12 +40,14 @@ struct V2FwdArgs {
   const int32_t* levels;
   T* out[NT];
   float* sums;  // [R][nslices][PH*PW][3] (NT == 2)
-  int C, PH, PW, ratio, nslices;
+  int C, PH, PW, ratio, nslices, plan_smem;
 };
 
+static size_t align128(size_t x) { return (x + 127) & ~(size_t)127; }
+
 template <typename T, int V, int NT>
-__global__ void __launch_bounds__(256, 2) v2_fwd_kernel(const __grid_constant__ V2FwdArgs<T, NT> a) {
-  extern __shared__ __align__(16) float v2_smem[];
+__global__ void __launch_bounds__(256, NT == 2 ? 2 : 3) v2_fwd_kernel(const __grid_constant__ V2FwdArgs<T, NT> a) {
+  extern __shared__ __align__(128) unsigned char v2_smem[];
   const int r = blockIdx.x / a.nslices, slice = blockIdx.x - r * a.nslices;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int* plan = a.plans + (size_t)r * a.stride;
@@ -62,16 +64,24 @@ __global__ void __launch_bounds__(256, 2) v2_fwd_kernel(const __grid_constant__ 
     outs[t] = a.out[t];
   }
   float* srs = NT == 2 ? a.sums + ((size_t)r * a.nslices + slice) * a.PH * a.PW * 3 : nullptr;
-  if (mode == V2_GENERIC) {
+  const v2_sptr plan_s = v2_sptr_of(v2_smem);
+  bool generic = mode == V2_GENERIC;  // (the whole CTA)
+  if (!generic) {
+    v2_stage_plan(plan, plan_s, a.PW + a.PH, threadIdx.x, blockDim.x);
+    __syncthreads();
+    if (v2_strip_rows_for(NT) <= kV2Sup) generic = v2_tallest_bin(plan_s, a.PH, a.PW) > v2_strip_rows_for(NT);
+  }
+  if (generic) {
     const RoiGeom g = roi_geometry(a.rois, a.levels, a.lv[0], r, a.PH, a.PW, a.ratio);
     for (int pw = warp; pw < a.PW; pw += nw)
       v2_generic_fwd_column<T, V, NT>(g, a.lv[0].H[g.level], a.lv[0].W[g.level], maps, outs, srs, r, pw, c, active, a.C, a.PH,
                                       a.PW, lane);
     return;
   }
-  float* strip = v2_smem + (size_t)warp * v2_strip_floats(V, NT);
+  const v2_sptr strip = plan_s + (uint32_t)a.plan_smem + warp * (uint32_t)(v2_strip_bytes(V, NT) + v2_sums_bytes(NT));
+  const v2_sptr sums_buf = strip + (uint32_t)v2_strip_bytes(V, NT);
   for (int pw = warp; pw < a.PW; pw += nw)
-    v2_fwd_column<T, V, NT>(plan, maps, outs, srs, strip, r, pw, c, active, a.C, a.PH, a.PW, lane);
+    v2_fwd_column<T, V, NT>(plan_s, maps, outs, srs, strip, sums_buf, r, pw, c, active, a.C, a.PH, a.PW, lane);
 }
 
 template <typename T>
@@ -84,38 +94,45 @@ struct V2BwdArgs {
   const T* a;          // upstream gradient [R][PH][PW][C], or the teacher's pooled tensor (fused)
   const T* b;          // the student's pooled tensor (fused)
   const float2* coef;  // [R][PH*PW] (fused)
-  int C, PH, PW, ratio, nslices;
+  int C, PH, PW, ratio, nslices, plan_smem;
 };
 
-template <typename T, int V, bool FUSED>
-__global__ void __launch_bounds__(256, 2) v2_bwd_kernel(const __grid_constant__ V2BwdArgs<T> a) {
-  extern __shared__ __align__(16) float v2_smem[];
+template <typename T, int V, bool FUSED, int NTHR>
+__global__ void __launch_bounds__(NTHR, 1024 / NTHR) v2_bwd_kernel(const __grid_constant__ V2BwdArgs<T> a) {
+  extern __shared__ __align__(128) unsigned char v2_smem[];
   const int r = blockIdx.x / a.nslices, slice = blockIdx.x - r * a.nslices;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int nw = NTHR / 32;
   const int* plan = a.plans + (size_t)r * a.stride;
   const int4 h0 = __ldg(reinterpret_cast<const int4*>(plan));
   const int mode = h0.x, level = h0.z;
   if (mode == V2_EMPTY) return;  // (the whole CTA)
+  const int4 h1 = __ldg(reinterpret_cast<const int4*>(plan + 4)), h2 = __ldg(reinterpret_cast<const int4*>(plan + 8));
+  const int FW = mode == V2_PLAN ? h1.w : 0, FH = mode == V2_PLAN ? h2.y - h2.x + 1 : 0;
   const int nbin = a.PH * a.PW;
   int c = (slice * 32 + lane) * V;
   const bool active = c < a.C;
   if (!active) c = 0;
+  const v2_sptr plan_s = v2_sptr_of(v2_smem), tile = plan_s + (uint32_t)a.plan_smem;
+  if (mode == V2_PLAN) {
+    v2_stage_plan(plan, plan_s, a.PW + a.PH + FW, threadIdx.x, NTHR);
+    v2_stage_records(plan, plan_s, a.PW + a.PH + kV2MaxFW, FH, threadIdx.x, NTHR);
+  }
   V2Grad<T, V, FUSED> src;
   src.a = a.a + (size_t)r * nbin * a.C + c;
   src.b = FUSED ? a.b + (size_t)r * nbin * a.C + c : nullptr;
   src.coef = FUSED ? a.coef + (size_t)r * nbin : nullptr;
-  v2_bwd_fill_tile<T, V, FUSED>(v2_smem, src, nbin, a.C, warp, nw, lane, active);
+  v2_bwd_fill_tile<T, V, FUSED>(tile, src, nbin, a.C, warp, nw, lane);
   __syncthreads();
   if (!active) return;  // idle lane of a ragged last slice (no warp-level primitive below)
   T* gmap = static_cast<T*>(a.lv.ptr[level]);
   if (mode == V2_GENERIC) {
     const RoiGeom g = roi_geometry(a.rois, a.levels, a.lv, r, a.PH, a.PW, a.ratio);
     for (int pw = warp; pw < a.PW; pw += nw)
-      v2_generic_bwd_column<T, V>(g, a.lv.H[g.level], a.lv.W[g.level], gmap, v2_smem, pw, c, a.C, a.PH, a.PW, lane);
+      v2_generic_bwd_column<T, V>(g, a.lv.H[g.level], a.lv.W[g.level], gmap, tile, pw, c, a.C, a.PH, a.PW, lane);
     return;
   }
-  const int FW = __ldg(plan + 7);
-  for (int k = warp; k < FW; k += nw) v2_bwd_pixcol<T, V>(plan, gmap, v2_smem, k, c, a.C, a.PH, a.PW, lane);
+  for (int k = warp; k < FW; k += nw) v2_bwd_pixcol<T, V>(plan_s, gmap, tile, k, c, a.C, a.PH, a.PW, lane);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -142,10 +159,12 @@ static int launch_fwd2(const LevelTable* lv, const int* plans, const float* rois
   const long long blocks = (long long)R * a.nslices;
   ABR_REQUIRE(blocks <= 0x7fffffffLL, ABR_ERR_UNSUPPORTED, "roi_align_forward: too many (RoI, slice) tasks");
   const int nw = fwd_warps(PW);
-  const size_t smem = (size_t)nw * v2_strip_floats(V, NT) * sizeof(float);
+  a.plan_smem = (int)align128(v2_plan_smem_bytes(PW + PH));
+  const size_t smem = a.plan_smem + (size_t)nw * (v2_strip_bytes(V, NT) + v2_sums_bytes(NT));
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
-    ABR_CUDA_OK(cudaFuncSetAttribute(v2_fwd_kernel<T, V, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (int)v2_strip_floats(V, NT) * (int)sizeof(float)));
+    ABR_CUDA_OK(cudaFuncSetAttribute(v2_fwd_kernel<T, V, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(align128(v2_plan_smem_bytes(32)) + 8 * (v2_strip_bytes(V, NT) + v2_sums_bytes(NT)))));
     attr_set = true;
   }
   v2_fwd_kernel<T, V, NT><<<(unsigned)blocks, 32 * nw, smem, st>>>(a);
@@ -173,13 +192,18 @@ static int launch_bwd2(const LevelTable& lv, const int* plans, const float* rois
   a.C = C; a.PH = PH; a.PW = PW; a.ratio = ratio; a.nslices = ceil_div(C, 32 * V);
   const long long blocks = (long long)R * a.nslices;
   ABR_REQUIRE(blocks <= 0x7fffffffLL, ABR_ERR_UNSUPPORTED, "roi_align_backward: too many (RoI, slice) tasks");
-  const size_t smem = (size_t)PH * PW * 32 * V * sizeof(float);  // the (RoI, slice) gradient tile
+  a.plan_smem = (int)align128(v2_plan_smem_bytes(PW + PH + kV2MaxFW + kV2MaxFH));
+  const size_t smem = a.plan_smem + (size_t)PH * PW * 32 * V * sizeof(float);  // the plan + the (RoI, slice) gradient tile
+  ABR_REQUIRE(smem <= 227 * 1024, ABR_ERR_UNSUPPORTED, "roi_align_backward: %dx%d bins of %d channels do not fit shared memory", PH, PW, 32 * V);
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
-    ABR_CUDA_OK(cudaFuncSetAttribute(v2_bwd_kernel<T, V, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    ABR_CUDA_OK(cudaFuncSetAttribute(v2_bwd_kernel<T, V, FUSED, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    ABR_CUDA_OK(cudaFuncSetAttribute(v2_bwd_kernel<T, V, FUSED, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  v2_bwd_kernel<T, V, FUSED><<<(unsigned)blocks, 256, smem, st>>>(a);
+  // large tiles leave room for two CTAs per SM at most: give those 16 warps each
+  if (PH * PW >= 100) v2_bwd_kernel<T, V, FUSED, 512><<<(unsigned)blocks, 512, smem, st>>>(a);
+  else v2_bwd_kernel<T, V, FUSED, 256><<<(unsigned)blocks, 256, smem, st>>>(a);
   ABR_CHECK_LAUNCH(FUSED ? "roi_align_backward (v2, fused ARD gradient)" : "roi_align_backward (v2)");
   return ABR_OK;
 }
@@ -190,7 +214,7 @@ int v2_backward(const LevelTable& lv, const int* plans, const float* rois, const
     if (C % 4 == 0) return launch_bwd2<float, 4, false>(lv, plans, rois, levels, gout, nullptr, nullptr, C, R, PH, PW, ratio, st);
     return launch_bwd2<float, 1, false>(lv, plans, rois, levels, gout, nullptr, nullptr, C, R, PH, PW, ratio, st);
   }
-  if (C % 8 == 0 && (size_t)PH * PW * 32 * 8 * sizeof(float) <= 227 * 1024)  // the tile of 8-channel lanes must fit shared memory
+  if (C % 8 == 0 && (size_t)PH * PW * 32 * 8 * sizeof(float) <= 220 * 1024)  // the tile of 8-channel lanes must fit shared memory
     return launch_bwd2<__nv_bfloat16, 8, false>(lv, plans, rois, levels, gout, nullptr, nullptr, C, R, PH, PW, ratio, st);
   return launch_bwd2<__nv_bfloat16, 1, false>(lv, plans, rois, levels, gout, nullptr, nullptr, C, R, PH, PW, ratio, st);
 }

@@ -32,6 +32,7 @@
 #ifndef ABR_EMU
 #include "common.cuh"
 #define ABR_DEV __device__ __forceinline__
+#define ABR_DEV_COLD __device__ __noinline__  // the rare per-sample paths: kept out of the hot paths' register budget
 #define ABR_DEVM __device__ __forceinline__
 #define ABR_HD __device__ __forceinline__
 #define ABR_HOSTDEV __host__ __device__ __forceinline__
@@ -87,14 +88,13 @@ ABR_HD float v2_sample_coord(float start, float bin, int p, int i, int grid) {
 constexpr int kV2Rec = 16;      // words per record: { lo | n << 16, w[0..14] }
 constexpr int kV2Sup = 15;      // widest support (map pixels of one bin / bins over one pixel) a record holds
 constexpr int kV2MaxFW = 64;    // widest footprint (map pixels) with pixel-column records
+constexpr int kV2MaxFH = 64;    // tallest footprint (map rows) with row records
 constexpr int kV2Hdr = 16;
 enum V2Mode { V2_EMPTY = 0, V2_PLAN = 1, V2_GENERIC = 3 };
 // hdr: [0] mode [1] batch [2] level [3] H [4] W [5] 1/count [6] X0 [7] FW [8] Y0 [9] Y1
 
-ABR_HOSTDEV size_t v2_plan_words(int PH, int PW) { return (size_t)kV2Hdr + (size_t)(PH + PW + kV2MaxFW) * kV2Rec; }
-ABR_HD const int* v2_col_rec(const int* plan, int pw) { return plan + kV2Hdr + pw * kV2Rec; }
-ABR_HD const int* v2_bin_rec(const int* plan, int PW, int ph) { return plan + kV2Hdr + (PW + ph) * kV2Rec; }
-ABR_HD const int* v2_pix_rec(const int* plan, int PH, int PW, int k) { return plan + kV2Hdr + (PW + PH + k) * kV2Rec; }
+// records after the header: PW bin columns, PH bin rows, kV2MaxFW footprint pixel columns, kV2MaxFH footprint rows
+ABR_HOSTDEV size_t v2_plan_words(int PH, int PW) { return (size_t)kV2Hdr + (size_t)(PH + PW + kV2MaxFW + kV2MaxFH) * kV2Rec; }
 
 // One bin of one axis (ROIAlign_cuda.cu:22-47 along one axis): the map indices its samples touch and the summed
 // bilinear weights.  Returns the support size n (0: no sample inside the map) or -1 when it exceeds kV2Sup.
@@ -153,7 +153,7 @@ ABR_HD void v2_plan_header(int* plan, const RoiGeom& g, int H, int W, int PH, in
   int mode = V2_PLAN;
   if (generic) mode = V2_GENERIC;
   else if (X1 < X0 || Y1 < Y0) mode = V2_EMPTY;
-  else if (X1 - X0 + 1 > kV2MaxFW) mode = V2_GENERIC;
+  else if (X1 - X0 + 1 > kV2MaxFW || Y1 - Y0 + 1 > kV2MaxFH) mode = V2_GENERIC;
   plan[0] = mode; plan[1] = g.batch; plan[2] = g.level; plan[3] = H; plan[4] = W;
   plan[5] = __float_as_int(1.f / g.count);
   plan[6] = X1 < X0 ? 0 : X0; plan[7] = X1 < X0 ? 0 : X1 - X0 + 1;
@@ -161,52 +161,119 @@ ABR_HD void v2_plan_header(int* plan, const RoiGeom& g, int H, int W, int PH, in
   for (int i = 10; i < kV2Hdr; i++) plan[i] = 0;
 }
 
-// Phase 3 (threads tid, tid + nth, ..., after phase 2 is visible): one record per footprint pixel column x = X0 + k --
-// the contiguous range of bin columns whose support contains x and their weights Wx[pw][x] (the transpose of the column
-// records; supports start and end monotonically in pw, so the covering columns are contiguous).
-ABR_HD void v2_plan_pix(int* plan, int PH, int PW, int tid, int nth) {
+// Phase 3 (threads tid, tid + nth, ..., after phase 2 is visible): the transposed records the backward walks.
+//   * one per footprint pixel column x = X0 + k -- the contiguous range of bin columns whose support contains x and their
+//     weights Wx[pw][x] (supports start and end monotonically in pw, so the covering columns are contiguous);
+//   * one per footprint row y = Y0 + j -- likewise the bin rows whose support contains y with a non-zero weight, and
+//     Wy[ph][y].
+// Record k of the pixel columns sits after the PW + PH axis records, row record j after kV2MaxFW pixel-column records.
+ABR_HD void v2_plan_transposed(int* plan, int PH, int PW, int tid, int nth) {
   if (plan[0] != V2_PLAN) return;
-  const int X0 = plan[6], FW = plan[7];
-  for (int k = tid; k < FW; k += nth) {
-    const int x = X0 + k;
-    int* rec = plan + kV2Hdr + (PW + PH + k) * kV2Rec;
+  const int X0 = plan[6], FW = plan[7], Y0 = plan[8], FH = plan[9] - plan[8] + 1;
+  for (int k = tid; k < FW + FH; k += nth) {
+    const bool is_row = k >= FW;
+    const int at = is_row ? Y0 + (k - FW) : X0 + k;                    // map column / row
+    const int first = is_row ? PW : 0, count = is_row ? PH : PW;       // the axis records to transpose
+    int* rec = plan + kV2Hdr + (PW + PH + (is_row ? kV2MaxFW + (k - FW) : k)) * kV2Rec;
     int q0 = -1, nq = 0;
     for (int i = 0; i < kV2Sup; i++) rec[1 + i] = 0;
-    for (int q = 0; q < PW; q++) {
-      const int* cr = plan + kV2Hdr + q * kV2Rec;
+    for (int q = 0; q < count; q++) {
+      const int* cr = plan + kV2Hdr + (first + q) * kV2Rec;
       const int lo = cr[0] & 0xffff, n = cr[0] >> 16;
-      if (n == 0 || x < lo || x > lo + n - 1) continue;
+      if (n == 0 || at < lo || at > lo + n - 1) continue;
+      const int w = cr[1 + (at - lo)];
+      if (is_row && __int_as_float(w) == 0.f) continue;  // e.g. the upper tap of a sample that sits exactly on a map row
       if (q0 < 0) q0 = q;
-      if (q - q0 < kV2Sup) rec[1 + (q - q0)] = cr[1 + (x - lo)];
+      if (q - q0 < kV2Sup) rec[1 + (q - q0)] = w;
       nq = q - q0 + 1;
     }
-    // a pixel under more than kV2Sup bin columns (a one-pixel RoI pooled to PW > 15) does not fit a record: the RoI goes
-    // to the per-sample path (several threads may store the same value)
+    // more than kV2Sup bins over one map pixel (a one-pixel RoI pooled to 16 bins) do not fit a record: the RoI goes to
+    // the per-sample path (several threads may store the same value)
     if (nq > kV2Sup) plan[0] = V2_GENERIC;
     rec[0] = (q0 < 0 ? 0 : q0) | ((nq > kV2Sup ? kV2Sup : nq) << 16);
   }
 }
 
-// ------------------------------------------------------------------------------------------------ record access
-struct V2Rec {
-  int lo, n;
-  float w0, w1, w2;
-  const int* p;
-};
-ABR_DEV V2Rec v2_load_rec(const int* __restrict__ rec) {
-  const int4 a = ABR_LDG4I(rec);
-  V2Rec r;
-  r.lo = a.x & 0xffff;
-  r.n = a.x >> 16;
-  r.w0 = __int_as_float(a.y);
-  r.w1 = __int_as_float(a.z);
-  r.w2 = __int_as_float(a.w);
-  r.p = rec;
-  return r;
+// ------------------------------------------------------------------------------------------------ shared memory
+// The kernels keep the RoI's plan, the forward's T strips and the backward's gradient tile in shared memory and address
+// them with 32-bit shared-window addresses (one cvta per kernel; no generic-pointer arithmetic in the inner loops).  The
+// host emulation maps the same helpers onto plain memory.
+#ifndef ABR_EMU
+typedef uint32_t v2_sptr;
+ABR_DEV v2_sptr v2_sptr_of(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+ABR_DEV int4 v2_lds4i(v2_sptr a) {
+  int4 v;
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
 }
-ABR_DEV float v2_rec_w(const V2Rec& r, int i) {  // warp-uniform i
-  return i == 0 ? r.w0 : i == 1 ? r.w1 : i == 2 ? r.w2 : __int_as_float(ABR_LDGI(r.p + 1 + i));
+ABR_DEV void v2_sts4i(v2_sptr a, int4 v) {
+  asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+ABR_DEV float v2_ldsf(v2_sptr a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+ABR_DEV void v2_stsf(v2_sptr a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+#else
+typedef char* v2_sptr;
+ABR_DEV v2_sptr v2_sptr_of(const void* p) { return (char*)p; }
+ABR_DEV int4 v2_lds4i(v2_sptr a) { int4 v; memcpy(&v, a, 16); return v; }
+ABR_DEV void v2_sts4i(v2_sptr a, int4 v) { memcpy(a, &v, 16); }
+ABR_DEV float v2_ldsf(v2_sptr a) { float v; memcpy(&v, a, 4); return v; }
+ABR_DEV void v2_stsf(v2_sptr a, float v) { memcpy(a, &v, 4); }
+#endif
+// V consecutive floats of one lane (16-byte accesses when V % 4 == 0)
+template <int V>
+ABR_DEV void v2_sm_store(v2_sptr a, const float (&v)[V]) {
+  if (V % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < V / 4; i++) {
+      int4 t;
+      t.x = __float_as_int(v[4 * i]); t.y = __float_as_int(v[4 * i + 1]); t.z = __float_as_int(v[4 * i + 2]); t.w = __float_as_int(v[4 * i + 3]);
+      v2_sts4i(a + 16 * i, t);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < V; i++) v2_stsf(a + 4 * i, v[i]);
+  }
+}
+template <int V>
+ABR_DEV void v2_sm_load(v2_sptr a, float (&v)[V]) {
+  if (V % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < V / 4; i++) {
+      const int4 t = v2_lds4i(a + 16 * i);
+      v[4 * i] = __int_as_float(t.x); v[4 * i + 1] = __int_as_float(t.y); v[4 * i + 2] = __int_as_float(t.z); v[4 * i + 3] = __int_as_float(t.w);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < V; i++) v[i] = v2_ldsf(a + 4 * i);
+  }
+}
+
+ABR_DEV v2_sptr v2_srec(v2_sptr plan_s, int k) { return plan_s + 64 * (1 + k); }
+ABR_DEV float v2_srec_w(v2_sptr rec, int i) { return v2_ldsf(rec + 4 + 4 * i); }
+
+// The RoI's plan, copied into shared memory by the whole CTA (a __syncthreads() follows in the kernel): `nrec` records
+// after the header.  Record k of the shared copy sits at plan_s + 64 * (1 + k).
+ABR_DEV void v2_stage_plan(const int* __restrict__ plan, v2_sptr plan_s, int nrec, int tid, int nth) {
+  for (int i = tid; i < 4 * (1 + nrec); i += nth) v2_sts4i(plan_s + 16 * i, ABR_LDG4I(plan + 4 * i));
+}
+// ... `nrec` records starting at record `first` (the backward's row records sit after a fixed-size gap)
+ABR_DEV void v2_stage_records(const int* __restrict__ plan, v2_sptr plan_s, int first, int nrec, int tid, int nth) {
+  for (int i = tid; i < 4 * nrec; i += nth) v2_sts4i(plan_s + 64 * (1 + first) + 16 * i, ABR_LDG4I(plan + kV2Hdr + first * kV2Rec + 4 * i));
+}
+// Tallest bin of the staged plan (rows); every thread of the CTA gets the same answer.
+ABR_DEV int v2_tallest_bin(v2_sptr plan_s, int PH, int PW) {
+  int n = 0;
+  for (int ph = 0; ph < PH; ph++) {
+    const int k = v2_lds4i(v2_srec(plan_s, PW + ph)).x >> 16;
+    n = k > n ? k : n;
+  }
+  return n;
+}
+ABR_HOSTDEV size_t v2_plan_smem_bytes(int nrec) { return (size_t)64 * (1 + nrec); }
 
 // Three warp totals with six shuffles (reduce-scatter): on return lane 0 holds sum(a), lane 16 sum(b), lane 8 sum(c).
 ABR_DEV float v2_reduce3(float a, float b, float c, int lane) {
@@ -227,10 +294,75 @@ ABR_DEV float v2_reduce3(float a, float b, float c, int lane) {
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-// Emits one output bin of NT tensors: scale by 1/count, store, and (NT == 2) the ARD channel sums of this slice.
-// sums_bin -> the three floats of (RoI, slice, bin).
+// ARD channel sums of the two-tensor forward.  Per output bin every lane has three partial sums over its V channels
+// (sum f_old^2, sum f_new^2, sum (f_new - f_old)^2); the warp totals go to sums[(RoI, slice)][bin][3].  Reducing each bin
+// with shuffles costs a dependent chain of five shuffle/add pairs per bin; instead the partials of up to kV2SumBins bins
+// are parked in a warp-private shared-memory table ([value][lane], rows skewed by one word so that both the lane-major
+// writes and the value-major reads are conflict-free) and folded by 3 * bins lanes at once, 32 sequential adds each.
+constexpr int kV2SumBins = 8;
+ABR_HOSTDEV size_t v2_sums_bytes(int NT) { return NT == 2 ? (size_t)(kV2SumBins * 3 * 33 * 4 + 127) / 128 * 128 : 0; }
+
+struct V2Sums {
+  float* rs;    // &sums[(r * nslices + slice) * PH * PW * 3]
+  v2_sptr buf;  // the warp's table (device only)
+  int pw, PW, first_ph, n;
+};
+ABR_DEV void v2_sums_flush(V2Sums& q, int lane) {
+#ifndef ABR_EMU
+  __syncwarp();
+  if (lane < q.n * 3) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; k++) s += v2_ldsf(q.buf + (lane * 33 + k) * 4);
+    const int b = lane / 3;
+    q.rs[((size_t)(q.first_ph + b) * q.PW + q.pw) * 3 + (lane - 3 * b)] = s;
+  }
+  __syncwarp();
+#else
+  (void)lane;
+#endif
+  q.first_ph += q.n;
+  q.n = 0;
+}
+ABR_DEV void v2_sums_add(V2Sums& q, float so, float sn, float sd, int lane) {
+#ifndef ABR_EMU
+  const v2_sptr at = q.buf + (q.n * 3 * 33 + lane) * 4;
+  v2_stsf(at, so);
+  v2_stsf(at + 33 * 4, sn);
+  v2_stsf(at + 2 * 33 * 4, sd);
+#else
+  float* o = q.rs + ((size_t)(q.first_ph + q.n) * q.PW + q.pw) * 3;  // the harness zeroes the buffer and runs the lanes in turn
+  o[0] += so; o[1] += sn; o[2] += sd;
+  (void)lane;
+#endif
+  if (++q.n == kV2SumBins) v2_sums_flush(q, lane);
+}
+
+// Emits one output bin of NT tensors: scale by 1/count, store, and (NT == 2) the lane's ARD partial sums.
 template <typename T, int V, int NT>
-ABR_DEV void v2_emit_bin(float (&acc)[NT][V], float inv_count, T* const (&o)[NT], bool active, float* sums_bin, int lane) {
+ABR_DEV void v2_emit_bin(float (&acc)[NT][V], float inv_count, T* const (&o)[NT], bool active, V2Sums& sums, int lane) {
+#pragma unroll
+  for (int t = 0; t < NT; t++) {
+#pragma unroll
+    for (int k = 0; k < V; k++) acc[t][k] *= inv_count;
+    if (active) VecIO<T, V>::store(o[t], acc[t]);
+  }
+  if (NT == 2) {
+    float so = 0.f, sn = 0.f, sd = 0.f;
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+      const float a = acc[0][k], b = acc[NT - 1][k], d = b - a;
+      so = fmaf(a, a, so);
+      sn = fmaf(b, b, sn);
+      sd = fmaf(d, d, sd);
+    }
+    if (!active) so = sn = sd = 0.f;
+    v2_sums_add(sums, so, sn, sd, lane);
+  }
+}
+// ... the same with the warp totals formed by shuffles and stored at once (the per-sample path)
+template <typename T, int V, int NT>
+ABR_DEV void v2_emit_bin_now(float (&acc)[NT][V], float inv_count, T* const (&o)[NT], bool active, float* sums_bin, int lane) {
 #pragma unroll
   for (int t = 0; t < NT; t++) {
 #pragma unroll
@@ -250,11 +382,9 @@ ABR_DEV void v2_emit_bin(float (&acc)[NT][V], float inv_count, T* const (&o)[NT]
     }
 #ifndef ABR_EMU
     const float v = v2_reduce3(so, sn, sd, lane);
-    if ((lane & 7) == 0) {
-      if (lane == 0) sums_bin[0] = v;
-      else if (lane == 16) sums_bin[1] = v;
-      else if (lane == 8) sums_bin[2] = v;
-    }
+    if (lane == 0) sums_bin[0] = v;
+    if (lane == 16) sums_bin[1] = v;
+    if (lane == 8) sums_bin[2] = v;
 #else
     (void)lane;
     sums_bin[0] += so; sums_bin[1] += sn; sums_bin[2] += sd;  // the harness zeroes the buffer and runs the lanes in turn
@@ -262,159 +392,191 @@ ABR_DEV void v2_emit_bin(float (&acc)[NT][V], float inv_count, T* const (&o)[NT]
   }
 }
 
-// Lane-private / CTA-shared fp32 staging in shared memory: V consecutive floats of one lane, 16-byte accesses when V % 4 == 0.
-template <int V>
-ABR_DEV void v2_sm_store(float* p, const float (&v)[V]) {
-#ifndef ABR_EMU
-  if (V % 4 == 0) {
+// Map rows per strip: 16 holds the tallest bin a record can describe (kV2Sup = 15 rows); the two-tensor kernel takes 12
+// so that two CTAs fit an SM, and sends the (rare) RoIs with a taller bin down the per-sample path.
+ABR_HOSTDEV constexpr int v2_strip_rows_for(int NT) { return NT == 2 ? 12 : 16; }
+
+// Bytes of shared memory one forward warp's strips take: [NT][ROWS][32 lanes][V] floats.
+ABR_HOSTDEV size_t v2_strip_bytes(int V, int NT) { return (size_t)NT * v2_strip_rows_for(NT) * 32 * V * sizeof(float); }
+
+// Phase 1 of a strip for a column NX map pixels wide (compile-time): T[row] = sum_k w[k] * V[row][k] for `nrows` rows,
+// RB rows -- RB * NX independent 16-byte loads per lane -- in flight at a time.  The last batch repeats the last row
+// instead of predicating (the strip has room for all ROWS rows -- a multiple of RB --; rows past nrows are never read).
+template <typename T, int V, int NX, int RB>
+ABR_DEV void v2_strip_rows(const T* colbase, size_t rowstride, size_t pix, int nrows, v2_sptr colrec, v2_sptr dst) {
+  float w[NX];
 #pragma unroll
-    for (int i = 0; i < V / 4; i++) reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-    return;
-  }
-#endif
+  for (int k = 0; k < NX; k++) w[k] = v2_srec_w(colrec, k);
+  const T* p = colbase;  // row i0 + j, stepping one map row per load group and stopping at the last row
+  for (int i0 = 0; i0 < nrows; i0 += RB) {
+    float v[RB][NX][V];
 #pragma unroll
-  for (int i = 0; i < V; i++) p[i] = v[i];
-}
-template <int V>
-ABR_DEV void v2_sm_load(const float* p, float (&v)[V]) {
-#ifndef ABR_EMU
-  if (V % 4 == 0) {
+    for (int j = 0; j < RB; j++) {
 #pragma unroll
-    for (int i = 0; i < V / 4; i++) {
-      const float4 t = reinterpret_cast<const float4*>(p)[i];
-      v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+      for (int k = 0; k < NX; k++) VecIO<T, V>::load(p + (size_t)k * pix, v[j][k]);
+      if (i0 + j + 1 < nrows) p += rowstride;
     }
-    return;
-  }
-#endif
 #pragma unroll
-  for (int i = 0; i < V; i++) v[i] = p[i];
+    for (int j = 0; j < RB; j++) {
+      float t[V];
+#pragma unroll
+      for (int q = 0; q < V; q++) {
+        float s = w[0] * v[j][0][q];
+#pragma unroll
+        for (int k = 1; k < NX; k++) s = fmaf(w[k], v[j][k][q], s);
+        t[q] = s;
+      }
+      v2_sm_store<V>(dst + (i0 + j) * (32 * V * 4), t);
+    }
+  }
+}
+// ... and for columns wider than four map pixels (fat bins of large RoIs): four rows at a time, pixel by pixel.
+template <typename T, int V>
+ABR_DEV void v2_strip_rows_wide(const T* colbase, size_t rowstride, size_t pix, int nrows, int nx, v2_sptr colrec, v2_sptr dst) {
+  constexpr int RB = V >= 8 ? 2 : 4;
+  for (int i0 = 0; i0 < nrows; i0 += RB) {
+    float t[RB][V];
+    const T* p[RB];
+#pragma unroll
+    for (int j = 0; j < RB; j++) {
+      p[j] = colbase + (size_t)(i0 + j < nrows ? i0 + j : nrows - 1) * rowstride;
+#pragma unroll
+      for (int q = 0; q < V; q++) t[j][q] = 0.f;
+    }
+    for (int k = 0; k < nx; k++) {
+      const float w = v2_srec_w(colrec, k);
+      float v[RB][V];
+#pragma unroll
+      for (int j = 0; j < RB; j++) VecIO<T, V>::load(p[j] + (size_t)k * pix, v[j]);
+#pragma unroll
+      for (int j = 0; j < RB; j++)
+#pragma unroll
+        for (int q = 0; q < V; q++) t[j][q] = fmaf(w, v[j][q], t[j][q]);
+    }
+#pragma unroll
+    for (int j = 0; j < RB; j++) v2_sm_store<V>(dst + (i0 + j) * (32 * V * 4), t[j]);
+  }
 }
 
-constexpr int kV2Rows = 16;  // map rows per strip (>= kV2Sup + 1, so the widest bin always fits one strip)
-
-// Floats of shared memory one forward warp needs: [NT][kV2Rows][32 lanes][V].
-ABR_HOSTDEV size_t v2_strip_floats(int V, int NT) { return (size_t)NT * kV2Rows * 32 * V; }
-
-// One bin column of one RoI from its plan.  maps[t]: the level's map of tensor t ([B][H][W][C]); outs[t]: pooled tensor
-// ([R][PH][PW][C]); c: first channel of this lane; sums_rs: &sums[(r * nslices + slice) * PH*PW * 3] (NT == 2);
-// strip: this WARP's v2_strip_floats(V, NT) floats of shared memory.
+// One bin column of one RoI.  plan_s: the plan in shared memory (header, PW column records, PH bin-row records);
+// maps[t]: the level's map of tensor t ([B][H][W][C]); outs[t]: pooled tensor ([R][PH][PW][C]); c: first channel of this
+// lane; sums_rs: &sums[(r * nslices + slice) * PH*PW * 3] (NT == 2); strip: this WARP's v2_strip_bytes(V, NT) of shared
+// memory.
 template <typename T, int V, int NT>
-ABR_DEV void v2_fwd_column(const int* __restrict__ plan, const T* const (&maps)[NT], T* const (&outs)[NT], float* sums_rs,
-                           float* strip, int r, int pw, int c, bool active, int C, int PH, int PW, int lane) {
-  const int4 h0 = ABR_LDG4I(plan), h1 = ABR_LDG4I(plan + 4), h2 = ABR_LDG4I(plan + 8);
+ABR_DEV void v2_fwd_column(v2_sptr plan_s, const T* const (&maps)[NT], T* const (&outs)[NT], float* sums_rs, v2_sptr strip,
+                           v2_sptr sums_buf, int r, int pw, int c, bool active, int C, int PH, int PW, int lane) {
+  constexpr int ROWB = 32 * V * 4;  // bytes of one strip row
+  constexpr int kV2Rows = v2_strip_rows_for(NT);
+  constexpr int RB2 = V >= 8 ? 1 : 2, RB4 = V >= 8 ? 2 : 4;
+  const int4 h0 = v2_lds4i(plan_s), h1 = v2_lds4i(plan_s + 16), h2 = v2_lds4i(plan_s + 32);
   const int mode = h0.x, batch = h0.y, H = h0.w, W = h1.x, Y1 = h2.y;
   const float inv_count = __int_as_float(h1.y);
   const size_t pix = (size_t)C, binstride = (size_t)PW * C;
   T* o[NT];
 #pragma unroll
   for (int t = 0; t < NT; t++) o[t] = outs[t] + ((size_t)r * PH * PW + pw) * C + c;
-  float* sb = NT == 2 ? sums_rs + (size_t)pw * 3 : nullptr;
-  const V2Rec col = v2_load_rec(v2_col_rec(plan, pw));
-  const int nx = mode == V2_PLAN ? col.n : 0;
+  V2Sums sums;
+  sums.rs = sums_rs; sums.buf = sums_buf; sums.pw = pw; sums.PW = PW; sums.first_ph = 0; sums.n = 0;
+  const v2_sptr colrec = v2_srec(plan_s, pw);
+  const int col0 = v2_lds4i(colrec).x;
+  const int nx = mode == V2_PLAN ? col0 >> 16 : 0;
   const size_t rowstride = (size_t)W * C;
   const T* base[NT];
 #pragma unroll
-  for (int t = 0; t < NT; t++) base[t] = maps[t] + ((size_t)batch * H * W + col.lo) * C + c;
-  float* mine = strip + (size_t)lane * V;  // [t][row] at (t * kV2Rows + row) * 32 * V
-  constexpr int RB = V >= 8 ? 2 : 4;       // rows whose loads are in flight together (register budget)
+  for (int t = 0; t < NT; t++) base[t] = maps[t] + ((size_t)batch * H * W + (col0 & 0xffff)) * C + c;
+  const v2_sptr mine = strip + lane * (V * 4);  // [t][row] at (t * kV2Rows + row) * ROWB
 
   int ph = 0;
   while (ph < PH) {
-    V2Rec bin = v2_load_rec(v2_bin_rec(plan, PW, ph));
-    if (nx == 0 || bin.n == 0) {  // no sample of this bin (column, RoI) falls inside the map
+    v2_sptr binrec = v2_srec(plan_s, PW + ph);
+    int4 b = v2_lds4i(binrec);
+    if (nx == 0 || (b.x >> 16) == 0) {  // no sample of this bin (column, RoI) falls inside the map
       float z[NT][V];
 #pragma unroll
       for (int t = 0; t < NT; t++)
 #pragma unroll
         for (int k = 0; k < V; k++) z[t][k] = 0.f;
-      v2_emit_bin<T, V, NT>(z, 0.f, o, active, sb, lane);
+      v2_emit_bin<T, V, NT>(z, 0.f, o, active, sums, lane);
 #pragma unroll
       for (int t = 0; t < NT; t++) o[t] += binstride;
-      if (NT == 2) sb += (size_t)PW * 3;
       ph++;
       continue;
     }
     // ---- phase 1: T of the rows ystart .. ystart + nrows - 1
-    const int ystart = bin.lo;
+    const int ystart = b.x & 0xffff;
     const int nrows = Y1 - ystart + 1 < kV2Rows ? Y1 - ystart + 1 : kV2Rows;
 #pragma unroll
     for (int t = 0; t < NT; t++) {
       const T* colbase = base[t] + (size_t)ystart * rowstride;
-      for (int i0 = 0; i0 < nrows; i0 += RB) {
-        float Tacc[RB][V];
-#pragma unroll
-        for (int j = 0; j < RB; j++)
-#pragma unroll
-          for (int k = 0; k < V; k++) Tacc[j][k] = 0.f;
-        for (int kg = 0; kg < nx; kg += 4) {  // warp-uniform; one trip unless the column is wider than four map pixels
-          float v[RB][4][V];
-#pragma unroll
-          for (int j = 0; j < RB; j++) {
-            if (i0 + j < nrows) {
-              const T* p = colbase + (size_t)(i0 + j) * rowstride + (size_t)kg * pix;
-              VecIO<T, V>::load(p, v[j][0]);
-              if (kg + 1 < nx) VecIO<T, V>::load(p + pix, v[j][1]);
-              if (kg + 2 < nx) VecIO<T, V>::load(p + 2 * pix, v[j][2]);
-              if (kg + 3 < nx) VecIO<T, V>::load(p + 3 * pix, v[j][3]);
-            }
-          }
-          const float w0 = v2_rec_w(col, kg);
-          const float w1 = kg + 1 < nx ? v2_rec_w(col, kg + 1) : 0.f;
-          const float w2 = kg + 2 < nx ? v2_rec_w(col, kg + 2) : 0.f;
-          const float w3 = kg + 3 < nx ? v2_rec_w(col, kg + 3) : 0.f;
-#pragma unroll
-          for (int j = 0; j < RB; j++) {
-            if (i0 + j < nrows) {
-#pragma unroll
-              for (int k = 0; k < V; k++) {
-                float s = fmaf(w0, v[j][0][k], Tacc[j][k]);
-                if (kg + 1 < nx) s = fmaf(w1, v[j][1][k], s);
-                if (kg + 2 < nx) s = fmaf(w2, v[j][2][k], s);
-                if (kg + 3 < nx) s = fmaf(w3, v[j][3][k], s);
-                Tacc[j][k] = s;
-              }
-            }
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < RB; j++)
-          if (i0 + j < nrows) v2_sm_store<V>(mine + (size_t)(t * kV2Rows + i0 + j) * 32 * V, Tacc[j]);
+      const v2_sptr dst = mine + t * (kV2Rows * ROWB);
+      switch (nx) {
+        case 1: v2_strip_rows<T, V, 1, RB4>(colbase, rowstride, pix, nrows, colrec, dst); break;
+        case 2: v2_strip_rows<T, V, 2, RB4>(colbase, rowstride, pix, nrows, colrec, dst); break;
+        case 3: v2_strip_rows<T, V, 3, RB2>(colbase, rowstride, pix, nrows, colrec, dst); break;
+        case 4: v2_strip_rows<T, V, 4, RB2>(colbase, rowstride, pix, nrows, colrec, dst); break;
+        default: v2_strip_rows_wide<T, V>(colbase, rowstride, pix, nrows, nx, colrec, dst); break;
       }
     }
-    // ---- phase 2: every bin whose rows lie inside the strip (at least the one that started it: n <= kV2Sup < kV2Rows)
+    // ---- phase 2: every bin whose rows lie inside the strip (at least the one that started it: n <= kV2Rows)
     while (true) {
+      const int n = b.x >> 16;
+      const v2_sptr src = mine + ((b.x & 0xffff) - ystart) * ROWB;
       float acc[NT][V];
 #pragma unroll
-      for (int t = 0; t < NT; t++)
+      for (int t = 0; t < NT; t++) {
+        float x[V];
+        v2_sm_load<V>(src + t * (kV2Rows * ROWB), x);
+        const float w0 = __int_as_float(b.y);
 #pragma unroll
-        for (int k = 0; k < V; k++) acc[t][k] = 0.f;
-      const int off = bin.lo - ystart;
-      for (int i = 0; i < bin.n; i++) {
-        const float wy = v2_rec_w(bin, i);
+        for (int k = 0; k < V; k++) acc[t][k] = w0 * x[k];
+      }
+      if (n > 1) {
+        const float w1 = __int_as_float(b.z);
 #pragma unroll
         for (int t = 0; t < NT; t++) {
           float x[V];
-          v2_sm_load<V>(mine + (size_t)(t * kV2Rows + off + i) * 32 * V, x);
+          v2_sm_load<V>(src + t * (kV2Rows * ROWB) + ROWB, x);
+#pragma unroll
+          for (int k = 0; k < V; k++) acc[t][k] = fmaf(w1, x[k], acc[t][k]);
+        }
+      }
+      if (n > 2) {
+        const float w2 = __int_as_float(b.w);
+#pragma unroll
+        for (int t = 0; t < NT; t++) {
+          float x[V];
+          v2_sm_load<V>(src + t * (kV2Rows * ROWB) + 2 * ROWB, x);
+#pragma unroll
+          for (int k = 0; k < V; k++) acc[t][k] = fmaf(w2, x[k], acc[t][k]);
+        }
+      }
+      for (int i = 3; i < n; i++) {
+        const float wy = v2_srec_w(binrec, i);
+#pragma unroll
+        for (int t = 0; t < NT; t++) {
+          float x[V];
+          v2_sm_load<V>(src + t * (kV2Rows * ROWB) + i * ROWB, x);
 #pragma unroll
           for (int k = 0; k < V; k++) acc[t][k] = fmaf(wy, x[k], acc[t][k]);
         }
       }
-      v2_emit_bin<T, V, NT>(acc, inv_count, o, active, sb, lane);
+      v2_emit_bin<T, V, NT>(acc, inv_count, o, active, sums, lane);
 #pragma unroll
       for (int t = 0; t < NT; t++) o[t] += binstride;
-      if (NT == 2) sb += (size_t)PW * 3;
       if (++ph >= PH) break;
-      bin = v2_load_rec(v2_bin_rec(plan, PW, ph));
-      if (bin.n == 0 || bin.lo + bin.n > ystart + nrows) break;  // an empty bin or one that needs a new strip: outer loop
+      binrec += 64;
+      b = v2_lds4i(binrec);
+      const int n2 = b.x >> 16;
+      if (n2 == 0 || (b.x & 0xffff) + n2 > ystart + nrows) break;  // an empty bin or one that needs a new strip: outer loop
     }
   }
+  if (NT == 2 && sums.n > 0) v2_sums_flush(sums, lane);
 }
 
 // Per-sample evaluation of one bin column, the reference's loop nest (ROIAlign_cuda.cu:64-122): for the rare RoIs the
 // plan marks GENERIC (a bin wider than kV2Sup map pixels, a footprint wider than kV2MaxFW).
 template <typename T, int V, int NT>
-ABR_DEV void v2_generic_fwd_column(const RoiGeom& g, int H, int W, const T* const (&maps)[NT], T* const (&outs)[NT],
+ABR_DEV_COLD void v2_generic_fwd_column(const RoiGeom& g, int H, int W, const T* const (&maps)[NT], T* const (&outs)[NT],
                                    float* sums_rs, int r, int pw, int c, bool active, int C, int PH, int PW, int lane) {
   const size_t binstride = (size_t)PW * C;
   T* o[NT];
@@ -457,7 +619,7 @@ ABR_DEV void v2_generic_fwd_column(const RoiGeom& g, int H, int W, const T* cons
         }
       }
     }
-    v2_emit_bin<T, V, NT>(acc, inv_count, o, active, sb, lane);
+    v2_emit_bin_now<T, V, NT>(acc, inv_count, o, active, sb, lane);
 #pragma unroll
     for (int t = 0; t < NT; t++) o[t] += binstride;
     if (NT == 2) sb += (size_t)PW * 3;
@@ -472,119 +634,125 @@ struct V2Grad {
   const T* a;          // gout, or f_old (FUSED), at [r][0][0][c]
   const T* b;          // f_new (FUSED)
   const float2* coef;  // [PH*PW] of this RoI (FUSED)
-  ABR_DEVM void load(int bin, size_t C, float (&g)[V]) const {
+  // V channels of bin `bin`; off = bin * C (elements)
+  ABR_DEVM void load(int bin, size_t off, float (&g)[V]) const {
     if (FUSED) {
       const float2 kc = ABR_LDG2F(coef + bin);
       float fo[V], fn[V];
-      VecIO<T, V>::load(a + (size_t)bin * C, fo);
-      VecIO<T, V>::load(b + (size_t)bin * C, fn);
+      VecIO<T, V>::load(a + off, fo);
+      VecIO<T, V>::load(b + off, fn);
 #pragma unroll
       for (int k = 0; k < V; k++) g[k] = fmaf(kc.x, fn[k] - fo[k], kc.y * fn[k]);
     } else {
-      VecIO<T, V>::load(a + (size_t)bin * C, g);
+      VecIO<T, V>::load(a + off, g);
     }
   }
 };
 
 // Phase 1 of the backward: warp `warp` of `nw` brings the bins warp, warp + nw, ... of this (RoI, slice) gradient tile into
-// shared memory -- tile[(bin * 32 + lane) * V .. + V) -- four bins' loads in flight at a time.  Lanes of a ragged last
-// slice (inactive) store zeros.
+// shared memory -- bin b of lane l at tile + (b * 32 + l) * V * 4 bytes -- U bins' loads in flight at a time (the last
+// batch repeats the last bin instead of predicating, so that every load is issued before the first is used).  Lanes of
+// a ragged last slice shadow channel 0; they never read the tile.
 template <typename T, int V, bool FUSED>
-ABR_DEV void v2_bwd_fill_tile(float* tile, const V2Grad<T, V, FUSED>& src, int nbin, int C, int warp, int nw, int lane, bool active) {
-  float* mine = tile + (size_t)lane * V;
-  for (int b0 = warp; b0 < nbin; b0 += 4 * nw) {
-    float g[4][V];
+ABR_DEV void v2_bwd_fill_tile(v2_sptr tile, const V2Grad<T, V, FUSED>& src, int nbin, int C, int warp, int nw, int lane) {
+  constexpr int BINB = 32 * V * 4;
+  constexpr int U = (FUSED || V >= 8) ? 4 : 8;  // bins in flight per warp
+  const v2_sptr mine = tile + lane * (V * 4);
+  const size_t step = (size_t)nw * C, last = (size_t)(nbin - 1) * C;
+  size_t off = (size_t)warp * C;
+  for (int b0 = warp; b0 < nbin; b0 += U * nw, off += U * step) {
+    float g[U][V];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-#pragma unroll
-      for (int k = 0; k < V; k++) g[j][k] = 0.f;
-      if (active && b0 + j * nw < nbin) src.load(b0 + j * nw, (size_t)C, g[j]);
+    for (int j = 0; j < U; j++) {
+      const bool in = b0 + j * nw < nbin;
+      src.load(in ? b0 + j * nw : nbin - 1, in ? off + j * step : last, g[j]);
     }
 #pragma unroll
-    for (int j = 0; j < 4; j++)
-      if (b0 + j * nw < nbin) v2_sm_store<V>(mine + (size_t)(b0 + j * nw) * 32 * V, g[j]);
+    for (int j = 0; j < U; j++)
+      if (b0 + j * nw < nbin) v2_sm_store<V>(mine + (b0 + j * nw) * BINB, g[j]);
   }
 }
 
-// Phase 2: one footprint pixel column x = X0 + k of one RoI.  gmap: the level's gradient map [B][H][W][C]; tile: the
-// (RoI, slice) gradient tile in shared memory.
-template <typename T, int V>
-ABR_DEV void v2_bwd_pixcol(const int* __restrict__ plan, T* gmap, const float* tile, int k, int c, int C, int PH, int PW, int lane) {
-  const int4 h0 = ABR_LDG4I(plan), h1 = ABR_LDG4I(plan + 4);
-  const int batch = h0.y, H = h0.w, W = h1.x, X0 = h1.z;
-  const float inv_count = __int_as_float(h1.y);
-  const V2Rec px = v2_load_rec(v2_pix_rec(plan, PH, PW, k));
-  const int nq = px.n;
-  if (nq == 0) return;  // a map column between two bin columns' supports (sparse fixed-ratio sampling)
-  const float wq3 = nq > 3 ? v2_rec_w(px, 3) : 0.f;
-  const size_t rowstride = (size_t)W * C;
-  T* gin = gmap + ((size_t)batch * H * W + (X0 + k)) * C + c;
-  const float* mine = tile + (size_t)lane * V;
-  float Sa[V], Sb[V];
-  int ya = -1, yb = -1;
+// The rows of one footprint pixel column covered by NQ bin columns (compile-time; NQ = 0: nq at run time).  For every
+// footprint row y:  dV[y][x] = (1/count) * sum_{ph over y} sum_{q < nq} Wy[ph][y] * Wx[q0 + q][x] * g[ph][q0 + q],
+// straight from the tile (no state carried between rows), then ONE vector reduction into the map.
+template <typename T, int V, int NQ>
+ABR_DEV void v2_bwd_rows(v2_sptr rowrec, int FH, v2_sptr tcol, int pwb, v2_sptr pxrec, int nq, float inv_count, T* gin, size_t rowstride) {
+  constexpr int BINB = 32 * V * 4;
+  float wq[NQ > 0 ? NQ : 1];
 #pragma unroll
-  for (int i = 0; i < V; i++) Sa[i] = Sb[i] = 0.f;
-  for (int ph = 0; ph < PH; ph++) {
-    const V2Rec bin = v2_load_rec(v2_bin_rec(plan, PW, ph));
-    if (bin.n == 0) continue;
-    // G = sum over the bin columns covering x of Wx[pw][x] * g[ph][pw]
-    float G[V];
-    {
-      float g0[V], g1[V], g2[V], g3[V];
-      const float* t0 = mine + (size_t)(ph * PW + px.lo) * 32 * V;
-      v2_sm_load<V>(t0, g0);
-      if (nq > 1) v2_sm_load<V>(t0 + 32 * V, g1);
-      if (nq > 2) v2_sm_load<V>(t0 + 2 * 32 * V, g2);
-      if (nq > 3) v2_sm_load<V>(t0 + 3 * 32 * V, g3);
+  for (int q = 0; q < NQ; q++) wq[q] = v2_srec_w(pxrec, q);
+  for (int j = 0; j < FH; j++, rowrec += 64, gin += rowstride) {
+    const int r0 = v2_lds4i(rowrec).x;
+    const int m = r0 >> 16;
+    if (m == 0) continue;
+    float S[V];
 #pragma unroll
-      for (int i = 0; i < V; i++) {
-        float s = px.w0 * g0[i];
-        if (nq > 1) s = fmaf(px.w1, g1[i], s);
-        if (nq > 2) s = fmaf(px.w2, g2[i], s);
-        if (nq > 3) s = fmaf(wq3, g3[i], s);
-        G[i] = s;
-      }
-      for (int j = 4; j < nq; j++) {
-        const float wj = v2_rec_w(px, j);
-        float gj[V];
-        v2_sm_load<V>(t0 + (size_t)j * 32 * V, gj);
+    for (int i = 0; i < V; i++) S[i] = 0.f;
+    v2_sptr p = tcol + (r0 & 0xffff) * pwb;
+    for (int i = 0; i < m; i++, p += pwb) {
+      const float wy = v2_srec_w(rowrec, i);
+      if (NQ > 0) {
 #pragma unroll
-        for (int i = 0; i < V; i++) G[i] = fmaf(wj, gj[i], G[i]);
-      }
-    }
-    for (int i = 0; i < bin.n; i++) {
-      const float wy = v2_rec_w(bin, i) * inv_count;
-      if (wy == 0.f) continue;
-      const int y = bin.lo + i;
-      if (y != yb && y != ya) {  // a new row: the older cached row is complete, reduce it into the map
-        if (ya >= 0) VecIO<T, V>::red_add(gin + (size_t)ya * rowstride, Sa);
+        for (int q = 0; q < NQ; q++) {
+          float g[V];
+          v2_sm_load<V>(p + q * BINB, g);
+          const float w = wy * wq[q];
 #pragma unroll
-        for (int q = 0; q < V; q++) { Sa[q] = Sb[q]; Sb[q] = 0.f; }
-        ya = yb;
-        yb = y;
-      }
-      if (y == yb) {
-#pragma unroll
-        for (int q = 0; q < V; q++) Sb[q] = fmaf(wy, G[q], Sb[q]);
+          for (int t = 0; t < V; t++) S[t] = fmaf(w, g[t], S[t]);
+        }
       } else {
+        for (int q = 0; q < nq; q++) {
+          float g[V];
+          v2_sm_load<V>(p + q * BINB, g);
+          const float w = wy * v2_srec_w(pxrec, q);
 #pragma unroll
-        for (int q = 0; q < V; q++) Sa[q] = fmaf(wy, G[q], Sa[q]);
+          for (int t = 0; t < V; t++) S[t] = fmaf(w, g[t], S[t]);
+        }
       }
     }
+#pragma unroll
+    for (int q = 0; q < V; q++) S[q] *= inv_count;
+    VecIO<T, V>::red_add(gin, S);
   }
-  if (ya >= 0) VecIO<T, V>::red_add(gin + (size_t)ya * rowstride, Sa);
-  if (yb >= 0) VecIO<T, V>::red_add(gin + (size_t)yb * rowstride, Sb);
+}
+
+// Phase 2: one footprint pixel column x = X0 + k of one RoI.  plan_s: the plan in shared memory (header, PW + PH axis
+// records, pixel-column records, row records); gmap: the level's gradient map [B][H][W][C]; tile: the (RoI, slice)
+// gradient tile in shared memory.
+template <typename T, int V>
+ABR_DEV void v2_bwd_pixcol(v2_sptr plan_s, T* gmap, v2_sptr tile, int k, int c, int C, int PH, int PW, int lane) {
+  constexpr int BINB = 32 * V * 4;
+  const int4 h0 = v2_lds4i(plan_s), h1 = v2_lds4i(plan_s + 16), h2 = v2_lds4i(plan_s + 32);
+  const int batch = h0.y, H = h0.w, W = h1.x, X0 = h1.z, Y0 = h2.x, FH = h2.y - h2.x + 1;
+  const float inv_count = __int_as_float(h1.y);
+  const v2_sptr pxrec = v2_srec(plan_s, PW + PH + k);
+  const int px0 = v2_lds4i(pxrec).x;
+  const int nq = px0 >> 16;
+  if (nq == 0) return;  // a map column between two bin columns' supports (sparse fixed-ratio sampling)
+  const size_t rowstride = (size_t)W * C;
+  T* gin = gmap + ((size_t)batch * H * W + (X0 + k)) * C + c + (size_t)Y0 * rowstride;
+  const v2_sptr tcol = tile + lane * (V * 4) + (px0 & 0xffff) * BINB;  // bins [.][q0 ..] of this lane
+  const v2_sptr rowrec = v2_srec(plan_s, PW + PH + kV2MaxFW);
+  const int pwb = PW * BINB;
+  switch (nq) {
+    case 1: v2_bwd_rows<T, V, 1>(rowrec, FH, tcol, pwb, pxrec, nq, inv_count, gin, rowstride); break;
+    case 2: v2_bwd_rows<T, V, 2>(rowrec, FH, tcol, pwb, pxrec, nq, inv_count, gin, rowstride); break;
+    case 3: v2_bwd_rows<T, V, 3>(rowrec, FH, tcol, pwb, pxrec, nq, inv_count, gin, rowstride); break;
+    case 4: v2_bwd_rows<T, V, 4>(rowrec, FH, tcol, pwb, pxrec, nq, inv_count, gin, rowstride); break;
+    default: v2_bwd_rows<T, V, 0>(rowrec, FH, tcol, pwb, pxrec, nq, inv_count, gin, rowstride); break;
+  }
 }
 
 // Per-sample backward of one bin column (ROIAlign_cuda.cu:177-254) for GENERIC RoIs, gradients from the tile.
 template <typename T, int V>
-ABR_DEV void v2_generic_bwd_column(const RoiGeom& g, int H, int W, T* gmap, const float* tile, int pw, int c, int C, int PH, int PW,
+ABR_DEV_COLD void v2_generic_bwd_column(const RoiGeom& g, int H, int W, T* gmap, v2_sptr tile, int pw, int c, int C, int PH, int PW,
                                    int lane) {
   const float fH = (float)H, fW = (float)W;
   T* img = gmap + (size_t)g.batch * H * W * C + c;
   for (int ph = 0; ph < PH; ph++) {
     float top[V];
-    v2_sm_load<V>(tile + ((size_t)(ph * PW + pw) * 32 + lane) * V, top);
+    v2_sm_load<V>(tile + ((ph * PW + pw) * 32 + lane) * (V * 4), top);
     for (int iy = 0; iy < g.grid_h; iy++) {
       float y = v2_sample_coord(g.start_h, g.bin_h, ph, iy, g.grid_h);
       if (y < -1.0f || y > fH) continue;

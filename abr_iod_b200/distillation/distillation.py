@@ -47,6 +47,7 @@ class _AttentiveRoIDistillation(Function):
         want_grad = f_second.requires_grad
         loss3, grad = _ard_launch(f_first, f_second, gamma, want_grad)
         ctx.first_needs_grad = f_first.requires_grad
+        ctx.wanted_grad = want_grad
         ctx.grad = grad  # dL/df_second for an upstream gradient of 1
         ctx.mark_non_differentiable(loss3)
         return loss3[0].clone(), loss3
@@ -57,9 +58,13 @@ class _AttentiveRoIDistillation(Function):
         if ctx.first_needs_grad:
             raise RuntimeError("ARD: gradient w.r.t. the first argument (old model features) is not implemented; "
                                "the reference computes them under torch.no_grad() (train_incremental.py:83-85)")
+        if not ctx.wanted_grad:
+            return None, None, None
         g = ctx.grad
         if g is None:
-            return None, None, None
+            # the gradient buffer (as large as the pooled tensor) is scaled in place and handed to autograd once
+            raise RuntimeError("ARD: backward called a second time over the same graph; the fused kernel's gradient buffer "
+                               "has been released (call the loss again instead of retain_graph=True)")
         scale = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
         with torch.cuda.device(g.device):
             _lib.check(_lib.lib().abr_scale_if_needed(g.data_ptr(), g.numel(), scale.data_ptr(), 1.0,
@@ -169,14 +174,6 @@ def calculate_attentive_roi_feature_distillation(f_map_s, f_map_t, gamma=1.0):
 
 # --------------------------------------------------------------------------------------------------------------------
 # Inclusive distillation of the box head's outputs (distillation/distillation.py:164-241 of the reference)
-def _scale_in_place(t, upstream):
-    scale = upstream.detach().to(torch.float32).reshape(1).contiguous()
-    with torch.cuda.device(t.device):
-        _lib.check(_lib.lib().abr_scale_if_needed(t.data_ptr(), t.numel(), scale.data_ptr(), 1.0, _lib.dtype_code(t),
-                                                  _lib.stream_ptr(t.device)))
-    return t
-
-
 class _RoIDistillationID(Function):
     @staticmethod
     def forward(ctx, soften_scores, soften_bboxes, target_scores, target_bboxes):
@@ -211,12 +208,12 @@ class _RoIDistillationID(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_loss, _grad_parts):
+        # out of place ([R, C]-sized tensors): a second backward over the same graph stays correct
         gs, gb = ctx.grads
-        ctx.grads = (None, None)
         if gs is not None:
-            gs = _scale_in_place(gs, grad_loss).to(ctx.dtypes[0])
+            gs = (gs * grad_loss.to(gs.dtype)).to(ctx.dtypes[0])
         if gb is not None:
-            gb = _scale_in_place(gb, grad_loss).to(ctx.dtypes[1])
+            gb = (gb * grad_loss.to(gb.dtype)).to(ctx.dtypes[1])
         return None, None, gs, gb
 
 

@@ -9,7 +9,7 @@ import random
 
 import torch
 
-from ...structures.bounding_box import BoxList
+from ...structures.bounding_box import BoxList, make_boxlist
 
 
 def select_soften_proposals(all_proposals, top_n=128, keep_n=64):
@@ -28,7 +28,7 @@ def select_soften_proposals(all_proposals, top_n=128, keep_n=64):
         else:  # :145-147
             picks = random.sample(range(0, top_n, 1), keep_n)
         idx = order[torch.as_tensor(picks, dtype=torch.long, device=order.device)]
-        out = BoxList(proposals.bbox[idx].reshape(-1, 4), proposals.size, proposals.mode)
+        out = make_boxlist(proposals.bbox[idx].reshape(-1, 4), proposals.size, proposals.mode)
         out.add_field("objectness", scores[idx].reshape(-1))
         selected.append(out)
     return selected

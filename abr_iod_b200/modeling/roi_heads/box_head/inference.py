@@ -8,7 +8,7 @@ import torch
 from torch import nn
 
 from .... import _lib
-from ....structures.bounding_box import BoxList
+from ....structures.bounding_box import make_boxlist
 from ...box_coder import BoxCoder
 
 
@@ -65,7 +65,8 @@ def box_postprocess(class_logits, box_regression, proposals, boxes_per_image, im
                 float(bbox_xform_clip), out["boxes"].data_ptr(), out["scores"].data_ptr(), out["labels"].data_ptr(),
                 out["rows"].data_ptr(), out["n"].data_ptr(), det_stride, out["bg_boxes"].data_ptr(),
                 out["bg_scores"].data_ptr(), out["bg_n"].data_ptr(), max_n, ws.data_ptr(), ws_bytes, _lib.stream_ptr(dev)))
-        out["n_host"] = out["n"].tolist()  # the one host synchronisation of the batch
+        both = torch.stack((out["n"], out["bg_n"])).tolist()  # the one host synchronisation (and D2H copy) of the batch
+        out["n_host"], out["bg_n_host"] = both
         worst = max(out["n_host"] + [0])
         if worst <= det_stride:
             return out
@@ -102,18 +103,18 @@ class PostProcessor(nn.Module):
         out = box_postprocess(class_logits, box_regression, concat_boxes, boxes_per_image, image_shapes, self.score_thresh,
                               self.nms, self.detections_per_img, self.box_coder.weights, self.box_coder.bbox_xform_clip,
                               self.cls_agnostic_bbox_reg)
-        bg_counts = out["bg_n"].tolist()
+        bg_counts = out["bg_n_host"]
         results = []
         for i, size in enumerate(image_shapes):
             n = out["n_host"][i]
-            boxlist = BoxList(out["boxes"][i, :n], size, mode="xyxy")
+            boxlist = make_boxlist(out["boxes"][i, :n], size, mode="xyxy")
             boxlist.add_field("scores", out["scores"][i, :n])
             boxlist.add_field("labels", out["labels"][i, :n])
             results.append(boxlist)
         results_background = None
         if image_shapes:
             i = len(image_shapes) - 1
-            results_background = BoxList(out["bg_boxes"][i, : bg_counts[i]], image_shapes[i], mode="xyxy")
+            results_background = make_boxlist(out["bg_boxes"][i, : bg_counts[i]], image_shapes[i], mode="xyxy")
             results_background.add_field("scores", out["bg_scores"][i, : bg_counts[i]])
             results_background.add_field("labels", torch.zeros((bg_counts[i],), dtype=torch.int64, device=class_logits.device))
         return results, results_background

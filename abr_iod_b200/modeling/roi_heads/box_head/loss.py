@@ -8,7 +8,6 @@ from torch.autograd.function import once_differentiable
 import ctypes
 
 from .... import _lib
-from ....distillation.distillation import _scale_in_place
 from ....structures.bounding_box import BoxList
 
 
@@ -79,12 +78,13 @@ class _FastRCNNLoss(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_cls, grad_box):
+        # out of place: the stored gradients (for upstream gradients of 1) survive, so a second backward over the same
+        # graph (retain_graph=True) is correct; the tensors are [R, C]-sized
         gl, gr = ctx.grads
-        ctx.grads = (None, None)
         if gl is not None:
-            gl = _scale_in_place(gl, grad_cls).to(ctx.meta[0])
+            gl = (gl * grad_cls.to(gl.dtype)).to(ctx.meta[0])
         if gr is not None:
-            gr = _scale_in_place(gr, grad_box).to(ctx.meta[1]).reshape(ctx.meta[2])
+            gr = (gr * grad_box.to(gr.dtype)).to(ctx.meta[1]).reshape(ctx.meta[2])
         return gl, gr, None, None, None, None, None
 
 

@@ -6,7 +6,7 @@ import ctypes
 import torch
 
 from ... import _lib
-from ...structures.bounding_box import BoxList
+from ...structures.bounding_box import BoxList, make_boxlist
 from ...structures.boxlist_ops import cat_boxlist
 from ..box_coder import BoxCoder
 
@@ -117,7 +117,7 @@ class RPNPostProcessor(torch.nn.Module):
         counts = n_out.tolist()  # the only host synchronisation of the batch
         result = []
         for i, size in enumerate(image_sizes):
-            boxlist = BoxList(proposals[i, : counts[i]], size, mode="xyxy")
+            boxlist = make_boxlist(proposals[i, : counts[i]], size, mode="xyxy")
             boxlist.add_field("objectness", scores[i, : counts[i]])
             result.append(boxlist)
         return result

@@ -49,9 +49,9 @@ def cat_boxlist(bboxes):
         if b.size != first.size or b.mode != first.mode or set(b.fields()) != names:
             raise ValueError("cat_boxlist: image size, mode and fields must agree")
     join = (lambda ts: ts[0]) if len(bboxes) == 1 else (lambda ts: torch.cat(ts, dim=0))
-    from .bounding_box import BoxList
+    from .bounding_box import make_boxlist
 
-    out = BoxList(join([b.bbox for b in bboxes]), first.size, first.mode)
+    out = make_boxlist(join([b.bbox for b in bboxes]), first.size, first.mode)
     for name in names:
         out.add_field(name, join([b.get_field(name) for b in bboxes]))
     return out

@@ -32,7 +32,8 @@ def test_install_and_patch_loaded_swap_entry_points_and_aliases():
         _fake("maskrcnn_benchmark")
         d = _fake("maskrcnn_benchmark.distillation.distillation", calculate_attentive_roi_feature_distillation=ref_ard,
                   calculate_roi_distillation_losses=ref_id)
-        ops = _fake("maskrcnn_benchmark.structures.boxlist_ops", boxlist_nms=object(), boxlist_iou=object())
+        ops = _fake("maskrcnn_benchmark.structures.boxlist_ops", boxlist_nms=lambda b, *a, **k: "reference nms",
+                    boxlist_iou=lambda a, b: "reference iou")
         rpn = _fake("maskrcnn_benchmark.modeling.rpn.inference", RPNPostProcessor=RefRPN, make_rpn_postprocessor=object())
         box = _fake("maskrcnn_benchmark.modeling.roi_heads.box_head.inference", PostProcessor=object(), make_roi_box_post_processor=object())
         loss = _fake("maskrcnn_benchmark.modeling.roi_heads.box_head.loss", FastRCNNLossComputation=object())
@@ -56,7 +57,8 @@ def test_install_and_patch_loaded_swap_entry_points_and_aliases():
 
         assert d.calculate_attentive_roi_feature_distillation is ours_d.calculate_attentive_roi_feature_distillation
         assert tool.calculate_attentive_roi_feature_distillation is ours_d.calculate_attentive_roi_feature_distillation
-        assert ops.boxlist_nms is ours_o.boxlist_nms and ops.boxlist_iou is ours_o.boxlist_iou
+        # boxlist_nms / boxlist_iou dispatch on the device: CUDA BoxLists -> the kernels, CPU BoxLists -> the reference's own
+        assert ops.boxlist_nms._abr_dispatch and ops.boxlist_iou._abr_dispatch
         assert ops.boxlist_nms_batched is ours_o.boxlist_nms_batched
         assert rpn.RPNPostProcessor is ours_r.RPNPostProcessor and tool.RPNPostProcessor is ours_r.RPNPostProcessor
         assert rpn.make_rpn_postprocessor is ours_r.make_rpn_postprocessor
@@ -65,6 +67,13 @@ def test_install_and_patch_loaded_swap_entry_points_and_aliases():
         # the legacy (non-'id') distillation keeps the reference's code; the alias in the tool module was swapped too
         assert d.calculate_roi_distillation_losses is tool.calculate_roi_distillation_losses is not ref_id
         assert d.calculate_roi_distillation_losses(None, None, dist="l2") == ("reference", "l2")
+        import torch
+
+        from abr_iod_b200.structures.bounding_box import BoxList
+
+        cpu_boxes = BoxList(torch.tensor([[0.0, 0.0, 4.0, 4.0]]), (10, 10))
+        assert ops.boxlist_iou(cpu_boxes, cpu_boxes) == "reference iou"  # voc_eval.py:125 runs on CPU BoxLists
+        assert ops.boxlist_nms(cpu_boxes, 0.5) == "reference nms"
         assert len(done) >= 10
         assert compat.patch_loaded() == [] or all(isinstance(x, str) for x in compat.patch_loaded())  # idempotent
     finally:

@@ -318,7 +318,7 @@ def test_fused_full_size_config1(P):
     rg = oracle.roi_align_backward(np.ascontiguousarray(dfn[:, sl]), rois, 1 / 16, P, P, B, sl.stop - sl.start, H, W, 0)
     # positions whose sign(A_new - A_old) fp32 cannot resolve: their exact effect on the map gradient is allowed on top
     allow, n_amb = ard_sign_allowance(u_old.detach(), u_new.detach(), sl, 1.0)
-    assert n_amb < 0.01 * R * P * P
+    assert n_amb < 0.03 * R * P * P
     allow_map = oracle.roi_align_backward(allow, rois, 1 / 16, P, P, B, sl.stop - sl.start, H, W, 0)
     close_allow(grad[:, sl].cpu().numpy(), rg, allow_map, 2e-5)
     close_allow(st.grad[:, sl].cpu().numpy(), rg, allow_map, 2e-5)

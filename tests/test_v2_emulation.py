@@ -147,3 +147,29 @@ def test_fused_pool_ard(emu, P):
     _, _, _, dfn = oracle.ard(ro, rn, 1.0)
     # RoIs whose attention difference is below fp32 resolution somewhere have an ill-defined sign(): leave them out
     close(nchw(gmap), oracle.roi_align_backward(dfn, rois, 1 / 16, P, P, B, C, H, W, 0), 2e-5)
+
+
+def test_fused_tall_bins_take_the_per_sample_path(emu):
+    """The two-tensor forward keeps 12 map rows per strip; a RoI with a taller bin (13..15 rows) runs the per-sample path
+    inside the same kernel, and the fused backward serves it from its plan as usual."""
+    rng = np.random.default_rng(9)
+    B, C, H, W, P, V = 1, 8, 40, 40, 2, 4
+    t = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    s = (t + 0.1 * rng.standard_normal(t.shape)).astype(np.float32)
+    rois = np.array([[0, 2, 3, 20, 27.5], [0, 5, 1, 30, 28.9], [0, 1, 10, 12, 36.2], [0, 3, 3, 9, 9]], np.float32)
+    R = len(rois)
+    plans = plans_for(emu, rois, H, W, 1.0, P, 0)
+    tallest = [max(int(plans[r, 16 + (P + ph) * 16]) >> 16 for ph in range(P)) for r in range(R)]
+    assert max(tallest) in (13, 14, 15) and min(tallest) <= 12 and all(plans[:, 0] == 1)
+    fo = np.full((R, P, P, C), np.nan, np.float32)
+    fn = np.full((R, P, P, C), np.nan, np.float32)
+    sums = np.zeros((R, 1, P * P, 3), np.float32)
+    emu.emu_fwd(_p(plans, _i32p), _p(rois), _p(nhwc(t)), _p(nhwc(s)), _p(fo), _p(fn), _p(sums), R, C, H, W, P, P, 1.0, 0, V)
+    ro, rn = oracle.roi_align_forward(t, rois, 1.0, P, P, 0), oracle.roi_align_forward(s, rois, 1.0, P, P, 0)
+    close(nchw(fo), ro)
+    close(nchw(fn), rn)
+    close(sums.sum(1)[..., 1], (rn.astype(np.float64) ** 2).sum(1).reshape(R, -1), 2e-5)
+    gout = rng.standard_normal(ro.shape).astype(np.float32)
+    gmap = np.zeros((B, H, W, C), np.float32)
+    emu.emu_bwd(_p(plans, _i32p), _p(rois), _p(gmap), _p(nhwc(gout)), None, None, R, C, H, W, P, P, 1.0, 0, V, 0)
+    close(nchw(gmap), oracle.roi_align_backward(gout, rois, 1.0, P, P, B, C, H, W, 0))

@@ -9,6 +9,7 @@
 #define ABR_EMU 1
 #define ABR_MAX_LEVELS 8
 #define ABR_DEV static inline
+#define ABR_DEV_COLD static inline
 #define ABR_DEVM inline
 #define ABR_HD static inline
 #define ABR_HOSTDEV static inline

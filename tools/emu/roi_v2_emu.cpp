@@ -32,7 +32,7 @@ __attribute__((visibility("default"))) void emu_plan(const float* rois, int R, i
     const RoiGeom g = roi_geometry(rois, nullptr, lv, r, PH, PW, ratio);
     for (int t = 0; t < nth; t++) v2_plan_axes(plan, g, H, W, PH, PW, t, nth);
     v2_plan_header(plan, g, H, W, PH, PW);
-    for (int t = 0; t < nth; t++) v2_plan_pix(plan, PH, PW, t, nth);
+    for (int t = 0; t < nth; t++) v2_plan_transposed(plan, PH, PW, t, nth);
   }
 }
 
@@ -48,7 +48,8 @@ static void fwd_t(const int* plans, const float* rois, const float* m0, const fl
   float* outs[NT];
   maps[0] = m0; outs[0] = o0;
   if (NT == 2) { maps[NT - 1] = m1; outs[NT - 1] = o1; }
-  float* strip = new float[v2_strip_floats(V, NT)];  // one warp's strip (lanes run one after the other, each in its own columns)
+  char* strip = new char[v2_strip_bytes(V, NT)];  // one warp's strip (lanes run one after the other, each in its own columns)
+  char* plan_s = new char[v2_plan_smem_bytes(PW + PH)];
   for (int r = 0; r < R; r++)
     for (int slice = 0; slice < nslices; slice++)
       for (int pw = 0; pw < PW; pw++)
@@ -58,14 +59,16 @@ static void fwd_t(const int* plans, const float* rois, const float* m0, const fl
           const bool active = c < C;
           if (!active) c = 0;
           float* srs = NT == 2 ? sums + ((size_t)r * nslices + slice) * PH * PW * 3 : nullptr;
-          if (plan[0] == V2_GENERIC) {
+          for (int t = 0; t < 7; t++) v2_stage_plan(plan, plan_s, PW + PH, t, 7);  // the CTA's copy, then __syncthreads()
+          if (plan[0] == V2_GENERIC || (plan[0] == V2_PLAN && v2_tallest_bin(plan_s, PH, PW) > v2_strip_rows_for(NT))) {
             const RoiGeom g = roi_geometry(rois, nullptr, lv, r, PH, PW, ratio);
             v2_generic_fwd_column<float, V, NT>(g, H, W, maps, outs, srs, r, pw, c, active, C, PH, PW, lane);
           } else {
-            v2_fwd_column<float, V, NT>(plan, maps, outs, srs, strip, r, pw, c, active, C, PH, PW, lane);
+            v2_fwd_column<float, V, NT>(plan_s, maps, outs, srs, strip, nullptr, r, pw, c, active, C, PH, PW, lane);
           }
         }
   delete[] strip;
+  delete[] plan_s;
 }
 
 extern "C" __attribute__((visibility("default"))) void emu_fwd(const int* plans, const float* rois, const float* m0, const float* m1, float* o0,
@@ -89,12 +92,18 @@ static void bwd_t(const int* plans, const float* rois, float* gmap, const float*
   const size_t stride = v2_plan_words(PH, PW);
   const int nslices = (C + 32 * V - 1) / (32 * V);
   const int nwarps = 8, nbin = PH * PW;
-  float* tile = new float[(size_t)nbin * 32 * V];
+  char* tile = new char[(size_t)nbin * 32 * V * 4];
+  char* plan_s = new char[v2_plan_smem_bytes(PW + PH + kV2MaxFW + kV2MaxFH)];
   for (int r = 0; r < R; r++)
     for (int slice = 0; slice < nslices; slice++) {
       const int* plan = plans + (size_t)r * stride;
       const int mode = plan[0];
       if (mode == V2_EMPTY) continue;
+      if (mode == V2_PLAN)
+        for (int t = 0; t < 5; t++) {
+          v2_stage_plan(plan, plan_s, PW + PH + plan[7], t, 5);
+          v2_stage_records(plan, plan_s, PW + PH + kV2MaxFW, plan[9] - plan[8] + 1, t, 5);
+        }
       for (int phase = 0; phase < 2; phase++)  // __syncthreads() between filling the tile and walking the pixel columns
         for (int warp = 0; warp < nwarps; warp++)
           for (int lane = 0; lane < 32; lane++) {
@@ -106,7 +115,7 @@ static void bwd_t(const int* plans, const float* rois, float* gmap, const float*
             src.b = FUSED ? b + (size_t)r * nbin * C + c : nullptr;
             src.coef = FUSED ? reinterpret_cast<const float2*>(coef) + (size_t)r * nbin : nullptr;
             if (phase == 0) {
-              v2_bwd_fill_tile<float, V, FUSED>(tile, src, nbin, C, warp, nwarps, lane, active);
+              v2_bwd_fill_tile<float, V, FUSED>(tile, src, nbin, C, warp, nwarps, lane);
               continue;
             }
             if (!active) continue;
@@ -115,11 +124,12 @@ static void bwd_t(const int* plans, const float* rois, float* gmap, const float*
               for (int pw = warp; pw < PW; pw += nwarps) v2_generic_bwd_column<float, V>(g, H, W, gmap, tile, pw, c, C, PH, PW, lane);
             } else {
               const int FW = plan[7];
-              for (int k = warp; k < FW; k += nwarps) v2_bwd_pixcol<float, V>(plan, gmap, tile, k, c, C, PH, PW, lane);
+              for (int k = warp; k < FW; k += nwarps) v2_bwd_pixcol<float, V>(plan_s, gmap, tile, k, c, C, PH, PW, lane);
             }
           }
     }
   delete[] tile;
+  delete[] plan_s;
 }
 
 extern "C" __attribute__((visibility("default"))) void emu_bwd(const int* plans, const float* rois, float* gmap, const float* a, const float* b,
