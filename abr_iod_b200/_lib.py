@@ -42,6 +42,8 @@ SIGNATURES = {
     "abr_last_error": (ctypes.c_char_p, []),
     "abr_launch_count": (ctypes.c_uint64, []),
     "abr_set_option": (_int, [ctypes.c_char_p, _int]),
+    "abr_stage_timing_begin": (_int, [_int]),
+    "abr_stage_timing_end": (_int, [_vp, _int]),
     "abr_roi_align_workspace_bytes": (_sz, [_int, _int, _int, _int]),
     "abr_roi_align_workspace_bytes_nchw": (_sz, [_int, _int, _int, _int, _int, _int, ctypes.c_longlong, _int]),
     "abr_roi_align_workspace_bytes_layout": (_sz, [_int, _int, _int, _int, _int, _int, ctypes.c_longlong, _int, _int]),
@@ -165,6 +167,22 @@ def roi_align_workspace(R, PH, PW, max_h, device, channels_last=True, nchw_stagi
 def set_option(key: str, value: int) -> None:
     """``abr_set_option``: kernel-family switches for measurements and tests ("roi_v2", "fwd_tma", ...)."""
     check(lib().abr_set_option(key.encode(), int(value)))
+
+
+FUSED_STAGES = ("plan", "pool_teacher_student", "ard_coefficients", "backward")
+
+
+def stage_timing_begin(max_calls: int) -> None:
+    check(lib().abr_stage_timing_begin(int(max_calls)))
+
+
+def stage_timing_end():
+    """(calls recorded, {stage: average ms per call}) of the ``abr_roi_ard_fused`` calls since ``stage_timing_begin``."""
+    buf = (ctypes.c_float * len(FUSED_STAGES))()
+    n = int(lib().abr_stage_timing_end(buf, len(FUSED_STAGES)))
+    if n < 0:
+        raise RuntimeError("abr_b200 error: %s" % lib().abr_last_error().decode())
+    return n, {k: float(buf[i]) for i, k in enumerate(FUSED_STAGES)}
 
 
 def launch_count() -> int:

@@ -1,6 +1,7 @@
 // api.cu -- library-wide entry points of libabr_b200: version, thread-local error text, launch counter.
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 
@@ -28,9 +29,49 @@ Options& options() {
   return o;
 }
 
+// ---- stage timing: (ABR_FUSED_STAGES + 1) events per recorded call
+static std::vector<cudaEvent_t> g_stage_events;
+static int g_stage_max = 0, g_stage_calls = 0;
+static bool g_stage_on = false;
+constexpr int kMarks = ABR_FUSED_STAGES + 1;
+
+void stage_mark(cudaStream_t st, int k) {
+  if (!g_stage_on || g_stage_calls >= g_stage_max) return;
+  cudaEventRecord(g_stage_events[(size_t)g_stage_calls * kMarks + k], st);
+  if (k == ABR_FUSED_STAGES) g_stage_calls++;
+}
+
 }  // namespace abr
 
 extern "C" {
+int abr_stage_timing_begin(int max_calls) {
+  using namespace abr;
+  ABR_REQUIRE(max_calls > 0 && max_calls <= 4096, ABR_ERR_BAD_ARG, "stage_timing_begin: max_calls %d (1..4096)", max_calls);
+  while ((int)g_stage_events.size() < max_calls * kMarks) {
+    cudaEvent_t e;
+    ABR_CUDA_OK(cudaEventCreate(&e));
+    g_stage_events.push_back(e);
+  }
+  g_stage_max = max_calls;
+  g_stage_calls = 0;
+  g_stage_on = true;
+  return ABR_OK;
+}
+int abr_stage_timing_end(float* avg_ms, int n_stages) {
+  using namespace abr;
+  g_stage_on = false;
+  if (!avg_ms || n_stages < ABR_FUSED_STAGES) { set_error("stage_timing_end: room for %d stages needed", ABR_FUSED_STAGES); return -ABR_ERR_BAD_ARG; }
+  for (int k = 0; k < n_stages; k++) avg_ms[k] = 0.f;
+  if (g_stage_calls == 0) return 0;
+  if (cudaEventSynchronize(g_stage_events[(size_t)g_stage_calls * kMarks - 1]) != cudaSuccess) { set_error("stage_timing_end: event synchronize failed"); return -ABR_ERR_CUDA; }
+  for (int c = 0; c < g_stage_calls; c++)
+    for (int k = 0; k < ABR_FUSED_STAGES; k++) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, g_stage_events[(size_t)c * kMarks + k], g_stage_events[(size_t)c * kMarks + k + 1]);
+      avg_ms[k] += ms / g_stage_calls;
+    }
+  return g_stage_calls;
+}
 int abr_set_option(const char* key, int value) {
   ABR_REQUIRE(key, ABR_ERR_BAD_ARG, "set_option: null key");
   abr::Options& o = abr::options();

@@ -51,6 +51,10 @@ struct Options {
 };
 Options& options();
 
+// Stage timing (api.cu; abr_stage_timing_begin / _end): stage_mark(st, k) records event k of the current call on `st`
+// when timing is on (k = 0 opens a call, k = n_stages closes it); a no-op otherwise.
+void stage_mark(cudaStream_t st, int k);
+
 inline int num_sms() {
   static int n = 0;
   if (n == 0) {

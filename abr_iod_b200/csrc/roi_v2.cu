@@ -65,19 +65,15 @@ __global__ void __launch_bounds__(256, NT == 2 ? 2 : 3) v2_fwd_kernel(const __gr
   }
   float* srs = NT == 2 ? a.sums + ((size_t)r * a.nslices + slice) * a.PH * a.PW * 3 : nullptr;
   const v2_sptr plan_s = v2_sptr_of(v2_smem);
-  bool generic = mode == V2_GENERIC;  // (the whole CTA)
-  if (!generic) {
-    v2_stage_plan(plan, plan_s, a.PW + a.PH, threadIdx.x, blockDim.x);
-    __syncthreads();
-    if (v2_strip_rows_for(NT) <= kV2Sup) generic = v2_tallest_bin(plan_s, a.PH, a.PW) > v2_strip_rows_for(NT);
-  }
-  if (generic) {
+  if (mode == V2_GENERIC) {  // (the whole CTA)
     const RoiGeom g = roi_geometry(a.rois, a.levels, a.lv[0], r, a.PH, a.PW, a.ratio);
     for (int pw = warp; pw < a.PW; pw += nw)
       v2_generic_fwd_column<T, V, NT>(g, a.lv[0].H[g.level], a.lv[0].W[g.level], maps, outs, srs, r, pw, c, active, a.C, a.PH,
                                       a.PW, lane);
     return;
   }
+  v2_stage_plan(plan, plan_s, a.PW + a.PH, threadIdx.x, blockDim.x);
+  __syncthreads();
   const v2_sptr strip = plan_s + (uint32_t)a.plan_smem + warp * (uint32_t)(v2_strip_bytes(V, NT) + v2_sums_bytes(NT));
   const v2_sptr sums_buf = strip + (uint32_t)v2_strip_bytes(V, NT);
   for (int pw = warp; pw < a.PW; pw += nw)
@@ -272,22 +268,30 @@ int abr_roi_ard_fused(const void* teacher_map, const void* student_map, const fl
     lv[t].H[0] = H; lv[t].W[0] = W; lv[t].scale[0] = spatial_scale;
   }
   int rc;
+  stage_mark(st, 0);
   if (!workspace_has_plan) {
     rc = v2_plan(lv[0], rois, nullptr, plans, R, PH, PW, sampling_ratio, st);
     if (rc) return rc;
   }
+  stage_mark(st, 1);
   void* outs[2] = {pooled_old, pooled_new};
   if (C % 4 == 0) rc = launch_fwd2<float, 4, 2>(lv, plans, rois, nullptr, outs, sums, C, R, PH, PW, sampling_ratio, st);
   else rc = launch_fwd2<float, 1, 2>(lv, plans, rois, nullptr, outs, sums, C, R, PH, PW, sampling_ratio, st);
   if (rc) return rc;
+  stage_mark(st, 2);
   rc = ard_coeff_run(sums, ceil_div(C, 32 * (C % 4 == 0 ? 4 : 1)), coef, loss3, R, C, PH * PW, gamma, grad_scale, ws + f.ard, st);
   if (rc) return rc;
-  if (!grad_student_map) return ABR_OK;
-  if (zero_init) ABR_CUDA_OK(cudaMemsetAsync(grad_student_map, 0, (size_t)B * C * H * W * sizeof(float), st));
-  LevelTable gl = lv[1];
-  gl.ptr[0] = grad_student_map;
-  if (C % 4 == 0) return launch_bwd2<float, 4, true>(gl, plans, rois, nullptr, pooled_old, pooled_new, coef, C, R, PH, PW, sampling_ratio, st);
-  return launch_bwd2<float, 1, true>(gl, plans, rois, nullptr, pooled_old, pooled_new, coef, C, R, PH, PW, sampling_ratio, st);
+  stage_mark(st, 3);
+  if (grad_student_map) {
+    if (zero_init) ABR_CUDA_OK(cudaMemsetAsync(grad_student_map, 0, (size_t)B * C * H * W * sizeof(float), st));
+    LevelTable gl = lv[1];
+    gl.ptr[0] = grad_student_map;
+    if (C % 4 == 0) rc = launch_bwd2<float, 4, true>(gl, plans, rois, nullptr, pooled_old, pooled_new, coef, C, R, PH, PW, sampling_ratio, st);
+    else rc = launch_bwd2<float, 1, true>(gl, plans, rois, nullptr, pooled_old, pooled_new, coef, C, R, PH, PW, sampling_ratio, st);
+    if (rc) return rc;
+  }
+  stage_mark(st, 4);
+  return ABR_OK;
 }
 
 }  // extern "C"

@@ -8,7 +8,7 @@
 //        out[ph][pw] = (1/count) * sum_y Wy[ph][y] * sum_x Wx[pw][x] * V[y][x]            (exactly)
 //     with per-axis tables Wy / Wx that depend on the RoI only.  plan kernel: one 16-word record per bin row, per bin
 //     column and per footprint pixel column:  { first index | count << 16, up to 15 weights }.
-//   * FORWARD, a warp owns (RoI, bin column pw, 32*V channels).  It works in STRIPS of up to kV2Rows map rows: phase 1
+//   * FORWARD, a warp owns (RoI, bin column pw, 32*V channels).  It works in STRIPS of up to 16 map rows: phase 1
 //     computes  T[y] = sum_x Wx[pw][x] * V[y][x]  for the strip's rows -- four rows at a time, all of their loads
 //     (nx coalesced 512-byte requests per row) issued before the first is used, so a warp keeps up to 16 requests in
 //     flight instead of one dependent gather after another -- into a lane-private strip of shared memory (every lane
@@ -264,15 +264,6 @@ ABR_DEV void v2_stage_plan(const int* __restrict__ plan, v2_sptr plan_s, int nre
 ABR_DEV void v2_stage_records(const int* __restrict__ plan, v2_sptr plan_s, int first, int nrec, int tid, int nth) {
   for (int i = tid; i < 4 * nrec; i += nth) v2_sts4i(plan_s + 64 * (1 + first) + 16 * i, ABR_LDG4I(plan + kV2Hdr + first * kV2Rec + 4 * i));
 }
-// Tallest bin of the staged plan (rows); every thread of the CTA gets the same answer.
-ABR_DEV int v2_tallest_bin(v2_sptr plan_s, int PH, int PW) {
-  int n = 0;
-  for (int ph = 0; ph < PH; ph++) {
-    const int k = v2_lds4i(v2_srec(plan_s, PW + ph)).x >> 16;
-    n = k > n ? k : n;
-  }
-  return n;
-}
 ABR_HOSTDEV size_t v2_plan_smem_bytes(int nrec) { return (size_t)64 * (1 + nrec); }
 
 // Three warp totals with six shuffles (reduce-scatter): on return lane 0 holds sum(a), lane 16 sum(b), lane 8 sum(c).
@@ -299,7 +290,7 @@ ABR_DEV float v2_reduce3(float a, float b, float c, int lane) {
 // with shuffles costs a dependent chain of five shuffle/add pairs per bin; instead the partials of up to kV2SumBins bins
 // are parked in a warp-private shared-memory table ([value][lane], rows skewed by one word so that both the lane-major
 // writes and the value-major reads are conflict-free) and folded by 3 * bins lanes at once, 32 sequential adds each.
-constexpr int kV2SumBins = 8;
+constexpr int kV2SumBins = 4;
 ABR_HOSTDEV size_t v2_sums_bytes(int NT) { return NT == 2 ? (size_t)(kV2SumBins * 3 * 33 * 4 + 127) / 128 * 128 : 0; }
 
 struct V2Sums {
@@ -392,8 +383,9 @@ ABR_DEV void v2_emit_bin_now(float (&acc)[NT][V], float inv_count, T* const (&o)
   }
 }
 
-// Map rows per strip: 16 holds the tallest bin a record can describe (kV2Sup = 15 rows); the two-tensor kernel takes 12
-// so that two CTAs fit an SM, and sends the (rare) RoIs with a taller bin down the per-sample path.
+// Map rows per strip: 16 for one tensor, 12 for two (so that two 7-warp CTAs of the two-tensor kernel fit an SM; 8 rows
+// and three CTAs measured the same -- shorter strips overlap more and recompute more rows).  A bin taller than the strip
+// (fat bins of very tall RoIs) is accumulated straight from the map instead (v2_bin_direct).
 ABR_HOSTDEV constexpr int v2_strip_rows_for(int NT) { return NT == 2 ? 12 : 16; }
 
 // Bytes of shared memory one forward warp's strips take: [NT][ROWS][32 lanes][V] floats.
@@ -458,6 +450,39 @@ ABR_DEV void v2_strip_rows_wide(const T* colbase, size_t rowstride, size_t pix, 
   }
 }
 
+// A bin taller than the strip: acc += sum_i Wy[i] * T[lo + i] with the rows of T formed on the fly, four rows of loads
+// in flight at a time (same clamping trick as above; the weight of a repeated row is zero).
+template <typename T, int V>
+ABR_DEV void v2_bin_direct(const T* colbase, size_t rowstride, size_t pix, int n, int nx, v2_sptr colrec, v2_sptr binrec, float (&acc)[V]) {
+  constexpr int RB = V >= 8 ? 2 : 4;
+  for (int i0 = 0; i0 < n; i0 += RB) {
+    float t[RB][V];
+    const T* p[RB];
+#pragma unroll
+    for (int j = 0; j < RB; j++) {
+      p[j] = colbase + (size_t)(i0 + j < n ? i0 + j : n - 1) * rowstride;
+#pragma unroll
+      for (int q = 0; q < V; q++) t[j][q] = 0.f;
+    }
+    for (int k = 0; k < nx; k++) {
+      const float w = v2_srec_w(colrec, k);
+      float v[RB][V];
+#pragma unroll
+      for (int j = 0; j < RB; j++) VecIO<T, V>::load(p[j] + (size_t)k * pix, v[j]);
+#pragma unroll
+      for (int j = 0; j < RB; j++)
+#pragma unroll
+        for (int q = 0; q < V; q++) t[j][q] = fmaf(w, v[j][q], t[j][q]);
+    }
+#pragma unroll
+    for (int j = 0; j < RB; j++) {
+      const float wy = i0 + j < n ? v2_srec_w(binrec, i0 + j) : 0.f;
+#pragma unroll
+      for (int q = 0; q < V; q++) acc[q] = fmaf(wy, t[j][q], acc[q]);
+    }
+  }
+}
+
 // One bin column of one RoI.  plan_s: the plan in shared memory (header, PW column records, PH bin-row records);
 // maps[t]: the level's map of tensor t ([B][H][W][C]); outs[t]: pooled tensor ([R][PH][PW][C]); c: first channel of this
 // lane; sums_rs: &sums[(r * nslices + slice) * PH*PW * 3] (NT == 2); strip: this WARP's v2_strip_bytes(V, NT) of shared
@@ -502,8 +527,22 @@ ABR_DEV void v2_fwd_column(v2_sptr plan_s, const T* const (&maps)[NT], T* const 
       ph++;
       continue;
     }
-    // ---- phase 1: T of the rows ystart .. ystart + nrows - 1
     const int ystart = b.x & 0xffff;
+    if ((b.x >> 16) > kV2Rows) {  // taller than a strip
+      float acc[NT][V];
+#pragma unroll
+      for (int t = 0; t < NT; t++) {
+#pragma unroll
+        for (int k = 0; k < V; k++) acc[t][k] = 0.f;
+        v2_bin_direct<T, V>(base[t] + (size_t)ystart * rowstride, rowstride, pix, b.x >> 16, nx, colrec, binrec, acc[t]);
+      }
+      v2_emit_bin<T, V, NT>(acc, inv_count, o, active, sums, lane);
+#pragma unroll
+      for (int t = 0; t < NT; t++) o[t] += binstride;
+      ph++;
+      continue;
+    }
+    // ---- phase 1: T of the rows ystart .. ystart + nrows - 1
     const int nrows = Y1 - ystart + 1 < kV2Rows ? Y1 - ystart + 1 : kV2Rows;
 #pragma unroll
     for (int t = 0; t < NT; t++) {
@@ -517,7 +556,7 @@ ABR_DEV void v2_fwd_column(v2_sptr plan_s, const T* const (&maps)[NT], T* const 
         default: v2_strip_rows_wide<T, V>(colbase, rowstride, pix, nrows, nx, colrec, dst); break;
       }
     }
-    // ---- phase 2: every bin whose rows lie inside the strip (at least the one that started it: n <= kV2Rows)
+    // ---- phase 2: every bin whose rows lie inside the strip (at least the one that started it)
     while (true) {
       const int n = b.x >> 16;
       const v2_sptr src = mine + ((b.x & 0xffff) - ystart) * ROWB;
@@ -567,7 +606,7 @@ ABR_DEV void v2_fwd_column(v2_sptr plan_s, const T* const (&maps)[NT], T* const 
       binrec += 64;
       b = v2_lds4i(binrec);
       const int n2 = b.x >> 16;
-      if (n2 == 0 || (b.x & 0xffff) + n2 > ystart + nrows) break;  // an empty bin or one that needs a new strip: outer loop
+      if (n2 == 0 || (b.x & 0xffff) + n2 > ystart + nrows) break;  // an empty bin, or one that needs a new strip: outer loop
     }
   }
   if (NT == 2 && sums.n > 0) v2_sums_flush(sums, lane);

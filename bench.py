@@ -1,20 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- the reference's headline metric on B200: ROIAlign+ARD RoIs/s, forward+backward.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--layout nhwc|nchw|nchw_cl]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload configs0|configs1_p7|fpn|paste] [--route fused|separate]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
 
-A "step" is one pass of the RoI hot path over one batch of synthetic input at the shapes of BASELINE.json
-configs[1] (VOC 15-5 ABR incremental step, batch 4 per GPU): teacher and student R-50-C4 feature maps
-[4,1024,50,76] fp32 (800x1216 images, stride 16), 512 RoIs per image, POOLER_RESOLUTION 7, adaptive sampling
-(sampling_ratio 0).  The work unit is the composite of SURVEY.md section 8d: one RoI through teacher ROIAlign
-forward, student ROIAlign forward, ARD loss forward+backward (gamma=1) and student ROIAlign backward.
-Work shards by image, so N GPUs run N independent batches (weak scaling, no data-path collective).
+Default workload = BASELINE.json configs[0], the configuration the metric is quoted on: teacher and student R-50-C4
+feature maps [2,1024,38,63] fp32 (two 600x1000 VOC images, stride 16), 512 RoIs per image, POOLER_RESOLUTION 14 (the
+code default, config/defaults.py:239), adaptive sampling (sampling_ratio 0).  A "step" is one pass of the RoI hot path
+over one batch: the composite unit of SURVEY.md section 8d -- teacher ROIAlign forward, student ROIAlign forward, ARD
+loss forward+backward (gamma=1) and student ROIAlign backward -- which this library runs as ONE call (abr_roi_ard_fused:
+plan, teacher+student pooling with the ARD channel sums in its epilogue, per-RoI coefficients, backward that forms the
+ARD gradient on the fly).  Work shards by image, so N GPUs run N independent batches (weak scaling, no data-path
+collective).
 
 One JSON line on rank 0: `value` = RoIs/s with inputs resident in HBM (CUDA events over exactly K steps, max over
-ranks); `e2e` = the same metric through the public Python API with HOST buffers (pinned H2D of both feature maps
-and the RoIs, D2H of the loss and of the student feature-map gradient inside the timed region); `roofline` for the
-dominant kernel from per-kernel CUDA events; `cpu_baseline` = the reference's CPU path on this box's host cores.
+ranks); `e2e` = the same metric through the public Python API with HOST buffers (pinned H2D of both feature maps and the
+RoIs, D2H of the loss and of the student feature-map gradient inside the timed region); `roofline` for the dominant
+kernel from CUDA events recorded around the kernels on their stream; `cpu_baseline` = the reference's CPU path on this
+box's host cores; `workloads` = the round-1 P=7 line, config 5 (FPN) and `secondary` = configs 3 and 4 with their CPU
+baselines.
 """
 import argparse
 import json
@@ -30,16 +35,22 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-WORKLOAD = dict(B=4, C=1024, H=50, W=76, rois_per_image=512, P=7, sampling_ratio=0, scale=1.0 / 16,
-                image_w=1216, image_h=800)
+WORKLOADS = {
+    # BASELINE.json configs[0] (SURVEY 8d "Config 1"): the quoted configuration
+    "configs0": dict(B=2, C=1024, H=38, W=63, rois_per_image=512, P=14, sampling_ratio=0, scale=1.0 / 16, image_w=1000,
+                     image_h=600, name="configs[0] ROIAlign 14x14 + ARD, synthetic VOC batch (2 imgs 600x1000, R-50-C4 1024ch "
+                                       "stride 16, 512 RoIs/img)"),
+    # round-1 headline: configs[1] shapes (VOC 15-5 ABR step, batch 4 per GPU) at the shipped POOLER_RESOLUTION 7
+    "configs1_p7": dict(B=4, C=1024, H=50, W=76, rois_per_image=512, P=7, sampling_ratio=0, scale=1.0 / 16, image_w=1216,
+                        image_h=800, name="configs[1] shapes: VOC 15-5 ABR step RoI path, batch 4 (800x1216), 512 RoIs/img, P=7"),
+}
 METRIC = "ROIAlign+ARD RoIs/s fwd+bwd"
 UNIT = "RoIs/s"
 
 
-def make_workload(seed=0, rois=None):
+def make_workload(w, seed=0, rois=None):
     """Synthetic VOC-shaped batch: student = teacher + 0.1*noise; RoI centres uniform in the image,
     sides U(16,400) px, clipped to the image, 5 % degenerate (< 1 px)."""
-    w = WORKLOAD
     rng = np.random.default_rng(seed)
     teacher = rng.standard_normal((w["B"], w["C"], w["H"], w["W"]), dtype=np.float32)
     student = teacher + np.float32(0.1) * rng.standard_normal(teacher.shape, dtype=np.float32)
@@ -55,16 +66,25 @@ def make_workload(seed=0, rois=None):
     return teacher, student, roi
 
 
-def algorithmic_bytes(R):
+def algorithmic_bytes(w, R):
     """per kernel and for the composite unit (3*BCHW*s + 60R + 6*R*C*P^2*s)."""
-    w = WORKLOAD
     fmap = w["B"] * w["C"] * w["H"] * w["W"] * 4
     pooled = R * w["C"] * w["P"] * w["P"] * 4
     return {"roi_align_fwd": fmap + 20 * R + pooled, "roi_align_bwd": pooled + 20 * R + fmap, "ard": 3 * pooled,
-            "composite": 3 * fmap + 60 * R + 6 * pooled}
+            "composite": 3 * fmap + 60 * R + 6 * pooled, "fmap": fmap, "pooled": pooled}
 
 
-# ------------------------------------------------------------------------------------------------ clocks
+def workload_config(w, route):
+    ab = algorithmic_bytes(w, w["B"] * w["rois_per_image"])
+    return {"workload": "%s: teacher+student maps [%d,%d,%d,%d] fp32 channels-last, %d RoIs/img, P=%d, sampling_ratio=%d; "
+                        "unit = teacher ROIAlign fwd + student ROIAlign fwd + ARD fwd+bwd + student ROIAlign bwd"
+                        % (w["name"], w["B"], w["C"], w["H"], w["W"], w["rois_per_image"], w["P"], w["sampling_ratio"]),
+            "route": route, "batch_per_gpu": w["B"], "rois_per_gpu": w["B"] * w["rois_per_image"],
+            "parallelism": "data-parallel by image",
+            "l2": "per-step inputs+outputs %.2f GB >> 126 MB L2, no explicit flush" % (ab["composite"] / 1e9)}
+
+
+# ------------------------------------------------------------------------------------------------ clocks / placement
 class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -73,7 +93,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -86,22 +106,48 @@ class ClockSampler:
     def summary(self, t0, t1):
         if self.proc is not None:
             self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15 and len(r) >= 6] or [r for _, r in self.rows if len(r) >= 6]
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.05 and len(r) >= 6]
+        note = "sampled inside the timed region"
+        if not rows:
+            rows, note = [r for _, r in self.rows if len(r) >= 6], "no sample fell inside the timed region: all samples of the run"
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         sm = sorted(float(r[0]) for r in rows)
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons, "samples": len(rows)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons, "samples": len(rows), "note": note}
+
+
+def bind_to_gpu_numa(index):
+    """Pin this process (and the pinned host buffers it allocates afterwards: first touch) to the NUMA node of GPU
+    `index`, so that N ranks do not all stage their copies through node 0.  Returns a description for the JSON line."""
+    try:
+        import torch
+
+        p = torch.cuda.get_device_properties(index)
+        bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return {"numa_node": None, "note": "the platform reports no NUMA affinity for %s" % bus}
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus_bound": len(cpus), "pci": bus}
+    except Exception as e:  # noqa: BLE001  (placement is best effort; the record says what happened)
+        return {"numa_node": None, "note": "not bound: %s" % e}
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference
-def cpu_reference_sample(n_rois, threads=None):
+def cpu_reference_sample(w, n_rois, threads=None):
     """The reference's CPU path for the composite unit on `n_rois` RoIs of the workload.  ROIAlign forward is the
     reference's own ROIAlign_forward_cpu (oracle/_ref, single-threaded by construction: csrc/cpu/ROIAlign_cpu.cpp:133)
     when it was compiled, else the C port; ARD is the PyTorch op sequence of distillation.py:86-130 on all host
     threads; ROIAlign backward has no CPU reference (csrc/ROIAlign.h:44) and is timed with the C port of the CUDA
-    kernel.  Returns (seconds, description)."""
+    kernel.  Returns (seconds, kind, description, threads)."""
     import torch
 
     import oracle
@@ -109,8 +155,7 @@ def cpu_reference_sample(n_rois, threads=None):
 
     if threads:
         torch.set_num_threads(threads)
-    w = WORKLOAD
-    teacher, student, rois = make_workload(0, rois=n_rois)
+    teacher, student, rois = make_workload(w, 0, rois=n_rois)
     use_ref = oracle.ref_available()
     t0 = time.perf_counter()
     f_old = oracle.roi_align_forward(teacher, rois, w["scale"], w["P"], w["P"], w["sampling_ratio"], use_ref=use_ref)
@@ -129,211 +174,414 @@ def cpu_reference_sample(n_rois, threads=None):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    # calibrate the bounded sample so that K steps take about a minute in total (8..256 RoIs per step)
-    cpu_reference_sample(8)
-    per_roi = cpu_reference_sample(16)[0] / 16
-    sample = int(max(8, min(256, 60.0 / max(args.steps, 1) / per_roi)))
+    w = WORKLOADS[args.workload if args.workload in WORKLOADS else "configs0"]
+    # calibrate the bounded sample so that K steps take about a minute in total (4..256 RoIs per step)
+    cpu_reference_sample(w, 4)
+    per_roi = cpu_reference_sample(w, 8)[0] / 8
+    sample = int(max(4, min(256, 60.0 / max(args.steps, 1) / per_roi)))
     for _ in range(min(args.warmup, 1)):
-        cpu_reference_sample(sample)
+        cpu_reference_sample(w, sample)
     t, kind, desc, cores = 0.0, "port", "", 1
     for _ in range(args.steps):
-        dt, kind, desc, cores = cpu_reference_sample(sample)
+        dt, kind, desc, cores = cpu_reference_sample(w, sample)
         t += dt
     value = sample * args.steps / t
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(), sample_rois_per_step=sample),
+            "config": dict(workload_config(w, "reference CPU path"), sample_rois_per_step=sample),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
-def workload_config():
-    w = WORKLOAD
-    return {"workload": "configs[1] VOC 15-5 ABR step, RoI hot path: teacher+student R-50-C4 maps [%d,%d,%d,%d] fp32, "
-                        "%d RoIs/img, P=%d, sampling_ratio=%d; unit = teacher ROIAlign fwd + student ROIAlign fwd + "
-                        "ARD fwd+bwd + student ROIAlign bwd" % (w["B"], w["C"], w["H"], w["W"], w["rois_per_image"],
-                                                              w["P"], w["sampling_ratio"]),
-            "batch_per_gpu": w["B"], "rois_per_gpu": w["B"] * w["rois_per_image"], "parallelism": "data-parallel by image",
-            "l2": "per-step inputs+outputs 2.65 GB >> 126 MB L2, no explicit flush"}
+# ------------------------------------------------------------------------------------------------ the RoI path
+class RoiPath:
+    """One workload resident on one GPU, runnable on the fused route (ONE C-ABI call per step) or on the separate ops."""
 
+    def __init__(self, w, dev, seed, route):
+        import torch
 
-# ------------------------------------------------------------------------------------------------ ours
-def run_ours(args, rank, world, local_rank):
-    import torch
-    import torch.distributed as dist
+        from abr_iod_b200 import _lib
 
-    from abr_iod_b200 import _lib
-    from abr_iod_b200.distillation.distillation import _ard_launch
-    from abr_iod_b200.distillation.distillation import calculate_attentive_roi_feature_distillation as ard
-    from abr_iod_b200.layers import ROIAlign
-    from abr_iod_b200.layers.roi_align import roi_align_backward, roi_align_forward
+        self.w, self.dev, self.route, self.torch, self._lib = w, dev, route, torch, _lib
+        self.teacher_np, self.student_np, self.rois_np = make_workload(w, seed=seed)
+        cl = torch.channels_last
+        self.teacher = torch.from_numpy(self.teacher_np).to(dev).contiguous(memory_format=cl)
+        self.student = torch.from_numpy(self.student_np).to(dev).contiguous(memory_format=cl)
+        self.rois = torch.from_numpy(self.rois_np).to(dev)
+        self.R = self.rois_np.shape[0]
+        P, C = w["P"], w["C"]
+        if route == "fused":
+            L = _lib.lib()
+            self.f_old = torch.empty((self.R, C, P, P), device=dev).contiguous(memory_format=cl)
+            self.f_new = torch.empty_like(self.f_old)
+            self.gmap = torch.empty_like(self.student)
+            self.loss3 = torch.empty(3, device=dev)
+            self.ws_bytes = int(L.abr_roi_ard_fused_workspace_bytes(self.R, C, P, P))
+            self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
 
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    sampler = ClockSampler(local_rank) if rank == 0 else None  # started early: nvidia-smi needs a second to warm up
-    w = WORKLOAD
-    nhwc = args.layout == "nhwc"
-    _lib.POOLED_CHANNELS_LAST = args.layout == "nchw_cl"  # contiguous maps, channels-last RoI features
-    fmt = torch.channels_last if nhwc else torch.contiguous_format
-    teacher_np, student_np, rois_np = make_workload(seed=rank)
-    R = rois_np.shape[0]
-    teacher = torch.from_numpy(teacher_np).to(dev).contiguous(memory_format=fmt)
-    student = torch.from_numpy(student_np).to(dev).contiguous(memory_format=fmt)
-    rois = torch.from_numpy(rois_np).to(dev)
-    P, ratio, scale = w["P"], w["sampling_ratio"], w["scale"]
-    names = ("roi_align_fwd_teacher", "roi_align_fwd_student", "ard", "roi_align_bwd")
+    def step(self, events=None):
+        w, _lib, torch = self.w, self._lib, self.torch
+        P, ratio, scale = w["P"], w["sampling_ratio"], w["scale"]
+        if self.route == "fused":
+            # buffers are reused from step to step; RoIs are re-planned every step (a new batch has new RoIs)
+            _lib.check(_lib.lib().abr_roi_ard_fused(
+                self.teacher.data_ptr(), self.student.data_ptr(), self.rois.data_ptr(), self.f_old.data_ptr(),
+                self.f_new.data_ptr(), self.gmap.data_ptr(), self.loss3.data_ptr(), w["B"], w["C"], w["H"], w["W"], self.R,
+                P, P, scale, ratio, 1.0, 1.0, _lib.ABR_F32, _lib.ABR_NHWC, 1, self.ws.data_ptr(), self.ws_bytes, 0,
+                _lib.stream_ptr(self.dev)))
+            return self.loss3, self.gmap
+        from abr_iod_b200.distillation.distillation import _ard_launch
+        from abr_iod_b200.layers.roi_align import roi_align_backward, roi_align_forward
 
-    def step(ev=None):
         marks = []
 
         def mark():
-            if ev is not None:
+            if events is not None:
                 e = torch.cuda.Event(enable_timing=True)
                 e.record()
                 marks.append(e)
         mark()
-        f_old, plan = roi_align_forward(teacher, rois, scale, P, P, ratio, return_plan=True)
+        f_old, plan = roi_align_forward(self.teacher, self.rois, scale, P, P, ratio, return_plan=True)
         mark()
-        f_new = roi_align_forward(student, rois, scale, P, P, ratio, plan=plan)  # same RoIs and map shape: plans reused
+        f_new = roi_align_forward(self.student, self.rois, scale, P, P, ratio, plan=plan)  # same RoIs: plans reused
         mark()
         loss3, g = _ard_launch(f_old, f_new, 1.0, True)
         mark()
-        gin = roi_align_backward(g, rois, scale, P, P, w["B"], w["C"], w["H"], w["W"], ratio, layout=_lib.roi_align_layout(student), plan=plan)
+        gin = roi_align_backward(g, self.rois, scale, P, P, w["B"], w["C"], w["H"], w["W"], ratio, layout=_lib.ABR_NHWC, plan=plan)
         mark()
-        if ev is not None:
-            ev.append(marks)
+        if events is not None:
+            events.append(marks)
         return loss3, gin
+
+    def kernel_bytes(self):
+        """Algorithmic bytes attributed to each timed stage of the route."""
+        ab = algorithmic_bytes(self.w, self.R)
+        if self.route == "fused":
+            return {"plan": 20 * self.R,
+                    "pool_teacher_student": 2 * ab["roi_align_fwd"],          # teacher fwd + student fwd
+                    "ard_coefficients": 0,
+                    "backward": ab["ard"] + ab["roi_align_bwd"]}              # ARD fwd+bwd + student bwd
+        return {"roi_align_fwd_teacher": ab["roi_align_fwd"], "roi_align_fwd_student": ab["roi_align_fwd"], "ard": ab["ard"],
+                "roi_align_bwd": ab["roi_align_bwd"]}
+
+    def timed(self, steps, warmup, barrier):
+        """(ms per step, {stage: ms}, launches, t0, t1) over exactly `steps` steps after `warmup` untimed ones."""
+        torch, _lib = self.torch, self._lib
+        for _ in range(warmup):
+            self.step()
+        barrier()
+        launches0 = _lib.launch_count()
+        events = []
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if self.route == "fused":
+            _lib.stage_timing_begin(min(steps, 4096))
+        t0 = time.time()
+        start.record()
+        for _ in range(steps):
+            self.step(events)
+        end.record()
+        barrier()
+        t1 = time.time()
+        ms = start.elapsed_time(end) / steps
+        if self.route == "fused":
+            _, per_kernel = _lib.stage_timing_end()
+        else:
+            names = ("roi_align_fwd_teacher", "roi_align_fwd_student", "ard", "roi_align_bwd")
+            per_kernel = {n: sum(m[i].elapsed_time(m[i + 1]) for m in events) / len(events) for i, n in enumerate(names)}
+        return ms, per_kernel, _lib.launch_count() - launches0, t0, t1
+
+    def e2e(self, steps, barrier):
+        """The same unit through the public autograd API with HOST buffers: per step pinned H2D of both maps and the
+        RoIs, D2H of the loss and of the student map's gradient.  Two streams, steps alternate between them: every step
+        pays its own copies, consecutive steps overlap (copy engines both ways + SMs) like a double-buffered input
+        pipeline.  Returns (ms per step, h2d bytes, d2h bytes)."""
+        torch, w, dev = self.torch, self.w, self.dev
+        from abr_iod_b200.distillation.distillation import calculate_attentive_roi_feature_distillation as ard
+        from abr_iod_b200.distillation.distillation import pooled_attentive_roi_distillation
+        from abr_iod_b200.layers import ROIAlign
+
+        P, ratio, scale = w["P"], w["sampling_ratio"], w["scale"]
+        cl = torch.channels_last
+        h_teacher = torch.from_numpy(self.teacher_np).contiguous(memory_format=cl).pin_memory()
+        h_student = torch.from_numpy(self.student_np).contiguous(memory_format=cl).pin_memory()
+        h_rois = torch.from_numpy(self.rois_np).pin_memory()
+        streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+        h_grad = [torch.empty_like(h_student).pin_memory() for _ in streams]
+        h_loss = [torch.empty((), dtype=torch.float32).pin_memory() for _ in streams]
+        pool = ROIAlign((P, P), scale, ratio)
+
+        def one(i):
+            k = i % len(streams)
+            with torch.cuda.stream(streams[k]):
+                t = h_teacher.to(dev, non_blocking=True)
+                s = h_student.to(dev, non_blocking=True).requires_grad_(True)
+                r = h_rois.to(dev, non_blocking=True)
+                if self.route == "fused":
+                    _, _, loss = pooled_attentive_roi_distillation(t, s, r, (P, P), scale, ratio, 1.0)
+                else:
+                    with torch.no_grad():
+                        f_old = pool(t, r)
+                    loss = ard(f_old, pool(s, r), 1.0)
+                loss.backward()
+                h_loss[k].copy_(loss.detach(), non_blocking=True)
+                h_grad[k].copy_(s.grad, non_blocking=True)
+
+        for i in range(4):
+            one(i)
+        barrier()
+        es, ee = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for st_ in streams:
+            st_.wait_stream(torch.cuda.current_stream(dev))
+        es.record(streams[0])
+        streams[1].wait_event(es)
+        for i in range(steps):
+            one(i)
+        streams[0].wait_stream(streams[1])
+        ee.record(streams[0])
+        barrier()
+        h2d = int(h_teacher.numel() * 4 + h_student.numel() * 4 + h_rois.numel() * 4)
+        d2h = int(h_grad[0].numel() * 4 + 4)
+        return es.elapsed_time(ee) / steps, h2d, d2h
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def kernel_table(per_kernel, kbytes, peak):
+    return {n: {"ms": round(per_kernel[n], 4), "algorithmic_bytes": kbytes[n],
+                "GB/s": round(kbytes[n] / (per_kernel[n] * 1e-3) / 1e9, 1) if per_kernel[n] > 0 else None,
+                "frac": round(kbytes[n] / (per_kernel[n] * 1e-3) / 1e9 / peak, 4) if per_kernel[n] > 0 else None}
+            for n in per_kernel}
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    placement = bind_to_gpu_numa(local_rank)
+    sampler = ClockSampler(local_rank) if rank == 0 else None  # started early: nvidia-smi needs a second to warm up
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    launches0 = _lib.launch_count()
-    events = []
-    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.time()
-    start.record()
-    for _ in range(args.steps):
-        step(events)
-    end.record()
-    barrier()
-    t1 = time.time()
-    elapsed_ms = start.elapsed_time(end)
-    launches = _lib.launch_count() - launches0
+    if args.workload in ("fpn", "paste"):
+        return run_other_workload(args, rank, world, dev, barrier, sampler)
+    w = WORKLOADS[args.workload]
+    path = RoiPath(w, dev, seed=rank, route=args.route)
+    R = path.R
+    warm = max(args.warmup, 3)
+    # the driver's default run is short (tens of milliseconds): precede the timed region by ~0.3 s of the same work so
+    # that clocks and the clock sampler have settled; these steps are warm-up, outside the K timed steps
+    t_settle = time.time()
+    while time.time() - t_settle < 0.3:
+        path.step()
+    ms_per_step, per_kernel, launches, t0, t1 = path.timed(args.steps, warm, barrier)
     clocks = sampler.summary(t0, t1) if sampler else None
-    per_kernel = {n: sum(m[i].elapsed_time(m[i + 1]) for m in events) / len(events) for i, n in enumerate(names)}
-
-    # ---- end to end through the public API with host buffers
-    pool = ROIAlign((P, P), scale, ratio)
-    h_teacher = torch.from_numpy(teacher_np).contiguous(memory_format=fmt).pin_memory()
-    h_student = torch.from_numpy(student_np).contiguous(memory_format=fmt).pin_memory()
-    h_rois = torch.from_numpy(rois_np).pin_memory()
-    # Two streams, steps alternate between them: every step still pays its own H2D of both maps + RoIs and its own D2H of
-    # the loss and the gradient map, but consecutive steps overlap (copy engines in both directions + SMs), the way a
-    # double-buffered input pipeline feeds a training loop.
-    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
-    h_grad = [torch.empty_like(h_student).pin_memory() for _ in streams]
-    h_loss = [torch.empty((), dtype=torch.float32).pin_memory() for _ in streams]
-
-    def e2e_step(i):
-        k = i % len(streams)
-        with torch.cuda.stream(streams[k]):
-            t = h_teacher.to(dev, non_blocking=True)
-            s = h_student.to(dev, non_blocking=True).requires_grad_(True)
-            r = h_rois.to(dev, non_blocking=True)
-            with torch.no_grad():
-                f_old = pool(t, r)
-            f_new = pool(s, r)
-            loss = ard(f_old, f_new, 1.0)
-            loss.backward()
-            h_loss[k].copy_(loss.detach(), non_blocking=True)
-            h_grad[k].copy_(s.grad, non_blocking=True)
-
-    for i in range(4):
-        e2e_step(i)
-    barrier()
     e2e_steps = max(4, min(args.steps, 40))
-    es, ee = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for st_ in streams:
-        st_.wait_stream(torch.cuda.current_stream(dev))
-    es.record(streams[0])
-    streams[1].wait_event(es)
-    for i in range(e2e_steps):
-        e2e_step(i)
-    streams[0].wait_stream(streams[1])
-    ee.record(streams[0])
-    barrier()
-    e2e_ms = es.elapsed_time(ee)
+    e2e_ms, h2d, d2h = path.e2e(e2e_steps, barrier)
 
     if world > 1:
-        t = torch.tensor([elapsed_ms, e2e_ms], device=dev)
+        t = torch.tensor([ms_per_step, e2e_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms, e2e_ms = t.tolist()
+        ms_per_step, e2e_ms = t.tolist()
         lt = torch.tensor([launches], device=dev, dtype=torch.int64)
         dist.all_reduce(lt)
         launches = int(lt.item())
     if rank != 0:
         return
 
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
-    else:
-        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-    ab = algorithmic_bytes(R)
-    kbytes = {"roi_align_fwd_teacher": ab["roi_align_fwd"], "roi_align_fwd_student": ab["roi_align_fwd"], "ard": ab["ard"],
-              "roi_align_bwd": ab["roi_align_bwd"]}
-    dominant = max(per_kernel, key=per_kernel.get)
+    peak, peak_src = measured_peak()
+    ab = algorithmic_bytes(w, R)
+    kbytes = path.kernel_bytes()
+    timed_kernels = {k: v for k, v in per_kernel.items() if kbytes[k] > 20 * R}
+    dominant = max(timed_kernels, key=timed_kernels.get)
     achieved = kbytes[dominant] / (per_kernel[dominant] * 1e-3) / 1e9
-    traffic, limiter = None, None
+    traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        tj = json.load(open(tpath))
-        traffic = tj.get(args.layout, {}).get(dominant)
-        # The dominant kernel is not DRAM-bound on this input (the map is L2-resident and RoIs overlap ~23x): next to the
-        # required HBM roofline, report it against the on-chip resource that does bound it -- bytes per launch from ncu,
-        # peak from the committed microbenchmarks, time from this run.
-        lim = tj.get("l2_limits", {}).get(dominant) if args.layout == "nhwc" else None
-        if lim:
-            got = lim["bytes_per_launch"] / (per_kernel[dominant] * 1e-3) / 1e9
-            limiter = {"resource": lim["resource"], "achieved": round(got, 1), "peak": lim["peak_gbs"], "unit": "GB/s",
-                       "frac": round(got / lim["peak_gbs"], 4), "source": lim["source"]}
-    ms_per_step = elapsed_ms / args.steps
+        traffic = json.load(open(tpath)).get("%s/%s" % (args.workload, args.route), {}).get(dominant)
     value = world * R / (ms_per_step * 1e-3)
-    kernels = {n: {"ms": round(per_kernel[n], 4), "GB/s": round(kbytes[n] / (per_kernel[n] * 1e-3) / 1e9, 1),
-                   "frac": round(kbytes[n] / (per_kernel[n] * 1e-3) / 1e9 / peak, 4)} for n in names}
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": dict(workload_config(), layout=args.layout),
-        "e2e": {"value": world * R / (e2e_ms / e2e_steps * 1e-3), "unit": UNIT,
-                "h2d_bytes_per_step": int(h_teacher.numel() * 4 + h_student.numel() * 4 + h_rois.numel() * 4),
-                "d2h_bytes_per_step": int(h_grad[0].numel() * 4 + 4), "steps": e2e_steps,
-                "pipelining": "2 streams, consecutive steps overlap"},
+        "data": "synthetic", "config": workload_config(w, args.route),
+        "e2e": {"value": world * R / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "pipelining": "2 streams, consecutive steps overlap",
+                "h2d_GBs_per_gpu": round(h2d / (e2e_ms * 1e-3) / 1e9, 2), "d2h_GBs_per_gpu": round(d2h / (e2e_ms * 1e-3) / 1e9, 2),
+                "h2d_GBs_aggregate": round(world * h2d / (e2e_ms * 1e-3) / 1e9, 2), "host_placement": placement,
+                "limiter": "kernels" if e2e_ms < 1.25 * ms_per_step else "host<->device copies (PCIe / host memory)"},
         "gpu_launches": launches, "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": kbytes[dominant], "limiter": limiter},
+                     "algorithmic_bytes_per_launch": kbytes[dominant],
+                     "note": "algorithmic bytes of SURVEY 8d attributed to the stage (fused route: pooling kernel = teacher "
+                             "fwd + student fwd; backward kernel = ARD fwd+bwd + student bwd, whose pooled-gradient tensor "
+                             "is never materialised)"},
         "composite": {"algorithmic_bytes_per_step": ab["composite"],
                       "GB/s": round(ab["composite"] / (ms_per_step * 1e-3) / 1e9, 1),
                       "frac_of_hbm_peak": round(ab["composite"] / (ms_per_step * 1e-3) / 1e9 / peak, 4)},
-        "kernels": kernels,
+        "kernels": kernel_table(per_kernel, kbytes, peak),
     }
     if world == 1 and not args.no_cpu:
-        dt, kind, desc, cores = cpu_reference_sample(args.cpu_rois)
+        dt, kind, desc, cores = cpu_reference_sample(w, args.cpu_rois)
         line["cpu_baseline"] = {"value": args.cpu_rois / dt, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
     if world == 1 and not args.no_secondary:
+        extra = {}
+        other = "configs1_p7" if args.workload == "configs0" else "configs0"
+        for route in ("fused", "separate"):
+            p2 = RoiPath(WORKLOADS[other], dev, seed=0, route=route)
+            ms2, pk2, _, _, _ = p2.timed(min(args.steps, 50), 3, barrier)
+            ab2 = algorithmic_bytes(p2.w, p2.R)
+            extra["%s/%s" % (other, route)] = {
+                "workload": WORKLOADS[other]["name"], "value": p2.R / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2,
+                "composite_frac_of_hbm_peak": round(ab2["composite"] / (ms2 * 1e-3) / 1e9 / peak, 4),
+                "kernels": kernel_table(pk2, p2.kernel_bytes(), peak)}
+            del p2
+        if args.route == "fused":
+            p3 = RoiPath(w, dev, seed=0, route="separate")
+            ms3, pk3, _, _, _ = p3.timed(min(args.steps, 50), 3, barrier)
+            extra["%s/separate" % args.workload] = {
+                "workload": w["name"], "value": p3.R / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3,
+                "composite_frac_of_hbm_peak": round(ab["composite"] / (ms3 * 1e-3) / 1e9 / peak, 4),
+                "kernels": kernel_table(pk3, p3.kernel_bytes(), peak)}
+            del p3
+        torch.cuda.empty_cache()
+        extra["configs4_fpn"] = fpn_metrics(dev, peak, steps=min(args.steps, 50))
+        line["workloads"] = extra
         line["secondary"] = secondary_metrics(dev)
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------------ config 5 (FPN)
+FPN = dict(B=2, C=256, image_w=1344, image_h=800, scales=(0.25, 0.125, 0.0625, 0.03125), rois_per_image=512, P=7, sampling_ratio=2)
+
+
+def make_fpn(dev, seed):
+    import torch
+
+    from abr_iod_b200.structures.bounding_box import BoxList
+
+    f = FPN
+    rng = np.random.default_rng(100 + seed)
+    feats = [torch.randn(f["B"], f["C"], int(f["image_h"] * s), int(f["image_w"] * s), device=dev).contiguous(
+        memory_format=torch.channels_last).requires_grad_(True) for s in f["scales"]]
+    boxes = []
+    for _ in range(f["B"]):
+        n = f["rois_per_image"]
+        side = np.exp(rng.uniform(np.log(16), np.log(800), n))          # log-uniform 16..800 px: all four levels are hit
+        aspect = rng.uniform(0.5, 2.0, n)
+        bw, bh = side * np.sqrt(aspect), side / np.sqrt(aspect)
+        cx, cy = rng.uniform(0, f["image_w"], n), rng.uniform(0, f["image_h"], n)
+        b = np.stack([np.clip(cx - bw / 2, 0, f["image_w"] - 1), np.clip(cy - bh / 2, 0, f["image_h"] - 1),
+                      np.clip(cx + bw / 2, 0, f["image_w"] - 1), np.clip(cy + bh / 2, 0, f["image_h"] - 1)], 1).astype(np.float32)
+        boxes.append(BoxList(torch.from_numpy(b).to(dev), (f["image_w"], f["image_h"]), "xyxy"))
+    return feats, boxes
+
+
+def fpn_step_fn(dev, seed):
+    import torch
+
+    from abr_iod_b200.modeling.poolers import Pooler
+
+    f = FPN
+    feats, boxes = make_fpn(dev, seed)
+    pooler = Pooler((f["P"], f["P"]), f["scales"], f["sampling_ratio"])
+    R = f["B"] * f["rois_per_image"]
+    gout = torch.randn(R, f["C"], f["P"], f["P"], device=dev).contiguous(memory_format=torch.channels_last)
+
+    def step():
+        for x in feats:
+            x.grad = None
+        out = pooler(feats, boxes)
+        out.backward(gout)
+        return out
+
+    maps = sum(x.numel() for x in feats) * 4
+    pooled = R * f["C"] * f["P"] * f["P"] * 4
+    return step, R, 2 * (maps + 20 * R + pooled)  # SURVEY 8d multi-level: fwd + bwd, sum over levels of B*C*H_l*W_l*s
+
+
+def fpn_metrics(dev, peak, steps=50):
+    """BASELINE.json configs[4] on one GPU's shard: 2 images 800x1344, 4-level FPN maps (256 ch),
+    512 RoIs per image with log-uniform sizes, P=7, sampling_ratio 2; Pooler forward + backward through the public API
+    (LevelMapper on the device, all levels in one launch per direction)."""
+    import torch
+
+    step, R, nbytes = fpn_step_fn(dev, 0)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        step()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / steps
+    return {"workload": "configs[4] COCO-shape FPN multi-level ROIAlign 7x7 fwd+bwd: levels [2,256,200,336] .. [2,256,25,42], "
+                        "512 RoIs/img, sampling_ratio 2, per-GPU shard of batch 16 / 8 GPUs",
+            "value": R / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "algorithmic_bytes_per_step": nbytes,
+            "roofline": {"bound": "hbm", "achieved": round(nbytes / (ms * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(nbytes / (ms * 1e-3) / 1e9 / peak, 4),
+                         "note": "includes the Python wrapper, LevelMapper kernel, plan kernel and the zero-fill of the four "
+                                 "gradient maps (183 MB); the call is launch/latency-bound at this size"}}
+
+
+def run_other_workload(args, rank, world, dev, barrier, sampler):
+    """--workload fpn / paste under torchrun: every rank runs its own shard (no data-path collective), RoIs/s resp.
+    imgs/s summed over ranks (weak scaling)."""
+    import torch
+    import torch.distributed as dist
+
+    peak, _ = measured_peak()
+    if args.workload == "fpn":
+        step, units, nbytes = fpn_step_fn(dev, rank)
+        metric, unit = "FPN multi-level ROIAlign 7x7 RoIs/s fwd+bwd", UNIT
+    else:
+        step, units = paste_step_fn(dev, rank)
+        nbytes, metric, unit = None, "ABR paste imgs/s (plan + H2D + one launch)", "imgs/s"
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    s.record()
+    for _ in range(args.steps):
+        step()
+    e.record()
+    barrier()
+    t1 = time.time()
+    ms = s.elapsed_time(e) / args.steps
+    if args.workload == "paste":
+        ms = (t1 - t0) * 1e3 / args.steps  # host planning is part of the call: wall clock between the barriers
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    if rank != 0:
+        return
+    line = {"metric": metric, "value": world * units / (ms * 1e-3), "unit": unit, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.workload == "fpn" else "u8", "data": "synthetic",
+            "config": {"workload": args.workload, "units_per_gpu_per_step": units}, "clocks": sampler.summary(t0, t1) if sampler else None}
+    if nbytes:
+        line["roofline"] = {"bound": "hbm", "achieved": round(nbytes / (ms * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
+                            "frac": round(nbytes / (ms * 1e-3) / 1e9 / peak, 4)}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ configs 3 and 4
 def _time_call(fn, graph, reps=10):
     """Seconds per call of `fn` (CUDA events on the current stream, after warm-up).  graph=False: issued from Python call
     by call (includes the wrapper's allocations and launches whenever the host is the slower side); graph=True: the same
@@ -365,28 +613,71 @@ def _time_call(fn, graph, reps=10):
     return s.elapsed_time(e) * 1e-3 / reps
 
 
-def secondary_metrics(dev):
-    """BASELINE.json's other two numbers, measured in the same run: batched RPN NMS boxes/s (config 3) and ABR paste
-    imgs/s (config 4, one GPU's shard)."""
+def rpn_shaped_boxes(rng, n, H=38, W=63, stride=16):
+    """SURVEY 8d config 3: anchors of a 38x63 grid x 15 anchors perturbed by N(0, 0.1) deltas, decoded and clipped;
+    scores sigmoid(N(0, 2)); the n best by score, in descending score order (what the RPN's sorted top-k hands to NMS)."""
+    from inputs import make_anchors
+
+    anchors = make_anchors(H, W, stride)
+    d = rng.normal(0, 0.1, anchors.shape).astype(np.float32)
+    wa, ha = anchors[:, 2] - anchors[:, 0] + 1, anchors[:, 3] - anchors[:, 1] + 1
+    cx, cy = anchors[:, 0] + 0.5 * wa + d[:, 0] * wa, anchors[:, 1] + 0.5 * ha + d[:, 1] * ha
+    w_, h_ = wa * np.exp(d[:, 2]), ha * np.exp(d[:, 3])
+    boxes = np.stack([cx - 0.5 * w_, cy - 0.5 * h_, cx + 0.5 * w_ - 1, cy + 0.5 * h_ - 1], 1)
+    boxes = np.clip(boxes, 0, [W * stride - 1, H * stride - 1, W * stride - 1, H * stride - 1]).astype(np.float32)
+    scores = (1.0 / (1.0 + np.exp(-rng.normal(0, 2, len(boxes))))).astype(np.float32)
+    order = np.argsort(-scores, kind="stable")[:n]
+    return np.ascontiguousarray(boxes[order]), np.ascontiguousarray(scores[order])
+
+
+def nms_metrics(dev):
+    """BASELINE.json configs[2]: RPN proposal NMS, N = 6000 boxes per image, IoU 0.7, post-NMS cut
+    2000, batch 1..16 (and N = 12000 -> 2000); boxes/s = batch * N / time including order check and compaction.
+    Beside it the reference's nms_cpu (csrc/cpu/nms_cpu.cpp, compiled in oracle/_ref) on one host core, per image, and
+    the keep lists of both compared in this run."""
     import torch
 
+    import oracle
     from abr_iod_b200.layers import nms_batched
+
+    rng = np.random.default_rng(3)
+    out = {"note": "boxes/s counts all N boxes per image; with a post-NMS cut and score-sorted input the kernels first run "
+                   "a prefix pass over the 2*max_proposals best boxes and skip the full pass for images it settles "
+                   "(DESIGN 3.3); nms_cpu always looks at all N"}
+    use_ref = oracle.ref_available()
+    for n, keep_n in ((6000, 2000), (12000, 2000)):
+        images = [rpn_shaped_boxes(rng, n) for _ in range(16)]
+        # CPU baseline: per image, single thread (nms_cpu has no batch form; the RPN calls it once per image)
+        t0 = time.perf_counter()
+        cpu_keep = [oracle.nms(b, s, 0.7, "cpu", use_ref=use_ref) for b, s in images[:2]]
+        cpu_s = (time.perf_counter() - t0) / 2
+        out["nms_cpu_boxes_per_s_n%d" % n] = {"value": round(n / cpu_s), "unit": "boxes/s", "cores": 1, "per_image_ms": round(cpu_s * 1e3, 2),
+                                              "kind": "reference" if use_ref else "port"}
+        boxes = [torch.from_numpy(b).to(dev) for b, _ in images]
+        scores = [torch.from_numpy(s).to(dev) for _, s in images]
+        keep, n_keep = nms_batched(boxes[:2], scores[:2], 0.7, keep_n, cpu_tie_rule=True)  # nms_cpu's '>=' rule
+        exact = all(np.array_equal(keep[i, : int(n_keep[i])].cpu().numpy(), cpu_keep[i][:keep_n]) for i in range(2))
+        out["nms_keep_lists_equal_nms_cpu_n%d" % n] = bool(exact)
+        for batch in (1, 2, 4, 8, 16):
+            key = "nms_boxes_per_s_n%d_b%d_keep%d" % (n, batch, keep_n)
+            call = lambda: nms_batched(boxes[:batch], scores[:batch], 0.7, keep_n)  # noqa: E731
+            out[key] = round(batch * n / _time_call(call, graph=False))
+            out[key + "_graph"] = round(batch * n / _time_call(call, graph=True))
+    # unsorted input (the box head's per-class segments): the rank sort runs first
     from inputs import make_boxes
 
+    data = [make_boxes(rng, 6000, 1216, 800) for _ in range(4)]
+    boxes = [torch.from_numpy(b).to(dev) for b, _ in data]
+    scores = [torch.from_numpy(s).to(dev) for _, s in data]
+    out["nms_boxes_per_s_n6000_b4_keep1000_unsorted_graph"] = round(4 * 6000 / _time_call(lambda: nms_batched(boxes, scores, 0.7, 1000), graph=True))
+    return out
+
+
+def secondary_metrics(dev):
+    """BASELINE.json's other two numbers, measured in the same run: batched RPN NMS boxes/s (config 3) and ABR paste
+    imgs/s (config 4, one GPU's shard), each with its CPU baseline, plus the rows either side of the path."""
     out = {}
-    rng = np.random.default_rng(3)
-    # RPN-shaped calls (SURVEY 8d config 3): per image N boxes, IoU 0.7, post-NMS cut; the RPN hands NMS the output of a
-    # sorted top-k (modeling/rpn/inference.py:94-95), so the scores arrive in descending order.  One unsorted line too.
-    for n, batch, keep_n, is_sorted in ((6000, 4, 1000, True), (6000, 16, 1000, True), (12000, 4, 2000, True), (12000, 16, 2000, True),
-                                        (6000, 4, 1000, False)):
-        data = [make_boxes(rng, n, 1216, 800) for _ in range(batch)]
-        if is_sorted:
-            data = [(np.ascontiguousarray(b[np.argsort(-s, kind="stable")]), np.ascontiguousarray(np.sort(s)[::-1])) for b, s in data]
-        boxes = [torch.from_numpy(b).to(dev) for b, _ in data]
-        scores = [torch.from_numpy(s).to(dev) for _, s in data]
-        key = "nms_boxes_per_s_n%d_b%d_keep%d_%s" % (n, batch, keep_n, "sorted" if is_sorted else "unsorted")
-        out[key] = round(batch * n / _time_call(lambda: nms_batched(boxes, scores, 0.7, keep_n), graph=False))
-        out[key + "_graph"] = round(batch * n / _time_call(lambda: nms_batched(boxes, scores, 0.7, keep_n), graph=True))
+    out.update(nms_metrics(dev))
     out.update(rpn_metrics(dev))
     out.update(box_post_metrics(dev))
     out.update(paste_metrics(dev))
@@ -440,29 +731,79 @@ def rpn_metrics(dev):
     return out
 
 
-def paste_metrics(dev, n_proto=2000, batch=16, rounds=8):
-    """Config 4 on one GPU's shard: 2000 synthetic prototypes (sides U(71,300)), batches of 16 images 375x500 at the
-    reference's 25/25/50 mixup/mosaic/untouched policy.  imgs/s for the whole call (host planning in the reference's
-    draw order + pinned H2D + ONE paste launch) and for the kernel alone."""
-    import random
-
-    import torch
+def make_paste_inputs(seed, n_proto=2000, batch=16):
+    """Config 4 inputs: 2000 synthetic prototypes (uint8 RGB, sides U(71,300)), 16 images 375x500 with 3 GT boxes each."""
     from PIL import Image
 
-    from abr_iod_b200.data.abr_paste import BoxRehearsalPaster
-
-    rng = np.random.default_rng(4)
+    rng = np.random.default_rng(4 + seed)
     protos = []
     for i in range(n_proto):
         h, w = int(rng.integers(71, 301)), int(rng.integers(71, 301))
         protos.append(("%d_%05d.jpg" % (int(rng.integers(1, 16)), i),
                        np.broadcast_to(rng.integers(0, 256, (1, 1, 3), dtype=np.uint8), (h, w, 3)).copy()))
-    paster = BoxRehearsalPaster(protos, batch_size=batch, device=dev)
     images = [Image.fromarray(rng.integers(0, 256, (375, 500, 3), dtype=np.uint8)) for _ in range(batch)]
     targets = []
     for _ in range(batch):
         x1, y1 = rng.uniform(0, 250, 3), rng.uniform(0, 180, 3)
         targets.append(np.stack([x1, y1, x1 + rng.uniform(30, 200, 3), y1 + rng.uniform(30, 150, 3), rng.integers(16, 21, 3)], 1))
+    return protos, images, targets
+
+
+def paste_step_fn(dev, seed, batch=16):
+    import random
+
+    import torch
+
+    from abr_iod_b200.data.abr_paste import BoxRehearsalPaster
+
+    protos, images, targets = make_paste_inputs(seed, batch=batch)
+    paster = BoxRehearsalPaster(protos, batch_size=batch, device=dev)
+    random.seed(seed)
+    torch.manual_seed(seed)
+
+    def step():
+        paster.execute([paster.plan_transform(im, g) for im, g in zip(images, targets)])
+
+    return step, batch
+
+
+def _paste_cpu_worker(args):
+    """One worker of the CPU baseline: the numpy restatement of voc_abr.py's transform on `rounds` batches."""
+    import random
+
+    import torch
+
+    from oracle import paste as opaste
+
+    seed, rounds, batch = args
+    torch.set_num_threads(1)
+    protos, images, targets = make_paste_inputs(0, batch=batch)
+    st = opaste.BoxRehearsalState([(n, opaste.as_pil(a)) for n, a in protos], batch)
+    random.seed(seed)
+    torch.manual_seed(seed)
+    arrays = [np.asarray(im) for im in images]
+    t0 = time.perf_counter()
+    for _ in range(rounds):
+        for a, g in zip(arrays, targets):
+            opaste.transform_current_data_with_abr(st, opaste.as_pil(a), g)
+    return time.perf_counter() - t0
+
+
+def paste_metrics(dev, batch=16, rounds=8):
+    """BASELINE.json configs[3] on one GPU's shard: 2000 synthetic prototypes, batches of 16 images
+    375x500 at the reference's 25/25/50 mixup/mosaic/untouched policy.  imgs/s for the whole call (host planning in
+    the reference's draw order + pinned H2D + ONE paste launch) and for H2D + kernel alone; beside it the CPU path
+    (numpy restatement of voc_abr.py:555-858, oracle/paste.py) on 1 core and on 4 worker processes (the reference runs
+    the transform inside 4 DataLoader workers, config/defaults.py:83)."""
+    import multiprocessing as mp
+    import random
+
+    import torch
+
+    from abr_iod_b200.data.abr_paste import BoxRehearsalPaster
+
+    protos, images, targets = make_paste_inputs(0, batch=batch)
+    paster = BoxRehearsalPaster(protos, batch_size=batch, device=dev)
     random.seed(0)
     torch.manual_seed(0)
     paster.paste_batch(images, targets)
@@ -476,14 +817,27 @@ def paste_metrics(dev, n_proto=2000, batch=16, rounds=8):
     torch.cuda.synchronize()
     t_all = time.perf_counter() - t0
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # kernel + H2D only (plans precomputed)
     s.record()
-    for plans in plans_all:
+    for plans in plans_all:  # kernel + H2D only (plans precomputed)
         paster.execute(plans)
     e.record()
     torch.cuda.synchronize()
-    return {"paste_imgs_per_s_plan+h2d+kernel": round(batch * rounds / t_all),
-            "paste_imgs_per_s_h2d+kernel": round(batch * rounds / (s.elapsed_time(e) * 1e-3))}
+    out = {"paste_imgs_per_s_plan+h2d+kernel": round(batch * rounds / t_all),
+           "paste_imgs_per_s_h2d+kernel": round(batch * rounds / (s.elapsed_time(e) * 1e-3))}
+    t1 = _paste_cpu_worker((0, rounds, batch))
+    out["paste_cpu_imgs_per_s_1core"] = {"value": round(batch * rounds / t1), "unit": "imgs/s", "cores": 1, "kind": "port",
+                                         "sample": "%d batches of %d images, numpy restatement of voc_abr.py (oracle/paste.py)" % (rounds, batch)}
+    try:
+        ctx = mp.get_context("spawn")
+        with ctx.Pool(4) as pool:
+            pool.map(_paste_cpu_worker, [(i, 1, batch) for i in range(4)])  # start-up and imports outside the timing
+            tw = time.perf_counter()
+            pool.map(_paste_cpu_worker, [(i, rounds, batch) for i in range(4)])
+            tw = time.perf_counter() - tw
+        out["paste_cpu_imgs_per_s_4workers"] = {"value": round(4 * batch * rounds / tw), "unit": "imgs/s", "cores": 4, "kind": "port"}
+    except Exception as ex:  # noqa: BLE001
+        out["paste_cpu_imgs_per_s_4workers"] = {"value": None, "note": "worker pool failed: %s" % ex}
+    return out
 
 
 def main():
@@ -492,10 +846,12 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--layout", default="nhwc", choices=["nhwc", "nchw", "nchw_cl"],
-                    help="nhwc: channels-last maps (default); nchw: contiguous maps and RoI features (an unmodified reference "
-                         "model); nchw_cl: contiguous maps, channels-last RoI features (_lib.POOLED_CHANNELS_LAST)")
-    ap.add_argument("--cpu-rois", type=int, default=192, help="RoIs in the bounded CPU-baseline sample")
+    ap.add_argument("--workload", default="configs0", choices=["configs0", "configs1_p7", "fpn", "paste"],
+                    help="configs0: BASELINE.json configs[0], P=14 (default, the quoted configuration); configs1_p7: the round-1 "
+                         "headline shapes; fpn / paste: configs[4] / configs[3] shards for multi-GPU runs")
+    ap.add_argument("--route", default="fused", choices=["fused", "separate"],
+                    help="fused: abr_roi_ard_fused, one call per step (default); separate: the four ops one by one")
+    ap.add_argument("--cpu-rois", type=int, default=64, help="RoIs in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()

@@ -59,6 +59,14 @@ ABR_API const char* abr_last_error(void);
  * output is at most 16x16: gather-form ROIAlign kernels instead of the TMA-staged ones), "fwd_tma",
  * "bwd_tma", "ard_cluster" (0 / 1).  They select between kernels that compute the same results. */
 ABR_API int abr_set_option(const char* key, int value);
+/* Stage timing of the multi-kernel entry points (measurement only; bench.py's per-kernel roofline).  Between
+ * abr_stage_timing_begin(max_calls) and abr_stage_timing_end(), every abr_roi_ard_fused call records CUDA events on the
+ * CALLER'S stream around its stages (0 plan, 1 teacher+student pooling, 2 ARD coefficients, 3 zero-fill + backward).
+ * abr_stage_timing_end synchronises on the last event, writes the average milliseconds per call of each stage into
+ * avg_ms[0..n_stages) and returns the number of calls recorded (< 0 on error).  Not re-entrant; one stream at a time. */
+#define ABR_FUSED_STAGES 4
+ABR_API int abr_stage_timing_begin(int max_calls);
+ABR_API int abr_stage_timing_end(float* avg_ms, int n_stages);
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 ABR_API uint64_t abr_launch_count(void);
 

@@ -13,8 +13,8 @@ import bench
 from abr_iod_b200 import _lib
 from abr_iod_b200.layers.roi_align import roi_align_backward, roi_align_forward
 
-t, s, rois = bench.make_workload(seed=0)
-w = bench.WORKLOAD
+w = bench.WORKLOADS["configs1_p7"]
+t, s, rois = bench.make_workload(w, seed=0)
 x = torch.from_numpy(s).cuda().contiguous(memory_format=torch.channels_last)
 r_all = torch.from_numpy(rois).cuda()
 P, ratio, scale = w["P"], w["sampling_ratio"], w["scale"]

@@ -12,8 +12,8 @@ import torch
 import bench
 from abr_iod_b200.layers.roi_align import roi_align_forward
 
-t, s, rois = bench.make_workload(seed=0)
-w = bench.WORKLOAD
+w = bench.WORKLOADS["configs1_p7"]
+t, s, rois = bench.make_workload(w, seed=0)
 x = torch.from_numpy(s).cuda().contiguous(memory_format=torch.channels_last)
 out, plan = roi_align_forward(x, torch.from_numpy(rois).cuda(), w["scale"], w["P"], w["P"], w["sampling_ratio"], return_plan=True)
 torch.cuda.synchronize()
