@@ -459,8 +459,61 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.empty_cache()
         extra["configs4_fpn"] = fpn_metrics(dev, peak, steps=min(args.steps, 50))
         line["workloads"] = extra
+        line["reference_cuda"] = reference_cuda_metrics(w, dev)
+        torch.cuda.empty_cache()
         line["secondary"] = secondary_metrics(dev)
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ reference kernels, same box
+def reference_cuda_metrics(w, dev, steps=10):
+    """The reference's own CUDA kernels recompiled as they are for sm_100a (oracle/_ref/libabr_ref_cuda.so: csrc/cuda/
+    ROIAlign_cuda.cu, nms.cu) and its PyTorch ARD (distillation.py:86-130, autograd) on THIS B200, on the same
+    tensors in the reference's layout (contiguous NCHW): "the bar is the reference kernels recompiled as-is" (SURVEY 2.2).
+    The comparator is test infrastructure; the product never links it."""
+    import torch
+
+    import oracle
+    from oracle import ard_torch
+
+    if not oracle.ref_cuda_available():
+        return {"unavailable": "oracle/_ref/libabr_ref_cuda.so was not built (needs /root/reference at build time)"}
+    L = oracle.ref_cuda_lib()
+    teacher_np, student_np, rois_np = make_workload(w, seed=0)
+    t = torch.from_numpy(teacher_np).to(dev)
+    s = torch.from_numpy(student_np).to(dev)
+    r = torch.from_numpy(rois_np).to(dev)
+    B, C, H, W, P, ratio, scale = w["B"], w["C"], w["H"], w["W"], w["P"], w["sampling_ratio"], w["scale"]
+    R = r.shape[0]
+    f_old = oracle.ref_cuda_roi_align_forward(t, r, scale, P, P, ratio)
+    f_new = oracle.ref_cuda_roi_align_forward(s, r, scale, P, P, ratio)
+    _, g = ard_torch.ard_fwd_bwd(f_old, f_new, 1.0)
+
+    def timeit(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / steps
+
+    out = {"roi_align_forward_ms": timeit(lambda: L.ref_cuda_roi_align_forward_nocopy(t.data_ptr(), r.data_ptr(), B, C, H, W, R, P, P, scale, ratio)),
+           "roi_align_backward_ms": timeit(lambda: L.ref_cuda_roi_align_backward_nocopy(g.data_ptr(), r.data_ptr(), B, C, H, W, R, P, P, scale, ratio)),
+           "ard_pytorch_fwd_bwd_ms": timeit(lambda: ard_torch.ard_fwd_bwd(f_old, f_new, 1.0))}
+    step_ms = 2 * out["roi_align_forward_ms"] + out["ard_pytorch_fwd_bwd_ms"] + out["roi_align_backward_ms"]
+    out.update({"step_ms": step_ms, "value": R / (step_ms * 1e-3), "unit": UNIT,
+                "what": "2 x ROIAlign_forward_cuda + PyTorch ARD forward+backward (autograd) + ROIAlign_backward_cuda, contiguous NCHW fp32, "
+                        "the reference's launch shapes, device-timed on this GPU"})
+    rng = np.random.default_rng(3)
+    b6, s6 = rpn_shaped_boxes(rng, 6000)
+    bt, st = torch.from_numpy(b6).to(dev), torch.from_numpy(s6).to(dev)
+    ms = timeit(lambda: oracle.ref_cuda_nms(bt, st, 0.7))
+    out["nms_cuda_boxes_per_s_n6000_b1"] = round(6000 / (ms * 1e-3))
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ config 5 (FPN)

@@ -83,6 +83,92 @@ def ref_lib() -> ctypes.CDLL:
     return _ref
 
 
+# ---------------------------------------------------------------- the reference's CUDA kernels (same-box comparator)
+_REF_CUDA_PATH = os.path.join(_HERE, "_ref", "libabr_ref_cuda.so")
+_ref_cuda = None
+
+
+def ref_cuda_available() -> bool:
+    return os.path.exists(_REF_CUDA_PATH)
+
+
+def ref_cuda_lib() -> ctypes.CDLL:
+    """``oracle/_ref/libabr_ref_cuda.so``: the reference's own csrc/cuda/{ROIAlign_cuda,ROIPool_cuda,nms}.cu compiled in
+    place for sm_100a (oracle/ref_cuda_shim.cu).  All arguments are DEVICE pointers of contiguous fp32 NCHW tensors."""
+    global _ref_cuda
+    if _ref_cuda is None:
+        import torch  # noqa: F401
+
+        L = ctypes.CDLL(_REF_CUDA_PATH)
+        vp, f = ctypes.c_void_p, ctypes.c_float
+        L.ref_cuda_roi_align_forward.argtypes = [vp, vp, vp] + [_int] * 7 + [f, _int]
+        L.ref_cuda_roi_align_backward.argtypes = [vp, vp, vp] + [_int] * 7 + [f, _int]
+        L.ref_cuda_roi_align_forward_nocopy.argtypes = [vp, vp] + [_int] * 7 + [f, _int]
+        L.ref_cuda_roi_align_backward_nocopy.argtypes = [vp, vp] + [_int] * 7 + [f, _int]
+        L.ref_cuda_roi_pool_forward.argtypes = [vp, vp, vp, vp] + [_int] * 7 + [f]
+        L.ref_cuda_roi_pool_backward.argtypes = [vp, vp, vp, vp, vp] + [_int] * 7 + [f]
+        L.ref_cuda_nms.argtypes = [vp, ctypes.c_int64, f, vp]
+        L.ref_cuda_nms.restype = ctypes.c_int64
+        _ref_cuda = L
+    return _ref_cuda
+
+
+def ref_cuda_roi_align_forward(x, rois, scale, ph, pw, ratio):
+    """The reference's ROIAlign_forward_cuda on torch CUDA tensors (contiguous NCHW fp32)."""
+    import torch
+
+    x, rois = x.contiguous().float(), rois.contiguous().float()
+    B, C, H, W = x.shape
+    out = torch.empty((rois.shape[0], C, ph, pw), device=x.device)
+    ref_cuda_lib().ref_cuda_roi_align_forward(x.data_ptr(), rois.data_ptr(), out.data_ptr(), B, C, H, W, rois.shape[0], ph, pw,
+                                             float(scale), int(ratio))
+    return out
+
+
+def ref_cuda_roi_align_backward(grad, rois, scale, ph, pw, B, C, H, W, ratio):
+    import torch
+
+    grad, rois = grad.contiguous().float(), rois.contiguous().float()
+    gin = torch.empty((B, C, H, W), device=grad.device)
+    ref_cuda_lib().ref_cuda_roi_align_backward(grad.data_ptr(), rois.data_ptr(), gin.data_ptr(), B, C, H, W, rois.shape[0], ph, pw,
+                                              float(scale), int(ratio))
+    return gin
+
+
+def ref_cuda_roi_pool_forward(x, rois, scale, ph, pw):
+    import torch
+
+    x, rois = x.contiguous().float(), rois.contiguous().float()
+    B, C, H, W = x.shape
+    out = torch.empty((rois.shape[0], C, ph, pw), device=x.device)
+    arg = torch.empty((rois.shape[0], C, ph, pw), device=x.device, dtype=torch.int32)
+    ref_cuda_lib().ref_cuda_roi_pool_forward(x.data_ptr(), rois.data_ptr(), out.data_ptr(), arg.data_ptr(), B, C, H, W,
+                                            rois.shape[0], ph, pw, float(scale))
+    return out, arg
+
+
+def ref_cuda_roi_pool_backward(grad, x, rois, argmax, scale, ph, pw):
+    import torch
+
+    grad, x, rois = grad.contiguous().float(), x.contiguous().float(), rois.contiguous().float()
+    B, C, H, W = x.shape
+    gin = torch.empty((B, C, H, W), device=x.device)
+    ref_cuda_lib().ref_cuda_roi_pool_backward(grad.data_ptr(), x.data_ptr(), rois.data_ptr(), argmax.contiguous().data_ptr(),
+                                             gin.data_ptr(), B, C, H, W, rois.shape[0], ph, pw, float(scale))
+    return gin
+
+
+def ref_cuda_nms(boxes, scores, thr):
+    """The reference's nms_cuda ('>' rule) on torch CUDA tensors; returns ascending original indices (device, int64)."""
+    import torch
+
+    b = torch.cat((boxes.float(), scores.float().unsqueeze(1)), 1).contiguous()  # csrc/nms.h:19-20
+    n = b.shape[0]
+    keep = torch.empty((max(n, 1),), dtype=torch.int64, device=b.device)
+    k = ref_cuda_lib().ref_cuda_nms(b.data_ptr(), n, float(thr), keep.data_ptr())
+    return keep[:k]
+
+
 def _f32(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.float32)
 
