@@ -337,14 +337,16 @@ class RoiPath:
             st_.wait_stream(torch.cuda.current_stream(dev))
         es.record(streams[0])
         streams[1].wait_event(es)
+        t_issue = time.perf_counter()
         for i in range(steps):
             one(i)
+        t_issue = (time.perf_counter() - t_issue) * 1e3 / steps  # host time to ISSUE a step (Python API, autograd, allocator)
         streams[0].wait_stream(streams[1])
         ee.record(streams[0])
         barrier()
         h2d = int(h_teacher.numel() * 4 + h_student.numel() * 4 + h_rois.numel() * 4)
         d2h = int(h_grad[0].numel() * 4 + 4)
-        return es.elapsed_time(ee) / steps, h2d, d2h
+        return es.elapsed_time(ee) / steps, h2d, d2h, t_issue
 
 
 def measured_peak():
@@ -389,7 +391,7 @@ def run_ours(args, rank, world, local_rank):
     ms_per_step, per_kernel, launches, t0, t1 = path.timed(args.steps, warm, barrier)
     clocks = sampler.summary(t0, t1) if sampler else None
     e2e_steps = max(4, min(args.steps, 40))
-    e2e_ms, h2d, d2h = path.e2e(e2e_steps, barrier)
+    e2e_ms, h2d, d2h, issue_ms = path.e2e(e2e_steps, barrier)
 
     if world > 1:
         t = torch.tensor([ms_per_step, e2e_ms], device=dev)
@@ -420,7 +422,10 @@ def run_ours(args, rank, world, local_rank):
                 "steps": e2e_steps, "pipelining": "2 streams, consecutive steps overlap",
                 "h2d_GBs_per_gpu": round(h2d / (e2e_ms * 1e-3) / 1e9, 2), "d2h_GBs_per_gpu": round(d2h / (e2e_ms * 1e-3) / 1e9, 2),
                 "h2d_GBs_aggregate": round(world * h2d / (e2e_ms * 1e-3) / 1e9, 2), "host_placement": placement,
-                "limiter": "kernels" if e2e_ms < 1.25 * ms_per_step else "host<->device copies (PCIe / host memory)"},
+                "host_issue_ms_per_step": round(issue_ms, 3),
+                "limiter": ("kernels" if e2e_ms < 1.15 * ms_per_step else
+                            "host issue rate (Python API + autograd per step)" if issue_ms > 0.85 * e2e_ms else
+                            "host<->device copies (PCIe / host memory)")},
         "gpu_launches": launches, "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
