@@ -11,7 +11,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libabr_b200.so")
+# ABR_B200_LIB: another build of the same library (A/B measurements of kernel variants with tools/*; nothing else)
+LIB_PATH = os.environ.get("ABR_B200_LIB") or os.path.join(_HERE, "lib", "libabr_b200.so")
 
 ABR_F32, ABR_BF16 = 0, 1
 ABR_NCHW, ABR_NHWC, ABR_NCHW_MAPS_NHWC_POOLED = 0, 1, 2
@@ -89,7 +90,11 @@ def lib() -> ctypes.CDLL:
                 "(or `make -C abr_iod_b200/csrc`); there is no CPU or PyTorch fallback." % LIB_PATH)
         L = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
-            fn = getattr(L, name)
+            fn = getattr(L, name, None)
+            if fn is None and os.environ.get("ABR_B200_LIB"):
+                continue  # an older build under A/B test may lack the newest entry points
+            if fn is None:
+                raise ImportError("abr_iod_b200: %s does not export %s -- rebuild it" % (LIB_PATH, name))
             fn.restype, fn.argtypes = res, args
         _lib = L
     return _lib

@@ -65,15 +65,21 @@ __global__ void __launch_bounds__(256, NT == 2 ? 2 : 3) v2_fwd_kernel(const __gr
   }
   float* srs = NT == 2 ? a.sums + ((size_t)r * a.nslices + slice) * a.PH * a.PW * 3 : nullptr;
   const v2_sptr plan_s = v2_sptr_of(v2_smem);
-  if (mode == V2_GENERIC) {  // (the whole CTA)
+  bool generic = mode == V2_GENERIC;  // (the whole CTA)
+  if (!generic) {
+    v2_stage_plan(plan, plan_s, a.PW + a.PH, threadIdx.x, blockDim.x);
+    __syncthreads();
+    // a bin taller than the strip (two-tensor kernel: 13..15 map rows, i.e. a RoI more than ~12 * PH map rows high)
+    // sends the RoI down the per-sample path
+    if (v2_strip_rows_for(NT) <= kV2Sup) generic = v2_tallest_bin(plan_s, a.PH, a.PW) > v2_strip_rows_for(NT);
+  }
+  if (generic) {
     const RoiGeom g = roi_geometry(a.rois, a.levels, a.lv[0], r, a.PH, a.PW, a.ratio);
     for (int pw = warp; pw < a.PW; pw += nw)
       v2_generic_fwd_column<T, V, NT>(g, a.lv[0].H[g.level], a.lv[0].W[g.level], maps, outs, srs, r, pw, c, active, a.C, a.PH,
                                       a.PW, lane);
     return;
   }
-  v2_stage_plan(plan, plan_s, a.PW + a.PH, threadIdx.x, blockDim.x);
-  __syncthreads();
   const v2_sptr strip = plan_s + (uint32_t)a.plan_smem + warp * (uint32_t)(v2_strip_bytes(V, NT) + v2_sums_bytes(NT));
   const v2_sptr sums_buf = strip + (uint32_t)v2_strip_bytes(V, NT);
   for (int pw = warp; pw < a.PW; pw += nw)

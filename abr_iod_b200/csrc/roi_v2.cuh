@@ -265,6 +265,15 @@ ABR_DEV void v2_stage_records(const int* __restrict__ plan, v2_sptr plan_s, int 
   for (int i = tid; i < 4 * nrec; i += nth) v2_sts4i(plan_s + 64 * (1 + first) + 16 * i, ABR_LDG4I(plan + kV2Hdr + first * kV2Rec + 4 * i));
 }
 ABR_HOSTDEV size_t v2_plan_smem_bytes(int nrec) { return (size_t)64 * (1 + nrec); }
+// Tallest bin of the staged plan (rows); every thread of the CTA gets the same answer.
+ABR_DEV int v2_tallest_bin(v2_sptr plan_s, int PH, int PW) {
+  int n = 0;
+  for (int ph = 0; ph < PH; ph++) {
+    const int k = v2_lds4i(v2_srec(plan_s, PW + ph)).x >> 16;
+    n = k > n ? k : n;
+  }
+  return n;
+}
 
 // Three warp totals with six shuffles (reduce-scatter): on return lane 0 holds sum(a), lane 16 sum(b), lane 8 sum(c).
 ABR_DEV float v2_reduce3(float a, float b, float c, int lane) {
@@ -290,7 +299,7 @@ ABR_DEV float v2_reduce3(float a, float b, float c, int lane) {
 // with shuffles costs a dependent chain of five shuffle/add pairs per bin; instead the partials of up to kV2SumBins bins
 // are parked in a warp-private shared-memory table ([value][lane], rows skewed by one word so that both the lane-major
 // writes and the value-major reads are conflict-free) and folded by 3 * bins lanes at once, 32 sequential adds each.
-constexpr int kV2SumBins = 4;
+constexpr int kV2SumBins = 8;
 ABR_HOSTDEV size_t v2_sums_bytes(int NT) { return NT == 2 ? (size_t)(kV2SumBins * 3 * 33 * 4 + 127) / 128 * 128 : 0; }
 
 struct V2Sums {
@@ -383,9 +392,9 @@ ABR_DEV void v2_emit_bin_now(float (&acc)[NT][V], float inv_count, T* const (&o)
   }
 }
 
-// Map rows per strip: 16 for one tensor, 12 for two (so that two 7-warp CTAs of the two-tensor kernel fit an SM; 8 rows
-// and three CTAs measured the same -- shorter strips overlap more and recompute more rows).  A bin taller than the strip
-// (fat bins of very tall RoIs) is accumulated straight from the map instead (v2_bin_direct).
+// Map rows per strip: 16 holds the tallest bin a record can describe (kV2Sup = 15 rows); the two-tensor kernel takes 12 so
+// that two 7-warp CTAs fit an SM (8 rows and three CTAs measured the same: shorter strips overlap more and recompute more
+// rows) and sends the rare RoIs with a taller bin down the per-sample path.
 ABR_HOSTDEV constexpr int v2_strip_rows_for(int NT) { return NT == 2 ? 12 : 16; }
 
 // Bytes of shared memory one forward warp's strips take: [NT][ROWS][32 lanes][V] floats.
@@ -422,6 +431,41 @@ ABR_DEV void v2_strip_rows(const T* colbase, size_t rowstride, size_t pix, int n
     }
   }
 }
+// The same for NT tensors at once (same rows, same weights): the loads of all tensors are issued before the first is used,
+// which halves the number of exposed gather latencies of the two-tensor kernel (0.66 -> 0.60 ms at configs[0]).
+template <typename T, int V, int NT, int NX, int RB>
+ABR_DEV void v2_strip_rows_nt(const T* const (&colbase)[NT], size_t rowstride, size_t pix, int nrows, v2_sptr colrec, v2_sptr dst0,
+                              int dst_stride) {
+  float w[NX];
+#pragma unroll
+  for (int k = 0; k < NX; k++) w[k] = v2_srec_w(colrec, k);
+  size_t off = 0;  // row i0 + j, stepping one map row per load group and stopping at the last row
+  for (int i0 = 0; i0 < nrows; i0 += RB) {
+    float v[NT][RB][NX][V];
+#pragma unroll
+    for (int j = 0; j < RB; j++) {
+#pragma unroll
+      for (int t = 0; t < NT; t++)
+#pragma unroll
+        for (int k = 0; k < NX; k++) VecIO<T, V>::load(colbase[t] + off + (size_t)k * pix, v[t][j][k]);
+      if (i0 + j + 1 < nrows) off += rowstride;
+    }
+#pragma unroll
+    for (int t = 0; t < NT; t++)
+#pragma unroll
+      for (int j = 0; j < RB; j++) {
+        float r[V];
+#pragma unroll
+        for (int q = 0; q < V; q++) {
+          float s = w[0] * v[t][j][0][q];
+#pragma unroll
+          for (int k = 1; k < NX; k++) s = fmaf(w[k], v[t][j][k][q], s);
+          r[q] = s;
+        }
+        v2_sm_store<V>(dst0 + t * dst_stride + (i0 + j) * (32 * V * 4), r);
+      }
+  }
+}
 // ... and for columns wider than four map pixels (fat bins of large RoIs): four rows at a time, pixel by pixel.
 template <typename T, int V>
 ABR_DEV void v2_strip_rows_wide(const T* colbase, size_t rowstride, size_t pix, int nrows, int nx, v2_sptr colrec, v2_sptr dst) {
@@ -447,39 +491,6 @@ ABR_DEV void v2_strip_rows_wide(const T* colbase, size_t rowstride, size_t pix, 
     }
 #pragma unroll
     for (int j = 0; j < RB; j++) v2_sm_store<V>(dst + (i0 + j) * (32 * V * 4), t[j]);
-  }
-}
-
-// A bin taller than the strip: acc += sum_i Wy[i] * T[lo + i] with the rows of T formed on the fly, four rows of loads
-// in flight at a time (same clamping trick as above; the weight of a repeated row is zero).
-template <typename T, int V>
-ABR_DEV void v2_bin_direct(const T* colbase, size_t rowstride, size_t pix, int n, int nx, v2_sptr colrec, v2_sptr binrec, float (&acc)[V]) {
-  constexpr int RB = V >= 8 ? 2 : 4;
-  for (int i0 = 0; i0 < n; i0 += RB) {
-    float t[RB][V];
-    const T* p[RB];
-#pragma unroll
-    for (int j = 0; j < RB; j++) {
-      p[j] = colbase + (size_t)(i0 + j < n ? i0 + j : n - 1) * rowstride;
-#pragma unroll
-      for (int q = 0; q < V; q++) t[j][q] = 0.f;
-    }
-    for (int k = 0; k < nx; k++) {
-      const float w = v2_srec_w(colrec, k);
-      float v[RB][V];
-#pragma unroll
-      for (int j = 0; j < RB; j++) VecIO<T, V>::load(p[j] + (size_t)k * pix, v[j]);
-#pragma unroll
-      for (int j = 0; j < RB; j++)
-#pragma unroll
-        for (int q = 0; q < V; q++) t[j][q] = fmaf(w, v[j][q], t[j][q]);
-    }
-#pragma unroll
-    for (int j = 0; j < RB; j++) {
-      const float wy = i0 + j < n ? v2_srec_w(binrec, i0 + j) : 0.f;
-#pragma unroll
-      for (int q = 0; q < V; q++) acc[q] = fmaf(wy, t[j][q], acc[q]);
-    }
   }
 }
 
@@ -528,22 +539,19 @@ ABR_DEV void v2_fwd_column(v2_sptr plan_s, const T* const (&maps)[NT], T* const 
       continue;
     }
     const int ystart = b.x & 0xffff;
-    if ((b.x >> 16) > kV2Rows) {  // taller than a strip
-      float acc[NT][V];
-#pragma unroll
-      for (int t = 0; t < NT; t++) {
-#pragma unroll
-        for (int k = 0; k < V; k++) acc[t][k] = 0.f;
-        v2_bin_direct<T, V>(base[t] + (size_t)ystart * rowstride, rowstride, pix, b.x >> 16, nx, colrec, binrec, acc[t]);
-      }
-      v2_emit_bin<T, V, NT>(acc, inv_count, o, active, sums, lane);
-#pragma unroll
-      for (int t = 0; t < NT; t++) o[t] += binstride;
-      ph++;
-      continue;
-    }
     // ---- phase 1: T of the rows ystart .. ystart + nrows - 1
     const int nrows = Y1 - ystart + 1 < kV2Rows ? Y1 - ystart + 1 : kV2Rows;
+    if (NT == 2 && nx <= 4) {  // both tensors' loads of a row batch in flight together
+      const T* cb[NT];
+#pragma unroll
+      for (int t = 0; t < NT; t++) cb[t] = base[t] + (size_t)ystart * rowstride;
+      switch (nx) {
+        case 1: v2_strip_rows_nt<T, V, NT, 1, RB4>(cb, rowstride, pix, nrows, colrec, mine, kV2Rows * ROWB); break;
+        case 2: v2_strip_rows_nt<T, V, NT, 2, RB2>(cb, rowstride, pix, nrows, colrec, mine, kV2Rows * ROWB); break;
+        case 3: v2_strip_rows_nt<T, V, NT, 3, RB2>(cb, rowstride, pix, nrows, colrec, mine, kV2Rows * ROWB); break;
+        default: v2_strip_rows_nt<T, V, NT, 4, RB2 / 2 ? RB2 / 2 : 1>(cb, rowstride, pix, nrows, colrec, mine, kV2Rows * ROWB); break;
+      }
+    } else
 #pragma unroll
     for (int t = 0; t < NT; t++) {
       const T* colbase = base[t] + (size_t)ystart * rowstride;
@@ -556,7 +564,7 @@ ABR_DEV void v2_fwd_column(v2_sptr plan_s, const T* const (&maps)[NT], T* const 
         default: v2_strip_rows_wide<T, V>(colbase, rowstride, pix, nrows, nx, colrec, dst); break;
       }
     }
-    // ---- phase 2: every bin whose rows lie inside the strip (at least the one that started it)
+    // ---- phase 2: every bin whose rows lie inside the strip (at least the one that started it: n <= kV2Rows)
     while (true) {
       const int n = b.x >> 16;
       const v2_sptr src = mine + ((b.x & 0xffff) - ystart) * ROWB;

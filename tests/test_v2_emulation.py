@@ -149,9 +149,9 @@ def test_fused_pool_ard(emu, P):
     close(nchw(gmap), oracle.roi_align_backward(dfn, rois, 1 / 16, P, P, B, C, H, W, 0), 2e-5)
 
 
-def test_fused_tall_bins_are_accumulated_from_the_map(emu):
-    """The two-tensor forward keeps 12 map rows per strip; a bin taller than that (13..15 rows) is accumulated straight
-    from the map inside the same column walk, and the fused backward serves it from its plan as usual."""
+def test_fused_tall_bins_take_the_per_sample_path(emu):
+    """The two-tensor forward keeps 12 map rows per strip; a RoI with a taller bin (13..15 rows) runs the per-sample path
+    inside the same kernel, and the fused backward serves it from its plan as usual."""
     rng = np.random.default_rng(9)
     B, C, H, W, P, V = 1, 8, 40, 40, 2, 4
     t = rng.standard_normal((B, C, H, W)).astype(np.float32)
