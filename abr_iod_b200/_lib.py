@@ -35,6 +35,13 @@ class PasteOp(ctypes.Structure):
                 ("pad_", ctypes.c_int32)]
 
 
+class ResizeJob(ctypes.Structure):
+    """``abr_resize_job_t``"""
+    _fields_ = [("src_offset", ctypes.c_int64), ("dst_offset", ctypes.c_int64), ("tmp_offset", ctypes.c_int64),
+                ("src_h", ctypes.c_int32), ("src_w", ctypes.c_int32), ("dst_h", ctypes.c_int32), ("dst_w", ctypes.c_int32),
+                ("x_taps", ctypes.c_int32), ("x_ksize", ctypes.c_int32), ("y_taps", ctypes.c_int32), ("y_ksize", ctypes.c_int32)]
+
+
 PASTE_FILL, PASTE_COPY, PASTE_BLEND = 0, 1, 2
 
 # name -> (restype, argtypes); mirrors include/abr_b200.h one to one (tests/test_abi.py checks the header)
@@ -76,6 +83,7 @@ SIGNATURES = {
     "abr_prototype_distances": (_int, [_vp, _int, _int, _vp, _vp, _vp]),
     "abr_scale_if_needed": (_int, [_vp, _sz, _vp, _f, _int, _vp]),
     "abr_paste_batch": (_int, [_vp, _vp, _int, _vp, _int, _vp, _int, _vp]),
+    "abr_resize_bicubic_batch": (_int, [_vp, _vp, _vp, _int, _vp, _int, _vp]),
 }
 
 _lib = None

@@ -21,6 +21,7 @@ from PIL import Image
 
 from .. import _lib
 from ..structures.bounding_box import BoxList
+from .resample import bicubic_taps
 
 
 @dataclass
@@ -28,7 +29,8 @@ class PasteOpPlan:
     kind: int                      # _lib.PASTE_FILL / PASTE_COPY / PASTE_BLEND
     dst: tuple                     # (y0, x0, y1, x1)
     proto: int = -1                # index into the resident pool, or -1 when `pixels` carries a resized crop
-    pixels: np.ndarray = None      # HWC uint8 (only when the prototype had to be resized on the host)
+    pixels: np.ndarray = None      # HWC uint8 (only when the prototype was resized on the host: device_resize=False)
+    resize: bool = False           # the prototype `proto` is resampled to `src_hw` on the device before the paste
     src_hw: tuple = (0, 0)         # prototype height, width
     src_origin: tuple = (0, 0)     # (sy0, sx0)
     lam: float = 0.0
@@ -56,8 +58,11 @@ class BoxRehearsalPaster:
         device: CUDA device of the pool and of the pasted batch.
     """
 
-    def __init__(self, prototypes, batch_size, bg_size=0, device="cuda"):
+    def __init__(self, prototypes, batch_size, bg_size=0, device="cuda", device_resize=True):
         self.device = torch.device(device)
+        # True: prototypes that the reference rescales (voc_abr.py:538-548) are resampled on the GPU from the resident
+        # pool (abr_resize_bicubic_batch, bit-exact with PIL's bicubic); False: PIL on the host + upload, as round 1 did
+        self.device_resize = bool(device_resize)
         if self.device.type != "cuda":
             raise RuntimeError("BoxRehearsalPaster needs a CUDA device: abr_iod_b200 has no CPU path")
         self.BoxRehearsal_path = [n for n, _ in prototypes]
@@ -68,12 +73,14 @@ class BoxRehearsalPaster:
         self.bg_size = bg_size
         # device-resident pool of the prototypes at their native size
         arrays = [np.ascontiguousarray(np.asarray(im)) for im in self._pil]
+        self._proto_hw = [a.shape[:2] for a in arrays]
         self._pool_offsets = np.zeros(len(arrays) + 1, np.int64)
         for i, a in enumerate(arrays):
             self._pool_offsets[i + 1] = self._pool_offsets[i] + a.size
         self._pool_bytes = int(self._pool_offsets[-1])
+        self._canvas_at = (self._pool_bytes + 255) & ~255  # the per-batch region starts aligned (it holds descriptor structs)
         host = np.concatenate([a.reshape(-1) for a in arrays]) if arrays else np.zeros(0, np.uint8)
-        self._arena = torch.empty((max(self._pool_bytes, 1) + (8 << 20),), dtype=torch.uint8, device=self.device)
+        self._arena = torch.empty((max(self._canvas_at, 1) + (8 << 20),), dtype=torch.uint8, device=self.device)
         if self._pool_bytes:
             self._arena[: self._pool_bytes].copy_(torch.from_numpy(host))
 
@@ -94,19 +101,33 @@ class BoxRehearsalPaster:
         w, h = int(box_scale * box_o_w), int(box_scale * box_o_h)
         pixels = None
         if (w, h) != (box_o_w, box_o_h):
-            pixels = np.ascontiguousarray(np.asarray(box_im.resize((w, h))))  # PIL default filter, as the reference
+            if self.device_resize and w > 0 and h > 0:
+                pixels = "device"  # resampled by the GPU in execute()
+            else:
+                pixels = np.ascontiguousarray(np.asarray(box_im.resize((w, h))))  # PIL default filter, as the reference
         return pid, w, h, int(cls_name), pixels
 
     @staticmethod
     def compute_overlap(a, b):
         """voc_abr.py:932-954"""
-        area = (b[2] - b[0] + 1) * (b[3] - b[1] + 1)
-        iw = np.maximum(np.minimum(a[2], b[2]) - np.maximum(a[0], b[0]) + 1, 0)
-        ih = np.maximum(np.minimum(a[3], b[3]) - np.maximum(a[1], b[1]) + 1, 0)
-        aa = (a[2] - a[0] + 1) * (a[3] - a[1] + 1)
+        # plain float arithmetic (the same IEEE double operations as the reference's numpy scalars, without their overhead)
+        a0, a1, a2, a3 = float(a[0]), float(a[1]), float(a[2]), float(a[3])
+        b0, b1, b2, b3 = float(b[0]), float(b[1]), float(b[2]), float(b[3])
+        area = (b2 - b0 + 1) * (b3 - b1 + 1)
+        iw = max(min(a2, b2) - max(a0, b0) + 1, 0)
+        ih = max(min(a3, b3) - max(a1, b1) + 1, 0)
+        aa = (a2 - a0 + 1) * (a3 - a1 + 1)
         inter = iw * ih
-        flag = bool(inter / aa > 0.3 or inter / area > 0.3)
-        return inter / area, flag
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ra, rb = np.float64(inter) / np.float64(aa), np.float64(inter) / np.float64(area)  # numpy semantics for a zero area
+        flag = bool(ra > 0.3 or rb > 0.3)
+        return rb, flag
+
+    def _beta(self, alpha, beta):
+        cache = self.__dict__.setdefault("_beta_cache", {})
+        if (alpha, beta) not in cache:
+            cache[(alpha, beta)] = torch.distributions.beta.Beta(alpha, beta)
+        return cache[(alpha, beta)]
 
     def _refill(self):
         if len(self.boxes_index) < self.batch_size:
@@ -124,7 +145,7 @@ class BoxRehearsalPaster:
             if (W - gw) < (W * 0.25) and (H - gh) < (H * 0.25):
                 mix = False
         if mix:
-            lam = torch.distributions.beta.Beta(alpha, beta).sample().item()
+            lam = self._beta(alpha, beta).sample().item()  # the reference's draw (voc_abr.py:590), distribution object cached
             self._refill()
             count = 0
             for i in range(3):
@@ -178,8 +199,10 @@ class BoxRehearsalPaster:
                     if (y1 - y0, x1 - x0) != (sy1 - sy0, sx1 - sx0):
                         raise ValueError("could not broadcast input array from shape (%d,%d,3) into shape (%d,%d,3)"
                                          % (sy1 - sy0, sx1 - sx0, y1 - y0, x1 - x0))
-                    plan.ops.append(PasteOpPlan(_lib.PASTE_BLEND, (y0, x0, y1, x1), proto=pid if pixels is None else -1,
-                                                pixels=pixels, src_hw=(bh, bw), src_origin=(sy0, sx0), lam=lam))
+                    on_dev = isinstance(pixels, str)
+                    plan.ops.append(PasteOpPlan(_lib.PASTE_BLEND, (y0, x0, y1, x1), proto=pid if (pixels is None or on_dev) else -1,
+                                                pixels=None if on_dev else pixels, resize=on_dev, src_hw=(bh, bw),
+                                                src_origin=(sy0, sx0), lam=lam))
                     row = np.array([[x0, y0, x1, y1, cls]], dtype=np.float64)
                     gts = row if gts.shape[0] == 0 else np.insert(gts, 0, values=row, axis=0)
                     if pid in self.boxes_index:
@@ -221,8 +244,9 @@ class BoxRehearsalPaster:
             if (y2a - y1a, x2a - x1a) != (y2b - y1b, x2b - x1b) or x1b < 0 or y1b < 0:
                 raise ValueError("could not broadcast input array from shape (%d,%d,3) into shape (%d,%d,3)"
                                  % (y2b - y1b, x2b - x1b, y2a - y1a, x2a - x1a))
-            plan.ops.append(PasteOpPlan(_lib.PASTE_COPY, (y1a, x1a, y2a, x2a), proto=pid if pixels is None else -1,
-                                        pixels=pixels, src_hw=(h, w), src_origin=(y1b, x1b)))
+            on_dev = isinstance(pixels, str)
+            plan.ops.append(PasteOpPlan(_lib.PASTE_COPY, (y1a, x1a, y2a, x2a), proto=pid if (pixels is None or on_dev) else -1,
+                                        pixels=None if on_dev else pixels, resize=on_dev, src_hw=(h, w), src_origin=(y1b, x1b)))
             padw, padh = x1a - x1b, y1a - y1b
             gt4.append(np.array([[0 + padw, 0 + padh, w + padw, h + padh, cls]]))
             if pid in self.boxes_index:
@@ -249,12 +273,21 @@ class BoxRehearsalPaster:
                          gts=np.array(gts, dtype=np.float64).reshape(-1, 5))
 
     # ------------------------------------------------------------------ execution (device)
+    def _pinned(self, nbytes):
+        """A persistent pinned staging buffer (grown, never shrunk): cudaHostAlloc per batch costs more than the paste."""
+        buf = getattr(self, "_staging", None)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty((nbytes + (nbytes >> 2) + 4096,), dtype=torch.uint8, pin_memory=True)
+            self._staging = buf
+        return buf
+
     def execute(self, plans):
-        """Run the plans of a batch in ONE ``abr_paste_batch`` launch.
+        """Run the plans of a batch: ONE pinned upload (images, host-resized crops, all descriptors), the two resampling
+        passes when prototypes are rescaled on the device, and ONE ``abr_paste_batch`` launch.
 
         Returns a list of uint8 CUDA tensors [H_i, W_i, 3] (views into an arena that the next call reuses)."""
         n = len(plans)
-        # staging layout after the resident pool: [image 0][image 1]...[extra crops...]
+        # arena after the resident pool: [image 0][image 1]...[host-resized crops...][descriptors][device-resized crops + scratch]
         img_off, cursor = [], 0
         for p in plans:
             img_off.append(cursor)
@@ -265,12 +298,43 @@ class BoxRehearsalPaster:
                 if op.pixels is not None:
                     extras.append((cursor, op))
                     cursor += op.pixels.size
-        need = self._pool_bytes + cursor
+        pixel_bytes = cursor
+        n_ops = sum(len(p.ops) for p in plans)
+        resized = [op for p in plans for op in p.ops if op.resize]
+        tables = []
+        for op in resized:
+            sh, sw = self._proto_hw[op.proto]
+            tables.append((bicubic_taps(sw, op.src_hw[1]), bicubic_taps(sh, op.src_hw[0])))
+        tap_words = sum(xt.size + yt.size for (xt, _), (yt, _) in tables)
+        img_bytes = ctypes.sizeof(_lib.PasteImage) * max(n, 1)
+        op_bytes = ctypes.sizeof(_lib.PasteOp) * max(n_ops, 1)
+        job_bytes = ctypes.sizeof(_lib.ResizeJob) * len(resized)
+        desc_at = (pixel_bytes + 15) & ~15
+        images_at, ops_at, jobs_at = desc_at, desc_at + img_bytes, desc_at + img_bytes + op_bytes
+        taps_at = jobs_at + job_bytes
+        upload_bytes = taps_at + 4 * tap_words
+        cursor = (upload_bytes + 15) & ~15
+        # crops resampled on the device: [crop][horizontal-pass scratch] per op
+        jobs, resize_off, max_rs_pix, tap_cursor = [], {}, 0, 0
+        for op, ((xt, xk), (yt, yk)) in zip(resized, tables):
+            sh, sw = self._proto_hw[op.proto]
+            dh, dw = op.src_hw
+            dst, tmp = cursor, cursor + dh * dw * 3
+            cursor = tmp + sh * dw * 3
+            resize_off[id(op)] = dst
+            jobs.append(_lib.ResizeJob(int(self._pool_offsets[op.proto]), self._canvas_at + dst, self._canvas_at + tmp,
+                                       sh, sw, dh, dw, tap_cursor, xk, tap_cursor + xt.size, yk))
+            tap_cursor += xt.size + yt.size
+            max_rs_pix = max(max_rs_pix, sh * dw, dh * dw)
+        need = self._canvas_at + cursor
         if need > self._arena.numel():
             arena = torch.empty((need + (need >> 2),), dtype=torch.uint8, device=self.device)
             arena[: self._pool_bytes].copy_(self._arena[: self._pool_bytes])
             self._arena = arena
-        staging = torch.empty((max(cursor, 1),), dtype=torch.uint8, pin_memory=True)
+        done = getattr(self, "_upload_done", None)
+        if done is not None:
+            done.synchronize()
+        staging = self._pinned(upload_bytes)
         snp = staging.numpy()
         for p, off in zip(plans, img_off):
             if p.base is not None:
@@ -279,7 +343,6 @@ class BoxRehearsalPaster:
         for off, op in extras:
             snp[off: off + op.pixels.size] = op.pixels.reshape(-1)
             extra_off[id(op)] = off
-        n_ops = sum(len(p.ops) for p in plans)
         images = (_lib.PasteImage * max(n, 1))()
         ops = (_lib.PasteOp * max(n_ops, 1))()
         k = 0
@@ -290,25 +353,41 @@ class BoxRehearsalPaster:
             for op in p.ops:
                 if op.kind == _lib.PASTE_FILL:
                     src_off = 0
+                elif op.resize:
+                    src_off = self._canvas_at + resize_off[id(op)]
                 elif op.pixels is not None:
-                    src_off = self._pool_bytes + extra_off[id(op)]
+                    src_off = self._canvas_at + extra_off[id(op)]
                 else:
                     src_off = int(self._pool_offsets[op.proto])
                 y0, x0, y1, x1 = op.dst
                 ops[k] = _lib.PasteOp(op.kind, y0, x0, y1, x1, op.src_hw[1], op.src_origin[0], op.src_origin[1],
                                       src_off, float(op.lam), int(op.fill), 0)
                 k += 1
-        canvas = self._arena[self._pool_bytes: self._pool_bytes + max(cursor, 1)]
+        snp[images_at: images_at + img_bytes] = np.frombuffer(images, dtype=np.uint8)
+        snp[ops_at: ops_at + op_bytes] = np.frombuffer(ops, dtype=np.uint8)
+        if jobs:
+            snp[jobs_at: jobs_at + job_bytes] = np.frombuffer((_lib.ResizeJob * len(jobs))(*jobs), dtype=np.uint8)
+            at = taps_at
+            for (xt, _), (yt, _) in tables:
+                for t in (xt, yt):
+                    snp[at: at + 4 * t.size] = t.reshape(-1).view(np.uint8)
+                    at += 4 * t.size
+        canvas = self._arena[self._canvas_at: self._canvas_at + max(cursor, 1)]
+        base = canvas.data_ptr()
         with torch.cuda.device(self.device):
-            canvas[: max(cursor, 1)].copy_(staging[: max(cursor, 1)], non_blocking=True)
+            canvas[:upload_bytes].copy_(staging[:upload_bytes], non_blocking=True)
+            if jobs:
+                _lib.check(_lib.lib().abr_resize_bicubic_batch(
+                    self._arena.data_ptr(), self._arena.data_ptr(), base + jobs_at, len(jobs), base + taps_at, max_rs_pix,
+                    _lib.stream_ptr(self.device)))
             if n_ops:
-                desc = torch.frombuffer(bytearray(bytes(images)) + bytearray(bytes(ops)), dtype=torch.uint8)
-                desc_dev = desc.to(self.device)
-                img_bytes = ctypes.sizeof(_lib.PasteImage) * max(n, 1)
                 _lib.check(_lib.lib().abr_paste_batch(
-                    canvas.data_ptr(), desc_dev.data_ptr(), n, desc_dev.data_ptr() + img_bytes, n_ops,
-                    self._arena.data_ptr(), max_pix, _lib.stream_ptr(self.device)))
-        self._keepalive = (staging,)
+                    base, base + images_at, n, base + ops_at, n_ops, self._arena.data_ptr(), max_pix,
+                    _lib.stream_ptr(self.device)))
+            # the pinned buffer is rewritten by the next call: let this upload finish first (the kernels still overlap the
+            # host's next planning)
+            self._upload_done = torch.cuda.Event()
+            self._upload_done.record()
         return [canvas[off: off + p.height * p.width * 3].view(p.height, p.width, 3) for p, off in zip(plans, img_off)]
 
     def paste_batch(self, images, targets):

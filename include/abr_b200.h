@@ -335,6 +335,22 @@ ABR_API int abr_paste_batch(uint8_t* canvas, const abr_paste_image_t* images, in
                     const abr_paste_op_t* ops, int n_ops, const uint8_t* pool, int max_pixels_per_image,
                     abr_stream_t stream);
 
+/* ---------------------------------------------------------------- prototype resize (before the paste)
+ * The rescaling of a Box-Rehearsal prototype in _sample_per_bbox_from_boxrehearsal (data/datasets/voc_abr.py:538-548:
+ * PIL Image.resize((int(s*w), int(s*h))), default filter BICUBIC) for all crops of a batch, bit-exact with Pillow's 8-bit
+ * resampling (horizontal pass into a uint8 intermediate, then the vertical pass; 22-bit fixed-point taps).
+ *   pool: the prototypes (HWC uint8 RGB) at src_offset;  out: receives the crops at dst_offset (tmp_offset: src_h*dst_w*3
+ *   bytes of scratch inside `out` for the intermediate);  taps (device int32): per axis and output coordinate
+ *   { first input index, tap count, ksize taps } starting at x_taps / y_taps -- the tables of Pillow's precompute_coeffs +
+ *   normalize_coeffs_8bpc, built by the host (abr_iod_b200/data/resample.py);  max_pixels: the largest pass output. */
+typedef struct abr_resize_job {
+  int64_t src_offset, dst_offset, tmp_offset;
+  int32_t src_h, src_w, dst_h, dst_w;
+  int32_t x_taps, x_ksize, y_taps, y_ksize; /* offsets in int32 units into `taps`; taps per output coordinate */
+} abr_resize_job_t;
+ABR_API int abr_resize_bicubic_batch(const uint8_t* pool, uint8_t* out, const abr_resize_job_t* jobs, int n_jobs,
+                                     const int32_t* taps, int max_pixels, abr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
