@@ -81,6 +81,8 @@ SIGNATURES = {
     "abr_fastrcnn_loss": (_int, [_vp, _vp, _int, _vp, _vp, _int, _int, _int, _int, _f, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
     "abr_channel_mean": (_int, [_vp, _int, _int, _int, _int, _int, _vp, _vp]),
     "abr_prototype_distances": (_int, [_vp, _int, _int, _vp, _vp, _vp]),
+    "abr_prototype_herding": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp, _sz, _vp]),
+    "abr_sample_fg_bg": (_int, [_vp, _vp, _vp, _int, _int, _int, _vp, _vp, _vp, _vp]),
     "abr_scale_if_needed": (_int, [_vp, _sz, _vp, _f, _int, _vp]),
     "abr_paste_batch": (_int, [_vp, _vp, _int, _vp, _int, _vp, _int, _vp]),
     "abr_resize_bicubic_batch": (_int, [_vp, _vp, _vp, _int, _vp, _int, _vp]),

@@ -97,7 +97,8 @@ def fastrcnn_loss(class_logits, box_regression, labels, regression_targets, n_ol
 class FastRCNNLossComputation(object):
     """Computes the loss for Faster R-CNN (same constructor, ``subsample`` and ``__call__`` as the reference's class).
     ``prepare_targets`` is ONE device launch for the whole batch (``abr_match_proposals``: IoU, Matcher, labels, box
-    encoding); the fg/bg sampling keeps the reference's ``torch.randperm`` stream (see the sampler's docstring)."""
+    encoding); the fg/bg sampling keeps the reference's ``torch.randperm`` stream by default and runs as one launch for the
+    batch with a sampler built with ``device_sampling=True`` (see the sampler's docstring)."""
 
     def __init__(self, proposal_matcher, fg_bg_sampler, box_coder, cls_agnostic_bbox_reg=False, dist_type=None, old_classes=[]):
         self.proposal_matcher = proposal_matcher
@@ -125,13 +126,21 @@ class FastRCNNLossComputation(object):
         """loss.py:86-120: positive/negative sampling; returns the sampled proposals with ``labels`` and
         ``regression_targets`` fields and remembers them for ``__call__``."""
         labels, regression_targets, _ = self.prepare_targets(proposals, targets)
-        sampled_pos_inds, sampled_neg_inds = self.fg_bg_sampler(labels)
         proposals = list(proposals)
         for lab, tgt, per_image in zip(labels, regression_targets, proposals):
             per_image.add_field("labels", lab)
             per_image.add_field("regression_targets", tgt)
-        for i, (pos, neg) in enumerate(zip(sampled_pos_inds, sampled_neg_inds)):
-            proposals[i] = proposals[i][torch.nonzero(pos | neg).squeeze(1)]
+        if getattr(self.fg_bg_sampler, "device_sampling", False):
+            # one launch for the batch and ONE host read (the per-image counts) instead of three nonzero() syncs per image
+            pos, neg, counts = self.fg_bg_sampler.sample_on_device(labels)
+            kept = counts.sum(1).tolist()
+            for i, (p_mask, n_mask) in enumerate(zip(pos, neg)):
+                idx = torch.nonzero_static(p_mask | n_mask, size=kept[i]).squeeze(1)  # size known: no synchronisation
+                proposals[i] = proposals[i][idx]
+        else:
+            sampled_pos_inds, sampled_neg_inds = self.fg_bg_sampler(labels)
+            for i, (pos, neg) in enumerate(zip(sampled_pos_inds, sampled_neg_inds)):
+                proposals[i] = proposals[i][torch.nonzero(pos | neg).squeeze(1)]
         self._proposals = proposals
         return proposals
 

@@ -305,6 +305,25 @@ ABR_API int abr_fastrcnn_loss(const float* class_logits, const float* box_regres
  * of each descriptor / |all descriptors|_F to it.  The n smallest-distance boxes (ascending) are the prototypes. */
 ABR_API int abr_channel_mean(const void* pooled, int R, int C, int HW, int dtype, int layout, float* out, abr_stream_t stream);
 ABR_API int abr_prototype_distances(const float* features, int n, int F, double* mean_out, double* dist, abr_stream_t stream);
+/* abr_prototype_herding: the greedy loop of Mem.herding_feature_sampling (tools/extract_memory.py:163-211) for one class:
+ * k times, among the boxes not yet chosen, the one whose inclusion brings the running centre
+ * (centre*f/(f+1) + feature/(f+1)) closest to the normalised class mean `mean` [F] (as abr_prototype_distances returns it);
+ * float64 in numpy's operation order, first index on ties.  selected [k] int64 (device) receives the order.
+ * workspace: 8-byte aligned, F*8 + n bytes. */
+ABR_API int abr_prototype_herding(const float* features, int n, int F, int k, const double* mean, int64_t* selected,
+                                  void* workspace, size_t workspace_bytes, abr_stream_t stream);
+
+/* ---------------------------------------------------------------- RoI sampling (fg / bg)
+ * BalancedPositiveNegativeSampler.__call__ (modeling/balanced_positive_negative_sampler.py:19-68) for a whole batch in one
+ * launch and without the per-image nonzero() synchronisations: per image (offsets_dev [n_images+1], device),
+ * num_pos = min(#positives, max_positives) positives (matched_idxs >= 1; max_positives = int(batch_size_per_image *
+ * positive_fraction), evaluated by the caller in double like the reference's Python) and
+ * num_neg = min(#negatives, batch_size_per_image - num_pos) negatives (== 0) are drawn -- the ones with the smallest
+ * caller-supplied random `keys` (one uniform float per RoI; ties by index), i.e. a uniformly random subset like the
+ * reference's randperm prefix, from the caller's own random stream.  pos_mask / neg_mask [N] uint8; counts [n_images][2]. */
+ABR_API int abr_sample_fg_bg(const int64_t* matched_idxs, const float* keys, const int* offsets_dev, int n_images,
+                             int batch_size_per_image, int max_positives, uint8_t* pos_mask, uint8_t* neg_mask,
+                             int* counts, abr_stream_t stream);
 
 /* ---------------------------------------------------------------- ABR paste (mixup / mosaic)
  * Pixel part of PascalVOCDataset_ABR._start_mixup / _start_boxes_mosaic

@@ -118,6 +118,18 @@ def test_subsample_counts_fields_and_random_stream():
         for box, v in zip(a.bbox.cpu().numpy().tolist(), lab.tolist()):
             assert key[tuple(box)] == v
     assert ev._proposals is out2
+    # the one-launch sampler (device_sampling=True): same counts and label classes, a random subset of its own stream
+    ev3 = FastRCNNLossComputation(Matcher(0.5, 0.3), BalancedPositiveNegativeSampler(64, 0.25, device_sampling=True),
+                                  BoxCoder((10.0, 10.0, 5.0, 5.0)))
+    torch.manual_seed(6)
+    out3 = ev3.subsample(*build())
+    for i, (a, b) in enumerate(zip(out1, out3)):
+        la, lb = a.get_field("labels").cpu().numpy(), b.get_field("labels").cpu().numpy()
+        assert (la > 0).sum() == (lb > 0).sum() and (la == 0).sum() == (lb == 0).sum() and (lb == -1).sum() == 0
+        m, l_ref, t_ref = om.prepare_targets(raw[i][0], raw[i][1], raw[i][2], 0.5, 0.3, (10.0, 10.0, 5.0, 5.0))
+        key = {tuple(r): int(v) for r, v in zip(raw[i][0].tolist(), l_ref.tolist())}
+        for box, v in zip(b.bbox.cpu().numpy().tolist(), lb.tolist()):
+            assert key[tuple(box)] == v
 
 
 def test_match_argument_errors():

@@ -47,3 +47,46 @@ def test_roi_descriptors_full_size_and_bf16(dtype):
     assert roi_descriptors(torch.zeros((0, 8, 7, 7), device="cuda")).shape == (0, 7, 7)
     with pytest.raises(RuntimeError):
         roi_descriptors(torch.zeros((2, 8, 7, 7)))
+
+
+def test_herding_selection_equals_the_numpy_restatement():
+    """abr_prototype_herding against the float64 restatement of Mem.herding_feature_sampling's loop
+    (tools/extract_memory.py:163-197; the reference's function itself stops with an unbound variable at :203 and cannot
+    produce a golden run): the same boxes in the same order, incl. a topped-up class."""
+    from abr_iod_b200.tools.prototype_box_selection import herding_ranking
+
+    rng = np.random.default_rng(7)
+    for n, per_cls in ((40, 6), (3, 6), (200, 25), (17, 17)):
+        feats = (rng.standard_normal((n, 7, 7)) + rng.uniform(0, 2, (1, 7, 7))).astype(np.float32)
+        order, source = herding_ranking(torch.from_numpy(feats).cuda(), per_cls)
+        want, wsource = op.herding_ranking(list(feats), per_cls)
+        assert np.array_equal(source.cpu().numpy(), wsource)
+        assert np.array_equal(order.cpu().numpy(), want)
+
+
+def test_device_fg_bg_sampling_counts_and_subset():
+    """abr_sample_fg_bg: the reference's per-image counts (balanced_positive_negative_sampler.py:19-68) and, for the same
+    keys, exactly the subset of the numpy restatement -- whole batch, one launch."""
+    from abr_iod_b200.modeling.balanced_positive_negative_sampler import BalancedPositiveNegativeSampler
+
+    rng = np.random.default_rng(2)
+    sizes = [2003, 517, 1, 64, 1200]
+    matched = [rng.integers(-1, 3, n) for n in sizes]
+    matched[2][:] = 0
+    matched[3][:] = 2      # positives only: min(#pos, 128) positives, no negatives
+    keys = rng.uniform(0, 1, sum(sizes)).astype(np.float32)
+    keys[5:9] = keys[4]    # equal keys: ties go to the lower index
+    sampler = BalancedPositiveNegativeSampler(512, 0.25, device_sampling=True)
+    pos, neg, counts = sampler.sample_on_device([torch.from_numpy(m).cuda() for m in matched], torch.from_numpy(keys).cuda())
+    at = 0
+    for i, (m, n) in enumerate(zip(matched, sizes)):
+        wp, wn = op.sample_fg_bg(m, keys[at: at + n], 512, 0.25)
+        assert np.array_equal(pos[i].cpu().numpy(), wp) and np.array_equal(neg[i].cpu().numpy(), wn)
+        assert counts[i].tolist() == [int(wp.sum()), int(wn.sum())]
+        at += n
+    # through __call__ (own torch.rand draw): right counts, right classes
+    p2, n2 = sampler([torch.from_numpy(m).cuda() for m in matched])
+    for m, a, b in zip(matched, p2, n2):
+        a, b = a.cpu().numpy(), b.cpu().numpy()
+        assert a.sum() == min((m >= 1).sum(), 128) and b.sum() == min((m == 0).sum(), 512 - a.sum())
+        assert (m[a == 1] >= 1).all() and (m[b == 1] == 0).all()
