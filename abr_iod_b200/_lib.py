@@ -179,6 +179,25 @@ def roi_align_workspace(R, PH, PW, max_h, device, channels_last=True, nchw_stagi
     return torch.empty((n,), dtype=torch.uint8, device=device), n
 
 
+def plan_only(ws, R, PH, PW, max_h):
+    """What an autograd context should keep of a ROIAlign workspace: only the per-RoI plans at its start (a few MB), not the
+    channels-last staging copies behind them (a B*C*H*W map copy plus an R*C*P*P pooled copy for a contiguous-NCHW call)."""
+    if ws is None:
+        return None
+    n = int(lib().abr_roi_align_workspace_bytes(R, PH, PW, max_h))
+    return ws if ws.numel() <= n else ws[:n].clone()
+
+
+def workspace_with_plan(plan, R, PH, PW, max_h, device, layout, nchw_staging):
+    """A full-size workspace for the backward of a call whose forward kept ``plan_only``: the staging room is allocated
+    afresh and the plans are copied to its start.  Returns (tensor, bytes)."""
+    ws, n = roi_align_workspace(R, PH, PW, max_h, device, layout=layout, nchw_staging=nchw_staging)
+    if ws is None or n <= plan.numel():
+        return plan, plan.numel()
+    ws[: plan.numel()].copy_(plan)
+    return ws, n
+
+
 def set_option(key: str, value: int) -> None:
     """``abr_set_option``: kernel-family switches for measurements and tests ("roi_v2", "fwd_tma", ...)."""
     check(lib().abr_set_option(key.encode(), int(value)))

@@ -1587,23 +1587,59 @@ static size_t workspace_need(int R, int PW, int Hs, int PH) {
 
 // Tensor maps of every level's [B*H rows][W pixels][C channels] view, one per box shape.  False when the driver entry point is
 // missing or a map cannot be encoded (the caller then uses the sweep kernel).
+// Encoding a tensor map costs a few microseconds of host time (six per level and call: 23-41 us per call in round 1, which
+// bounds the small per-image calls of the real step), and a map depends only on (pointer, C, W, rows, element size): a small
+// per-thread cache of the most recent (level view -> its six box-shape maps) makes repeated calls on the same feature-map
+// buffers (the teacher / student pair, the backward after the forward, a caching allocator handing the same block back)
+// skip the driver.
+struct TmaCacheEntry {
+  const void* ptr;
+  cuuint64_t c, w, rows;
+  int esize;
+  unsigned long long stamp;
+  CUtensorMap m[kTmaBoxes];
+};
+constexpr int kTmaCacheSize = 32;
+
+template <typename T>
+static bool encode_level(EncodeTiledFn enc, const void* ptr, cuuint64_t C, cuuint64_t W, cuuint64_t rows, CUtensorMap* out) {
+  static thread_local TmaCacheEntry cache[kTmaCacheSize];
+  static thread_local unsigned long long clock = 0;
+  int victim = 0;
+  for (int i = 0; i < kTmaCacheSize; i++) {
+    TmaCacheEntry& e = cache[i];
+    if (e.stamp && e.ptr == ptr && e.c == C && e.w == W && e.rows == rows && e.esize == (int)sizeof(T)) {
+      e.stamp = ++clock;
+      for (int b = 0; b < kTmaBoxes; b++) out[b] = e.m[b];
+      return true;
+    }
+    if (e.stamp < cache[victim].stamp) victim = i;
+  }
+  const cuuint64_t dims[3] = {C, W, rows};
+  const cuuint64_t strides[2] = {C * sizeof(T), W * C * sizeof(T)};
+  if (strides[0] % 16 != 0 || (reinterpret_cast<uintptr_t>(ptr) & 15)) return false;
+  TmaCacheEntry e;
+  for (int b = 0; b < kTmaBoxes; b++) {
+    const cuuint32_t box[3] = {(cuuint32_t)(512 / sizeof(T)), (cuuint32_t)(2 << b), (cuuint32_t)(kTileMaxPx >> (b + 1))};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult rc = enc(&e.m[b], sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                            const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return false;
+  }
+  e.ptr = ptr; e.c = C; e.w = W; e.rows = rows; e.esize = (int)sizeof(T); e.stamp = ++clock;
+  cache[victim] = e;
+  for (int b = 0; b < kTmaBoxes; b++) out[b] = e.m[b];
+  return true;
+}
+
 template <typename T>
 static bool build_tma_maps(const Call& c, TmaMaps& maps) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc || c.L > kTmaLevels) return false;
   for (int l = 0; l < kTmaLevels; l++) {
     const int ll = l < c.L ? l : 0;
-    const cuuint64_t dims[3] = {(cuuint64_t)c.C, (cuuint64_t)c.lv.W[ll], (cuuint64_t)c.B * c.lv.H[ll]};
-    const cuuint64_t strides[2] = {(cuuint64_t)c.C * sizeof(T), (cuuint64_t)c.lv.W[ll] * c.C * sizeof(T)};
-    if (strides[0] % 16 != 0 || (reinterpret_cast<uintptr_t>(c.lv.ptr[ll]) & 15)) return false;
-    for (int b = 0; b < kTmaBoxes; b++) {
-      const cuuint32_t box[3] = {(cuuint32_t)(512 / sizeof(T)), (cuuint32_t)(2 << b), (cuuint32_t)(kTileMaxPx >> (b + 1))};
-      const cuuint32_t estr[3] = {1, 1, 1};
-      const CUresult rc = enc(&maps.m[l][b], sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
-                              c.lv.ptr[ll], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (rc != CUDA_SUCCESS) return false;
-    }
+    if (!encode_level<T>(enc, c.lv.ptr[ll], (cuuint64_t)c.C, (cuuint64_t)c.lv.W[ll], (cuuint64_t)c.B * c.lv.H[ll], maps.m[l])) return false;
   }
   return true;
 }

@@ -67,7 +67,9 @@ def roi_align_backward(grad, rois, spatial_scale, pooled_h, pooled_w, batch_size
     with torch.cuda.device(g.device):
         has_plan = int(plan is not None)
         if has_plan:
-            ws, ws_bytes = plan, plan.numel()
+            # (a contiguous-NCHW call needs its staging room again: the context only kept the plans)
+            ws, ws_bytes = _lib.workspace_with_plan(plan, rois.size(0), pooled_h, pooled_w, height, g.device, layout,
+                                                    (batch_size, channels, height * width, _lib.dtype_code(g)))
         else:
             ws, ws_bytes = _lib.roi_align_workspace(rois.size(0), pooled_h, pooled_w, height, g.device, layout=layout,
                                                     nchw_staging=(batch_size, channels, height * width, _lib.dtype_code(g)))
@@ -87,8 +89,9 @@ class _ROIAlign(Function):
         ctx.sampling_ratio = sampling_ratio
         ctx.input_shape = input.size()
         ctx.layout = _lib.roi_align_layout(input)
-        out, ctx.plan = roi_align_forward(input, roi, spatial_scale, ctx.output_size[0], ctx.output_size[1], sampling_ratio,
-                                          return_plan=True)
+        out, ws = roi_align_forward(input, roi, spatial_scale, ctx.output_size[0], ctx.output_size[1], sampling_ratio,
+                                    return_plan=True)
+        ctx.plan = _lib.plan_only(ws, roi.size(0), ctx.output_size[0], ctx.output_size[1], input.size(2))
         return out
 
     @staticmethod

@@ -9,6 +9,7 @@ import ctypes
 
 import torch
 from torch import nn
+from torch.nn.modules.utils import _pair
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
@@ -86,7 +87,7 @@ class _MultiLevelROIAlign(Function):
                     ptrs, hs, ws, sc, len(feats), rois.data_ptr(), levels.data_ptr(), out.data_ptr(), B, C, R, PH, PW,
                     int(sampling_ratio), _lib.dtype_code(out), layout,
                     wk.data_ptr() if wk is not None else None, wk_bytes, 0, _lib.stream_ptr(out.device)))
-                ctx.plan = wk
+                ctx.plan = _lib.plan_only(wk, R, PH, PW, max(f.shape[2] for f in feats))
         return out
 
     @staticmethod
@@ -102,7 +103,9 @@ class _MultiLevelROIAlign(Function):
         with torch.cuda.device(g.device):
             has_plan = int(ctx.plan is not None)
             if has_plan:
-                wk, wk_bytes = ctx.plan, ctx.plan.numel()
+                wk, wk_bytes = _lib.workspace_with_plan(
+                    ctx.plan, rois.size(0), PH, PW, max(s[2] for s in shapes), g.device, layout,
+                    (B, C, sum(s[2] * s[3] for s in shapes), _lib.dtype_code(g)))
             else:
                 wk, wk_bytes = _lib.roi_align_workspace(
                     rois.size(0), PH, PW, max(s[2] for s in shapes), g.device, layout=layout,
@@ -145,7 +148,7 @@ class Pooler(nn.Module):
         feats = [_lib.as_compute_dtype(f) for f in x]
         rois32 = _prep_rois(rois, feats[0].device)
         levels = self.map_levels.levels_of_rois(rois32)
-        out = _MultiLevelROIAlign.apply(rois32, levels, tuple(self.output_size), self.scales, self.sampling_ratio, *feats)
+        out = _MultiLevelROIAlign.apply(rois32, levels, _pair(self.output_size), self.scales, self.sampling_ratio, *feats)
         return out.to(dtype)
 
 

@@ -463,11 +463,26 @@ def run_ours(args, rank, world, local_rank):
             del p3
         torch.cuda.empty_cache()
         extra["configs4_fpn"] = fpn_metrics(dev, peak, steps=min(args.steps, 50))
+        extra["ard_call_of_the_real_step"] = small_call_metrics(dev)
         line["workloads"] = extra
         line["reference_cuda"] = reference_cuda_metrics(w, dev)
         torch.cuda.empty_cache()
         line["secondary"] = secondary_metrics(dev)
     print(json.dumps(line))
+
+
+def small_call_metrics(dev):
+    """The distillation call at the size the real step makes it (batch 4, 64 soften RoIs per image = 256 RoIs,
+    P = 7, maps [4,1024,50,76]): one abr_roi_ard_fused call issued from Python vs. the same call replayed from a CUDA
+    graph (the library only enqueues work on the caller's stream, so the whole call is capturable) -- at this size the
+    host's issue time matters as much as the kernels."""
+    w = dict(WORKLOADS["configs1_p7"], rois_per_image=64)
+    path = RoiPath(w, dev, seed=0, route="fused")
+    t_py = _time_call(path.step, graph=False, reps=50)
+    t_graph = _time_call(path.step, graph=True, reps=50)
+    return {"workload": "abr_roi_ard_fused, %d RoIs (64/img), P=7, maps [4,1024,50,76]" % path.R,
+            "us_per_call_issued_from_python": round(t_py * 1e6, 1), "us_per_call_cuda_graph_replay": round(t_graph * 1e6, 1),
+            "RoIs_per_s_cuda_graph": round(path.R / t_graph)}
 
 
 # ------------------------------------------------------------------------------------------------ reference kernels, same box

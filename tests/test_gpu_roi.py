@@ -382,3 +382,40 @@ def test_roi_align_wide_rois_on_the_staged_path():
         close(out.detach().cpu().numpy(), oracle.roi_align_forward(x, rois, 1 / 16, P, P, ratio))
         out.backward(dev(gout, True))
         close(xt.grad.cpu().numpy(), oracle.roi_align_backward(gout, rois, 1 / 16, P, P, B, C, H, W, ratio))
+
+
+def test_pooler_accepts_int_output_size_and_context_keeps_only_the_plans():
+    """Pooler(7, ...) like the reference (its ROIAlign goes through _pair); and for a contiguous-NCHW call the autograd
+    context keeps the per-RoI plans only, not the channels-last staging copies."""
+    from abr_iod_b200 import _lib
+    from abr_iod_b200.layers.roi_align import _ROIAlign
+    from abr_iod_b200.modeling.poolers import Pooler
+    from abr_iod_b200.structures.bounding_box import BoxList
+
+    rng = np.random.default_rng(3)
+    scales = (0.25, 0.125)
+    feats = [torch.randn(1, 16, 64, 80, device="cuda", requires_grad=True), torch.randn(1, 16, 32, 40, device="cuda", requires_grad=True)]
+    x1, y1 = rng.uniform(0, 200, 20), rng.uniform(0, 150, 20)
+    b = np.stack([x1, y1, x1 + rng.uniform(8, 110, 20), y1 + rng.uniform(8, 100, 20)], 1).astype(np.float32)
+    boxes = [BoxList(torch.from_numpy(b).cuda(), (320, 256), "xyxy")]
+    a = Pooler(7, scales, 2)(feats, boxes)
+    c = Pooler((7, 7), scales, 2)(feats, boxes)
+    assert torch.equal(a, c)
+    a.sum().backward()
+    assert all(f.grad is not None for f in feats)
+
+    class Ctx:  # a stand-in for the autograd context: what does forward keep?
+        def save_for_backward(self, *t):
+            self.saved = t
+
+    x = torch.randn(2, 256, 50, 76, device="cuda")
+    rois = torch.from_numpy(make_rois(rng, 300, 2, 76 * 16, 50 * 16)).cuda()
+    ctx = Ctx()
+    out = _ROIAlign.forward(ctx, x, rois, (7, 7), 1 / 16, 0)
+    plan_bytes = int(_lib.lib().abr_roi_align_workspace_bytes(300, 7, 7, 50))
+    assert ctx.plan.numel() == plan_bytes < out.numel() * 4  # no map / pooled staging copies kept alive
+    ctx.saved_tensors = ctx.saved
+    g = torch.randn_like(out)
+    gin = _ROIAlign.backward(ctx, g)[0]
+    ref = oracle.roi_align_backward(g.cpu().numpy(), rois.cpu().numpy(), 1 / 16, 7, 7, 2, 256, 50, 76, 0)
+    close(gin.cpu().numpy(), ref)
