@@ -8,7 +8,8 @@
 //     built on the host in float64 exactly as Pillow's precompute_coeffs / normalize_coeffs_8bpc do
 //     (abr_iod_b200/data/resample.py), uploaded with the batch;
 //   * horizontal pass into a uint8 intermediate [src_h][dst_w] (rounded and clipped, as Pillow does), then the vertical
-//     pass; a pass whose size does not change is skipped, like Pillow's need_horizontal / need_vertical.
+//     pass; a pass whose size does not change is skipped, like Pillow's need_horizontal / need_vertical.  (Pillow 12
+//     resamples columns first when a source is more than 100x taller than wide; the caller keeps such slivers on PIL.)
 // One thread per output pixel (3 channels), one launch per pass for ALL crops of a batch.  Byte work, bound by the
 // (tiny) traffic; bit-exactness against PIL is what the tests check.
 #include "common.cuh"

@@ -101,7 +101,9 @@ class BoxRehearsalPaster:
         w, h = int(box_scale * box_o_w), int(box_scale * box_o_h)
         pixels = None
         if (w, h) != (box_o_w, box_o_h):
-            if self.device_resize and w > 0 and h > 0:
+            # (Pillow 12 resamples columns first when a source is more than 100x taller than wide -- measured, see
+            # tools/fuzz_v2.py; such slivers are not prototypes, they keep the reference's own PIL call)
+            if self.device_resize and w > 0 and h > 0 and box_o_h <= 100 * box_o_w:
                 pixels = "device"  # resampled by the GPU in execute()
             else:
                 pixels = np.ascontiguousarray(np.asarray(box_im.resize((w, h))))  # PIL default filter, as the reference
