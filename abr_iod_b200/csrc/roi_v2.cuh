@@ -255,6 +255,26 @@ ABR_DEV void v2_sm_load(v2_sptr a, float (&v)[V]) {
 ABR_DEV v2_sptr v2_srec(v2_sptr plan_s, int k) { return plan_s + 64 * (1 + k); }
 ABR_DEV float v2_srec_w(v2_sptr rec, int i) { return v2_ldsf(rec + 4 + 4 * i); }
 
+// acc += w * x over V channels: with an even V two channels go through one packed fp32 FMA (fma.rn.f32x2, sm_100: the
+// same IEEE result per element, half the issue slots; worth 0.5-2 % here -- the kernels are latency-, not issue-bound).
+template <int V>
+ABR_DEV void v2_axpy(float w, const float (&x)[V], float (&acc)[V]) {
+#if !defined(ABR_V2_NO_FFMA2) && !defined(ABR_EMU)
+  if (V % 2 == 0) {
+    const float2 ww = make_float2(w, w);
+#pragma unroll
+    for (int i = 0; i < V / 2; i++) {
+      const float2 r = __ffma2_rn(ww, make_float2(x[2 * i], x[2 * i + 1]), make_float2(acc[2 * i], acc[2 * i + 1]));
+      acc[2 * i] = r.x;
+      acc[2 * i + 1] = r.y;
+    }
+    return;
+  }
+#endif
+#pragma unroll
+  for (int i = 0; i < V; i++) acc[i] = fmaf(w, x[i], acc[i]);
+}
+
 // The RoI's plan, copied into shared memory by the whole CTA (a __syncthreads() follows in the kernel): `nrec` records
 // after the header.  Record k of the shared copy sits at plan_s + 64 * (1 + k).
 ABR_DEV void v2_stage_plan(const int* __restrict__ plan, v2_sptr plan_s, int nrec, int tid, int nth) {
@@ -421,12 +441,9 @@ ABR_DEV void v2_strip_rows(const T* colbase, size_t rowstride, size_t pix, int n
     for (int j = 0; j < RB; j++) {
       float t[V];
 #pragma unroll
-      for (int q = 0; q < V; q++) {
-        float s = w[0] * v[j][0][q];
+      for (int q = 0; q < V; q++) t[q] = w[0] * v[j][0][q];
 #pragma unroll
-        for (int k = 1; k < NX; k++) s = fmaf(w[k], v[j][k][q], s);
-        t[q] = s;
-      }
+      for (int k = 1; k < NX; k++) v2_axpy<V>(w[k], v[j][k], t);
       v2_sm_store<V>(dst + (i0 + j) * (32 * V * 4), t);
     }
   }
@@ -456,12 +473,9 @@ ABR_DEV void v2_strip_rows_nt(const T* const (&colbase)[NT], size_t rowstride, s
       for (int j = 0; j < RB; j++) {
         float r[V];
 #pragma unroll
-        for (int q = 0; q < V; q++) {
-          float s = w[0] * v[t][j][0][q];
+        for (int q = 0; q < V; q++) r[q] = w[0] * v[t][j][0][q];
 #pragma unroll
-          for (int k = 1; k < NX; k++) s = fmaf(w[k], v[t][j][k][q], s);
-          r[q] = s;
-        }
+        for (int k = 1; k < NX; k++) v2_axpy<V>(w[k], v[t][j][k], r);
         v2_sm_store<V>(dst0 + t * dst_stride + (i0 + j) * (32 * V * 4), r);
       }
   }
@@ -583,8 +597,7 @@ ABR_DEV void v2_fwd_column(v2_sptr plan_s, const T* const (&maps)[NT], T* const 
         for (int t = 0; t < NT; t++) {
           float x[V];
           v2_sm_load<V>(src + t * (kV2Rows * ROWB) + ROWB, x);
-#pragma unroll
-          for (int k = 0; k < V; k++) acc[t][k] = fmaf(w1, x[k], acc[t][k]);
+          v2_axpy<V>(w1, x, acc[t]);
         }
       }
       if (n > 2) {
@@ -593,8 +606,7 @@ ABR_DEV void v2_fwd_column(v2_sptr plan_s, const T* const (&maps)[NT], T* const 
         for (int t = 0; t < NT; t++) {
           float x[V];
           v2_sm_load<V>(src + t * (kV2Rows * ROWB) + 2 * ROWB, x);
-#pragma unroll
-          for (int k = 0; k < V; k++) acc[t][k] = fmaf(w2, x[k], acc[t][k]);
+          v2_axpy<V>(w2, x, acc[t]);
         }
       }
       for (int i = 3; i < n; i++) {
@@ -603,8 +615,7 @@ ABR_DEV void v2_fwd_column(v2_sptr plan_s, const T* const (&maps)[NT], T* const 
         for (int t = 0; t < NT; t++) {
           float x[V];
           v2_sm_load<V>(src + t * (kV2Rows * ROWB) + i * ROWB, x);
-#pragma unroll
-          for (int k = 0; k < V; k++) acc[t][k] = fmaf(wy, x[k], acc[t][k]);
+          v2_axpy<V>(wy, x, acc[t]);
         }
       }
       v2_emit_bin<T, V, NT>(acc, inv_count, o, active, sums, lane);
@@ -744,9 +755,7 @@ ABR_DEV void v2_bwd_rows(v2_sptr rowrec, int FH, v2_sptr tcol, int pwb, v2_sptr 
         for (int q = 0; q < NQ; q++) {
           float g[V];
           v2_sm_load<V>(p + q * BINB, g);
-          const float w = wy * wq[q];
-#pragma unroll
-          for (int t = 0; t < V; t++) S[t] = fmaf(w, g[t], S[t]);
+          v2_axpy<V>(wy * wq[q], g, S);
         }
       } else {
         for (int q = 0; q < nq; q++) {
