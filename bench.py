@@ -840,6 +840,82 @@ def paste_step_fn(dev, seed, batch=16):
     return step, batch
 
 
+def _reference_voc_abr():
+    """The reference's own PascalVOCDataset_ABR class from the staged sources (baseline/_ref, tools/stage_reference.py),
+    loaded by file path with the imports this image lacks stubbed (as tests/golden/make_golden.py does); None when the
+    sources are not staged."""
+    import importlib.util
+    import types
+
+    from refmods import reference_root
+
+    root = reference_root()
+    if root is None:
+        return None
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    apex, amp = types.ModuleType("apex"), types.ModuleType("apex.amp")
+    amp.float_function = lambda f: f
+    apex.amp = amp
+    sys.modules.setdefault("apex", apex)
+    sys.modules.setdefault("apex.amp", amp)
+    C = types.ModuleType("maskrcnn_benchmark._C")
+    sys.modules.setdefault("maskrcnn_benchmark._C", C)
+    data, tr = types.ModuleType("maskrcnn_benchmark.data"), types.ModuleType("maskrcnn_benchmark.data.transforms")
+    tr.Compose = object
+    data.transforms = tr
+    sys.modules["maskrcnn_benchmark.data"], sys.modules["maskrcnn_benchmark.data.transforms"] = data, tr
+    tools, em = types.ModuleType("tools"), types.ModuleType("tools.extract_memory")
+    em.Mem = object
+    tools.extract_memory = em
+    sys.modules["tools"], sys.modules["tools.extract_memory"] = tools, em
+    spec = importlib.util.spec_from_file_location("ref_voc_abr", os.path.join(root, "maskrcnn_benchmark/data/datasets/voc_abr.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _paste_reference_worker(args):
+    """The reference's own transform_current_data_with_ABR (data/datasets/voc_abr.py:821-858, with _start_mixup /
+    _start_boxes_mosaic and PIL file reads of the prototypes, as its DataLoader workers run it) on `rounds` batches.
+    Returns seconds, or None when the reference sources are not staged."""
+    import random
+    import tempfile
+    import types
+
+    import torch
+    from PIL import Image
+
+    seed, rounds, batch = args
+    torch.set_num_threads(1)
+    mod = _reference_voc_abr()
+    if mod is None:
+        return None
+    from maskrcnn_benchmark.structures.bounding_box import BoxList
+
+    protos, images, targets = make_paste_inputs(0, batch=batch)
+    tmp = tempfile.mkdtemp(prefix="abr_protos_")
+    for name, arr in protos:  # file-per-box memory, as tools/extract_memory.py:213-236 writes it (PNG: lossless, same decode cost class)
+        Image.fromarray(arr).save(os.path.join(tmp, name.replace(".jpg", ".png")))
+    ds = mod.PascalVOCDataset_ABR.__new__(mod.PascalVOCDataset_ABR)
+    ds.PrototypeBoxSelection = types.SimpleNamespace(current_mem_path=tmp, first_mem_path=tmp)
+    ds.BoxRehearsal_path = [n.replace(".jpg", ".png") for n, _ in protos]
+    ds.boxes_index = list(range(len(protos)))
+    ds.batch_size, ds.bg_size = batch, 0
+    tl = []
+    for im, g in zip(images, targets):
+        t = BoxList(torch.tensor(g[:, :4]), im.size, mode="xyxy")
+        t.add_field("labels", torch.tensor(g[:, 4]).long())
+        tl.append(t)
+    random.seed(seed)
+    torch.manual_seed(seed)
+    t0 = time.perf_counter()
+    for _ in range(rounds):
+        for im, t in zip(images, tl):
+            ds.transform_current_data_with_ABR(im, t)
+    return time.perf_counter() - t0
+
+
 def _paste_cpu_worker(args):
     """One worker of the CPU baseline: the numpy restatement of voc_abr.py's transform on `rounds` batches."""
     import random
@@ -904,10 +980,18 @@ def paste_metrics(dev, batch=16, rounds=8):
         ctx = mp.get_context("spawn")
         with ctx.Pool(4) as pool:
             pool.map(_paste_cpu_worker, [(i, 1, batch) for i in range(4)])  # start-up and imports outside the timing
-            tw = time.perf_counter()
-            pool.map(_paste_cpu_worker, [(i, rounds, batch) for i in range(4)])
-            tw = time.perf_counter() - tw
-        out["paste_cpu_imgs_per_s_4workers"] = {"value": round(4 * batch * rounds / tw), "unit": "imgs/s", "cores": 4, "kind": "port"}
+            tw = max(pool.map(_paste_cpu_worker, [(i, rounds, batch) for i in range(4)]))  # the slowest worker's own clock
+            out["paste_cpu_imgs_per_s_4workers"] = {"value": round(4 * batch * rounds / tw), "unit": "imgs/s", "cores": 4, "kind": "port"}
+            # the reference's own code (staged sources): 1 core here, 4 workers in the pool
+            tr1 = _paste_reference_worker((0, rounds, batch))
+            if tr1 is not None:
+                out["paste_reference_imgs_per_s_1core"] = {
+                    "value": round(batch * rounds / tr1), "unit": "imgs/s", "cores": 1, "kind": "reference",
+                    "sample": "%d batches of %d images through PascalVOCDataset_ABR.transform_current_data_with_ABR "
+                              "(voc_abr.py:821-858), prototypes read from one file per box" % (rounds, batch)}
+                tw = max(pool.map(_paste_reference_worker, [(i, rounds, batch) for i in range(4)]))  # (set-up is outside each worker's clock)
+                out["paste_reference_imgs_per_s_4workers"] = {"value": round(4 * batch * rounds / tw), "unit": "imgs/s", "cores": 4,
+                                                              "kind": "reference"}
     except Exception as ex:  # noqa: BLE001
         out["paste_cpu_imgs_per_s_4workers"] = {"value": None, "note": "worker pool failed: %s" % ex}
     return out
