@@ -708,14 +708,64 @@ struct V2Grad {
 };
 
 // Phase 1 of the backward: warp `warp` of `nw` brings the bins warp, warp + nw, ... of this (RoI, slice) gradient tile into
-// shared memory -- bin b of lane l at tile + (b * 32 + l) * V * 4 bytes -- U bins' loads in flight at a time (the last
-// batch repeats the last bin instead of predicating, so that every load is issued before the first is used).  Lanes of
-// a ragged last slice shadow channel 0; they never read the tile.
+// shared memory -- bin b of lane l at tile + (b * 32 + l) * V * 4 bytes.  Lanes of a ragged last slice shadow channel 0;
+// they never read the tile.  (Generic form: U bins' loads in flight at a time through registers, the last batch repeating
+// the last bin instead of predicating so that every load is issued before the first is used.)
+#ifndef ABR_EMU
+ABR_DEV void v2_cp_async16(v2_sptr dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+ABR_DEV void v2_cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+#endif
+
 template <typename T, int V, bool FUSED>
 ABR_DEV void v2_bwd_fill_tile(v2_sptr tile, const V2Grad<T, V, FUSED>& src, int nbin, int C, int warp, int nw, int lane) {
   constexpr int BINB = 32 * V * 4;
-  constexpr int U = (FUSED || V >= 8) ? 4 : 8;  // bins in flight per warp
   const v2_sptr mine = tile + lane * (V * 4);
+#ifndef ABR_EMU
+  if (sizeof(T) == 4 && V == 4) {
+    // fp32, 16 bytes per lane: the first operand (the upstream gradient, or the teacher's pooled tensor when FUSED) goes
+    // straight into the tile with asynchronous copies -- ALL of this warp's bins in flight at once, no registers held --
+    // while the second operand of the fused form streams through registers, eight bins at a time.
+    for (int b = warp; b < nbin; b += nw) v2_cp_async16(mine + b * BINB, src.a + (size_t)b * C);
+    if (!FUSED) {
+      v2_cp_async_wait_all();
+      return;
+    }
+    constexpr int U = 8;
+    const size_t step = (size_t)nw * C, last = (size_t)(nbin - 1) * C;
+    size_t off = (size_t)warp * C;
+    bool landed = false;
+    for (int b0 = warp; b0 < nbin; b0 += U * nw, off += U * step) {
+      float fn[U][V];
+      float2 kc[U];
+#pragma unroll
+      for (int j = 0; j < U; j++) {
+        const bool in = b0 + j * nw < nbin;
+        VecIO<T, V>::load(src.b + (in ? off + j * step : last), fn[j]);
+        kc[j] = __ldg(src.coef + (in ? b0 + j * nw : nbin - 1));
+      }
+      if (!landed) {
+        v2_cp_async_wait_all();
+        landed = true;
+      }
+#pragma unroll
+      for (int j = 0; j < U; j++) {
+        if (b0 + j * nw < nbin) {
+          float fo[V], g[V];
+          v2_sm_load<V>(mine + (b0 + j * nw) * BINB, fo);
+#pragma unroll
+          for (int k = 0; k < V; k++) g[k] = fmaf(kc[j].x, fn[j][k] - fo[k], kc[j].y * fn[j][k]);
+          v2_sm_store<V>(mine + (b0 + j * nw) * BINB, g);
+        }
+      }
+    }
+    return;
+  }
+#endif
+  constexpr int U = (FUSED || V >= 8) ? 4 : 8;  // bins in flight per warp
   const size_t step = (size_t)nw * C, last = (size_t)(nbin - 1) * C;
   size_t off = (size_t)warp * C;
   for (int b0 = warp; b0 < nbin; b0 += U * nw, off += U * step) {
