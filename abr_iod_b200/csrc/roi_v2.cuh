@@ -737,6 +737,8 @@ ABR_DEV void v2_bwd_fill_tile(v2_sptr tile, const V2Grad<T, V, FUSED>& src, int 
     constexpr int U = 8;
     const size_t step = (size_t)nw * C, last = (size_t)(nbin - 1) * C;
     size_t off = (size_t)warp * C;
+    if ((lane & 7) == 0)  // one request per 128-byte line: the second operand's later batches start towards L2 now (1 %)
+      for (int b = warp + U * nw; b < nbin; b += nw) asm volatile("prefetch.global.L2 [%0];" ::"l"(src.b + (size_t)b * C));
     bool landed = false;
     for (int b0 = warp; b0 < nbin; b0 += U * nw, off += U * step) {
       float fn[U][V];
