@@ -47,42 +47,26 @@ class PastePlan:
     gts: np.ndarray = None         # [G,5] x1,y1,x2,y2,label (float64 for mixup/none, int64 for mosaic)
 
 
-class BoxRehearsalPaster:
-    """Holds the Box-Rehearsal memory (prototype crops) and replays it into images.
+class BoxRehearsalPlanner:
+    """The host half of the replay: the reference's random draws and integer rectangle arithmetic
+    (``_sample_per_bbox_from_boxrehearsal``, ``_start_mixup``, ``_start_boxes_mosaic``, ``transform_current_data_with_ABR``)
+    producing :class:`PastePlan` objects -- no CUDA, picklable plans.  It only needs the prototypes' NAMES and SIZES (the
+    pixels stay in the device pool of the :class:`BoxRehearsalPaster` that executes the plans), so planning can run in
+    DataLoader worker processes -- each with its own ``boxes_index`` state, exactly like the reference's dataset copies in
+    its workers (config/defaults.py:83) -- while one process per GPU executes the plans.
 
-    Arguments:
-        prototypes: list of ``(file_name, image)`` with ``file_name = "{class}_{index}.ext"`` as written by
-            tools/extract_memory.py:220-236 and ``image`` a PIL image or HWC uint8 array -- the list is used in
-            the given order (the reference shuffles it once, voc_abr.py:397).
-        batch_size: ``cfg.SOLVER.IMS_PER_BATCH``; ``boxes_index`` is refilled when fewer entries remain.
-        device: CUDA device of the pool and of the pasted batch.
-    """
+    Arguments: ``names`` (``"{class}_{index}.ext"``), ``sizes`` ([(h, w)] per prototype), ``batch_size``, ``bg_size``;
+    ``pil`` (optional PIL images) is only needed when ``device_resize`` is off or for sources more than 100x taller than
+    wide, which keep the reference's own PIL call."""
 
-    def __init__(self, prototypes, batch_size, bg_size=0, device="cuda", device_resize=True):
-        self.device = torch.device(device)
-        # True: prototypes that the reference rescales (voc_abr.py:538-548) are resampled on the GPU from the resident
-        # pool (abr_resize_bicubic_batch, bit-exact with PIL's bicubic); False: PIL on the host + upload, as round 1 did
+    def __init__(self, names, sizes, batch_size, bg_size=0, pil=None, device_resize=True):
+        self.BoxRehearsal_path = list(names)
+        self._proto_hw = [(int(h), int(w)) for h, w in sizes]
+        self._pil = pil
         self.device_resize = bool(device_resize)
-        if self.device.type != "cuda":
-            raise RuntimeError("BoxRehearsalPaster needs a CUDA device: abr_iod_b200 has no CPU path")
-        self.BoxRehearsal_path = [n for n, _ in prototypes]
-        self._pil = [im if isinstance(im, Image.Image) else Image.fromarray(np.asarray(im)) for _, im in prototypes]
-        self._pil = [im.convert("RGB") for im in self._pil]
         self.boxes_index = list(range(len(self.BoxRehearsal_path)))
         self.batch_size = batch_size
         self.bg_size = bg_size
-        # device-resident pool of the prototypes at their native size
-        arrays = [np.ascontiguousarray(np.asarray(im)) for im in self._pil]
-        self._proto_hw = [a.shape[:2] for a in arrays]
-        self._pool_offsets = np.zeros(len(arrays) + 1, np.int64)
-        for i, a in enumerate(arrays):
-            self._pool_offsets[i + 1] = self._pool_offsets[i] + a.size
-        self._pool_bytes = int(self._pool_offsets[-1])
-        self._canvas_at = (self._pool_bytes + 255) & ~255  # the per-batch region starts aligned (it holds descriptor structs)
-        host = np.concatenate([a.reshape(-1) for a in arrays]) if arrays else np.zeros(0, np.uint8)
-        self._arena = torch.empty((max(self._canvas_at, 1) + (8 << 20),), dtype=torch.uint8, device=self.device)
-        if self._pool_bytes:
-            self._arena[: self._pool_bytes].copy_(torch.from_numpy(host))
 
     # ------------------------------------------------------------------ planning (host; reference draw order)
     def _sample_per_bbox_from_boxrehearsal(self, i, im_shape):
@@ -90,8 +74,7 @@ class BoxRehearsalPaster:
         pid = self.boxes_index[i]
         name = self.BoxRehearsal_path[pid]
         cls_name, _ = os.path.splitext(name)[0].split("_")
-        box_im = self._pil[pid]
-        box_o_w, box_o_h = box_im.size
+        box_o_h, box_o_w = self._proto_hw[pid]
         im_mean_size = np.mean(im_shape)
         box_mean_size = np.mean(np.array([int(box_o_w), int(box_o_h)]))
         if float(im_mean_size * 0.2) <= float(box_mean_size) <= float(im_mean_size * 0.7):
@@ -106,7 +89,9 @@ class BoxRehearsalPaster:
             if self.device_resize and w > 0 and h > 0 and box_o_h <= 100 * box_o_w:
                 pixels = "device"  # resampled by the GPU in execute()
             else:
-                pixels = np.ascontiguousarray(np.asarray(box_im.resize((w, h))))  # PIL default filter, as the reference
+                if self._pil is None:
+                    raise RuntimeError("this planner was built without the prototype images: host-side resize is not available")
+                pixels = np.ascontiguousarray(np.asarray(self._pil[pid].resize((w, h))))  # PIL default filter, as the reference
         return pid, w, h, int(cls_name), pixels
 
     @staticmethod
@@ -273,6 +258,44 @@ class BoxRehearsalPaster:
         arr = np.ascontiguousarray(np.asarray(image))
         return PastePlan("none", arr.shape[0], arr.shape[1], base=arr,
                          gts=np.array(gts, dtype=np.float64).reshape(-1, 5))
+
+
+class BoxRehearsalPaster(BoxRehearsalPlanner):
+    """Holds the Box-Rehearsal memory (prototype crops) and replays it into images.
+
+    Arguments:
+        prototypes: list of ``(file_name, image)`` with ``file_name = "{class}_{index}.ext"`` as written by
+            tools/extract_memory.py:220-236 and ``image`` a PIL image or HWC uint8 array -- the list is used in
+            the given order (the reference shuffles it once, voc_abr.py:397).
+        batch_size: ``cfg.SOLVER.IMS_PER_BATCH``; ``boxes_index`` is refilled when fewer entries remain.
+        device: CUDA device of the pool and of the pasted batch.
+    """
+
+    def __init__(self, prototypes, batch_size, bg_size=0, device="cuda", device_resize=True):
+        self.device = torch.device(device)
+        # device_resize True: prototypes that the reference rescales (voc_abr.py:538-548) are resampled on the GPU from the
+        # resident pool (abr_resize_bicubic_batch, bit-exact with PIL's bicubic); False: PIL on the host + upload, as round 1 did
+        if self.device.type != "cuda":
+            raise RuntimeError("BoxRehearsalPaster needs a CUDA device: abr_iod_b200 has no CPU path")
+        pil = [im if isinstance(im, Image.Image) else Image.fromarray(np.asarray(im)) for _, im in prototypes]
+        pil = [im.convert("RGB") for im in pil]
+        # device-resident pool of the prototypes at their native size
+        arrays = [np.ascontiguousarray(np.asarray(im)) for im in pil]
+        BoxRehearsalPlanner.__init__(self, [n for n, _ in prototypes], [a.shape[:2] for a in arrays], batch_size, bg_size, pil,
+                                     device_resize)
+        self._pool_offsets = np.zeros(len(arrays) + 1, np.int64)
+        for i, a in enumerate(arrays):
+            self._pool_offsets[i + 1] = self._pool_offsets[i] + a.size
+        self._pool_bytes = int(self._pool_offsets[-1])
+        self._canvas_at = (self._pool_bytes + 255) & ~255  # the per-batch region starts aligned (it holds descriptor structs)
+        host = np.concatenate([a.reshape(-1) for a in arrays]) if arrays else np.zeros(0, np.uint8)
+        self._arena = torch.empty((max(self._canvas_at, 1) + (8 << 20),), dtype=torch.uint8, device=self.device)
+        if self._pool_bytes:
+            self._arena[: self._pool_bytes].copy_(torch.from_numpy(host))
+
+    def planner(self):
+        """A CUDA-free planner over the same memory (for worker processes); its plans are executed by ``execute``."""
+        return BoxRehearsalPlanner(self.BoxRehearsal_path, self._proto_hw, self.batch_size, self.bg_size, None, self.device_resize)
 
     # ------------------------------------------------------------------ execution (device)
     def _pinned(self, nbytes):

@@ -57,3 +57,30 @@ def test_sample_fg_bg_restatement_counts():
     pos, neg = op.sample_fg_bg(m, keys, 64, 0.25)
     assert pos.sum() == min((m >= 1).sum(), 16) and neg.sum() == min((m == 0).sum(), 64 - pos.sum())
     assert not (pos & neg).any() and (m[pos == 1] >= 1).all() and (m[neg == 1] == 0).all()
+
+
+def test_planner_runs_without_cuda_and_its_plans_pickle():
+    """BoxRehearsalPlanner (the host half of the paste) needs only prototype names and sizes: it runs in a CPU-only worker
+    and its plans travel between processes; a seeded planner reproduces its own draws."""
+    import pickle
+
+    import torch
+
+    from abr_iod_b200.data.abr_paste import BoxRehearsalPlanner
+
+    rng = np.random.default_rng(5)
+    names = ["%d_%05d.jpg" % (1 + i % 15, i) for i in range(40)]
+    sizes = [(int(rng.integers(71, 301)), int(rng.integers(71, 301))) for _ in names]
+    images = [Image.fromarray(rng.integers(0, 256, (200, 260, 3), dtype=np.uint8)) for _ in range(12)]
+    targets = [np.array([[20.0, 30.0, 120.0, 110.0, 17.0]]) for _ in images]
+    runs = []
+    for _ in range(2):
+        planner = BoxRehearsalPlanner(names, sizes, batch_size=4)
+        random.seed(9)
+        torch.manual_seed(9)
+        plans = [planner.plan_transform(im, g) for im, g in zip(images, targets)]
+        runs.append(pickle.loads(pickle.dumps(plans)))
+    assert {p.kind for p in runs[0]} == {"none", "mixup", "mosaic"}
+    for a, b in zip(*runs):
+        assert a.kind == b.kind and np.array_equal(a.gts, b.gts) and len(a.ops) == len(b.ops)
+        assert all(x.dst == y.dst and x.proto == y.proto and x.resize == y.resize for x, y in zip(a.ops, b.ops))
