@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(1024) ard_nhwc_kernel(ArdParams p, const T* __
         VecIO<T, V>::load(rn + c, b);
 #pragma unroll
         for (int k = 0; k < V; k++) o[k] = fmaf(ka, b[k] - a[k], kb * b[k]);
-        VecIO<T, V>::store(rg + c, o);
+        VecIO<T, V>::store_stream(rg + c, o);
       }
     }
   }
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(1024) ard_nchw_kernel(ArdParams p, const T* __
       VecIO<T, 1>::load(fo + (size_t)c * HW + pos, a);
       VecIO<T, 1>::load(fn + (size_t)c * HW + pos, b);
       o[0] = fmaf(ka, b[0] - a[0], kb * b[0]);
-      VecIO<T, 1>::store(g + (size_t)c * HW + pos, o);
+      VecIO<T, 1>::store_stream(g + (size_t)c * HW + pos, o);
     }
   }
   __syncthreads();  // red[] and the per-position tables are reused by the next RoI

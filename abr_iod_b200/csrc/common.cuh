@@ -76,6 +76,7 @@ template <>
 struct VecIO<float, 1> {
   static __device__ __forceinline__ void load(const float* p, float (&v)[1]) { v[0] = __ldg(p); }
   static __device__ __forceinline__ void store(float* p, const float (&v)[1]) { *p = v[0]; }
+  static __device__ __forceinline__ void store_stream(float* p, const float (&v)[1]) { __stcs(p, v[0]); }
   static __device__ __forceinline__ void red_add(float* p, const float (&v)[1]) { atomicAdd(p, v[0]); }
 };
 template <>
@@ -87,6 +88,11 @@ struct VecIO<float, 4> {
   static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   }
+  // write-once tensors (pooled outputs, gradients of pooled tensors): st.global.cs, evict-first in L2, so that the
+  // stream of output lines does not push the re-read feature maps out of the cache
+  static __device__ __forceinline__ void store_stream(float* p, const float (&v)[4]) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+  }
   // one 16-byte reduction per thread: a warp issues a single contiguous 512 B request
   static __device__ __forceinline__ void red_add(float* p, const float (&v)[4]) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3])
@@ -97,6 +103,9 @@ template <>
 struct VecIO<__nv_bfloat16, 1> {
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[1]) { v[0] = __bfloat162float(*p); }
   static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[1]) { *p = __float2bfloat16_rn(v[0]); }
+  static __device__ __forceinline__ void store_stream(__nv_bfloat16* p, const float (&v)[1]) {
+    __stcs(reinterpret_cast<unsigned short*>(p), __bfloat16_as_ushort(__float2bfloat16_rn(v[0])));
+  }
   static __device__ __forceinline__ void red_add(__nv_bfloat16* p, const float (&v)[1]) {
     atomicAdd(p, __float2bfloat16_rn(v[0]));
   }
@@ -118,6 +127,13 @@ struct VecIO<__nv_bfloat16, 8> {
 #pragma unroll
     for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
     *reinterpret_cast<uint4*>(p) = t;
+  }
+  static __device__ __forceinline__ void store_stream(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 t;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    __stcs(reinterpret_cast<uint4*>(p), t);
   }
   static __device__ __forceinline__ void red_add(__nv_bfloat16* p, const float (&v)[8]) {
     uint4 t;

@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(256) roi_align_fwd_sweep_kernel(LevelTable lv,
 #pragma unroll
     for (int i = 0; i < V; i++) z[i] = 0.f;
     if (k.active)
-      for (int ph = 0; ph < PH; ph++) VecIO<T, V>::store(o + (size_t)ph * binstride, z);
+      for (int ph = 0; ph < PH; ph++) VecIO<T, V>::store_stream(o + (size_t)ph * binstride, z);
     return;
   }
   const size_t rowstride = (size_t)k.W * C;
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(256) roi_align_fwd_sweep_kernel(LevelTable lv,
         do {
 #pragma unroll
           for (int i = 0; i < V; i++) accA[i] *= inv_count;
-          if (k.active) VecIO<T, V>::store(o + (size_t)a * binstride, accA);
+          if (k.active) VecIO<T, V>::store_stream(o + (size_t)a * binstride, accA);
 #pragma unroll
           for (int i = 0; i < V; i++) { accA[i] = accB[i]; accB[i] = 0.f; }
         } while (++a < info.x);
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(256) roi_align_fwd_sweep_kernel(LevelTable lv,
     for (; a < PH; a++) {
 #pragma unroll
       for (int i = 0; i < V; i++) accA[i] *= inv_count;
-      if (k.active) VecIO<T, V>::store(o + (size_t)a * binstride, accA);
+      if (k.active) VecIO<T, V>::store_stream(o + (size_t)a * binstride, accA);
 #pragma unroll
       for (int i = 0; i < V; i++) { accA[i] = accB[i]; accB[i] = 0.f; }
     }
@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(256) roi_align_fwd_sweep_kernel(LevelTable lv,
       if (p < PH && k.active) {
 #pragma unroll
         for (int i = 0; i < V; i++) acc[p][i] *= inv_count;
-        VecIO<T, V>::store(o + (size_t)p * binstride, acc[p]);
+        VecIO<T, V>::store_stream(o + (size_t)p * binstride, acc[p]);
       }
     }
   }
@@ -791,7 +791,7 @@ __global__ void __launch_bounds__(256, 3) roi_align_fwd_tma_kernel(const __grid_
 #pragma unroll
         for (int i = 0; i < V; i++) z[i] = 0.f;
         if (active)
-          for (int p = 0; p < PH; p++) VecIO<T, V>::store(o + (size_t)p * binstride, z);
+          for (int p = 0; p < PH; p++) VecIO<T, V>::store_stream(o + (size_t)p * binstride, z);
         mb_arrive(&pempty[pb]);
         continue;
       }
@@ -845,7 +845,7 @@ __global__ void __launch_bounds__(256, 3) roi_align_fwd_tma_kernel(const __grid_
               do {
 #pragma unroll
                 for (int i = 0; i < V; i++) accA[i] *= inv_count;
-                if (active) VecIO<T, V>::store(oa, accA);
+                if (active) VecIO<T, V>::store_stream(oa, accA);
                 oa += binstride;
 #pragma unroll
                 for (int i = 0; i < V; i++) { accA[i] = accB[i]; accB[i] = 0.f; }
@@ -863,7 +863,7 @@ __global__ void __launch_bounds__(256, 3) roi_align_fwd_tma_kernel(const __grid_
         for (; a < PH; a++, oa += binstride) {
 #pragma unroll
           for (int i = 0; i < V; i++) accA[i] *= inv_count;
-          if (active) VecIO<T, V>::store(oa, accA);
+          if (active) VecIO<T, V>::store_stream(oa, accA);
 #pragma unroll
           for (int i = 0; i < V; i++) { accA[i] = accB[i]; accB[i] = 0.f; }
         }
@@ -896,7 +896,7 @@ __global__ void __launch_bounds__(256, 3) roi_align_fwd_tma_kernel(const __grid_
           if (p < PH && active) {
 #pragma unroll
             for (int i = 0; i < V; i++) acc[p][i] *= inv_count;
-            VecIO<T, V>::store(o + (size_t)p * binstride, acc[p]);
+            VecIO<T, V>::store_stream(o + (size_t)p * binstride, acc[p]);
           }
         }
       }
@@ -1168,7 +1168,7 @@ __global__ void __launch_bounds__(256) roi_align_fwd_nhwc_kernel(LevelTable lv, 
       }
 #pragma unroll
       for (int k = 0; k < V; k++) acc[k] = acc[k] / g.count;
-      VecIO<T, V>::store(o + ((size_t)ph * PW + pw) * C, acc);
+      VecIO<T, V>::store_stream(o + ((size_t)ph * PW + pw) * C, acc);
     }
   }
 }
