@@ -596,9 +596,12 @@ static int launch_nchw_cluster(const ArdParams& p, const void* fo, const void* f
 //     dL/df_new = ka * (f_new - f_old) + kb * f_new
 // which the fused backward applies on the fly; the loss partials are reduced by the last CTA (ard_finish).
 __global__ void __launch_bounds__(256) ard_coeff_kernel(ArdParams p, const float* __restrict__ sums, int nslices,
-                                                       float2* __restrict__ coef) {
+                                                       float2* __restrict__ coef, float4* __restrict__ zero_fill, size_t zero_n) {
   extern __shared__ float sm[];
   const int HW = p.HW, n = blockIdx.x;
+  // the gradient map the next kernel accumulates into: zero-filled here (stores retire behind the loads below)
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < zero_n; i += (size_t)gridDim.x * blockDim.x)
+    zero_fill[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   float* m_old = sm;
   float* m_new = m_old + HW;
   float* dd = m_new + HW;
@@ -622,15 +625,16 @@ __global__ void __launch_bounds__(256) ard_coeff_kernel(ArdParams p, const float
 size_t ard_coeff_workspace_bytes(int N) { return 256 + (size_t)(N > 0 ? N : 0) * 2 * sizeof(float); }
 
 int ard_coeff_run(const float* sums, int nslices, float2* coef, float* loss3, int N, int C, int HW, float gamma, float grad_scale,
-                  void* ws, cudaStream_t st) {
+                  void* ws, cudaStream_t st, bool counter_is_clear, void* zero_fill, size_t zero_bytes) {
   ArdParams p;
   p.N = N; p.C = C; p.HW = HW; p.gamma = gamma; p.grad_scale = grad_scale;
   p.counter = static_cast<unsigned int*>(ws);
   p.partials = reinterpret_cast<float*>(static_cast<char*>(ws) + 256);
   p.loss3 = loss3;
-  ABR_CUDA_OK(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), st));
+  if (!counter_is_clear) ABR_CUDA_OK(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), st));
   const int threads = HW >= 192 ? 256 : (HW >= 96 ? 128 : 64);
-  ard_coeff_kernel<<<N, threads, (size_t)5 * HW * sizeof(float), st>>>(p, sums, nslices, coef);
+  ard_coeff_kernel<<<N, threads, (size_t)5 * HW * sizeof(float), st>>>(p, sums, nslices, coef, static_cast<float4*>(zero_fill),
+                                                                       zero_fill ? zero_bytes / 16 : 0);
   ABR_CHECK_LAUNCH("ard_coefficients");
   return ABR_OK;
 }

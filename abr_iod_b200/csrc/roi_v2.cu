@@ -16,19 +16,30 @@
 
 namespace abr {
 
+// Header + axis records of one RoI (PH, PW <= 16): the planning warp's working copy in shared memory
+constexpr int kV2PlanStage = kV2Hdr + 32 * kV2Rec;
+
 __global__ void __launch_bounds__(128) v2_plan_kernel(LevelTable lv, const float* __restrict__ rois,
                                                      const int32_t* __restrict__ levels, int* __restrict__ plans, size_t stride,
                                                      int R, int PH, int PW, int ratio) {
+  // The header and the transposed records are derived from the axis records: those are built in shared memory (the
+  // dependent reads of the later phases cost ~30 cycles there instead of an L2 round trip each) and copied out at the end.
+  __shared__ __align__(16) int stage[4][kV2PlanStage];
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (r >= R) return;
   const RoiGeom g = roi_geometry(rois, levels, lv, r, PH, PW, ratio);
   const int H = lv.H[g.level], W = lv.W[g.level];
   int* plan = plans + (size_t)r * stride;
-  v2_plan_axes(plan, g, H, W, PH, PW, lane, 32);
+  int* mine = stage[threadIdx.x >> 5];
+  v2_plan_axes(mine, g, H, W, PH, PW, lane, 32);
   __syncwarp();
-  if (lane == 0) v2_plan_header(plan, g, H, W, PH, PW);
+  if (lane == 0) v2_plan_header(mine, g, H, W, PH, PW);
   __syncwarp();
-  v2_plan_transposed(plan, PH, PW, lane, 32);
+  v2_plan_transposed(mine, plan, PH, PW, lane, 32);
+  __syncwarp();
+  const int4* src = reinterpret_cast<const int4*>(mine);
+  int4* dst = reinterpret_cast<int4*>(plan);
+  for (int i = lane; i < (kV2Hdr + (PW + PH) * kV2Rec) / 4; i += 32) dst[i] = src[i];
 }
 
 template <typename T, int NT>
@@ -40,6 +51,7 @@ struct V2FwdArgs {
   const int32_t* levels;
   T* out[NT];
   float* sums;  // [R][nslices][PH*PW][3] (NT == 2)
+  unsigned int* clear_word;  // set to 0 by the first thread (the completion counter of the coefficient kernel that follows), or null
   int C, PH, PW, ratio, nslices, plan_smem;
 };
 
@@ -53,6 +65,7 @@ __global__ void __launch_bounds__(256, NT == 2 ? 2 : 3) v2_fwd_kernel(const __gr
   const int* plan = a.plans + (size_t)r * a.stride;
   const int4 h0 = __ldg(reinterpret_cast<const int4*>(plan));
   const int mode = h0.x, level = h0.z;
+  if (a.clear_word && blockIdx.x == 0 && threadIdx.x == 0) *a.clear_word = 0u;
   int c = (slice * 32 + lane) * V;
   const bool active = c < a.C;
   if (!active) c = 0;  // idle lanes of a ragged last slice shadow channel 0 and never store
@@ -153,10 +166,10 @@ static int fwd_warps(int PW) { return PW <= 8 ? PW : ceil_div(PW, ceil_div(PW, 8
 
 template <typename T, int V, int NT>
 static int launch_fwd2(const LevelTable* lv, const int* plans, const float* rois, const int32_t* levels, void* const* outs,
-                       float* sums, int C, int R, int PH, int PW, int ratio, cudaStream_t st) {
+                       float* sums, int C, int R, int PH, int PW, int ratio, cudaStream_t st, unsigned int* clear_word = nullptr) {
   V2FwdArgs<T, NT> a;
   for (int t = 0; t < NT; t++) { a.lv[t] = lv[t]; a.out[t] = static_cast<T*>(outs[t]); }
-  a.plans = plans; a.stride = v2_plan_words(PH, PW); a.rois = rois; a.levels = levels; a.sums = sums;
+  a.plans = plans; a.stride = v2_plan_words(PH, PW); a.rois = rois; a.levels = levels; a.sums = sums; a.clear_word = clear_word;
   a.C = C; a.PH = PH; a.PW = PW; a.ratio = ratio; a.nslices = ceil_div(C, 32 * V);
   const long long blocks = (long long)R * a.nslices;
   ABR_REQUIRE(blocks <= 0x7fffffffLL, ABR_ERR_UNSUPPORTED, "roi_align_forward: too many (RoI, slice) tasks");
@@ -281,15 +294,23 @@ int abr_roi_ard_fused(const void* teacher_map, const void* student_map, const fl
   }
   stage_mark(st, 1);
   void* outs[2] = {pooled_old, pooled_new};
-  if (C % 4 == 0) rc = launch_fwd2<float, 4, 2>(lv, plans, rois, nullptr, outs, sums, C, R, PH, PW, sampling_ratio, st);
-  else rc = launch_fwd2<float, 1, 2>(lv, plans, rois, nullptr, outs, sums, C, R, PH, PW, sampling_ratio, st);
+  // the pooling kernel also clears the completion counter of the coefficient kernel, and the coefficient kernel -- one
+  // small latency-bound CTA per RoI -- also zero-fills the gradient map (when its size is a 16-byte multiple): no memset
+  // node between the four kernels of the step
+  unsigned int* counter = reinterpret_cast<unsigned int*>(ws + f.ard);
+  if (C % 4 == 0) rc = launch_fwd2<float, 4, 2>(lv, plans, rois, nullptr, outs, sums, C, R, PH, PW, sampling_ratio, st, counter);
+  else rc = launch_fwd2<float, 1, 2>(lv, plans, rois, nullptr, outs, sums, C, R, PH, PW, sampling_ratio, st, counter);
   if (rc) return rc;
   stage_mark(st, 2);
-  rc = ard_coeff_run(sums, ceil_div(C, 32 * (C % 4 == 0 ? 4 : 1)), coef, loss3, R, C, PH * PW, gamma, grad_scale, ws + f.ard, st);
+  const size_t gmap_bytes = (size_t)B * C * H * W * sizeof(float);
+  const bool fill_in_kernel = grad_student_map && zero_init && R >= 256 /* enough CTAs to stream the fill */ && gmap_bytes % 16 == 0 &&
+                              (reinterpret_cast<uintptr_t>(grad_student_map) & 15) == 0;
+  rc = ard_coeff_run(sums, ceil_div(C, 32 * (C % 4 == 0 ? 4 : 1)), coef, loss3, R, C, PH * PW, gamma, grad_scale, ws + f.ard, st,
+                     /*counter_is_clear=*/true, fill_in_kernel ? grad_student_map : nullptr, fill_in_kernel ? gmap_bytes : 0);
   if (rc) return rc;
   stage_mark(st, 3);
   if (grad_student_map) {
-    if (zero_init) ABR_CUDA_OK(cudaMemsetAsync(grad_student_map, 0, (size_t)B * C * H * W * sizeof(float), st));
+    if (zero_init && !fill_in_kernel) ABR_CUDA_OK(cudaMemsetAsync(grad_student_map, 0, gmap_bytes, st));
     LevelTable gl = lv[1];
     gl.ptr[0] = grad_student_map;
     if (C % 4 == 0) rc = launch_bwd2<float, 4, true>(gl, plans, rois, nullptr, pooled_old, pooled_new, coef, C, R, PH, PW, sampling_ratio, st);

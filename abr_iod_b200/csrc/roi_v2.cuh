@@ -167,30 +167,40 @@ ABR_HD void v2_plan_header(int* plan, const RoiGeom& g, int H, int W, int PH, in
 //   * one per footprint row y = Y0 + j -- likewise the bin rows whose support contains y with a non-zero weight, and
 //     Wy[ph][y].
 // Record k of the pixel columns sits after the PW + PH axis records, row record j after kV2MaxFW pixel-column records.
-ABR_HD void v2_plan_transposed(int* plan, int PH, int PW, int tid, int nth) {
-  if (plan[0] != V2_PLAN) return;
-  const int X0 = plan[6], FW = plan[7], Y0 = plan[8], FH = plan[9] - plan[8] + 1;
+ABR_HD void v2_plan_transposed(int* axes, int* plan, int PH, int PW, int tid, int nth) {
+  // `axes`: where the header and the PW + PH axis records are read (the plan itself, or the planning warp's copy in
+  // shared memory, which is written to the plan afterwards); the transposed records go to `plan`.
+  if (axes[0] != V2_PLAN) return;
+  const int X0 = axes[6], FW = axes[7], Y0 = axes[8], FH = axes[9] - axes[8] + 1;
   for (int k = tid; k < FW + FH; k += nth) {
     const bool is_row = k >= FW;
     const int at = is_row ? Y0 + (k - FW) : X0 + k;                    // map column / row
     const int first = is_row ? PW : 0, count = is_row ? PH : PW;       // the axis records to transpose
     int* rec = plan + kV2Hdr + (PW + PH + (is_row ? kV2MaxFW + (k - FW) : k)) * kV2Rec;
     int q0 = -1, nq = 0;
-    for (int i = 0; i < kV2Sup; i++) rec[1 + i] = 0;
+    int w[kV2Sup];
+#pragma unroll
+    for (int i = 0; i < kV2Sup; i++) w[i] = 0;
     for (int q = 0; q < count; q++) {
-      const int* cr = plan + kV2Hdr + (first + q) * kV2Rec;
+      const int* cr = axes + kV2Hdr + (first + q) * kV2Rec;
       const int lo = cr[0] & 0xffff, n = cr[0] >> 16;
       if (n == 0 || at < lo || at > lo + n - 1) continue;
-      const int w = cr[1 + (at - lo)];
-      if (is_row && __int_as_float(w) == 0.f) continue;  // e.g. the upper tap of a sample that sits exactly on a map row
+      const int wq = cr[1 + (at - lo)];
+      if (is_row && __int_as_float(wq) == 0.f) continue;  // e.g. the upper tap of a sample that sits exactly on a map row
       if (q0 < 0) q0 = q;
-      if (q - q0 < kV2Sup) rec[1 + (q - q0)] = w;
+      if (q - q0 < kV2Sup) {
+#pragma unroll
+        for (int i = 0; i < kV2Sup; i++)
+          if (i == q - q0) w[i] = wq;
+      }
       nq = q - q0 + 1;
     }
     // more than kV2Sup bins over one map pixel (a one-pixel RoI pooled to 16 bins) do not fit a record: the RoI goes to
     // the per-sample path (several threads may store the same value)
-    if (nq > kV2Sup) plan[0] = V2_GENERIC;
+    if (nq > kV2Sup) axes[0] = V2_GENERIC;
     rec[0] = (q0 < 0 ? 0 : q0) | ((nq > kV2Sup ? kV2Sup : nq) << 16);
+#pragma unroll
+    for (int i = 0; i < kV2Sup; i++) rec[1 + i] = w[i];
   }
 }
 

@@ -21,7 +21,9 @@ int v2_backward(const LevelTable& lv, const int* plans, const float* rois, const
 // ARD from per-slice channel sums (ard.cu): sums [N][nslices][HW][3] -> coef [N][HW] (ka, kb) and loss3; `ws` holds
 // ard_coeff_workspace_bytes(N) bytes.
 size_t ard_coeff_workspace_bytes(int N);
+// counter_is_clear: the caller has already zeroed the completion counter at the start of `ws` on this stream;
+// zero_fill / zero_bytes: a buffer (16-byte aligned, a 16-byte multiple long) the kernel also fills with zeros, or null.
 int ard_coeff_run(const float* sums, int nslices, float2* coef, float* loss3, int N, int C, int HW, float gamma, float grad_scale,
-                  void* ws, cudaStream_t st);
+                  void* ws, cudaStream_t st, bool counter_is_clear = false, void* zero_fill = nullptr, size_t zero_bytes = 0);
 
 }  // namespace abr

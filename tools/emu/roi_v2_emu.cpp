@@ -32,7 +32,7 @@ __attribute__((visibility("default"))) void emu_plan(const float* rois, int R, i
     const RoiGeom g = roi_geometry(rois, nullptr, lv, r, PH, PW, ratio);
     for (int t = 0; t < nth; t++) v2_plan_axes(plan, g, H, W, PH, PW, t, nth);
     v2_plan_header(plan, g, H, W, PH, PW);
-    for (int t = 0; t < nth; t++) v2_plan_transposed(plan, PH, PW, t, nth);
+    for (int t = 0; t < nth; t++) v2_plan_transposed(plan, plan, PH, PW, t, nth);
   }
 }
 
