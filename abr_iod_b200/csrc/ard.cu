@@ -595,7 +595,7 @@ static int launch_nchw_cluster(const ArdParams& p, const void* fo, const void* f
 // position phase as the kernels above and writes the two per-position coefficients of
 //     dL/df_new = ka * (f_new - f_old) + kb * f_new
 // which the fused backward applies on the fly; the loss partials are reduced by the last CTA (ard_finish).
-__global__ void __launch_bounds__(256) ard_coeff_kernel(ArdParams p, const float* __restrict__ sums, int nslices,
+__global__ void __launch_bounds__(256, 8) ard_coeff_kernel(ArdParams p, const float* __restrict__ sums, int nslices,
                                                        float2* __restrict__ coef, float4* __restrict__ zero_fill, size_t zero_n) {
   extern __shared__ float sm[];
   const int HW = p.HW, n = blockIdx.x;
