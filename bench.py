@@ -349,20 +349,40 @@ class RoiPath:
         h2d = int(h_teacher.numel() * 4 + h_student.numel() * 4 + h_rois.numel() * 4)
         d2h = int(h_grad[0].numel() * 4 + 4)
         e2e_ms = es.elapsed_time(ee) / steps
-        # what this host's PCIe link sustains for one pinned copy each way (128 MB, best of 3), measured in the same run
-        big_h = torch.empty(128 << 20, dtype=torch.uint8).pin_memory()
-        big_d = torch.empty(128 << 20, dtype=torch.uint8, device=dev)
+        # what this host's PCIe links sustain for pinned 128 MB copies, measured in the same run: each way alone, and both
+        # ways at once (what the pipelined leg asks for); every rank copies at the same time (barrier), so at N GPUs the
+        # figures are per GPU under the load of all N
+        big_h = [torch.empty(128 << 20, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        big_d = [torch.empty(128 << 20, dtype=torch.uint8, device=dev) for _ in range(2)]
+        s_up, s_dn = streams[0], streams[1]
         peak = {}
-        for name, (dst, src) in (("h2d", (big_d, big_h)), ("d2h", (big_h, big_d))):
-            best = 0.0
+
+        def copy_rate(up, down):
+            best = [0.0, 0.0]
             for _ in range(3):
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                dst.copy_(src, non_blocking=True)
-                b.record()
+                barrier()
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                if up:
+                    with torch.cuda.stream(s_up):
+                        ev[0].record()
+                        big_d[0].copy_(big_h[0], non_blocking=True)
+                        ev[1].record()
+                if down:
+                    with torch.cuda.stream(s_dn):
+                        ev[2].record()
+                        big_h[1].copy_(big_d[1], non_blocking=True)
+                        ev[3].record()
                 torch.cuda.synchronize()
-                best = max(best, big_h.numel() / (a.elapsed_time(b) * 1e-3) / 1e9)
-            peak[name] = round(best, 1)
+                if up:
+                    best[0] = max(best[0], big_h[0].numel() / (ev[0].elapsed_time(ev[1]) * 1e-3) / 1e9)
+                if down:
+                    best[1] = max(best[1], big_h[1].numel() / (ev[2].elapsed_time(ev[3]) * 1e-3) / 1e9)
+            return best
+
+        peak["h2d"] = round(copy_rate(True, False)[0], 1)
+        peak["d2h"] = round(copy_rate(False, True)[1], 1)
+        both = copy_rate(True, True)
+        peak["h2d_while_d2h"], peak["d2h_while_h2d"] = round(both[0], 1), round(both[1], 1)
         self.pcie_peak, self.e2e_streams = peak, len(streams)
         return e2e_ms, h2d, d2h, t_issue
 
@@ -441,11 +461,15 @@ def run_ours(args, rank, world, local_rank):
                 "h2d_GBs_per_gpu": round(h2d / (e2e_ms * 1e-3) / 1e9, 2), "d2h_GBs_per_gpu": round(d2h / (e2e_ms * 1e-3) / 1e9, 2),
                 "h2d_GBs_aggregate": round(world * h2d / (e2e_ms * 1e-3) / 1e9, 2), "host_placement": placement,
                 "host_issue_ms_per_step": round(issue_ms, 3),
-                "pcie_peak_GBs_measured": path.pcie_peak,
+                "pcie_peak_GBs_measured": dict(path.pcie_peak, note="128 MB pinned copies per GPU, all %d ranks copying at the "
+                                               "same time; *_while_*: both directions at once" % world),
                 "h2d_frac_of_pcie_peak": round(h2d / (e2e_ms * 1e-3) / 1e9 / max(path.pcie_peak["h2d"], 1e-9), 3),
+                "copy_GBs_per_gpu_both_ways": round((h2d + d2h) / (e2e_ms * 1e-3) / 1e9, 2),
+                "probe_GBs_per_gpu_both_ways": round(path.pcie_peak["h2d_while_d2h"] + path.pcie_peak["d2h_while_h2d"], 1),
                 "limiter": ("the device step (copies hidden behind the kernels)" if e2e_ms < 1.15 * ms_per_step else
                             "host issue rate (Python API + autograd per step)" if issue_ms > 0.85 * e2e_ms else
-                            "host->device copy of the step's inputs (PCIe; see h2d_frac_of_pcie_peak)")},
+                            "host<->device copies: the host side shared by the ranks (compare copy_GBs_per_gpu_both_ways "
+                            "with probe_GBs_per_gpu_both_ways, plain pinned copies under the same N-rank load)")},
         "gpu_launches": launches, "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
