@@ -51,6 +51,7 @@ SIGNATURES = {
     "abr_launch_count": (ctypes.c_uint64, []),
     "abr_set_option": (_int, [ctypes.c_char_p, _int]),
     "abr_stage_timing_begin": (_int, [_int]),
+    "abr_stage_timing_begin_every": (_int, [_int, _int]),
     "abr_stage_timing_end": (_int, [_vp, _int]),
     "abr_roi_align_workspace_bytes": (_sz, [_int, _int, _int, _int]),
     "abr_roi_align_workspace_bytes_nchw": (_sz, [_int, _int, _int, _int, _int, _int, ctypes.c_longlong, _int]),
@@ -206,8 +207,9 @@ def set_option(key: str, value: int) -> None:
 FUSED_STAGES = ("plan", "pool_teacher_student", "ard_coefficients", "backward")
 
 
-def stage_timing_begin(max_calls: int) -> None:
-    check(lib().abr_stage_timing_begin(int(max_calls)))
+def stage_timing_begin(max_calls: int, every: int = 1) -> None:
+    """Record stage events for every ``every``-th ``abr_roi_ard_fused`` call from now on (at most ``max_calls`` calls)."""
+    check(lib().abr_stage_timing_begin_every(int(max_calls), int(every)))
 
 
 def stage_timing_end():

@@ -31,22 +31,30 @@ Options& options() {
 
 // ---- stage timing: (ABR_FUSED_STAGES + 1) events per recorded call
 static std::vector<cudaEvent_t> g_stage_events;
-static int g_stage_max = 0, g_stage_calls = 0;
+static int g_stage_max = 0, g_stage_calls = 0, g_stage_every = 1, g_stage_seen = 0;
 static bool g_stage_on = false;
 constexpr int kMarks = ABR_FUSED_STAGES + 1;
 
 void stage_mark(cudaStream_t st, int k) {
-  if (!g_stage_on || g_stage_calls >= g_stage_max) return;
-  cudaEventRecord(g_stage_events[(size_t)g_stage_calls * kMarks + k], st);
-  if (k == ABR_FUSED_STAGES) g_stage_calls++;
+  if (!g_stage_on) return;
+  const bool sampled = g_stage_seen % g_stage_every == 0 && g_stage_calls < g_stage_max;  // every g_stage_every-th call
+  if (sampled) cudaEventRecord(g_stage_events[(size_t)g_stage_calls * kMarks + k], st);
+  if (k == ABR_FUSED_STAGES) {
+    if (sampled) g_stage_calls++;
+    g_stage_seen++;
+  }
 }
 
 }  // namespace abr
 
 extern "C" {
-int abr_stage_timing_begin(int max_calls) {
+int abr_stage_timing_begin(int max_calls) { return abr_stage_timing_begin_every(max_calls, 1); }
+int abr_stage_timing_begin_every(int max_calls, int every) {
   using namespace abr;
   ABR_REQUIRE(max_calls > 0 && max_calls <= 4096, ABR_ERR_BAD_ARG, "stage_timing_begin: max_calls %d (1..4096)", max_calls);
+  ABR_REQUIRE(every > 0, ABR_ERR_BAD_ARG, "stage_timing_begin: every %d (>= 1)", every);
+  g_stage_every = every;
+  g_stage_seen = 0;
   while ((int)g_stage_events.size() < max_calls * kMarks) {
     cudaEvent_t e;
     ABR_CUDA_OK(cudaEventCreate(&e));

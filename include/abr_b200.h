@@ -63,9 +63,12 @@ ABR_API int abr_set_option(const char* key, int value);
  * abr_stage_timing_begin(max_calls) and abr_stage_timing_end(), every abr_roi_ard_fused call records CUDA events on the
  * CALLER'S stream around its stages (0 plan, 1 teacher+student pooling, 2 ARD coefficients, 3 zero-fill + backward).
  * abr_stage_timing_end synchronises on the last event, writes the average milliseconds per call of each stage into
- * avg_ms[0..n_stages) and returns the number of calls recorded (< 0 on error).  Not re-entrant; one stream at a time. */
+ * avg_ms[0..n_stages) and returns the number of calls recorded (< 0 on error).  Not re-entrant; one stream at a time.
+ * abr_stage_timing_begin_every(max_calls, every) records only every `every`-th call (the five event records of a call
+ * cost ~15 us of stream time at configs[0]; sampling keeps that out of most timed steps). */
 #define ABR_FUSED_STAGES 4
 ABR_API int abr_stage_timing_begin(int max_calls);
+ABR_API int abr_stage_timing_begin_every(int max_calls, int every);
 ABR_API int abr_stage_timing_end(float* avg_ms, int n_stages);
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 ABR_API uint64_t abr_launch_count(void);
