@@ -322,3 +322,27 @@ def test_fused_full_size_config1(P):
     allow_map = oracle.roi_align_backward(allow, rois, 1 / 16, P, P, B, sl.stop - sl.start, H, W, 0)
     close_allow(grad[:, sl].cpu().numpy(), rg, allow_map, 2e-5)
     close_allow(st.grad[:, sl].cpu().numpy(), rg, allow_map, 2e-5)
+
+
+def test_stage_timing_samples_every_nth_fused_call():
+    """abr_stage_timing_begin_every: events around the four stages of every n-th abr_roi_ard_fused call on the caller's stream."""
+    from abr_iod_b200 import _lib
+    from abr_iod_b200.distillation.distillation import pooled_attentive_roi_distillation as fused_op
+
+    rng = np.random.default_rng(2)
+    B, C, H, W, P = 1, 32, 12, 16, 7
+    t = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    rois = make_rois(rng, 12, B, W * 16, H * 16)
+    tt, rr = dev(t, True), dev(rois)
+    for every, calls, want in ((1, 3, 3), (4, 9, 3), (2, 5, 3)):
+        _lib.stage_timing_begin(16, every)
+        for _ in range(calls):
+            ss = dev(t + 0.1, True).requires_grad_(True)
+            fused_op(tt, ss, rr, (P, P), 1 / 16, 0, 1.0)
+        n, stages = _lib.stage_timing_end()
+        assert n == want, (every, calls, n)
+        assert set(stages) == set(_lib.FUSED_STAGES) and all(v > 0 for v in stages.values())
+    # outside begin/end nothing is recorded
+    fused_op(tt, dev(t + 0.1, True).requires_grad_(True), rr, (P, P), 1 / 16, 0, 1.0)
+    _lib.stage_timing_begin(4)
+    assert _lib.stage_timing_end()[0] == 0
