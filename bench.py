@@ -74,6 +74,16 @@ def algorithmic_bytes(w, R):
             "composite": 3 * fmap + 60 * R + 6 * pooled, "fmap": fmap, "pooled": pooled}
 
 
+_JSON_OUT = None  # the real stdout, when fd 1 has been pointed at stderr for the duration of the run (main)
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 INPUT_SETS = 4  # device copies of the (teacher, student) maps used in rotation: 4 x 39 MB = 157 MB > the 126 MB L2
 
 
@@ -200,7 +210,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ the RoI path
@@ -533,7 +543,7 @@ def run_ours(args, rank, world, local_rank):
         line["reference_cuda"] = reference_cuda_metrics(w, dev)
         torch.cuda.empty_cache()
         line["secondary"] = secondary_metrics(dev)
-    print(json.dumps(line))
+    emit(line)
 
 
 def small_call_metrics(dev):
@@ -722,7 +732,7 @@ def run_other_workload(args, rank, world, dev, barrier, sampler):
     if nbytes:
         line["roofline"] = {"bound": "hbm", "achieved": round(nbytes / (ms * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
                             "frac": round(nbytes / (ms * 1e-3) / 1e9 / peak, 4)}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ configs 3 and 4
@@ -1090,6 +1100,12 @@ def main():
         run_reference(args, rank, world)
         return
     if world > 1:
+        # stdout carries the ONE JSON line and nothing else: libraries that write to fd 1 themselves (NCCL prints its version
+        # banner there) are sent to stderr for the duration of the run
+        global _JSON_OUT
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
         import torch
         import torch.distributed as dist
 
