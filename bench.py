@@ -120,10 +120,14 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def summary(self, t0, t1):
+    def summary(self, t0, t1, t_load0=None):
+        """Median SM clock and the throttle reasons seen in [t0, t1] (the timed region); with t_load0 also over the whole
+        stretch of identical load that starts there (settle loop + warm-up + timed steps) -- a 20-step region is ~20 ms,
+        one or two nvidia-smi samples."""
         if self.proc is not None:
             self.proc.terminate()
         rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.05 and len(r) >= 6]
+        load = [r for t, r in self.rows if t_load0 is not None and t_load0 + 0.1 <= t <= t1 + 0.05 and len(r) >= 6]
         note = "sampled inside the timed region"
         if not rows:
             rows, note = [r for _, r in self.rows if len(r) >= 6], "no sample fell inside the timed region: all samples of the run"
@@ -132,7 +136,13 @@ class ClockSampler:
         sm = sorted(float(r[0]) for r in rows)
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons, "samples": len(rows), "note": note}
+        out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons, "samples": len(rows), "note": note}
+        if load:
+            lsm = sorted(float(r[0]) for r in load)
+            out["load_phase"] = {"sm_mhz": lsm[len(lsm) // 2], "sm_mhz_min": lsm[0], "samples": len(load),
+                                 "reasons": [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in load)],
+                                 "note": "settle loop + warm-up + timed steps: the same work, back to back"}
+        return out
 
 
 def bind_to_gpu_numa(index):
@@ -456,7 +466,7 @@ def run_ours(args, rank, world, local_rank):
     while time.time() - t_settle < 0.3:
         path.step()
     ms_per_step, per_kernel, launches, t0, t1 = path.timed(args.steps, warm, barrier)
-    clocks = sampler.summary(t0, t1) if sampler else None
+    clocks = sampler.summary(t0, t1, t_settle) if sampler else None
     e2e_steps = max(4, min(args.steps, 40))
     e2e_ms, h2d, d2h, issue_ms = path.e2e(e2e_steps, barrier)
 
