@@ -404,6 +404,49 @@ ABR_DEV void v2_store_out(T* p, const float (&v)[V]) {
 #endif
 }
 
+// The lane's three ARD partial sums over its V channels of one bin (sum a^2, sum b^2, sum (b - a)^2).  With an even V the
+// channels go two at a time through packed fp32 FMAs (even channels in one half, odd ones in the other; d = b - a as one
+// fused a * -1 + b: the same rounding) -- 0.9 % of the fused step; the scalar form adds in the same order.
+template <int V>
+ABR_DEV void v2_ard_partials(const float (&a)[V], const float (&b)[V], float& so, float& sn, float& sd) {
+#if !defined(ABR_V2_NO_FFMA2) && !defined(ABR_EMU)
+  if (V % 2 == 0) {
+    float2 o2 = make_float2(0.f, 0.f), n2 = o2, d2 = o2;
+    const float2 m1 = make_float2(-1.f, -1.f);
+#pragma unroll
+    for (int i = 0; i < V / 2; i++) {
+      const float2 av = make_float2(a[2 * i], a[2 * i + 1]), bv = make_float2(b[2 * i], b[2 * i + 1]);
+      const float2 dv = __ffma2_rn(av, m1, bv);
+      o2 = __ffma2_rn(av, av, o2);
+      n2 = __ffma2_rn(bv, bv, n2);
+      d2 = __ffma2_rn(dv, dv, d2);
+    }
+    so = o2.x + o2.y; sn = n2.x + n2.y; sd = d2.x + d2.y;
+    return;
+  }
+#endif
+  if (V % 2 == 0) {
+    float o2[2] = {0.f, 0.f}, n2[2] = {0.f, 0.f}, d2[2] = {0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+      const float d = b[k] - a[k];
+      o2[k & 1] = fmaf(a[k], a[k], o2[k & 1]);
+      n2[k & 1] = fmaf(b[k], b[k], n2[k & 1]);
+      d2[k & 1] = fmaf(d, d, d2[k & 1]);
+    }
+    so = o2[0] + o2[1]; sn = n2[0] + n2[1]; sd = d2[0] + d2[1];
+    return;
+  }
+  so = sn = sd = 0.f;
+#pragma unroll
+  for (int k = 0; k < V; k++) {
+    const float d = b[k] - a[k];
+    so = fmaf(a[k], a[k], so);
+    sn = fmaf(b[k], b[k], sn);
+    sd = fmaf(d, d, sd);
+  }
+}
+
 // Emits one output bin of NT tensors: scale by 1/count, store, and (NT == 2) the lane's ARD partial sums.
 template <typename T, int V, int NT>
 ABR_DEV void v2_emit_bin(float (&acc)[NT][V], float inv_count, T* const (&o)[NT], bool active, V2Sums& sums, int lane) {
@@ -414,14 +457,8 @@ ABR_DEV void v2_emit_bin(float (&acc)[NT][V], float inv_count, T* const (&o)[NT]
     if (active) v2_store_out<T, V>(o[t], acc[t]);
   }
   if (NT == 2) {
-    float so = 0.f, sn = 0.f, sd = 0.f;
-#pragma unroll
-    for (int k = 0; k < V; k++) {
-      const float a = acc[0][k], b = acc[NT - 1][k], d = b - a;
-      so = fmaf(a, a, so);
-      sn = fmaf(b, b, sn);
-      sd = fmaf(d, d, sd);
-    }
+    float so, sn, sd;
+    v2_ard_partials<V>(acc[0], acc[NT - 1], so, sn, sd);
     if (!active) so = sn = sd = 0.f;
     v2_sums_add(sums, so, sn, sd, lane);
   }
