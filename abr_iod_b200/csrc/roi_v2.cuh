@@ -459,8 +459,7 @@ ABR_DEV void v2_emit_bin(float (&acc)[NT][V], float inv_count, T* const (&o)[NT]
   if (NT == 2) {
     float so, sn, sd;
     v2_ard_partials<V>(acc[0], acc[NT - 1], so, sn, sd);
-    if (!active) so = sn = sd = 0.f;
-    v2_sums_add(sums, so, sn, sd, lane);
+    v2_sums_add(sums, so, sn, sd, lane);  // (an idle lane of a ragged slice has inv_count = 0: zero sums)
   }
 }
 // ... the same with the warp totals formed by shuffles and stored at once (the per-sample path)
@@ -603,7 +602,7 @@ ABR_DEV void v2_fwd_column(v2_sptr plan_s, const T* const (&maps)[NT], T* const 
   constexpr int RB2 = V >= 8 ? 1 : 2, RB4 = V >= 8 ? 2 : 4;
   const int4 h0 = v2_lds4i(plan_s), h1 = v2_lds4i(plan_s + 16), h2 = v2_lds4i(plan_s + 32);
   const int mode = h0.x, batch = h0.y, H = h0.w, W = h1.x, Y1 = h2.y;
-  const float inv_count = __int_as_float(h1.y);
+  const float inv_count = active ? __int_as_float(h1.y) : 0.f;  // idle lanes of a ragged slice emit zeros (and park zero sums)
   const size_t pix = (size_t)C, binstride = (size_t)PW * C;
   T* o[NT];
 #pragma unroll
@@ -819,35 +818,24 @@ ABR_DEV void v2_bwd_fill_tile(v2_sptr tile, const V2Grad<T, V, FUSED>& src, int 
       v2_cp_async_wait_all();
       return;
     }
-    constexpr int U = 8;
-    const size_t step = (size_t)nw * C, last = (size_t)(nbin - 1) * C;
-    size_t off = (size_t)warp * C;
-    if ((lane & 7) == 0)  // one request per 128-byte line: the second operand's later batches start towards L2 now (1 %)
-      for (int b = warp + U * nw; b < nbin; b += nw) asm volatile("prefetch.global.L2 [%0];" ::"l"(src.b + (size_t)b * C));
+    // The second operand: every line is requested from L2 at once (one prefetch per 128-byte line), then the bins go through
+    // registers one at a time.  (Batches of loads held in registers were slower -- 8 bins per batch: +5 % on the fused step
+    // at configs[0] -- the prefetches already put all of the tile's traffic in flight.)
+    if ((lane & 7) == 0)
+      for (int b = warp; b < nbin; b += nw) asm volatile("prefetch.global.L2 [%0];" ::"l"(src.b + (size_t)b * C));
     bool landed = false;
-    for (int b0 = warp; b0 < nbin; b0 += U * nw, off += U * step) {
-      float fn[U][V];
-      float2 kc[U];
-#pragma unroll
-      for (int j = 0; j < U; j++) {
-        const bool in = b0 + j * nw < nbin;
-        v2_load_hint<T, V>(src.b + (in ? off + j * step : last), fn[j], pol1);
-        kc[j] = __ldg(src.coef + (in ? b0 + j * nw : nbin - 1));
-      }
-      if (!landed) {
+    for (int b = warp; b < nbin; b += nw) {
+      float fn[V], fo[V], g[V];
+      v2_load_hint<T, V>(src.b + (size_t)b * C, fn, pol1);
+      const float2 kc = __ldg(src.coef + b);
+      if (!landed) {  // the first operand's copies (all of this warp's bins) have to have landed
         v2_cp_async_wait_all();
         landed = true;
       }
+      v2_sm_load<V>(mine + b * BINB, fo);
 #pragma unroll
-      for (int j = 0; j < U; j++) {
-        if (b0 + j * nw < nbin) {
-          float fo[V], g[V];
-          v2_sm_load<V>(mine + (b0 + j * nw) * BINB, fo);
-#pragma unroll
-          for (int k = 0; k < V; k++) g[k] = fmaf(kc[j].x, fn[j][k] - fo[k], kc[j].y * fn[j][k]);
-          v2_sm_store<V>(mine + (b0 + j * nw) * BINB, g);
-        }
-      }
+      for (int q = 0; q < V; q++) g[q] = fmaf(kc.x, fn[q] - fo[q], kc.y * fn[q]);
+      v2_sm_store<V>(mine + b * BINB, g);
     }
     return;
   }
