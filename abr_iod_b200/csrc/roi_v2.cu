@@ -147,7 +147,15 @@ __global__ void __launch_bounds__(NTHR, 1024 / NTHR) v2_bwd_kernel(const __grid_
       v2_generic_bwd_column<T, V>(g, a.lv.H[g.level], a.lv.W[g.level], gmap, tile, pw, c, a.C, a.PH, a.PW, lane);
     return;
   }
-  for (int k = warp; k < FW; k += nw) v2_bwd_pixcol<T, V>(plan_s, gmap, tile, k, c, a.C, a.PH, a.PW, lane);
+  if (NTHR >= 512) {
+    const int S = v2_bwd_row_chunks(FW, nw), chunk = (FH + S - 1) / S;
+    for (int task = warp; task < FW * S; task += nw) {
+      const int k = task / S, j0 = (task - k * S) * chunk, j1 = j0 + chunk < FH ? j0 + chunk : FH;
+      if (j0 < j1) v2_bwd_pixcol<T, V>(plan_s, gmap, tile, k, j0, j1, c, a.C, a.PH, a.PW, lane);
+    }
+  } else {
+    for (int k = warp; k < FW; k += nw) v2_bwd_pixcol<T, V>(plan_s, gmap, tile, k, 0, FH, c, a.C, a.PH, a.PW, lane);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ host side

@@ -898,14 +898,23 @@ ABR_DEV void v2_bwd_rows(v2_sptr rowrec, int FH, v2_sptr tcol, int pwb, v2_sptr 
   }
 }
 
-// Phase 2: one footprint pixel column x = X0 + k of one RoI.  plan_s: the plan in shared memory (header, PW + PH axis
+// How phase 2 is cut into warp tasks in the 16-warp kernel: a footprint of FW pixel columns gives FW tasks, fewer than the
+// CTA has warps for most RoIs; every column is therefore split into up to four row chunks (the rows of a column are
+// independent) so that every warp has a task.  Returns the chunks per column.  (The 8-warp kernel of the small outputs
+// keeps whole columns: the split costs it 1 %.)
+ABR_HD int v2_bwd_row_chunks(int FW, int nw) {
+  int s = FW > 0 ? (nw + FW - 1) / FW : 1;
+  return s < 1 ? 1 : (s > 4 ? 4 : s);
+}
+
+// Phase 2: rows j0 .. j1 - 1 of one footprint pixel column x = X0 + k of one RoI.  plan_s: the plan in shared memory (header, PW + PH axis
 // records, pixel-column records, row records); gmap: the level's gradient map [B][H][W][C]; tile: the (RoI, slice)
 // gradient tile in shared memory.
 template <typename T, int V>
-ABR_DEV void v2_bwd_pixcol(v2_sptr plan_s, T* gmap, v2_sptr tile, int k, int c, int C, int PH, int PW, int lane) {
+ABR_DEV void v2_bwd_pixcol(v2_sptr plan_s, T* gmap, v2_sptr tile, int k, int j0, int j1, int c, int C, int PH, int PW, int lane) {
   constexpr int BINB = 32 * V * 4;
   const int4 h0 = v2_lds4i(plan_s), h1 = v2_lds4i(plan_s + 16), h2 = v2_lds4i(plan_s + 32);
-  const int batch = h0.y, H = h0.w, W = h1.x, X0 = h1.z, Y0 = h2.x, FH = h2.y - h2.x + 1;
+  const int batch = h0.y, H = h0.w, W = h1.x, X0 = h1.z, Y0 = h2.x + j0, FH = j1 - j0;  // footprint rows j0 .. j1 - 1 of the column
   const float inv_count = __int_as_float(h1.y);
   const v2_sptr pxrec = v2_srec(plan_s, PW + PH + k);
   const int px0 = v2_lds4i(pxrec).x;
@@ -914,7 +923,7 @@ ABR_DEV void v2_bwd_pixcol(v2_sptr plan_s, T* gmap, v2_sptr tile, int k, int c, 
   const size_t rowstride = (size_t)W * C;
   T* gin = gmap + ((size_t)batch * H * W + (X0 + k)) * C + c + (size_t)Y0 * rowstride;
   const v2_sptr tcol = tile + lane * (V * 4) + (px0 & 0xffff) * BINB;  // bins [.][q0 ..] of this lane
-  const v2_sptr rowrec = v2_srec(plan_s, PW + PH + kV2MaxFW);
+  const v2_sptr rowrec = v2_srec(plan_s, PW + PH + kV2MaxFW + j0);
   const int pwb = PW * BINB;
   switch (nq) {
     case 1: v2_bwd_rows<T, V, 1>(rowrec, FH, tcol, pwb, pxrec, nq, inv_count, gin, rowstride); break;

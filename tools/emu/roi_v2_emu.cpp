@@ -124,7 +124,11 @@ static void bwd_t(const int* plans, const float* rois, float* gmap, const float*
               for (int pw = warp; pw < PW; pw += nwarps) v2_generic_bwd_column<float, V>(g, H, W, gmap, tile, pw, c, C, PH, PW, lane);
             } else {
               const int FW = plan[7];
-              for (int k = warp; k < FW; k += nwarps) v2_bwd_pixcol<float, V>(plan_s, gmap, tile, k, c, C, PH, PW, lane);
+              const int FH = plan[9] - plan[8] + 1, S = v2_bwd_row_chunks(FW, nwarps), chunk = (FH + S - 1) / S;
+              for (int task = warp; task < FW * S; task += nwarps) {
+                const int k = task / S, j0 = (task - k * S) * chunk, j1 = j0 + chunk < FH ? j0 + chunk : FH;
+                if (j0 < j1) v2_bwd_pixcol<float, V>(plan_s, gmap, tile, k, j0, j1, c, C, PH, PW, lane);
+              }
             }
           }
     }
