@@ -119,25 +119,30 @@ __global__ void __launch_bounds__(NTHR, 1024 / NTHR) v2_bwd_kernel(const __grid_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int nw = NTHR / 32;
   const int* plan = a.plans + (size_t)r * a.stride;
-  const int4 h0 = __ldg(reinterpret_cast<const int4*>(plan));
-  const int mode = h0.x, level = h0.z;
-  if (mode == V2_EMPTY) return;  // (the whole CTA)
-  const int4 h1 = __ldg(reinterpret_cast<const int4*>(plan + 4)), h2 = __ldg(reinterpret_cast<const int4*>(plan + 8));
-  const int FW = mode == V2_PLAN ? h1.w : 0, FH = mode == V2_PLAN ? h2.y - h2.x + 1 : 0;
   const int nbin = a.PH * a.PW;
   int c = (slice * 32 + lane) * V;
   const bool active = c < a.C;
   if (!active) c = 0;
   const v2_sptr plan_s = v2_sptr_of(v2_smem), tile = plan_s + (uint32_t)a.plan_smem;
-  if (mode == V2_PLAN) {
-    v2_stage_plan(plan, plan_s, a.PW + a.PH + FW, threadIdx.x, NTHR);
-    v2_stage_records(plan, plan_s, a.PW + a.PH + kV2MaxFW, FH, threadIdx.x, NTHR);
-  }
   V2Grad<T, V, FUSED> src;
   src.a = a.a + (size_t)r * nbin * a.C + c;
   src.b = FUSED ? a.b + (size_t)r * nbin * a.C + c : nullptr;
   src.coef = FUSED ? a.coef + (size_t)r * nbin : nullptr;
-  v2_bwd_fill_tile<T, V, FUSED>(tile, src, nbin, a.C, warp, nw, lane);
+  // the plain form puts the tile's traffic in flight first: it does not depend on the plan, whose header and records cost
+  // two L2 round trips (3 % on the kernel); for the fused form, with twice the requests per warp, the old order measured
+  // 0.3 % better
+  if (!FUSED) v2_bwd_fill_issue<T, V, FUSED>(tile, src, nbin, a.C, warp, nw, lane);
+  const int4 h0 = __ldg(reinterpret_cast<const int4*>(plan)), h1 = __ldg(reinterpret_cast<const int4*>(plan + 4)),
+             h2 = __ldg(reinterpret_cast<const int4*>(plan + 8));
+  const int mode = h0.x, level = h0.z;
+  const int FW = mode == V2_PLAN ? h1.w : 0, FH = mode == V2_PLAN ? h2.y - h2.x + 1 : 0;
+  if (mode == V2_PLAN) {
+    v2_stage_plan(plan, plan_s, a.PW + a.PH + FW, threadIdx.x, NTHR);
+    v2_stage_records(plan, plan_s, a.PW + a.PH + kV2MaxFW, FH, threadIdx.x, NTHR);
+  }
+  if (FUSED) v2_bwd_fill_issue<T, V, FUSED>(tile, src, nbin, a.C, warp, nw, lane);
+  v2_bwd_fill_combine<T, V, FUSED>(tile, src, nbin, a.C, warp, nw, lane);  // (also drains the asynchronous copies)
+  if (mode == V2_EMPTY) return;  // (the whole CTA) no sample of the RoI falls inside the map
   __syncthreads();
   if (!active) return;  // idle lane of a ragged last slice (no warp-level primitive below)
   T* gmap = static_cast<T*>(a.lv.ptr[level]);

@@ -803,26 +803,39 @@ ABR_DEV void v2_cp_async_wait_all() {
 }
 #endif
 
+// Phase 1 in two parts, so that the kernel can put the tile's traffic in flight BEFORE it reads the RoI's plan (two
+// dependent L2 round trips) and combine afterwards.  v2_bwd_fill_issue: the asynchronous part (fp32, 16 bytes per lane:
+// the first operand by cp.async straight into the tile, every line of the second requested from L2); nothing for the
+// other types.  v2_bwd_fill_tile = issue + the rest.
 template <typename T, int V, bool FUSED>
-ABR_DEV void v2_bwd_fill_tile(v2_sptr tile, const V2Grad<T, V, FUSED>& src, int nbin, int C, int warp, int nw, int lane) {
+ABR_DEV void v2_bwd_fill_issue(v2_sptr tile, const V2Grad<T, V, FUSED>& src, int nbin, int C, int warp, int nw, int lane) {
+#ifndef ABR_EMU
+  if (sizeof(T) == 4 && V == 4) {
+    constexpr int BINB = 32 * V * 4;
+    const v2_sptr mine = tile + lane * (V * 4);
+    const uint64_t pol1 = v2_policy_evict_first();
+    for (int b = warp; b < nbin; b += nw) v2_cp_async16_hint(mine + b * BINB, src.a + (size_t)b * C, pol1);
+    if (FUSED && (lane & 7) == 0)  // one request per 128-byte line
+      for (int b = warp; b < nbin; b += nw) asm volatile("prefetch.global.L2 [%0];" ::"l"(src.b + (size_t)b * C));
+  }
+#else
+  (void)tile; (void)src; (void)nbin; (void)C; (void)warp; (void)nw; (void)lane;
+#endif
+}
+
+template <typename T, int V, bool FUSED>
+ABR_DEV void v2_bwd_fill_combine(v2_sptr tile, const V2Grad<T, V, FUSED>& src, int nbin, int C, int warp, int nw, int lane) {
   constexpr int BINB = 32 * V * 4;
   const v2_sptr mine = tile + lane * (V * 4);
 #ifndef ABR_EMU
   if (sizeof(T) == 4 && V == 4) {
-    // fp32, 16 bytes per lane: the first operand (the upstream gradient, or the teacher's pooled tensor when FUSED) goes
-    // straight into the tile with asynchronous copies -- ALL of this warp's bins in flight at once, no registers held --
-    // while the second operand of the fused form streams through registers, eight bins at a time.
-    const uint64_t pol1 = v2_policy_evict_first();
-    for (int b = warp; b < nbin; b += nw) v2_cp_async16_hint(mine + b * BINB, src.a + (size_t)b * C, pol1);
     if (!FUSED) {
       v2_cp_async_wait_all();
       return;
     }
-    // The second operand: every line is requested from L2 at once (one prefetch per 128-byte line), then the bins go through
-    // registers one at a time.  (Batches of loads held in registers were slower -- 8 bins per batch: +5 % on the fused step
-    // at configs[0] -- the prefetches already put all of the tile's traffic in flight.)
-    if ((lane & 7) == 0)
-      for (int b = warp; b < nbin; b += nw) asm volatile("prefetch.global.L2 [%0];" ::"l"(src.b + (size_t)b * C));
+    // The second operand goes through registers one bin at a time.  (Batches of loads held in registers were slower -- 8
+    // bins per batch: +5 % on the fused step at configs[0] -- the prefetches already put all of the tile's traffic in flight.)
+    const uint64_t pol1 = v2_policy_evict_first();
     bool landed = false;
     for (int b = warp; b < nbin; b += nw) {
       float fn[V], fo[V], g[V];
@@ -854,6 +867,12 @@ ABR_DEV void v2_bwd_fill_tile(v2_sptr tile, const V2Grad<T, V, FUSED>& src, int 
     for (int j = 0; j < U; j++)
       if (b0 + j * nw < nbin) v2_sm_store<V>(mine + (b0 + j * nw) * BINB, g[j]);
   }
+}
+
+template <typename T, int V, bool FUSED>
+ABR_DEV void v2_bwd_fill_tile(v2_sptr tile, const V2Grad<T, V, FUSED>& src, int nbin, int C, int warp, int nw, int lane) {
+  v2_bwd_fill_issue<T, V, FUSED>(tile, src, nbin, C, warp, nw, lane);
+  v2_bwd_fill_combine<T, V, FUSED>(tile, src, nbin, C, warp, nw, lane);
 }
 
 // The rows of one footprint pixel column covered by NQ bin columns (compile-time; NQ = 0: nq at run time).  For every
