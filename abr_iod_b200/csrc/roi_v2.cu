@@ -63,7 +63,11 @@ __global__ void __launch_bounds__(256, NT == 2 ? 2 : 3) v2_fwd_kernel(const __gr
   const int r = blockIdx.x / a.nslices, slice = blockIdx.x - r * a.nslices;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int* plan = a.plans + (size_t)r * a.stride;
-  const int4 h0 = __ldg(reinterpret_cast<const int4*>(plan));
+  // the plan is staged before its header is looked at (one L2 round trip instead of two; a GENERIC RoI does not use it)
+  const v2_sptr plan_s = v2_sptr_of(v2_smem);
+  v2_stage_plan(plan, plan_s, a.PW + a.PH, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const int4 h0 = v2_lds4i(plan_s);
   const int mode = h0.x, level = h0.z;
   if (a.clear_word && blockIdx.x == 0 && threadIdx.x == 0) *a.clear_word = 0u;
   int c = (slice * 32 + lane) * V;
@@ -77,15 +81,10 @@ __global__ void __launch_bounds__(256, NT == 2 ? 2 : 3) v2_fwd_kernel(const __gr
     outs[t] = a.out[t];
   }
   float* srs = NT == 2 ? a.sums + ((size_t)r * a.nslices + slice) * a.PH * a.PW * 3 : nullptr;
-  const v2_sptr plan_s = v2_sptr_of(v2_smem);
   bool generic = mode == V2_GENERIC;  // (the whole CTA)
-  if (!generic) {
-    v2_stage_plan(plan, plan_s, a.PW + a.PH, threadIdx.x, blockDim.x);
-    __syncthreads();
-    // a bin taller than the strip (two-tensor kernel: 13..15 map rows, i.e. a RoI more than ~12 * PH map rows high)
-    // sends the RoI down the per-sample path
-    if (v2_strip_rows_for(NT) <= kV2Sup) generic = v2_tallest_bin(plan_s, a.PH, a.PW) > v2_strip_rows_for(NT);
-  }
+  // a bin taller than the strip (two-tensor kernel: 13..15 map rows, i.e. a RoI more than ~12 * PH map rows high)
+  // sends the RoI down the per-sample path
+  if (!generic && v2_strip_rows_for(NT) <= kV2Sup) generic = v2_tallest_bin(plan_s, a.PH, a.PW) > v2_strip_rows_for(NT);
   if (generic) {
     const RoiGeom g = roi_geometry(a.rois, a.levels, a.lv[0], r, a.PH, a.PW, a.ratio);
     for (int pw = warp; pw < a.PW; pw += nw)
