@@ -135,11 +135,25 @@ __global__ void __launch_bounds__(NTHR, 1024 / NTHR) v2_bwd_kernel(const __grid_
              h2 = __ldg(reinterpret_cast<const int4*>(plan + 8));
   const int mode = h0.x, level = h0.z;
   const int FW = mode == V2_PLAN ? h1.w : 0, FH = mode == V2_PLAN ? h2.y - h2.x + 1 : 0;
-  if (mode == V2_PLAN) {
-    v2_stage_plan(plan, plan_s, a.PW + a.PH + FW, threadIdx.x, NTHR);
-    v2_stage_records(plan, plan_s, a.PW + a.PH + kV2MaxFW, FH, threadIdx.x, NTHR);
+  const int na = 4 * (1 + a.PW + a.PH + FW), nb = 4 * FH;  // 16-byte pieces of the plan's two staged ranges
+  if (FUSED && mode == V2_PLAN && na <= NTHR && nb <= NTHR) {
+    // one piece of each range per thread: the loads are issued, then the tile's traffic, then the pieces are parked -- the
+    // plan's round trip and the tile's overlap
+    const int tid = threadIdx.x;
+    int4 pa = make_int4(0, 0, 0, 0), pb = pa;
+    const int* rows = plan + kV2Hdr + (a.PW + a.PH + kV2MaxFW) * kV2Rec;
+    if (tid < na) pa = __ldg(reinterpret_cast<const int4*>(plan) + tid);
+    if (tid < nb) pb = __ldg(reinterpret_cast<const int4*>(rows) + tid);
+    v2_bwd_fill_issue<T, V, FUSED>(tile, src, nbin, a.C, warp, nw, lane);
+    if (tid < na) v2_sts4i(plan_s + 16 * tid, pa);
+    if (tid < nb) v2_sts4i(plan_s + 64 * (1 + a.PW + a.PH + kV2MaxFW) + 16 * tid, pb);
+  } else {
+    if (mode == V2_PLAN) {
+      v2_stage_plan(plan, plan_s, a.PW + a.PH + FW, threadIdx.x, NTHR);
+      v2_stage_records(plan, plan_s, a.PW + a.PH + kV2MaxFW, FH, threadIdx.x, NTHR);
+    }
+    if (FUSED) v2_bwd_fill_issue<T, V, FUSED>(tile, src, nbin, a.C, warp, nw, lane);
   }
-  if (FUSED) v2_bwd_fill_issue<T, V, FUSED>(tile, src, nbin, a.C, warp, nw, lane);
   v2_bwd_fill_combine<T, V, FUSED>(tile, src, nbin, a.C, warp, nw, lane);  // (also drains the asynchronous copies)
   if (mode == V2_EMPTY) return;  // (the whole CTA) no sample of the RoI falls inside the map
   __syncthreads();
