@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256, NT == 2 ? 2 : 3) v2_fwd_kernel(const __gr
   bool generic = mode == V2_GENERIC;  // (the whole CTA)
   // a bin taller than the strip (two-tensor kernel: 13..15 map rows, i.e. a RoI more than ~12 * PH map rows high)
   // sends the RoI down the per-sample path
-  if (!generic && v2_strip_rows_for(NT) <= kV2Sup) generic = v2_tallest_bin(plan_s, a.PH, a.PW) > v2_strip_rows_for(NT);
+  if (!generic && v2_strip_rows_for(NT) <= kV2Sup) generic = v2_lds4i(plan_s + 32).z > v2_strip_rows_for(NT);  // hdr[10]
   if (generic) {
     const RoiGeom g = roi_geometry(a.rois, a.levels, a.lv[0], r, a.PH, a.PW, a.ratio);
     for (int pw = warp; pw < a.PW; pw += nw)

@@ -91,7 +91,7 @@ constexpr int kV2MaxFW = 64;    // widest footprint (map pixels) with pixel-colu
 constexpr int kV2MaxFH = 64;    // tallest footprint (map rows) with row records
 constexpr int kV2Hdr = 16;
 enum V2Mode { V2_EMPTY = 0, V2_PLAN = 1, V2_GENERIC = 3 };
-// hdr: [0] mode [1] batch [2] level [3] H [4] W [5] 1/count [6] X0 [7] FW [8] Y0 [9] Y1
+// hdr: [0] mode [1] batch [2] level [3] H [4] W [5] 1/count [6] X0 [7] FW [8] Y0 [9] Y1 [10] tallest bin (map rows)
 
 // records after the header: PW bin columns, PH bin rows, kV2MaxFW footprint pixel columns, kV2MaxFH footprint rows
 ABR_HOSTDEV size_t v2_plan_words(int PH, int PW) { return (size_t)kV2Hdr + (size_t)(PH + PW + kV2MaxFW + kV2MaxFH) * kV2Rec; }
@@ -140,7 +140,7 @@ ABR_HD void v2_plan_axes(int* plan, const RoiGeom& g, int H, int W, int PH, int 
 
 // Phase 2 (one thread, after phase 1 is visible): header.
 ABR_HD void v2_plan_header(int* plan, const RoiGeom& g, int H, int W, int PH, int PW) {
-  int X0 = W, X1 = -1, Y0 = H, Y1 = -1;
+  int X0 = W, X1 = -1, Y0 = H, Y1 = -1, tallest = 0;
   bool generic = false;
   for (int i = 0; i < PW + PH; i++) {
     const int w0 = plan[kV2Hdr + i * kV2Rec];
@@ -148,7 +148,7 @@ ABR_HD void v2_plan_header(int* plan, const RoiGeom& g, int H, int W, int PH, in
     const int lo = w0 & 0xffff, n = w0 >> 16;
     if (n == 0) continue;
     if (i < PW) { X0 = lo < X0 ? lo : X0; X1 = lo + n - 1 > X1 ? lo + n - 1 : X1; }
-    else { Y0 = lo < Y0 ? lo : Y0; Y1 = lo + n - 1 > Y1 ? lo + n - 1 : Y1; }
+    else { Y0 = lo < Y0 ? lo : Y0; Y1 = lo + n - 1 > Y1 ? lo + n - 1 : Y1; tallest = n > tallest ? n : tallest; }
   }
   int mode = V2_PLAN;
   if (generic) mode = V2_GENERIC;
@@ -158,7 +158,8 @@ ABR_HD void v2_plan_header(int* plan, const RoiGeom& g, int H, int W, int PH, in
   plan[5] = __float_as_int(1.f / g.count);
   plan[6] = X1 < X0 ? 0 : X0; plan[7] = X1 < X0 ? 0 : X1 - X0 + 1;
   plan[8] = Y1 < Y0 ? 0 : Y0; plan[9] = Y1 < Y0 ? 0 : Y1;
-  for (int i = 10; i < kV2Hdr; i++) plan[i] = 0;
+  plan[10] = tallest;  // the forward sends RoIs with a bin taller than its strip down the per-sample path
+  for (int i = 11; i < kV2Hdr; i++) plan[i] = 0;
 }
 
 // Phase 3 (threads tid, tid + nth, ..., after phase 2 is visible): the transposed records the backward walks.
@@ -295,16 +296,6 @@ ABR_DEV void v2_stage_records(const int* __restrict__ plan, v2_sptr plan_s, int 
   for (int i = tid; i < 4 * nrec; i += nth) v2_sts4i(plan_s + 64 * (1 + first) + 16 * i, ABR_LDG4I(plan + kV2Hdr + first * kV2Rec + 4 * i));
 }
 ABR_HOSTDEV size_t v2_plan_smem_bytes(int nrec) { return (size_t)64 * (1 + nrec); }
-// Tallest bin of the staged plan (rows); every thread of the CTA gets the same answer.
-ABR_DEV int v2_tallest_bin(v2_sptr plan_s, int PH, int PW) {
-  int n = 0;
-  for (int ph = 0; ph < PH; ph++) {
-    const int k = v2_lds4i(v2_srec(plan_s, PW + ph)).x >> 16;
-    n = k > n ? k : n;
-  }
-  return n;
-}
-
 // Three warp totals with six shuffles (reduce-scatter): on return lane 0 holds sum(a), lane 16 sum(b), lane 8 sum(c).
 ABR_DEV float v2_reduce3(float a, float b, float c, int lane) {
 #ifndef ABR_EMU

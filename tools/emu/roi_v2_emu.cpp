@@ -60,7 +60,7 @@ static void fwd_t(const int* plans, const float* rois, const float* m0, const fl
           if (!active) c = 0;
           float* srs = NT == 2 ? sums + ((size_t)r * nslices + slice) * PH * PW * 3 : nullptr;
           for (int t = 0; t < 7; t++) v2_stage_plan(plan, plan_s, PW + PH, t, 7);  // the CTA's copy, then __syncthreads()
-          if (plan[0] == V2_GENERIC || (plan[0] == V2_PLAN && v2_tallest_bin(plan_s, PH, PW) > v2_strip_rows_for(NT))) {
+          if (plan[0] == V2_GENERIC || (plan[0] == V2_PLAN && plan[10] > v2_strip_rows_for(NT))) {
             const RoiGeom g = roi_geometry(rois, nullptr, lv, r, PH, PW, ratio);
             v2_generic_fwd_column<float, V, NT>(g, H, W, maps, outs, srs, r, pw, c, active, C, PH, PW, lane);
           } else {
